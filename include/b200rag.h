@@ -1,0 +1,137 @@
+/* b200rag.h — C ABI of libb200rag.so: the B200-native (sm_100a) retrieval hot
+ * path that stands behind RAG-DPO's injected `collection` / `chunk_bm25_index`
+ * objects.  The reference has NO FFI of its own (pure Python, duck typing);
+ * each entry point below names the reference call it replaces (paths relative
+ * to /root/reference).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative RAG_E* code; the text
+ *     of the last failure on the calling thread is rag_last_error().
+ *   - "host" pointers are plain host memory owned by the caller; "_dev"
+ *     entry points take device pointers (HBM-resident inputs / torch interop).
+ *   - the library owns all device memory behind its handles; every call is
+ *     synchronous (returns after its stream work finished) and handles are
+ *     serialised by an internal lock.
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with RAG_ENODEV.
+ *   - dense scores are the CANONICAL fp64 scores of DESIGN.md §3 (fixed-order
+ *     fp64 sum of exact products), so ids and scores are bit-identical to the
+ *     oracle.  Order: score descending, ties -> lowest row.
+ */
+#ifndef B200RAG_H
+#define B200RAG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAG_OK 0
+#define RAG_EINVAL (-1)   /* bad argument */
+#define RAG_ENODEV (-2)   /* no usable sm_100 device / CUDA error */
+#define RAG_ENOMEM (-3)
+#define RAG_ERANGE (-4)   /* k, dim or batch outside the supported range */
+#define RAG_ECUDA (-5)
+
+/* storage dtype of corpus rows */
+#define RAG_F32 0
+#define RAG_BF16 1
+#define RAG_F16 2
+
+#define RAG_MAX_K 224     /* largest n_results / top_k served by the fused select */
+
+typedef struct rag_corpus rag_corpus_t;
+typedef struct rag_bm25 rag_bm25_t;
+
+/* ---- runtime ------------------------------------------------------------ */
+int rag_init(int device);                 /* bind the calling process to one GPU (one process per GPU) */
+int rag_set_stream(void* cuda_stream);    /* run on the caller's stream (e.g. torch's current stream); NULL = own */
+const char* rag_last_error(void);
+int rag_abi_version(void);
+int rag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
+/* per-stage device time (ms, CUDA events on the launching stream) of the last
+ * dense / bm25 call: [0] main scan or contraction kernel, [1] candidate merge,
+ * [2] fp64 refine + select, [3] fallback pass (0 if not taken), rest 0. */
+int rag_last_timings(float* ms, int n);
+/* counters since rag_init: [0] kernels launched, [1] fallback passes taken */
+int rag_counters(int64_t* out, int n);
+
+/* ---- corpus: the chunk-embedding matrix -----------------------------------
+ * replaces the vector segment behind chromadb's Collection: written through
+ * collection.add (src/processing/create_chromadb_index.py:374-379,
+ * src/processing/ingest_enterprise.py:241-246). Rows are appended in order;
+ * row index == insertion order. dim % 64 == 0, dim <= 2048 (fp32: <= 1024). */
+int rag_corpus_create(rag_corpus_t** out, int64_t capacity_rows, int dim, int dtype);
+int rag_corpus_destroy(rag_corpus_t* c);
+int rag_corpus_reserve(rag_corpus_t* c, int64_t capacity_rows);
+/* append nrows fp32 host rows at row0 (== current count, or overwrite below it);
+ * rows are converted to the storage dtype on the device (round-to-nearest-even). */
+int rag_corpus_upload(rag_corpus_t* c, int64_t row0, int64_t nrows, const float* host_rows);
+/* stored values widened to fp32 (collection.get(include=["embeddings"])) */
+int rag_corpus_download(const rag_corpus_t* c, int64_t row0, int64_t nrows, float* host_rows);
+/* keep only the listed rows, in the listed (ascending) order (collection.delete,
+ * src/processing/ingest_enterprise.py:272,304) */
+int rag_corpus_compact(rag_corpus_t* c, const int64_t* keep_rows, int64_t nkeep);
+int rag_corpus_count(const rag_corpus_t* c, int64_t* n);
+/* deterministic synthetic unit rows generated on the device (bench/test input:
+ * counter-based hash of (seed, gen_row0 + i, col) -> uniform(-1,1) -> L2-normalised,
+ * written to local rows row0 + i; gen_row0 is the shard's offset in the global corpus) */
+int rag_corpus_fill_synthetic(rag_corpus_t* c, uint64_t seed, int64_t gen_row0, int64_t row0, int64_t nrows);
+int rag_corpus_device_ptr(const rag_corpus_t* c, void** rows_dev);
+
+/* ---- dense similarity + exact top-k ---------------------------------------
+ * replaces collection.query(query_embeddings=[vec], n_results=k, where=...)
+ * at src/rag/retriever.py:215-220 and :380-385 (cosine space,
+ * src/processing/create_chromadb_index.py:100-106).
+ *   q            B x dim fp32, row-major (already L2-normalised by the caller)
+ *   allow_bitmap NULL or ceil(count/8) bytes, bit r set = row r passes `where`
+ *   out_rows     B x k local row indices, -1 padded
+ *   out_scores   B x k canonical fp64 <q,x>  (distance = 1 - score)
+ *   out_counts   B     number of valid results (< k if the filter leaves fewer) */
+int rag_dense_topk(rag_corpus_t* c, const float* q, int B, int k, const uint8_t* allow_bitmap,
+                   int32_t* out_rows, double* out_scores, int32_t* out_counts);
+/* same, every pointer is a DEVICE pointer (inputs resident in HBM) */
+int rag_dense_topk_dev(rag_corpus_t* c, const float* q_dev, int B, int k, const uint8_t* allow_bitmap_dev,
+                       int32_t* out_rows_dev, double* out_scores_dev, int32_t* out_counts_dev);
+/* multi-GPU exchange step (one process per GPU): after an all-gather of the G
+ * ranks' (score, global id) lists, keep the global top-k per query, order
+ * (score desc, id asc).  Device pointers: scores/ids are G x B x k. */
+int rag_merge_topk_dev(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k,
+                       double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev);
+
+/* ---- BM25 keyword scoring over CSR postings -------------------------------
+ * replaces rank_bm25.BM25Okapi(corpus_tokens) / .get_scores(tokens)
+ * (src/rag/bm25_index.py:126,153,236,265) and the select loop of
+ * ChunkBM25Index.search (src/rag/bm25_index.py:267-279).
+ *   term_ptr  n_terms+1 offsets into the postings, postings sorted by row
+ *   idf       per-term weight AFTER the negative-idf epsilon floor
+ * fp64 arithmetic in numpy's evaluation order; scores bit-identical. */
+int rag_bm25_create(rag_bm25_t** out, int64_t n_docs, int64_t n_terms, int64_t nnz, const int64_t* term_ptr,
+                    const int32_t* post_row, const int32_t* post_tf, const int32_t* doc_len, const double* idf,
+                    double avgdl, double k1, double b);
+int rag_bm25_destroy(rag_bm25_t* ix);
+/* Q queries; q_terms are the concatenated term ids (in token order, repeats
+ * kept, -1 = token outside the vocabulary), q_ptr has Q+1 offsets.
+ * allow_bitmap: NULL or one bitmap shared by all queries (doc_filter).
+ * Results: score > 0 only, score desc, ties -> lowest row; -1 padded. */
+int rag_bm25_search(rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr, int Q, int k,
+                    const uint8_t* allow_bitmap, int32_t* out_rows, double* out_scores, int32_t* out_counts);
+/* full score vector of one query (BM25Okapi.get_scores parity), n_docs doubles */
+int rag_bm25_scores(rag_bm25_t* ix, const int32_t* q_terms, int n_q_terms, double* out_scores);
+
+/* ---- weighted Reciprocal Rank Fusion --------------------------------------
+ * replaces reciprocal_rank_fusion (src/rag/retriever.py:66-90) + the stable
+ * descending sort and cut of the fusion tail (:464-467) for Q questions at once.
+ *   ids      Q x R x L integer ids, negative = padding (skipped, rank not advanced)
+ *   weights  Q x R
+ * Output per question: distinct ids by (fused score desc, first-seen order),
+ * at most `top`; -1 padded. */
+int rag_rrf_fuse(const int32_t* ids, const double* weights, int Q, int R, int L, int rrf_k, int top,
+                 int32_t* out_ids, double* out_scores, int32_t* out_counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RAG_H */

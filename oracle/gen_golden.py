@@ -1,0 +1,323 @@
+"""ORACLE — test infrastructure, not product code.
+
+Generates tests/golden/* by running the reference's OWN unmodified Python
+(/root/reference/src/rag/{retriever,bm25_index}.py via oracle/ref_harness.py)
+around the oracle's ExactCollection and restated rank_bm25.  Run in the build
+container only:   python -m oracle.gen_golden
+
+Floats are stored as float.hex() strings so comparisons are bit-exact.
+"""
+import json
+import os
+import random
+
+import numpy as np
+
+from . import numpy_oracle as no
+from . import ref_harness
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# vocabulary for synthetic French-legal chunks (own list; includes stopwords,
+# accents, hyphenated compounds, digits and 1-letter tokens on purpose)
+_CONTENT = """données personnelles traitement responsable sous-traitant consentement finalité durée
+conservation registre violation notification cnil rgpd délégué protection analyse impact aipd
+sécurité chiffrement pseudonymisation transfert pays tiers clauses contractuelles-types base légale
+intérêt légitime obligation contrat mission publique droit accès rectification effacement
+portabilité opposition limitation profilage décision automatisée vidéosurveillance salarié employeur
+recrutement candidat cv cookies traceurs bannière prospection commerciale newsletter fichier client
+santé biométrie géolocalisation mineur parent école association collectivité mairie élu sanction
+amende mise-en-demeure contrôle plainte réclamation délai mois jours article 28 30 32 33 35 6 7 13
+archivage intermédiaire anonymisation minimisation proportionnalité nécessité information personne
+concernée tiers destinataire hébergeur cloud logiciel paie badgeuse télétravail bring-your-own-device
+e-mail sms démarchage téléphonique opt-in opt-out b2b b2c dpo rssi dsi rh ce cse""".split()
+_STOP = "le la les de des du un une et en au aux ce ces qui que dans sur avec sans pour par est sont d l".split()
+
+
+def _hex(x):
+    return float(x).hex()
+
+
+def make_text(rng, n_words):
+    words = []
+    for _ in range(n_words):
+        if rng.random() < 0.3:
+            words.append(rng.choice(_STOP))
+        else:
+            # Zipf-ish pick
+            idx = min(int(rng.paretovariate(1.1)) - 1, len(_CONTENT) - 1)
+            words.append(_CONTENT[idx])
+    s = " ".join(words)
+    s = s[0].upper() + s[1:]
+    if rng.random() < 0.5:
+        s += " (art. %d RGPD) ?" % rng.choice([6, 7, 13, 28, 30, 32, 33, 35])
+    else:
+        s += "."
+    return s
+
+
+def gen_rrf(ref):
+    f = ref["retriever"].reciprocal_rank_fusion
+    rng = random.Random(11)
+    cases = [
+        {"rankings": [["a", "b"], ["b", "c"]], "weights": [2.0, 3.0], "k": 60},
+        {"rankings": [["a", "b", "c"]], "weights": None, "k": 60},
+        {"rankings": [[], ["x"]], "weights": [2.0, 3.0], "k": 60},
+        {"rankings": [["a", "b"], ["b", "a"]], "weights": [1.0, 1.0], "k": 60},   # exact tie -> first-seen
+    ]
+    ref_w = [2.0, 3.0, 1.0, 0.75, 1.0, 0.75, 1.0, 0.75]      # retriever.py:374,405,431-432
+    for R, L, universe in [(8, 50, 120), (5, 50, 80), (2, 50, 60), (8, 50, 400), (3, 7, 9)]:
+        ids = [f"doc{j}_{j % 7}" for j in range(universe)]
+        rankings = []
+        for _ in range(R):
+            ln = rng.randint(max(0, L - 10), L)
+            rankings.append(rng.sample(ids, min(ln, universe)))
+        w = ref_w[:R] if R in (8, 2) else ([2.0, 2.0, 1.0, 1.0, 1.0][:R])
+        cases.append({"rankings": rankings, "weights": w, "k": 60})
+    out = []
+    for c in cases:
+        kw = {"k": c["k"]}
+        if c["weights"] is not None:
+            kw["weights"] = c["weights"]
+        scores = f(c["rankings"], **kw)
+        order = list(scores.keys())                          # first-seen order (chunk_map order)
+        order.sort(key=lambda i: scores[i], reverse=True)    # retriever.py:464-465 (stable)
+        out.append({**c, "scores": {i: _hex(s) for i, s in scores.items()}, "order": order})
+    return out
+
+
+def gen_tokenizer(ref):
+    tok = ref["bm25_index"].tokenize_french
+    rng = random.Random(5)
+    texts = [
+        "Quelle est la durée de conservation des CV d'un sous-traitant (art. 28 RGPD) ?",
+        "L'employeur peut-il géolocaliser les véhicules ? Œuvre, ÉLÈVE, aujourd'hui, c'est-à-dire…",
+        "", "   ", "à y d l", "A1 b2-c3 --x-- 12-34-56 e-mail@cnil.fr https://www.cnil.fr/fr/rgpd-de-quoi-parle-t-on",
+        "Naïveté ambiguë : çà et là, où ? Ÿ ÿ æ Æ œ Œ", "UPPER lower MiXeD Sous-Traitant SOUS-TRAITANT",
+    ] + [make_text(rng, rng.randint(3, 30)) for _ in range(24)]
+    return [{"text": t, "tokens": tok(t)} for t in texts]
+
+
+def make_corpus(rng, n_docs, dim, seed, common_rate=0.0):
+    chunks = []
+    natures = ["DOCTRINE", "GUIDE", "SANCTION", "TECHNIQUE"]
+    for d in range(n_docs):
+        path = f"data/keep/cnil/doc_{d:03d}.html"
+        src = "ENTREPRISE" if d % 9 == 4 else "CNIL"
+        for ci in range(rng.randint(2, 11)):
+            text = make_text(rng, rng.randint(12, 70))
+            if rng.random() < common_rate:
+                text += " Données RGPD."           # df > N/2 -> negative idf -> epsilon floor
+            if d % 13 == 5 and ci == 1:
+                text = "   "                      # skipped by build_from_collection (:220-221)
+            if d % 17 == 3 and ci == 0:
+                text = "le la les de des"          # tokenises to nothing (:223-225)
+            meta = {"document_path": path, "chunk_nature": natures[(d + ci) % 4], "chunk_index": ci,
+                    "confidence": "high" if ci % 2 == 0 else "medium", "source": src,
+                    "source_url": f"https://www.cnil.fr/fr/doc-{d % 37}", "title": f"Titre {d}"}
+            if src == "ENTREPRISE" and d % 2 == 0:
+                meta["tag_rh"] = True
+            chunks.append({"id": f"doc{d:03d}_{ci}", "text": text, "metadata": meta})
+    g = np.random.default_rng(seed)
+    emb = no.l2_normalize_rows(g.standard_normal((len(chunks), dim)).astype(np.float32))
+    return chunks, emb
+
+
+def fill_collection(col, chunks, emb, batch=100):
+    for s in range(0, len(chunks), batch):
+        part = chunks[s:s + batch]
+        col.add(ids=[c["id"] for c in part], documents=[c["text"] for c in part],
+                embeddings=emb[s:s + batch], metadatas=[c["metadata"] for c in part])
+
+
+def gen_bm25(ref):
+    rng = random.Random(21)
+    chunks, emb = make_corpus(rng, 45, 64, 3, common_rate=0.7)
+    col = no.ExactCollection(dim=64)
+    fill_collection(col, chunks, emb)
+    idx = ref["bm25_index"].ChunkBM25Index()
+    idx.build_from_collection(col, batch_size=70)
+    queries = [make_text(rng, rng.randint(3, 12)) for _ in range(20)]
+    queries += ["données données données personnelles", "zzzz inconnu", "le la les", "",
+                "sous-traitant article 28", "cookies traceurs bannière consentement"]
+    doc_paths = sorted({c["metadata"]["document_path"] for c in chunks})
+    cases = []
+    for qi, q in enumerate(queries):
+        for top_k, filt in [(50, None), (5, None), (50, doc_paths[qi % 5::5]), (3, doc_paths[:2])]:
+            res = idx.search(q, top_k=top_k, doc_filter=set(filt) if filt is not None else None)
+            cases.append({"query": q, "top_k": top_k, "doc_filter": filt,
+                          "results": [{"doc_key": r.doc_key, "score": _hex(r.score)} for r in res]})
+    # all-common-terms corpus: every idf is negative -> floor is negative -> empty result
+    common = [{"id": f"c{i}", "text": "données traitement rgpd", "metadata": {"document_path": f"p{i}"}}
+              for i in range(6)]
+    col2 = no.ExactCollection(dim=64)
+    fill_collection(col2, common, no.l2_normalize_rows(np.random.default_rng(1).standard_normal((6, 64))))
+    idx2 = ref["bm25_index"].ChunkBM25Index()
+    idx2.build_from_collection(col2)
+    res2 = idx2.search("données rgpd", top_k=10)
+    return {"chunks": chunks, "kept_ids": list(idx.chunk_ids), "avgdl": _hex(idx.index.avgdl),
+            "idf": {w: _hex(v) for w, v in idx.index.idf.items()}, "cases": cases,
+            "common_corpus": common, "common_results": [{"doc_key": r.doc_key, "score": _hex(r.score)} for r in res2]}
+
+
+def gen_summary(ref):
+    rng = random.Random(33)
+    summaries = {}
+    for d in range(30):
+        s = make_text(rng, rng.randint(15, 50))
+        if d == 7:
+            s = "ERREUR: génération impossible"
+        if d == 11:
+            s = ""
+        summaries[f"data/keep/cnil/doc_{d:03d}.html"] = {
+            "summary": s, "document_title": make_text(rng, 4), "source_url": f"https://www.cnil.fr/fr/doc-{d}"}
+    path = os.path.join(OUT, "summaries_input.json")
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(summaries, f, ensure_ascii=False, indent=0)
+    idx = ref["bm25_index"].SummaryBM25Index()
+    idx.build(path)
+    queries = [make_text(rng, rng.randint(3, 10)) for _ in range(10)] + ["", "zzzz"]
+    cases = []
+    for q in queries:
+        for top_k in (40, 5):
+            res = idx.search(q, top_k=top_k)
+            cases.append({"query": q, "top_k": top_k,
+                          "results": [{"doc_key": r.doc_key, "score": _hex(r.score)} for r in res]})
+    return {"doc_keys": list(idx.doc_keys), "cases": cases}
+
+
+def gen_dense():
+    g = np.random.default_rng(77)
+    n, d, nq = 1024, 128, 12
+    x = no.l2_normalize_rows(g.standard_normal((n, d)).astype(np.float32))
+    q = no.l2_normalize_rows(g.standard_normal((nq, d)).astype(np.float32))
+    # planted structure: exact duplicates (ties -> lowest row) and a near-duplicate of a query
+    x[700] = x[13]; x[701] = x[13]; x[5] = x[13]
+    x[300] = q[0]; x[301] = q[0]; x[900] = q[0]
+    x[302] = no.l2_normalize_rows((q[0] + 1e-4 * g.standard_normal(d)).astype(np.float32))[0]
+    q[1] = x[13]
+    np.savez_compressed(os.path.join(OUT, "dense_small.npz"), x=x, q=q)
+    allow = (np.arange(n) % 3 != 0)
+    out = {"n": n, "d": d, "cases": []}
+    for name, dt in (("f32", no.DT_F32), ("bf16", no.DT_BF16), ("f16", no.DT_F16)):
+        xs = no.quantize(x, dt)
+        for k in (1, 10, 50, 100):
+            for filt in (False, True):
+                rows_all, sc_all = [], []
+                for qi in range(nq):
+                    r, s = no.dense_topk(q[qi], xs, k, allow if filt else None)
+                    rows_all.append([int(v) for v in r])
+                    sc_all.append([_hex(v) for v in s])
+                out["cases"].append({"dtype": name, "k": k, "filtered": filt, "rows": rows_all, "scores": sc_all})
+    return out
+
+
+def _chunk_dump(c):
+    return {"chunk_id": c.chunk_id, "distance": _hex(c.distance), "semantic": _hex(c.semantic_score),
+            "bm25": _hex(c.bm25_score), "hybrid": _hex(c.hybrid_score),
+            "document_path": c.document_path, "chunk_index": c.chunk_index}
+
+
+def _stable_nature(doc):
+    """RetrievedDocument.primary_nature is max(set(natures), key=count) (retriever.py:59-61): on a
+    count tie the winner depends on str hash order, i.e. on PYTHONHASHSEED.  Record it only when
+    it is unambiguous."""
+    natures = [c.chunk_nature for c in doc.chunks]
+    counts = sorted((natures.count(n) for n in set(natures)), reverse=True)
+    return doc.primary_nature if len(counts) == 1 or counts[0] > counts[1] else None
+
+
+def gen_e2e(ref):
+    rng = random.Random(42)
+    dim = 128
+    chunks, emb = make_corpus(rng, 60, dim, 9)
+    col = no.ExactCollection(dim=dim)
+    fill_collection(col, chunks, emb)
+    bm = ref["bm25_index"].ChunkBM25Index()
+    bm.build_from_collection(col)
+    # summaries for the prefilter
+    summaries = {}
+    by_doc = {}
+    for c in chunks:
+        by_doc.setdefault(c["metadata"]["document_path"], []).append(c["text"])
+    for p, texts in by_doc.items():
+        summaries[p] = {"summary": " ".join(texts)[:300], "document_title": texts[0][:40],
+                        "source_url": "https://www.cnil.fr/" + p[-12:]}
+    spath = os.path.join(OUT, "e2e_summaries.json")
+    with open(spath, "w", encoding="utf-8") as f:
+        json.dump(summaries, f, ensure_ascii=False, indent=0)
+    sm = ref["bm25_index"].SummaryBM25Index()
+    sm.build(spath)
+
+    g = np.random.default_rng(123)
+    queries, qemb, expansions = [], {}, {}
+    for qi in range(8):
+        ci = rng.randrange(len(chunks))
+        words = [w for w in chunks[ci]["text"].split() if len(w) > 3][:6]
+        text = "Comment gérer " + " ".join(words) + " ?"
+        if qi == 3:
+            text = "Rôle du DPO dans le RGPD ?"            # acronym expansion path (acronyms.py:151-198)
+        queries.append(text)
+        exps = [f"{text} reformulation {j} " + make_text(rng, 5) for j in range(3)]
+        expansions[text] = exps
+    from src.utils.acronyms import expand_query_with_acronyms
+    embed_table = {}
+    expanded_of = {}
+    for text in queries:
+        et = expand_query_with_acronyms(text)
+        expanded_of[text] = et
+        expansions[et] = expansions[text]
+        for t in [et] + expansions[text]:
+            ci = rng.randrange(len(chunks))
+            v = emb[ci] + 0.6 * no.l2_normalize_rows(g.standard_normal(dim).astype(np.float32))[0]
+            embed_table[t] = no.l2_normalize_rows(v)[0]
+    provider = ref_harness.FixedEmbeddingProvider(embed_table)
+    R = ref["retriever"].RAGRetriever
+    where_cases = [None, {"source": "CNIL"}, {"$or": [{"source": "CNIL"}, {"$and": [{"source": "ENTREPRISE"}, {"tag_rh": True}]}]},
+                   {"source": {"$ne": "ENTREPRISE"}}, {"chunk_nature": {"$in": ["GUIDE", "SANCTION"]}}]
+    runs = []
+    for cfg in [
+        {"expander": False, "prefilter": False, "hybrid": True},
+        {"expander": True, "prefilter": False, "hybrid": True},
+        {"expander": True, "prefilter": True, "hybrid": True},
+        {"expander": False, "prefilter": True, "hybrid": False},
+    ]:
+        r = R(collection=col, llm_provider=None, embedding_provider=provider,
+              summary_bm25_index=sm if cfg["prefilter"] else None, chunk_bm25_index=bm,
+              query_expander=ref_harness.FixedQueryExpander(expansions) if cfg["expander"] else None,
+              n_documents=5, n_chunks_per_doc=3, summary_prefilter_k=8,
+              enable_hybrid=cfg["hybrid"], enable_summary_prefilter=cfg["prefilter"])
+        for qi, text in enumerate(queries):
+            w = where_cases[qi % len(where_cases)]
+            cands = r.retrieve_candidates(text, n_candidates=40, where_filter=w)
+            docs = r.retrieve(text, where_filter=w)
+            runs.append({"config": cfg, "query": text, "where": w,
+                         "candidates": [_chunk_dump(c) for c in cands],
+                         "documents": [{"document_path": d.document_path, "avg_similarity": _hex(d.avg_similarity),
+                                        "primary_nature": _stable_nature(d),
+                                        "chunks": [_chunk_dump(c) for c in d.chunks]} for d in docs]})
+    np.savez_compressed(os.path.join(OUT, "e2e_embeddings.npz"), emb=emb,
+                        qtexts=np.array(list(embed_table.keys())),
+                        qemb=np.stack([embed_table[t] for t in embed_table]))
+    return {"chunks": chunks, "queries": queries, "expanded": expanded_of, "expansions": expansions, "runs": runs}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_harness.load()
+
+    def dump(name, obj):
+        with open(os.path.join(OUT, name), "w", encoding="utf-8") as f:
+            json.dump(obj, f, ensure_ascii=False, indent=0)
+        print("wrote", name)
+
+    dump("rrf.json", gen_rrf(ref))
+    dump("tokenizer.json", gen_tokenizer(ref))
+    dump("bm25_small.json", gen_bm25(ref))
+    dump("summary_bm25.json", gen_summary(ref))
+    dump("dense_small.json", gen_dense())
+    dump("e2e_retrieve.json", gen_e2e(ref))
+
+
+if __name__ == "__main__":
+    main()

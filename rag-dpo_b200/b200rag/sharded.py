@@ -1,0 +1,104 @@
+"""Row-sharded dense search: one process per GPU, candidates merged with one
+all-gather (NCCL over NVLink on the B200 box; gloo in the CPU tests).
+
+The reference is single-process; this is the B200 scale-out of
+collection.query (src/rag/retriever.py:215-220, 380-385): rank g owns the
+contiguous rows [g*ceil(N/G), (g+1)*ceil(N/G)), every rank scores the same
+query batch against its shard, and the exact (score, global id) top-k lists
+are exchanged and merged with ties -> lowest global id.  Exactness: the global
+top-k is a subset of the union of the local top-k lists.
+"""
+import numpy as np
+
+
+def shard_bounds(n_rows, world, rank):
+    per = (n_rows + world - 1) // world
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per)
+
+
+def merge_lists_torch(scores, ids, k):
+    """(G,B,k) -> (B,k) by (score desc, id asc); ids < 0 are padding.  Host-side
+    restatement used only where no GPU exists (gloo tests)."""
+    import torch
+    G, B, kk = scores.shape
+    s = scores.permute(1, 0, 2).reshape(B, G * kk)
+    i = ids.permute(1, 0, 2).reshape(B, G * kk)
+    s = torch.where(i >= 0, s, torch.full_like(s, float("-inf")))
+    big = torch.where(i >= 0, i, torch.full_like(i, 2 ** 62))
+    order1 = torch.argsort(big, dim=1, stable=True)
+    s1, i1 = torch.gather(s, 1, order1), torch.gather(big, 1, order1)
+    order2 = torch.argsort(s1, dim=1, descending=True, stable=True)
+    s2, i2 = torch.gather(s1, 1, order2)[:, :k], torch.gather(i1, 1, order2)[:, :k]
+    valid = i2 < 2 ** 62
+    return torch.where(valid, s2, torch.zeros_like(s2)), torch.where(valid, i2, torch.full_like(i2, -1)), valid.sum(1).to(torch.int32)
+
+
+class ShardedDenseIndex:
+    """local_topk(q32 np (B,d), k) -> (rows int32 (B,k) [-1 pad], scores f64 (B,k), counts).
+    On the GPU box leave local_topk/merge at None: the shard lives in a
+    DeviceCorpus and the merge runs in rag_merge_topk_dev."""
+
+    def __init__(self, dim, n_rows_total, dtype="bf16", group=None, local_topk=None, merge=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.dim = dim
+        self.n_rows_total = int(n_rows_total)
+        self.row_lo, self.row_hi = shard_bounds(self.n_rows_total, self.world, self.rank)
+        self._local_topk = local_topk
+        self._merge = merge
+        self.corpus = None
+        if local_topk is None:
+            from . import _lib
+            from .collection import DeviceCorpus
+            self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            self.corpus = DeviceCorpus(dim, dtype, capacity=self.row_hi - self.row_lo)
+        else:
+            self.device = torch.device("cpu")
+
+    def fill_synthetic(self, seed):
+        """each rank generates exactly its own rows of the global synthetic corpus"""
+        self.corpus.fill_synthetic(seed, self.row_hi - self.row_lo, gen_row0=self.row_lo)
+
+    def topk(self, q32, k):
+        """q32: numpy (B,dim) fp32, identical on every rank.  Returns numpy
+        (ids int64 (B,k) [-1 pad], scores f64 (B,k), counts int32 (B,))."""
+        torch, dist = self.torch, self.dist
+        B = q32.shape[0]
+        kk = int(k)
+        if self._local_topk is not None:
+            rows, scores, counts = self._local_topk(q32, kk)
+        else:
+            n_local = self.row_hi - self.row_lo
+            kl = min(kk, n_local)
+            rows = np.full((B, kk), -1, np.int32)
+            scores = np.zeros((B, kk), np.float64)
+            if kl > 0:
+                r, s, c = self.corpus.topk(q32, kl)
+                rows[:, :kl], scores[:, :kl] = r, s
+        ids = np.where(rows >= 0, rows.astype(np.int64) + self.row_lo, -1)
+        t_scores = torch.from_numpy(np.ascontiguousarray(scores)).to(self.device)
+        t_ids = torch.from_numpy(np.ascontiguousarray(ids)).to(self.device)
+        if self.world > 1:
+            g_scores = torch.empty((self.world, B, kk), dtype=torch.float64, device=self.device)
+            g_ids = torch.empty((self.world, B, kk), dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(g_scores, t_scores, group=self.group)
+            dist.all_gather_into_tensor(g_ids, t_ids, group=self.group)
+        else:
+            g_scores, g_ids = t_scores[None], t_ids[None]
+        if self._merge is not None or self.corpus is None:
+            merge = self._merge or merge_lists_torch
+            o_s, o_i, o_c = merge(g_scores, g_ids, kk)
+        else:
+            from . import _lib
+            torch.cuda.current_stream(self.device).synchronize()     # the gather must have landed
+            o_s = torch.empty((B, kk), dtype=torch.float64, device=self.device)
+            o_i = torch.empty((B, kk), dtype=torch.int64, device=self.device)
+            o_c = torch.empty((B,), dtype=torch.int32, device=self.device)
+            _lib.check(_lib.lib().rag_merge_topk_dev(g_scores.data_ptr(), g_ids.data_ptr(), self.world, B, kk,
+                                                     o_s.data_ptr(), o_i.data_ptr(), o_c.data_ptr()))
+        return o_i.cpu().numpy(), o_s.cpu().numpy(), o_c.cpu().numpy()

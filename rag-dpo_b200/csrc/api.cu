@@ -1,0 +1,834 @@
+// api.cu — the C ABI of libb200rag.so (include/b200rag.h): handles, staging,
+// stream/event plumbing and the orchestration of the kernels.  No CPU compute
+// path exists here: without an sm_100 device every entry point fails.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace b200rag;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(e__ == cudaErrorMemoryAllocation ? RAG_ENOMEM : RAG_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
+    } while (0)
+
+#define RAG_TRY(expr)             \
+    do {                          \
+        int r__ = (expr);         \
+        if (r__ != RAG_OK) return r__; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return RAG_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        size_t want = need + need / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(RAG_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        bytes = want;
+        return RAG_OK;
+    }
+    template <typename T>
+    T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct Ctx {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 0, cc_major = 0, cc_minor = 0, smem_optin = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    bool ev_valid[6] = {};
+    float timings[8] = {};
+    int64_t n_launch = 0, n_fallback = 0;
+    std::mutex mu;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    int32_t* pinned_small = nullptr;    // 4 KB for flags / counters read back inside a call
+    // scratch (device)
+    DevBuf q, allow, cand, top, flags, tau, nflag, o_rows, o_scores, o_counts;
+    DevBuf fb_q, fb_tau, fb_counts, fb_rows, fb_scores, fb_index;
+    DevBuf bm_terms, bm_ranges, bm_cand, bm_rows, bm_scores, bm_counts, bm_allow;
+    DevBuf rrf_ids, rrf_w, rrf_oi, rrf_os, rrf_oc;
+    DevBuf stage_f32;
+};
+Ctx g;
+
+int ensure_pinned(size_t need) {
+    if (need <= g.pinned_bytes) return RAG_OK;
+    if (g.pinned) cudaFreeHost(g.pinned);
+    g.pinned = nullptr;
+    g.pinned_bytes = 0;
+    size_t want = need + need / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&g.pinned, want);
+    if (e != cudaSuccess) return fail(RAG_ENOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+    g.pinned_bytes = want;
+    return RAG_OK;
+}
+
+int require_init() {
+    if (!g.inited) return fail(RAG_ENODEV, "rag_init() has not succeeded: no sm_100 device bound (no CPU fallback)");
+    cudaError_t e = cudaSetDevice(g.device);
+    if (e != cudaSuccess) return fail(RAG_ENODEV, "cudaSetDevice(%d): %s", g.device, cudaGetErrorString(e));
+    return RAG_OK;
+}
+
+int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+void rec(int i) {
+    if (cudaEventRecord(g.ev[i], g.stream) == cudaSuccess) g.ev_valid[i] = true;
+}
+
+}  // namespace
+
+struct rag_corpus {
+    int dim = 0, dtype = 0;
+    int64_t cap = 0, n = 0;
+    size_t row_bytes = 0;
+    void* rows = nullptr;
+    float* max_norm = nullptr;   // device scalar
+};
+
+struct rag_bm25 {
+    Bm25Device d{};
+    std::vector<int64_t> h_term_ptr;
+    std::vector<double> h_idf;
+};
+
+extern "C" {
+
+const char* rag_last_error(void) { return g_err; }
+int rag_abi_version(void) { return 1; }
+
+int rag_init(int device) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(RAG_ENODEV, "no CUDA device: %s (b200rag has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(RAG_EINVAL, "device %d out of range (0..%d)", device, count - 1);
+    if (g.inited && g.device == device) return RAG_OK;
+    if (g.inited) return fail(RAG_EINVAL, "already bound to device %d (one process per GPU)", g.device);
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(RAG_ENODEV, "device %d is sm_%d%d; b200rag kernels are sm_100a only", device, prop.major, prop.minor);
+    g.device = device;
+    g.sm_count = prop.multiProcessorCount;
+    g.cc_major = prop.major;
+    g.cc_minor = prop.minor;
+    g.smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CU_TRY(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
+    for (auto& ev : g.ev) CU_TRY(cudaEventCreate(&ev));
+    CU_TRY(cudaMallocHost((void**)&g.pinned_small, 4096));
+    g.inited = true;
+    return RAG_OK;
+}
+
+int rag_set_stream(void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    g.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : g.own_stream;
+    return RAG_OK;
+}
+
+int rag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (sm_count) *sm_count = g.sm_count;
+    if (cc_major) *cc_major = g.cc_major;
+    if (cc_minor) *cc_minor = g.cc_minor;
+    size_t f = 0, t = 0;
+    CU_TRY(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return RAG_OK;
+}
+
+int rag_last_timings(float* ms, int n) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    for (int i = 0; i < n; ++i) ms[i] = i < 8 ? g.timings[i] : 0.f;
+    return RAG_OK;
+}
+
+int rag_counters(int64_t* out, int n) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (n > 0) out[0] = g.n_launch;
+    if (n > 1) out[1] = g.n_fallback;
+    for (int i = 2; i < n; ++i) out[i] = 0;
+    return RAG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// corpus
+// ---------------------------------------------------------------------------
+int rag_corpus_create(rag_corpus_t** out, int64_t capacity_rows, int dim, int dtype) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!out) return fail(RAG_EINVAL, "out is NULL");
+    if (dtype != RAG_F32 && dtype != RAG_BF16 && dtype != RAG_F16) return fail(RAG_EINVAL, "bad dtype %d", dtype);
+    if (dim <= 0 || dim % 64 != 0) return fail(RAG_ERANGE, "dim %d must be a positive multiple of 64", dim);
+    if (dim > (dtype == RAG_F32 ? 1024 : 2048)) return fail(RAG_ERANGE, "dim %d too large for dtype %d", dim, dtype);
+    if (capacity_rows < 0) return fail(RAG_EINVAL, "negative capacity");
+    if (capacity_rows > 0x7FFFFFF0LL) return fail(RAG_ERANGE, "more than 2^31 rows per shard");
+    rag_corpus* c = new rag_corpus();
+    c->dim = dim;
+    c->dtype = dtype;
+    c->row_bytes = (size_t)dim * (dtype == RAG_F32 ? 4 : 2);
+    c->cap = std::max<int64_t>(capacity_rows, 1);
+    cudaError_t e = cudaMalloc(&c->rows, (size_t)c->cap * c->row_bytes);
+    if (e != cudaSuccess) {
+        const size_t want = (size_t)c->cap * c->row_bytes;
+        delete c;
+        return fail(RAG_ENOMEM, "cudaMalloc(%zu) for corpus failed: %s", want, cudaGetErrorString(e));
+    }
+    e = cudaMalloc(&c->max_norm, sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->max_norm, 0, sizeof(float));
+    if (e != cudaSuccess) {
+        cudaFree(c->rows);
+        delete c;
+        return fail(RAG_ECUDA, "corpus init: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return RAG_OK;
+}
+
+int rag_corpus_destroy(rag_corpus_t* c) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!c) return RAG_OK;
+    if (g.inited) {
+        cudaSetDevice(g.device);
+        cudaStreamSynchronize(g.stream);
+        cudaFree(c->rows);
+        cudaFree(c->max_norm);
+    }
+    delete c;
+    return RAG_OK;
+}
+
+static int corpus_reserve_locked(rag_corpus* c, int64_t cap) {
+    if (cap <= c->cap) return RAG_OK;
+    if (cap > 0x7FFFFFF0LL) return fail(RAG_ERANGE, "more than 2^31 rows per shard");
+    int64_t want = std::max(cap, c->cap + c->cap / 2);
+    void* nr = nullptr;
+    cudaError_t e = cudaMalloc(&nr, (size_t)want * c->row_bytes);
+    if (e != cudaSuccess) {
+        want = cap;
+        e = cudaMalloc(&nr, (size_t)want * c->row_bytes);
+    }
+    if (e != cudaSuccess) return fail(RAG_ENOMEM, "cudaMalloc(%zu) growing corpus: %s", (size_t)want * c->row_bytes,
+                                      cudaGetErrorString(e));
+    CU_TRY(cudaMemcpyAsync(nr, c->rows, (size_t)c->n * c->row_bytes, cudaMemcpyDeviceToDevice, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    cudaFree(c->rows);
+    c->rows = nr;
+    c->cap = want;
+    return RAG_OK;
+}
+
+int rag_corpus_reserve(rag_corpus_t* c, int64_t capacity_rows) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!c) return fail(RAG_EINVAL, "corpus is NULL");
+    return corpus_reserve_locked(c, capacity_rows);
+}
+
+int rag_corpus_upload(rag_corpus_t* c, int64_t row0, int64_t nrows, const float* host_rows) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!c || (!host_rows && nrows > 0)) return fail(RAG_EINVAL, "NULL argument");
+    if (row0 < 0 || nrows < 0 || row0 > c->n) return fail(RAG_EINVAL, "rows [%lld,+%lld) not contiguous with count %lld",
+                                                          (long long)row0, (long long)nrows, (long long)c->n);
+    if (nrows == 0) return RAG_OK;
+    RAG_TRY(corpus_reserve_locked(c, row0 + nrows));
+    const size_t chunk_rows = std::max<size_t>(1, (size_t)(32u << 20) / ((size_t)c->dim * 4));
+    RAG_TRY(ensure_pinned(chunk_rows * c->dim * 4));
+    if (c->dtype != RAG_F32) RAG_TRY(g.stage_f32.ensure(chunk_rows * c->dim * 4));
+    for (int64_t r = 0; r < nrows; r += (int64_t)chunk_rows) {
+        const int64_t nr = std::min<int64_t>((int64_t)chunk_rows, nrows - r);
+        const size_t bytes = (size_t)nr * c->dim * 4;
+        memcpy(g.pinned, host_rows + (size_t)r * c->dim, bytes);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(c->rows) + (size_t)(row0 + r) * c->row_bytes;
+        if (c->dtype == RAG_F32) {
+            CU_TRY(cudaMemcpyAsync(dst, g.pinned, bytes, cudaMemcpyHostToDevice, g.stream));
+        } else {
+            CU_TRY(cudaMemcpyAsync(g.stage_f32.p, g.pinned, bytes, cudaMemcpyHostToDevice, g.stream));
+            CU_TRY(convert_rows_launch(g.stage_f32.as<float>(), dst, c->dtype, nr * c->dim, g.stream));
+            ++g.n_launch;
+        }
+        CU_TRY(row_norm_max_launch(dst, c->dtype, nr, c->dim, c->max_norm, g.stream));
+        ++g.n_launch;
+        CU_TRY(cudaStreamSynchronize(g.stream));      // the pinned chunk is reused
+    }
+    c->n = std::max(c->n, row0 + nrows);
+    return RAG_OK;
+}
+
+int rag_corpus_download(const rag_corpus_t* c, int64_t row0, int64_t nrows, float* host_rows) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!c || (!host_rows && nrows > 0)) return fail(RAG_EINVAL, "NULL argument");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > c->n) return fail(RAG_EINVAL, "rows out of range");
+    if (nrows == 0) return RAG_OK;
+    const size_t chunk_rows = std::max<size_t>(1, (size_t)(32u << 20) / ((size_t)c->dim * 4));
+    RAG_TRY(ensure_pinned(chunk_rows * c->dim * 4));
+    RAG_TRY(g.stage_f32.ensure(chunk_rows * c->dim * 4));
+    for (int64_t r = 0; r < nrows; r += (int64_t)chunk_rows) {
+        const int64_t nr = std::min<int64_t>((int64_t)chunk_rows, nrows - r);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(c->rows) + (size_t)(row0 + r) * c->row_bytes;
+        CU_TRY(widen_rows_launch(src, c->dtype, g.stage_f32.as<float>(), nr * c->dim, g.stream));
+        ++g.n_launch;
+        CU_TRY(cudaMemcpyAsync(g.pinned, g.stage_f32.p, (size_t)nr * c->dim * 4, cudaMemcpyDeviceToHost, g.stream));
+        CU_TRY(cudaStreamSynchronize(g.stream));
+        memcpy(host_rows + (size_t)r * c->dim, g.pinned, (size_t)nr * c->dim * 4);
+    }
+    return RAG_OK;
+}
+
+int rag_corpus_compact(rag_corpus_t* c, const int64_t* keep_rows, int64_t nkeep) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!c || (!keep_rows && nkeep > 0) || nkeep < 0 || nkeep > c->n) return fail(RAG_EINVAL, "bad compact arguments");
+    for (int64_t i = 0; i < nkeep; ++i) {
+        if (keep_rows[i] < 0 || keep_rows[i] >= c->n || (i > 0 && keep_rows[i] <= keep_rows[i - 1]))
+            return fail(RAG_EINVAL, "keep_rows must be strictly ascending rows below the count");
+    }
+    if (nkeep == c->n) return RAG_OK;
+    void* nr = nullptr;
+    const int64_t ncap = std::max<int64_t>(nkeep, 1);
+    CU_TRY(cudaMalloc(&nr, (size_t)ncap * c->row_bytes));
+    if (nkeep > 0) {
+        DevBuf keep;
+        int rc = keep.ensure((size_t)nkeep * 8);
+        if (rc != RAG_OK) { cudaFree(nr); return rc; }
+        CU_TRY(cudaMemcpyAsync(keep.p, keep_rows, (size_t)nkeep * 8, cudaMemcpyHostToDevice, g.stream));
+        CU_TRY(gather_rows_launch(c->rows, nr, keep.as<int64_t>(), nkeep, (int)c->row_bytes, g.stream));
+        ++g.n_launch;
+        CU_TRY(cudaStreamSynchronize(g.stream));
+        cudaFree(keep.p);
+    }
+    cudaFree(c->rows);
+    c->rows = nr;
+    c->cap = ncap;
+    c->n = nkeep;
+    // the max norm only ever over-estimates after a delete, which keeps the bound valid
+    return RAG_OK;
+}
+
+int rag_corpus_count(const rag_corpus_t* c, int64_t* n) {
+    if (!c || !n) return fail(RAG_EINVAL, "NULL argument");
+    *n = c->n;
+    return RAG_OK;
+}
+
+int rag_corpus_fill_synthetic(rag_corpus_t* c, uint64_t seed, int64_t gen_row0, int64_t row0, int64_t nrows) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!c) return fail(RAG_EINVAL, "corpus is NULL");
+    if (row0 < 0 || nrows < 0 || row0 > c->n) return fail(RAG_EINVAL, "rows not contiguous with count");
+    if (nrows == 0) return RAG_OK;
+    RAG_TRY(corpus_reserve_locked(c, row0 + nrows));
+    CU_TRY(fill_synthetic_launch(c->rows, c->dtype, row0, nrows, c->dim, seed, gen_row0, g.stream));
+    uint8_t* dst = reinterpret_cast<uint8_t*>(c->rows) + (size_t)row0 * c->row_bytes;
+    CU_TRY(row_norm_max_launch(dst, c->dtype, nrows, c->dim, c->max_norm, g.stream));
+    g.n_launch += 2;
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    c->n = std::max(c->n, row0 + nrows);
+    return RAG_OK;
+}
+
+int rag_corpus_device_ptr(const rag_corpus_t* c, void** rows_dev) {
+    if (!c || !rows_dev) return fail(RAG_EINVAL, "NULL argument");
+    *rows_dev = c->rows;
+    return RAG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// dense top-k
+// ---------------------------------------------------------------------------
+// filter error bound of the fp32 CUDA-core scan, relative to |q|*max|x|:
+// <= 16 chained FMAs + 2 + 5 tree levels, each 2^-24 -> < 2^-19.
+static const double kEpsScan = 1.0 / 524288.0;
+
+static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev, int32_t* o_rows,
+                      double* o_scores, int32_t* o_counts) {
+    const int kp = std::max(16, next_pow2(k + 6));
+    for (auto& v : g.ev_valid) v = false;
+    for (auto& t : g.timings) t = 0.f;
+
+    RAG_TRY(g.top.ensure((size_t)B * kp * 8));
+    RAG_TRY(g.flags.ensure((size_t)B * 4));
+    RAG_TRY(g.tau.ensure((size_t)B * 4));
+    RAG_TRY(g.nflag.ensure(4));
+    CU_TRY(cudaMemsetAsync(g.nflag.p, 0, 4, g.stream));
+
+    if (c->n == 0) {
+        CU_TRY(cudaMemsetAsync(g.top.p, 0, (size_t)B * kp * 8, g.stream));
+    } else {
+        // plan once (geometry does not depend on the group), then one scan launch per <= 4 queries
+        ScanParams p{};
+        p.rows = c->rows;
+        p.n_rows = c->n;
+        p.dim = c->dim;
+        p.kp = kp;
+        p.mode = 0;
+        p.allow = allow_dev;
+        const int n_groups = (B + 3) / 4;
+        // every group of the call uses the template width of the first one, so the
+        // consumer-warp count (hence n_lists and the cand layout) is uniform
+        p.n_queries = std::min(B, 4);
+        p.nq_t = scan_nq_template(p.n_queries);
+        int grid = 0, nch = 0;
+        const size_t smem = scan_plan(p, c->dtype, g.sm_count, g.smem_optin, &grid, &nch);
+        if (smem == 0) return fail(RAG_ERANGE, "k=%d does not fit the scan kernel's shared memory", k);
+        const int n_lists = p.n_lists;
+        RAG_TRY(g.cand.ensure((size_t)B * n_lists * kp * 8));
+        rec(0);
+        for (int gi = 0; gi < n_groups; ++gi) {
+            ScanParams pg = p;
+            pg.n_queries = std::min(4, B - gi * 4);
+            pg.q = q_dev + (size_t)gi * 4 * c->dim;
+            pg.cand = g.cand.as<uint64_t>() + (size_t)gi * 4 * n_lists * kp;
+            CU_TRY(scan_launch(pg, c->dtype, nch, grid, smem, g.stream));
+            ++g.n_launch;
+        }
+        rec(1);
+        CU_TRY(merge_launch(g.cand.as<uint64_t>(), B, n_lists, kp, g.top.as<uint64_t>(), g.stream));
+        ++g.n_launch;
+    }
+    rec(2);
+    RefineParams rp{};
+    rp.top = g.top.as<uint64_t>();
+    rp.rows = c->rows;
+    rp.q = q_dev;
+    rp.dtype = c->dtype;
+    rp.dim = c->dim;
+    rp.kp = kp;
+    rp.k = k;
+    rp.B = B;
+    rp.eps_rel = kEpsScan;
+    rp.max_row_norm = c->max_norm;
+    rp.out_rows = o_rows;
+    rp.out_scores = o_scores;
+    rp.out_counts = o_counts;
+    rp.flags = g.flags.as<int32_t>();
+    rp.tau = g.tau.as<float>();
+    rp.n_flagged = g.nflag.as<int32_t>();
+    CU_TRY(refine_launch(rp, g.stream));
+    ++g.n_launch;
+    rec(3);
+
+    int32_t* h_nflag = g.pinned_small;
+    CU_TRY(cudaMemcpyAsync(h_nflag, g.nflag.p, 4, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    const int n_flagged = *h_nflag;
+
+    if (n_flagged > 0) {
+        // ---- fallback: the margin check failed for some queries (near-ties deeper than
+        // the candidate list).  Collect every row whose filter score can still reach
+        // the exact k-th score, re-score all of them exactly, select.
+        ++g.n_fallback;
+        std::vector<int32_t> h_flags(B);
+        std::vector<float> h_tau(B);
+        CU_TRY(cudaMemcpyAsync(h_flags.data(), g.flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, g.stream));
+        CU_TRY(cudaMemcpyAsync(h_tau.data(), g.tau.p, (size_t)B * 4, cudaMemcpyDeviceToHost, g.stream));
+        CU_TRY(cudaStreamSynchronize(g.stream));
+        std::vector<int32_t> idx;
+        for (int b = 0; b < B; ++b)
+            if (h_flags[b]) idx.push_back(b);
+        const int nf = (int)idx.size();
+        RAG_TRY(g.fb_q.ensure((size_t)nf * c->dim * 4));
+        RAG_TRY(g.fb_tau.ensure((size_t)nf * 4));
+        RAG_TRY(g.fb_counts.ensure((size_t)nf * 4));
+        RAG_TRY(g.fb_index.ensure((size_t)nf * 4));
+        std::vector<float> tau_c(nf);
+        for (int i = 0; i < nf; ++i) {
+            tau_c[i] = h_tau[idx[i]];
+            CU_TRY(cudaMemcpyAsync(g.fb_q.as<float>() + (size_t)i * c->dim, q_dev + (size_t)idx[i] * c->dim,
+                                   (size_t)c->dim * 4, cudaMemcpyDeviceToDevice, g.stream));
+        }
+        CU_TRY(cudaMemcpyAsync(g.fb_tau.p, tau_c.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, g.stream));
+        CU_TRY(cudaMemcpyAsync(g.fb_index.p, idx.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, g.stream));
+        int cap = 4096;
+        std::vector<unsigned> h_counts(nf);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            RAG_TRY(g.fb_rows.ensure((size_t)nf * cap * 4));
+            RAG_TRY(g.fb_scores.ensure((size_t)nf * cap * 8));
+            CU_TRY(cudaMemsetAsync(g.fb_counts.p, 0, (size_t)nf * 4, g.stream));
+            for (int gi = 0; gi * 4 < nf; ++gi) {
+                ScanParams p{};
+                p.rows = c->rows;
+                p.n_rows = c->n;
+                p.dim = c->dim;
+                p.kp = 16;
+                p.mode = 1;
+                p.allow = allow_dev;
+                p.n_queries = std::min(4, nf - gi * 4);
+                p.nq_t = scan_nq_template(p.n_queries);
+                p.q = g.fb_q.as<float>() + (size_t)gi * 4 * c->dim;
+                p.tau = g.fb_tau.as<float>() + gi * 4;
+                p.collect_count = g.fb_counts.as<unsigned>() + gi * 4;
+                p.collect_rows = g.fb_rows.as<uint32_t>() + (size_t)gi * 4 * cap;
+                p.collect_cap = cap;
+                int grid = 0, nch = 0;
+                size_t smem = scan_plan(p, c->dtype, g.sm_count, g.smem_optin, &grid, &nch);
+                if (smem == 0) return fail(RAG_ERANGE, "fallback scan does not fit shared memory");
+                CU_TRY(scan_launch(p, c->dtype, nch, grid, smem, g.stream));
+                ++g.n_launch;
+            }
+            CU_TRY(cudaMemcpyAsync(h_counts.data(), g.fb_counts.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, g.stream));
+            CU_TRY(cudaStreamSynchronize(g.stream));
+            unsigned mx = 0;
+            for (unsigned v : h_counts) mx = std::max(mx, v);
+            if (mx <= (unsigned)cap) break;
+            if (attempt == 1) return fail(RAG_ECUDA, "fallback collect overflowed twice (%u > %d)", mx, cap);
+            cap = (int)mx + 64;
+        }
+        CollectSelectParams sp{};
+        sp.rows_list = g.fb_rows.as<uint32_t>();
+        sp.counts = g.fb_counts.as<unsigned>();
+        sp.cap = cap;
+        sp.query_index = g.fb_index.as<int32_t>();
+        sp.rows = c->rows;
+        sp.q = g.fb_q.as<float>();
+        sp.dtype = c->dtype;
+        sp.dim = c->dim;
+        sp.k = k;
+        sp.nq = nf;
+        sp.scratch_scores = g.fb_scores.as<double>();
+        sp.out_rows = o_rows;
+        sp.out_scores = o_scores;
+        sp.out_counts = o_counts;
+        CU_TRY(collect_select_launch(sp, g.stream));
+        ++g.n_launch;
+        rec(4);
+        CU_TRY(cudaStreamSynchronize(g.stream));
+    }
+    // stage timings (events are complete: the stream was synchronised)
+    auto el = [&](int a, int b) {
+        float ms = 0.f;
+        if (g.ev_valid[a] && g.ev_valid[b] && cudaEventElapsedTime(&ms, g.ev[a], g.ev[b]) == cudaSuccess) return ms;
+        return 0.f;
+    };
+    g.timings[0] = el(0, 1);
+    g.timings[1] = el(1, 2);
+    g.timings[2] = el(2, 3);
+    g.timings[3] = n_flagged > 0 ? el(3, 4) : 0.f;
+    return RAG_OK;
+}
+
+static int dense_check(rag_corpus* c, const void* q, int B, int k, const void* o_rows, const void* o_scores,
+                       const void* o_counts) {
+    if (!c || !q || !o_rows || !o_scores || !o_counts) return fail(RAG_EINVAL, "NULL argument");
+    if (B <= 0) return fail(RAG_EINVAL, "B must be positive");
+    if (k <= 0 || k > RAG_MAX_K) return fail(RAG_ERANGE, "k=%d outside 1..%d", k, RAG_MAX_K);
+    return RAG_OK;
+}
+
+int rag_dense_topk_dev(rag_corpus_t* c, const float* q_dev, int B, int k, const uint8_t* allow_bitmap_dev,
+                       int32_t* out_rows_dev, double* out_scores_dev, int32_t* out_counts_dev) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    RAG_TRY(dense_check(c, q_dev, B, k, out_rows_dev, out_scores_dev, out_counts_dev));
+    return dense_core(c, q_dev, B, k, allow_bitmap_dev, out_rows_dev, out_scores_dev, out_counts_dev);
+}
+
+int rag_dense_topk(rag_corpus_t* c, const float* q, int B, int k, const uint8_t* allow_bitmap, int32_t* out_rows,
+                   double* out_scores, int32_t* out_counts) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    RAG_TRY(dense_check(c, q, B, k, out_rows, out_scores, out_counts));
+    const size_t qb = (size_t)B * c->dim * 4;
+    const size_t ab = allow_bitmap ? (size_t)((c->n + 7) / 8) : 0;
+    const size_t rb = (size_t)B * k * 4, sb = (size_t)B * k * 8, cb = (size_t)B * 4;
+    RAG_TRY(g.q.ensure(qb));
+    RAG_TRY(g.o_rows.ensure(rb));
+    RAG_TRY(g.o_scores.ensure(sb));
+    RAG_TRY(g.o_counts.ensure(cb));
+    if (ab) RAG_TRY(g.allow.ensure(ab + 16));
+    // inputs -> pinned -> device
+    RAG_TRY(ensure_pinned(std::max(qb + ab, sb + rb + cb)));
+    uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
+    memcpy(pin, q, qb);
+    CU_TRY(cudaMemcpyAsync(g.q.p, pin, qb, cudaMemcpyHostToDevice, g.stream));
+    if (ab) {
+        memcpy(pin + qb, allow_bitmap, ab);
+        CU_TRY(cudaMemcpyAsync(g.allow.p, pin + qb, ab, cudaMemcpyHostToDevice, g.stream));
+    }
+    RAG_TRY(dense_core(c, g.q.as<float>(), B, k, ab ? g.allow.as<uint8_t>() : nullptr, g.o_rows.as<int32_t>(),
+                       g.o_scores.as<double>(), g.o_counts.as<int32_t>()));
+    CU_TRY(cudaMemcpyAsync(pin, g.o_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaMemcpyAsync(pin + sb, g.o_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaMemcpyAsync(pin + sb + rb, g.o_counts.p, cb, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    memcpy(out_scores, pin, sb);
+    memcpy(out_rows, pin + sb, rb);
+    memcpy(out_counts, pin + sb + rb, cb);
+    return RAG_OK;
+}
+
+int rag_merge_topk_dev(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k, double* out_scores_dev,
+                       int64_t* out_ids_dev, int32_t* out_counts_dev) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!scores_dev || !ids_dev || !out_scores_dev || !out_ids_dev || !out_counts_dev)
+        return fail(RAG_EINVAL, "NULL argument");
+    if (G <= 0 || B <= 0 || k <= 0 || k > RAG_MAX_K || (int64_t)G * k > 8192)
+        return fail(RAG_ERANGE, "G=%d B=%d k=%d outside the supported range", G, B, k);
+    CU_TRY(merge_exact_launch(scores_dev, ids_dev, G, B, k, out_scores_dev, out_ids_dev, out_counts_dev, g.stream));
+    ++g.n_launch;
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return RAG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// BM25
+// ---------------------------------------------------------------------------
+int rag_bm25_create(rag_bm25_t** out, int64_t n_docs, int64_t n_terms, int64_t nnz, const int64_t* term_ptr,
+                    const int32_t* post_row, const int32_t* post_tf, const int32_t* doc_len, const double* idf,
+                    double avgdl, double k1, double b) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!out || !term_ptr || !doc_len || !idf || (nnz > 0 && (!post_row || !post_tf)))
+        return fail(RAG_EINVAL, "NULL argument");
+    if (n_docs <= 0 || n_terms < 0 || nnz < 0 || n_docs > 0x7FFFFFF0LL) return fail(RAG_EINVAL, "bad sizes");
+    if (term_ptr[0] != 0 || term_ptr[n_terms] != nnz) return fail(RAG_EINVAL, "term_ptr does not span the postings");
+    rag_bm25* ix = new rag_bm25();
+    ix->d.n_docs = n_docs;
+    ix->d.n_terms = n_terms;
+    ix->d.nnz = nnz;
+    ix->h_term_ptr.assign(term_ptr, term_ptr + n_terms + 1);
+    ix->h_idf.assign(idf, idf + n_terms);
+    int32_t *d_tf = nullptr, *d_dl = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(ix->d.term_ptr); cudaFree(ix->d.post_row); cudaFree(ix->d.post_impact);
+        cudaFree(ix->d.idf); cudaFree(ix->d.score); cudaFree(d_tf); cudaFree(d_dl);
+        delete ix;
+    };
+    const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void**)&ix->d.term_ptr, (size_t)(n_terms + 1) * 8);
+    A((void**)&ix->d.post_row, nz * 4);
+    A((void**)&ix->d.post_impact, nz * 8);
+    A((void**)&ix->d.idf, (size_t)std::max<int64_t>(n_terms, 1) * 8);
+    A((void**)&ix->d.score, (size_t)n_docs * 8);
+    A((void**)&d_tf, nz * 4);
+    A((void**)&d_dl, (size_t)n_docs * 4);
+    auto C = [&](void* d, const void* h, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, g.stream);
+    };
+    C(ix->d.term_ptr, term_ptr, (size_t)(n_terms + 1) * 8);
+    C(ix->d.post_row, post_row, (size_t)nnz * 4);
+    C(d_tf, post_tf, (size_t)nnz * 4);
+    C(d_dl, doc_len, (size_t)n_docs * 4);
+    C(ix->d.idf, idf, (size_t)n_terms * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ix->d.score, 0, (size_t)n_docs * 8, g.stream);
+    if (e == cudaSuccess && nnz > 0) {
+        e = bm25_impact_launch(ix->d.post_row, d_tf, d_dl, nnz, avgdl, k1, b, ix->d.post_impact, g.stream);
+        ++g.n_launch;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(e == cudaErrorMemoryAllocation ? RAG_ENOMEM : RAG_ECUDA, "bm25 build: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_tf);
+    cudaFree(d_dl);
+    *out = ix;
+    return RAG_OK;
+}
+
+int rag_bm25_destroy(rag_bm25_t* ix) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!ix) return RAG_OK;
+    if (g.inited) {
+        cudaSetDevice(g.device);
+        cudaStreamSynchronize(g.stream);
+        cudaFree(ix->d.term_ptr); cudaFree(ix->d.post_row); cudaFree(ix->d.post_impact);
+        cudaFree(ix->d.idf); cudaFree(ix->d.score);
+    }
+    delete ix;
+    return RAG_OK;
+}
+
+// launches the per-token accumulation of one query; fills `ranges` with the
+// [lo,hi) posting ranges of its distinct scoring tokens
+static int bm25_accumulate_query(rag_bm25* ix, const int32_t* terms, int nt, std::vector<int64_t>& ranges,
+                                 int64_t* total) {
+    ranges.clear();
+    *total = 0;
+    std::vector<int32_t> seen;
+    for (int i = 0; i < nt; ++i) {
+        const int32_t t = terms[i];
+        if (t < 0 || t >= ix->d.n_terms) continue;          // (idf.get(q) or 0) == 0
+        const double w = ix->h_idf[t];
+        const int64_t lo = ix->h_term_ptr[t], hi = ix->h_term_ptr[t + 1];
+        if (w == 0.0 || hi <= lo) continue;
+        CU_TRY(bm25_accumulate_launch(ix->d, lo, hi, w, g.stream));
+        ++g.n_launch;
+        if (std::find(seen.begin(), seen.end(), t) == seen.end()) {
+            seen.push_back(t);
+            ranges.push_back(lo);
+            ranges.push_back(hi);
+            *total += hi - lo;
+        }
+    }
+    return RAG_OK;
+}
+
+int rag_bm25_search(rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr, int Q, int k,
+                    const uint8_t* allow_bitmap, int32_t* out_rows, double* out_scores, int32_t* out_counts) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!ix || !q_ptr || !out_rows || !out_scores || !out_counts || Q <= 0) return fail(RAG_EINVAL, "NULL argument");
+    if (k <= 0 || k > RAG_MAX_K) return fail(RAG_ERANGE, "k=%d outside 1..%d", k, RAG_MAX_K);
+    const int kp = std::max(16, next_pow2(k));
+    for (auto& v : g.ev_valid) v = false;
+    for (auto& t : g.timings) t = 0.f;
+    const uint8_t* allow_dev = nullptr;
+    if (allow_bitmap) {
+        const size_t ab = (size_t)((ix->d.n_docs + 7) / 8);
+        RAG_TRY(g.bm_allow.ensure(ab + 16));
+        CU_TRY(cudaMemcpyAsync(g.bm_allow.p, allow_bitmap, ab, cudaMemcpyHostToDevice, g.stream));
+        allow_dev = g.bm_allow.as<uint8_t>();
+    }
+    RAG_TRY(g.bm_rows.ensure((size_t)Q * k * 4));
+    RAG_TRY(g.bm_scores.ensure((size_t)Q * k * 8));
+    RAG_TRY(g.bm_counts.ensure((size_t)Q * 4));
+    const int max_grid = g.sm_count * 2;
+    RAG_TRY(g.bm_cand.ensure((size_t)max_grid * 8 * kp * bm25_key_bytes()));
+    std::vector<int64_t> ranges;
+    rec(0);
+    for (int qi = 0; qi < Q; ++qi) {
+        const int32_t* terms = q_terms + q_ptr[qi];
+        const int nt = q_ptr[qi + 1] - q_ptr[qi];
+        int64_t total = 0;
+        RAG_TRY(bm25_accumulate_query(ix, terms, nt, ranges, &total));
+        int32_t* o_r = g.bm_rows.as<int32_t>() + (size_t)qi * k;
+        double* o_s = g.bm_scores.as<double>() + (size_t)qi * k;
+        int32_t* o_c = g.bm_counts.as<int32_t>() + qi;
+        const int n_ranges = (int)ranges.size() / 2;
+        const int grid = bm25_harvest_grid(total, g.sm_count);
+        RAG_TRY(g.bm_ranges.ensure(std::max<size_t>(16, ranges.size() * 8)));
+        if (n_ranges > 0) {
+            // pageable -> device copy of a few bytes: synchronous w.r.t. the host buffer
+            CU_TRY(cudaMemcpyAsync(g.bm_ranges.p, ranges.data(), ranges.size() * 8, cudaMemcpyHostToDevice, g.stream));
+            CU_TRY(cudaStreamSynchronize(g.stream));
+        }
+        CU_TRY(bm25_harvest_launch(ix->d, g.bm_ranges.as<int64_t>(), n_ranges, allow_dev, kp, grid, g.bm_cand.p,
+                                   g.stream));
+        CU_TRY(bm25_select_launch(g.bm_cand.p, grid * 8, kp, k, o_r, o_s, o_c, g.stream));
+        g.n_launch += 2;
+    }
+    rec(1);
+    const size_t rb = (size_t)Q * k * 4, sb = (size_t)Q * k * 8, cb = (size_t)Q * 4;
+    RAG_TRY(ensure_pinned(sb + rb + cb));
+    uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
+    CU_TRY(cudaMemcpyAsync(pin, g.bm_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaMemcpyAsync(pin + sb, g.bm_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaMemcpyAsync(pin + sb + rb, g.bm_counts.p, cb, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    memcpy(out_scores, pin, sb);
+    memcpy(out_rows, pin + sb, rb);
+    memcpy(out_counts, pin + sb + rb, cb);
+    float ms = 0.f;
+    if (g.ev_valid[0] && g.ev_valid[1] && cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]) == cudaSuccess) g.timings[0] = ms;
+    return RAG_OK;
+}
+
+int rag_bm25_scores(rag_bm25_t* ix, const int32_t* q_terms, int n_q_terms, double* out_scores) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!ix || !out_scores || (n_q_terms > 0 && !q_terms)) return fail(RAG_EINVAL, "NULL argument");
+    std::vector<int64_t> ranges;
+    int64_t total = 0;
+    RAG_TRY(bm25_accumulate_query(ix, q_terms, n_q_terms, ranges, &total));
+    CU_TRY(cudaMemcpyAsync(out_scores, ix->d.score, (size_t)ix->d.n_docs * 8, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    const int n_ranges = (int)ranges.size() / 2;
+    if (n_ranges > 0) {
+        RAG_TRY(g.bm_ranges.ensure(ranges.size() * 8));
+        CU_TRY(cudaMemcpyAsync(g.bm_ranges.p, ranges.data(), ranges.size() * 8, cudaMemcpyHostToDevice, g.stream));
+        CU_TRY(cudaStreamSynchronize(g.stream));
+        CU_TRY(bm25_reset_launch(ix->d, g.bm_ranges.as<int64_t>(), n_ranges, bm25_harvest_grid(total, g.sm_count),
+                                 g.stream));
+        ++g.n_launch;
+        CU_TRY(cudaStreamSynchronize(g.stream));
+    }
+    return RAG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// RRF
+// ---------------------------------------------------------------------------
+int rag_rrf_fuse(const int32_t* ids, const double* weights, int Q, int R, int L, int rrf_k, int top, int32_t* out_ids,
+                 double* out_scores, int32_t* out_counts) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!ids || !weights || !out_ids || !out_scores || !out_counts) return fail(RAG_EINVAL, "NULL argument");
+    if (Q <= 0 || R <= 0 || L <= 0 || top <= 0) return fail(RAG_EINVAL, "sizes must be positive");
+    if ((int64_t)R * L > rrf_max_entries()) return fail(RAG_ERANGE, "R*L=%lld exceeds %d", (long long)R * L,
+                                                        rrf_max_entries());
+    const size_t ib = (size_t)Q * R * L * 4, wb = (size_t)Q * R * 8;
+    const size_t oi = (size_t)Q * top * 4, os = (size_t)Q * top * 8, oc = (size_t)Q * 4;
+    RAG_TRY(g.rrf_ids.ensure(ib));
+    RAG_TRY(g.rrf_w.ensure(wb));
+    RAG_TRY(g.rrf_oi.ensure(oi));
+    RAG_TRY(g.rrf_os.ensure(os));
+    RAG_TRY(g.rrf_oc.ensure(oc));
+    RAG_TRY(ensure_pinned(std::max(ib + wb, oi + os + oc)));
+    uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
+    memcpy(pin, weights, wb);
+    memcpy(pin + wb, ids, ib);
+    CU_TRY(cudaMemcpyAsync(g.rrf_w.p, pin, wb, cudaMemcpyHostToDevice, g.stream));
+    CU_TRY(cudaMemcpyAsync(g.rrf_ids.p, pin + wb, ib, cudaMemcpyHostToDevice, g.stream));
+    CU_TRY(rrf_launch(g.rrf_ids.as<int32_t>(), g.rrf_w.as<double>(), Q, R, L, rrf_k, top, g.rrf_oi.as<int32_t>(),
+                      g.rrf_os.as<double>(), g.rrf_oc.as<int32_t>(), g.stream));
+    ++g.n_launch;
+    CU_TRY(cudaMemcpyAsync(pin, g.rrf_os.p, os, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaMemcpyAsync(pin + os, g.rrf_oi.p, oi, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaMemcpyAsync(pin + os + oi, g.rrf_oc.p, oc, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    memcpy(out_scores, pin, os);
+    memcpy(out_ids, pin + os, oi);
+    memcpy(out_counts, pin + os + oi, oc);
+    return RAG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+// dense_select.cu — the exact tail of the dense path: merge the per-warp
+// candidate lists, re-score the survivors with the CANONICAL fp64 dot product
+// (DESIGN.md §3), sort by (score desc, row asc) and check the filter margin.
+//
+// Together with dense_scan.cu / dense_gemm.cu this replaces the selection done
+// inside collection.query(...) (src/rag/retriever.py:215-220, 380-385): the
+// result is the exact top-k of the fp64 brute force, ties -> lowest row.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200rag {
+
+// ---------------------------------------------------------------------------
+// merge: one CTA per query, 8 warps each scanning a strided share of the keys
+// ---------------------------------------------------------------------------
+constexpr int kMergeWarps = 8;
+
+__global__ void __launch_bounds__(kMergeWarps * 32) merge_kernel(const uint64_t* __restrict__ cand, int n_lists,
+                                                                 int kp, uint64_t* __restrict__ top) {
+    extern __shared__ __align__(16) uint64_t sm_keys[];   // kMergeWarps * 2 * kp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
+    const uint64_t* src = cand + (size_t)b * n_lists * kp;
+    const int64_t total = (int64_t)n_lists * kp;
+
+    WarpTopK t;
+    t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
+    const int64_t per_iter = (int64_t)kMergeWarps * 32;
+    const int64_t n_iter = (total + per_iter - 1) / per_iter;
+    for (int64_t it = 0; it < n_iter; ++it) {
+        int64_t i = it * per_iter + warp * 32 + lane;
+        uint64_t key = i < total ? src[i] : 0ull;
+        t.offer(key, lane);
+    }
+    t.finish(lane);
+    __syncthreads();
+    int n_all = kMergeWarps * 2 * kp;          // power of two
+    block_bitonic_desc(sm_keys, n_all);
+    for (int i = threadIdx.x; i < kp; i += blockDim.x) top[(size_t)b * kp + i] = sm_keys[i];
+}
+
+cudaError_t merge_launch(const uint64_t* cand, int B, int n_lists, int kp, uint64_t* top, cudaStream_t st) {
+    size_t smem = (size_t)kMergeWarps * 2 * kp * sizeof(uint64_t);
+    merge_kernel<<<B, kMergeWarps * 32, smem, st>>>(cand, n_lists, kp, top);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// canonical fp64 score (warp-cooperative).  Valid in lane 0.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double load_elem_f64(const void* rows, int dtype, size_t idx) {
+    if (dtype == RAG_F32) return (double)reinterpret_cast<const float*>(rows)[idx];
+    if (dtype == RAG_BF16) return (double)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[idx]);
+    return (double)__half2float(reinterpret_cast<const __half*>(rows)[idx]);
+}
+
+__device__ __forceinline__ double canonical_dot(const float* __restrict__ q, const void* __restrict__ rows, int dtype,
+                                                size_t row, int dim, int lane) {
+    double p = 0.0;
+    const size_t base = row * (size_t)dim;
+    for (int j = 0; j < dim / 32; ++j) {
+        double a = (double)q[32 * j + lane];
+        double x = load_elem_f64(rows, dtype, base + 32 * j + lane);
+        p = __fma_rn(a, x, p);      // the product is exact in fp64, so this is one rounding: p + a*x
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) p = __dadd_rn(p, __shfl_down_sync(0xffffffffu, p, off));
+    return p;
+}
+
+struct ExactKey {
+    double s;
+    uint32_t row;
+    uint32_t pad;
+    // "a < b" == a ranks AFTER b under (score desc, row asc)
+    __device__ __forceinline__ bool operator<(const ExactKey& o) const {
+        return s < o.s || (s == o.s && row > o.row);
+    }
+};
+
+__global__ void __launch_bounds__(256) refine_kernel(RefineParams p) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    ExactKey* ek = reinterpret_cast<ExactKey*>(sm_raw);          // max(kp,32)
+    __shared__ double s_qnorm2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
+    const float* q = p.q + (size_t)b * p.dim;
+    const uint64_t* top = p.top + (size_t)b * p.kp;
+    const int nsort = p.kp < 32 ? 32 : p.kp;
+
+    for (int j = warp; j < nsort; j += 8) {
+        uint64_t key = j < p.kp ? top[j] : 0ull;
+        ExactKey e;
+        e.pad = 0;
+        if (key == 0ull) {
+            e.s = -INFINITY; e.row = 0xFFFFFFFFu;
+        } else {
+            e.row = key_row(key);
+            e.s = canonical_dot(q, p.rows, p.dtype, e.row, p.dim, lane);
+        }
+        if (lane == 0) ek[j] = e;
+    }
+    if (warp == 0) {
+        double s = 0.0;
+        for (int i = lane; i < p.dim; i += 32) s += (double)q[i] * (double)q[i];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) s_qnorm2 = s;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    warp_bitonic_desc(ek, nsort, lane);
+
+    int count = 0;
+    for (int i = lane; i < p.kp; i += 32) count += (ek[i].row != 0xFFFFFFFFu);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) count += __shfl_xor_sync(0xffffffffu, count, off);
+    const int nout = count < p.k ? count : p.k;
+    for (int i = lane; i < p.k; i += 32) {
+        p.out_rows[(size_t)b * p.k + i] = i < nout ? (int32_t)ek[i].row : -1;
+        p.out_scores[(size_t)b * p.k + i] = i < nout ? ek[i].s : 0.0;
+    }
+    if (lane == 0) {
+        p.out_counts[b] = nout;
+        int flag = 0;
+        float tau = 0.f;
+        if (count == p.kp) {
+            // the list is full: rows outside it have filter score <= a_min, hence
+            // exact score <= a_min + eps.  Safe iff the k-th exact beats that.
+            double eps = p.eps_rel * sqrt(s_qnorm2) * (double)(*p.max_row_norm);
+            double a_min = (double)key_score(top[p.kp - 1]);
+            double e_k = ek[p.k - 1].s;
+            if (!(e_k > a_min + eps)) {
+                flag = 1;
+                tau = __double2float_rd(e_k - eps);
+                atomicAdd(p.n_flagged, 1);
+            }
+        }
+        p.flags[b] = flag;
+        p.tau[b] = tau;
+    }
+}
+
+cudaError_t refine_launch(const RefineParams& p, cudaStream_t st) {
+    int nsort = p.kp < 32 ? 32 : p.kp;
+    refine_kernel<<<p.B, 256, (size_t)nsort * sizeof(ExactKey), st>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// fallback tail: exact scores of every collected row, then a streaming
+// best-k select (sort 2048 at a time, keep the head).
+// ---------------------------------------------------------------------------
+constexpr int kSelN = 2048;
+
+__global__ void __launch_bounds__(256) collect_select_kernel(CollectSelectParams p) {
+    __shared__ ExactKey ek[kSelN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x;
+    const float* q = p.q + (size_t)qi * p.dim;
+    const uint32_t* list = p.rows_list + (size_t)qi * p.cap;
+    double* sc = p.scratch_scores + (size_t)qi * p.cap;
+    const int cnt = (int)(p.counts[qi] < (unsigned)p.cap ? p.counts[qi] : (unsigned)p.cap);
+
+    for (int j = warp; j < cnt; j += 8) {
+        double s = canonical_dot(q, p.rows, p.dtype, list[j], p.dim, lane);
+        if (lane == 0) sc[j] = s;
+    }
+    __syncthreads();
+    const int keep = p.k;                       // head kept between rounds
+    for (int i = threadIdx.x; i < kSelN; i += blockDim.x) { ek[i].s = -INFINITY; ek[i].row = 0xFFFFFFFFu; ek[i].pad = 0; }
+    __syncthreads();
+    const int chunk = kSelN - keep;
+    for (int base = 0; base < cnt || base == 0; base += chunk) {
+        for (int i = threadIdx.x; i < chunk; i += blockDim.x) {
+            int j = base + i;
+            ExactKey e;
+            e.pad = 0;
+            if (j < cnt) { e.s = sc[j]; e.row = list[j]; } else { e.s = -INFINITY; e.row = 0xFFFFFFFFu; }
+            ek[keep + i] = e;
+        }
+        block_bitonic_desc(ek, kSelN);
+        if (cnt == 0) break;
+    }
+    const int out = p.query_index[qi];
+    int nout = cnt < p.k ? cnt : p.k;
+    for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
+        p.out_rows[(size_t)out * p.k + i] = i < nout ? (int32_t)ek[i].row : -1;
+        p.out_scores[(size_t)out * p.k + i] = i < nout ? ek[i].s : 0.0;
+    }
+    if (threadIdx.x == 0) p.out_counts[out] = nout;
+}
+
+cudaError_t collect_select_launch(const CollectSelectParams& p, cudaStream_t st) {
+    collect_select_kernel<<<p.nq, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU exchange tail: G ranks' exact (score, global id) lists -> top-k
+// ---------------------------------------------------------------------------
+struct ExactKey64 {
+    double s;
+    int64_t id;
+    __device__ __forceinline__ bool operator<(const ExactKey64& o) const {
+        return s < o.s || (s == o.s && id > o.id);
+    }
+};
+
+__global__ void __launch_bounds__(256) merge_exact_kernel(const double* __restrict__ scores,
+                                                          const int64_t* __restrict__ ids, int G, int B, int k,
+                                                          int nsort, double* out_scores, int64_t* out_ids,
+                                                          int32_t* out_counts) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    ExactKey64* ek = reinterpret_cast<ExactKey64*>(sm_raw);
+    __shared__ int s_count;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
+        ExactKey64 e;
+        e.s = -INFINITY; e.id = INT64_MAX;
+        if (i < G * k) {
+            int g = i / k, j = i % k;
+            size_t src = ((size_t)g * B + b) * k + j;
+            int64_t id = ids[src];
+            if (id >= 0) { e.s = scores[src]; e.id = id; ++local; }
+        }
+        ek[i] = e;
+    }
+    atomicAdd(&s_count, local);
+    block_bitonic_desc(ek, nsort);
+    const int nout = s_count < k ? s_count : k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        out_ids[(size_t)b * k + i] = i < nout ? ek[i].id : -1;
+        out_scores[(size_t)b * k + i] = i < nout ? ek[i].s : 0.0;
+    }
+    if (threadIdx.x == 0) out_counts[b] = nout;
+}
+
+cudaError_t merge_exact_launch(const double* scores, const int64_t* ids, int G, int B, int k, double* out_scores,
+                               int64_t* out_ids, int32_t* out_counts, cudaStream_t st) {
+    int nsort = 32;
+    while (nsort < G * k) nsort <<= 1;
+    size_t smem = (size_t)nsort * sizeof(ExactKey64);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    merge_exact_kernel<<<B, 256, smem, st>>>(scores, ids, G, B, k, nsort, out_scores, out_ids, out_counts);
+    return cudaGetLastError();
+}
+
+}  // namespace b200rag

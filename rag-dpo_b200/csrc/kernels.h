@@ -1,0 +1,113 @@
+// kernels.h — host-visible launchers of the b200rag kernels (internal header).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/b200rag.h"
+
+namespace b200rag {
+
+// ---- dense_scan.cu ---------------------------------------------------------
+struct ScanParams {
+    const void* rows;        // n_rows x dim, storage dtype, row-major
+    const float* q;          // n_queries x dim fp32 (device)
+    const uint8_t* allow;    // nullable row bitmap (device)
+    int64_t n_rows;
+    int dim;
+    int n_queries;           // 1..4 in this launch
+    int nq_t;                // kernel template width (1, 2 or 4) >= n_queries; fixes the warp count
+    int kp;                  // per-list capacity (power of two >= 16)
+    int mode;                // 0 = running top-k, 1 = collect >= tau
+    // derived by scan_plan
+    int row_bytes, tile_rows, tile_bytes, n_stages, n_lists;
+    // mode 0 output: n_queries x n_lists x kp keys
+    uint64_t* cand;
+    // mode 1
+    const float* tau;        // per-query filter-score threshold
+    unsigned* collect_count; // per query
+    uint32_t* collect_rows;  // n_queries x collect_cap
+    int collect_cap;
+};
+int scan_nq_template(int n_queries);
+size_t scan_plan(ScanParams& p, int dtype, int sm_count, int smem_limit, int* grid_out, int* nch_out);
+cudaError_t scan_launch(const ScanParams& p, int dtype, int nch, int grid, size_t smem, cudaStream_t st);
+
+// ---- dense_select.cu -------------------------------------------------------
+// merge: cand (B x n_lists x kp, any order, 0 = empty) -> top (B x kp sorted desc)
+cudaError_t merge_launch(const uint64_t* cand, int B, int n_lists, int kp, uint64_t* top, cudaStream_t st);
+// refine: canonical fp64 score of every candidate in top, sort by (score desc,
+// row asc), write the first k, and raise flag[b] when the margin check fails.
+struct RefineParams {
+    const uint64_t* top;     // B x kp
+    const void* rows;
+    const float* q;          // B x dim
+    int dtype, dim, kp, k, B;
+    double eps_rel;          // filter error bound / (|q| * max|x|)
+    const float* max_row_norm;  // device scalar
+    int32_t* out_rows;       // B x k
+    double* out_scores;      // B x k
+    int32_t* out_counts;     // B
+    int32_t* flags;          // B: 1 = margin check failed -> fallback pass needed
+    float* tau;              // B: threshold for the fallback collect pass
+    int32_t* n_flagged;      // scalar counter
+};
+cudaError_t refine_launch(const RefineParams& p, cudaStream_t st);
+// fallback tail: exact scores of the collected rows + top-k select, one CTA per query
+struct CollectSelectParams {
+    const uint32_t* rows_list;   // nq x cap
+    const unsigned* counts;      // nq
+    int cap;
+    const int32_t* query_index;  // nq: which output slot each collected query maps to
+    const void* rows;
+    const float* q;              // nq x dim (the flagged queries, compacted)
+    int dtype, dim, k, nq;
+    double* scratch_scores;      // nq x cap
+    int32_t* out_rows;           // B x k (indexed through query_index)
+    double* out_scores;
+    int32_t* out_counts;
+};
+cudaError_t collect_select_launch(const CollectSelectParams& p, cudaStream_t st);
+// G sorted (score,id) lists per query -> global top-k
+cudaError_t merge_exact_launch(const double* scores, const int64_t* ids, int G, int B, int k, double* out_scores,
+                               int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
+
+// ---- corpus.cu -------------------------------------------------------------
+cudaError_t convert_rows_launch(const float* src, void* dst, int dtype, int64_t n_elems, cudaStream_t st);
+cudaError_t widen_rows_launch(const void* src, int dtype, float* dst, int64_t n_elems, cudaStream_t st);
+cudaError_t row_norm_max_launch(const void* rows, int dtype, int64_t n_rows, int dim, float* max_norm,
+                                cudaStream_t st);
+cudaError_t fill_synthetic_launch(void* rows, int dtype, int64_t row0, int64_t n_rows, int dim, uint64_t seed,
+                                  int64_t gen_row0, cudaStream_t st);
+cudaError_t gather_rows_launch(const void* src, void* dst, const int64_t* keep, int64_t nkeep, int row_bytes,
+                               cudaStream_t st);
+
+// ---- bm25.cu ---------------------------------------------------------------
+struct Bm25Device {
+    int64_t n_docs, n_terms, nnz;
+    int64_t* term_ptr;      // n_terms + 1
+    int32_t* post_row;      // nnz
+    double* post_impact;    // nnz: tf*(k1+1) / (tf + k1*(1-b+b*dl/avgdl))
+    double* idf;            // n_terms
+    double* score;          // n_docs accumulator, all-zero between queries
+};
+cudaError_t bm25_impact_launch(const int32_t* post_row, const int32_t* post_tf, const int32_t* doc_len, int64_t nnz,
+                               double avgdl, double k1, double b, double* impact, cudaStream_t st);
+// one token of one query: score[row] += w * impact[p] over postings [lo, hi)
+cudaError_t bm25_accumulate_launch(const Bm25Device& ix, int64_t lo, int64_t hi, double w, cudaStream_t st);
+// harvest the touched rows (ranges = [lo,hi) pairs of the query's distinct tokens):
+// claim + zero the accumulator, keep score > 0 and allowed rows, per-warp top-kp.
+int bm25_harvest_grid(int64_t total_postings, int sm_count);     // lists = grid * 8
+cudaError_t bm25_harvest_launch(const Bm25Device& ix, const int64_t* d_ranges, int n_ranges, const uint8_t* allow,
+                                int kp, int grid, void* cand, cudaStream_t st);
+cudaError_t bm25_select_launch(const void* cand, int n_lists, int kp, int k, int32_t* out_rows, double* out_scores,
+                               int32_t* out_count, cudaStream_t st);
+cudaError_t bm25_reset_launch(const Bm25Device& ix, const int64_t* d_ranges, int n_ranges, int grid, cudaStream_t st);
+size_t bm25_key_bytes();
+
+// ---- rrf.cu ----------------------------------------------------------------
+int rrf_max_entries();
+cudaError_t rrf_launch(const int32_t* ids, const double* weights, int Q, int R, int L, int rrf_k, int top,
+                       int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st);
+
+}  // namespace b200rag

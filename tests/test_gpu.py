@@ -1,0 +1,368 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the
+C ABI (libb200rag.so) and is compared bit-for-bit with the oracle / the golden
+vectors produced by the reference's own code."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from conftest import load_golden, unhex
+from oracle import c_oracle
+from oracle import numpy_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f32": no.DT_F32, "bf16": no.DT_BF16, "f16": no.DT_F16}
+
+
+def raw_rows(x32, dt):
+    """storage-dtype bit patterns for the C oracle, from fp32 values that are already representable"""
+    if dt == no.DT_F32:
+        return np.ascontiguousarray(x32, np.float32)
+    if dt == no.DT_BF16:
+        return no.f32_to_bf16_bits(x32)
+    return x32.astype(np.float16).view(np.uint16)
+
+
+def check_topk(corpus, q, k, dt, allow=None):
+    bitmap = np.packbits(allow, bitorder="little") if allow is not None else None
+    rows, scores, counts = corpus.topk(q, k, bitmap)
+    stored = corpus.download()
+    er, es, ec = c_oracle.dense_topk(q, raw_rows(stored, dt), dt, k, bitmap)
+    assert counts.tolist() == ec.tolist()
+    for b in range(len(q)):
+        c = counts[b]
+        assert rows[b, :c].tolist() == er[b, :c].tolist(), f"query {b}"
+        assert [float(v).hex() for v in scores[b, :c]] == [float(v).hex() for v in es[b, :c]]
+        assert (rows[b, c:] == -1).all()
+    return rows, scores, counts
+
+
+def test_device_is_b200():
+    from b200rag import _lib
+    info = _lib.device_info()
+    assert info["cc"][0] == 10 and info["sm_count"] >= 100
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+def test_dense_golden(dense_small, dtype):
+    from b200rag import DeviceCorpus
+    x, q, gold = dense_small
+    c = DeviceCorpus(x.shape[1], dtype)
+    c.append(x)
+    assert np.array_equal(c.download(), no.quantize(x, DT[dtype]))      # RNE conversion on the device
+    allow = (np.arange(len(x)) % 3 != 0)
+    bitmap = np.packbits(allow, bitorder="little")
+    for case in gold["cases"]:
+        if case["dtype"] != dtype:
+            continue
+        rows, scores, counts = c.topk(q, case["k"], bitmap if case["filtered"] else None)
+        for qi in range(len(q)):
+            assert rows[qi, :counts[qi]].tolist() == case["rows"][qi], (case["k"], case["filtered"], qi)
+            assert [float(v).hex() for v in scores[qi, :counts[qi]]] == case["scores"][qi]
+    c.close()
+
+
+@pytest.mark.parametrize("dtype,n,d", [("bf16", 20011, 1024), ("f32", 9001, 1024), ("f16", 5000, 768),
+                                       ("bf16", 3000, 64), ("f32", 777, 256), ("bf16", 4097, 2048)])
+def test_dense_random_vs_oracle(dtype, n, d):
+    from b200rag import DeviceCorpus
+    x = helpers.synth_unit(n, d, seed=n)
+    q = helpers.synth_unit(7, d, seed=n + 1)
+    q[2] = x[n // 2]                                   # a query equal to a row
+    c = DeviceCorpus(d, dtype)
+    c.append(x[: n // 3])
+    c.append(x[n // 3:])                               # appended in two uploads
+    assert c.count() == n
+    for B, k in [(1, 10), (2, 50), (3, 1), (4, 100), (7, 10), (5, 224)]:
+        check_topk(c, q[:B], min(k, n), DT[dtype])
+    allow = np.random.default_rng(5).random(n) < 0.3
+    check_topk(c, q[:3], 10, DT[dtype], allow)
+    allow[:] = False
+    allow[[3, n - 1]] = True
+    rows, scores, counts = check_topk(c, q[:2], 10, DT[dtype], allow)
+    assert counts.tolist() == [2, 2]
+    c.close()
+
+
+def test_dense_many_exact_ties_take_the_fallback_pass():
+    """More identical best rows than the candidate list holds: the margin check must fail, the
+    fallback pass must run, and ties must resolve to the lowest rows."""
+    from b200rag import DeviceCorpus, _lib
+    n, d = 6000, 128
+    x = helpers.synth_unit(n, d, seed=2)
+    q = helpers.synth_unit(3, d, seed=3)
+    dup = np.random.default_rng(9).choice(n, size=700, replace=False)
+    x[dup] = q[0]                                      # 700 rows tie for the best score of query 0
+    c = DeviceCorpus(d, "f32")
+    c.append(x)
+    before = _lib.counters()["fallbacks"]
+    rows, scores, counts = check_topk(c, q, 10, no.DT_F32)
+    assert rows[0].tolist() == sorted(dup.tolist())[:10]
+    assert _lib.counters()["fallbacks"] == before + 1
+    check_topk(c, q[:1], 100, no.DT_F32)
+    c.close()
+
+
+def test_dense_near_ties_within_filter_error():
+    """rows that differ from the best row by less than the fp32 filter error: order must still be the fp64 order"""
+    from b200rag import DeviceCorpus
+    n, d = 4000, 1024
+    g = np.random.default_rng(11)
+    x = helpers.synth_unit(n, d, seed=12)
+    q = helpers.synth_unit(1, d, seed=13)
+    for j in range(60):                                # 60 tiny perturbations of the query itself
+        x[100 + 37 * j] = no.l2_normalize_rows(q[0] + 3e-5 * g.standard_normal(d).astype(np.float32))[0]
+    for dtype in ("f32", "bf16"):
+        c = DeviceCorpus(d, dtype)
+        c.append(x)
+        check_topk(c, q, 10, DT[dtype])
+        check_topk(c, q, 50, DT[dtype])
+        c.close()
+
+
+def test_dense_edge_cases():
+    from b200rag import DeviceCorpus, DeviceCollection, B200RagError
+    d = 128
+    c = DeviceCorpus(d, "bf16")
+    q = helpers.synth_unit(2, d, seed=1)
+    rows, scores, counts = c.topk(q, 5)                 # empty corpus
+    assert counts.tolist() == [0, 0] and (rows == -1).all()
+    x = helpers.synth_unit(3, d, seed=2)
+    c.append(x)
+    rows, scores, counts = check_topk(c, q, 10, no.DT_BF16)   # fewer rows than k
+    assert counts.tolist() == [3, 3]
+    with pytest.raises(B200RagError):
+        c.topk(q, 225)
+    with pytest.raises(B200RagError):
+        DeviceCorpus(100, "bf16")
+    with pytest.raises(ValueError):
+        c.topk(np.zeros((1, 64), np.float32), 1)
+    c.close()
+    col = DeviceCollection(dim=d, dtype="f32")
+    out = col.query(query_embeddings=[q[0].tolist()], n_results=5)
+    assert out["ids"] == [[]] and out["distances"] == [[]]
+
+
+def test_collection_matches_exact_collection(e2e_data):
+    from b200rag import DeviceCollection
+    gold, emb, table = e2e_data
+    for dtype in ("f32", "bf16"):
+        dev = DeviceCollection(dim=emb.shape[1], dtype=dtype)
+        ora = no.ExactCollection(dim=emb.shape[1], dtype=DT[dtype])
+        helpers.fill(dev, gold["chunks"], emb)
+        helpers.fill(ora, gold["chunks"], emb)
+        assert dev.count() == ora.count()
+        qs = [list(map(float, v)) for v in list(table.values())[:6]]
+        wheres = [None, {"source": "CNIL"}, {"source": {"$ne": "ENTREPRISE"}}, {"tag_rh": True},
+                  {"$or": [{"source": "CNIL"}, {"$and": [{"source": "ENTREPRISE"}, {"tag_rh": True}]}]},
+                  {"chunk_nature": {"$in": ["GUIDE", "SANCTION"]}}, {"source": "NOPE"}]
+        for w in wheres:
+            for n_res in (50, 7):
+                assert dev.query(query_embeddings=qs[:2], n_results=n_res, where=w,
+                                 include=["documents", "metadatas", "distances"]) == \
+                    ora.query(query_embeddings=qs[:2], n_results=n_res, where=w,
+                              include=["documents", "metadatas", "distances"])
+        a = dev.get(limit=20, offset=10, include=["documents", "metadatas", "embeddings"])
+        b = ora.get(limit=20, offset=10, include=["documents", "metadatas", "embeddings"])
+        assert a["ids"] == b["ids"] and a["documents"] == b["documents"] and a["metadatas"] == b["metadatas"]
+        assert np.array_equal(a["embeddings"], b["embeddings"])
+        # delete + update, then the same queries again
+        victims = [c["id"] for c in gold["chunks"][5:60:3]]
+        dev.delete(ids=victims); ora.delete(ids=victims)
+        dev.delete(where={"tag_rh": True}); ora.delete(where={"tag_rh": True})
+        some = dev.get(limit=3)["ids"]
+        dev.update(ids=some, metadatas=[{"source": "CNIL", "document_path": "x"}] * 3)
+        ora.update(ids=some, metadatas=[{"source": "CNIL", "document_path": "x"}] * 3)
+        assert dev.count() == ora.count()
+        assert dev.query(query_embeddings=qs[2:4], n_results=40, where={"source": "CNIL"}) == \
+            ora.query(query_embeddings=qs[2:4], n_results=40, where={"source": "CNIL"})
+        assert np.array_equal(dev.get(include=["embeddings"])["embeddings"], ora.get(include=["embeddings"])["embeddings"])
+
+
+def test_synthetic_fill_matches_numpy_twin():
+    from b200rag import DeviceCorpus
+    from b200rag import synth
+    for dtype in ("f32", "bf16"):
+        c = DeviceCorpus(256, dtype)
+        c.fill_synthetic(seed=77, nrows=1000)
+        c.fill_synthetic(seed=77, nrows=500, gen_row0=5000)
+        want = np.concatenate([synth.synth_rows(77, 0, 1000, 256), synth.synth_rows(77, 5000, 500, 256)])
+        assert np.array_equal(c.download(), no.quantize(want, DT[dtype]))
+        q = synth.unit_queries(2, 256, 1)
+        check_topk(c, q, 10, DT[dtype])
+        c.close()
+
+
+# ---------------------------------------------------------------- BM25 ----
+def test_bm25_golden_from_reference_index():
+    from b200rag import DeviceCollection, DeviceChunkBM25Index
+    gold = load_golden("bm25_small.json")
+    col = DeviceCollection(dim=64, dtype="f32")
+    emb = helpers.synth_unit(len(gold["chunks"]), 64, seed=3)
+    helpers.fill(col, gold["chunks"], emb)
+    idx = DeviceChunkBM25Index()
+    with pytest.raises(RuntimeError):
+        idx.search("x")
+    idx.build_from_collection(col, batch_size=70)
+    assert idx.is_built and idx.chunk_ids == gold["kept_ids"]
+    for case in gold["cases"]:
+        res = idx.search(case["query"], top_k=case["top_k"],
+                         doc_filter=set(case["doc_filter"]) if case["doc_filter"] is not None else None)
+        assert [{"doc_key": r.doc_key, "score": float(r.score).hex()} for r in res] == case["results"], case["query"]
+        for r in res:
+            assert "text" in r.metadata and r.metadata["document_path"]
+    col2 = DeviceCollection(dim=64, dtype="f32")
+    helpers.fill(col2, gold["common_corpus"], helpers.synth_unit(6, 64, seed=1))
+    idx2 = DeviceChunkBM25Index()
+    idx2.build_from_collection(col2)
+    assert idx2.search("données rgpd", top_k=10) == []
+
+
+def test_summary_bm25_golden(golden_dir):
+    from b200rag import DeviceSummaryBM25Index
+    gold = load_golden("summary_bm25.json")
+    sm = DeviceSummaryBM25Index()
+    sm.build(os.path.join(golden_dir, "summaries_input.json"))
+    assert sm._is_built and sm.doc_keys == gold["doc_keys"]
+    for case in gold["cases"]:
+        res = sm.search(case["query"], top_k=case["top_k"])
+        assert [{"doc_key": r.doc_key, "score": float(r.score).hex()} for r in res] == case["results"]
+
+
+@pytest.mark.parametrize("n_docs,vocab", [(5000, 2000), (60000, 30000)])
+def test_bm25_scores_and_select_vs_oracle(n_docs, vocab):
+    from b200rag.bm25 import DeviceBM25, Postings
+    docs, n_terms = helpers.zipf_docs(n_docs, vocab, seed=n_docs)
+    p = Postings.from_term_ids(docs, n_terms=n_terms)
+    o = no.CsrBM25(docs)
+    assert np.array_equal(o.idf, p.idf) and np.array_equal(o.post_row, p.post_row)
+    ix = DeviceBM25(p)
+    g = np.random.default_rng(1)
+    allow = g.random(n_docs) < 0.5
+    bitmap = np.packbits(allow, bitorder="little")
+    queries = []
+    for _ in range(12):
+        qt = g.integers(0, min(n_terms, 400), size=g.integers(1, 14)).astype(np.int32)
+        if g.random() < 0.4:
+            qt[g.integers(0, len(qt))] = -1               # unknown token
+        if g.random() < 0.4:
+            qt = np.concatenate([qt, qt[:2]])             # repeated tokens are added again
+        queries.append(qt)
+    for qt in queries[:4]:
+        want = c_oracle.bm25_scores(o.term_ptr, o.post_row, o.post_tf, o.doc_len.astype(np.int32), o.idf, o.avgdl,
+                                    1.5, 0.75, qt)
+        got = ix.scores(qt)
+        assert np.array_equal(got, want)
+        assert np.array_equal(want, o.get_scores(qt.tolist()))
+    for k in (50, 10, 224):
+        rows, scores, counts = ix.search_ids(queries, k)
+        rows_f, scores_f, counts_f = ix.search_ids(queries, k, bitmap)
+        for i, qt in enumerate(queries):
+            er, es = o.search(qt.tolist(), k)
+            assert rows[i, :counts[i]].tolist() == er.tolist() and np.array_equal(scores[i, :counts[i]], es)
+            er, es = o.search(qt.tolist(), k, allow)
+            assert rows_f[i, :counts_f[i]].tolist() == er.tolist() and np.array_equal(scores_f[i, :counts_f[i]], es)
+    # accumulator is clean after all of that
+    assert not ix.scores(np.array([-1], np.int32)).any()
+    ix.close()
+
+
+# ----------------------------------------------------------------- RRF ----
+def test_rrf_golden_from_reference():
+    from b200rag import reciprocal_rank_fusion, fuse_ranked
+    for case in load_golden("rrf.json"):
+        kw = {"k": case["k"]}
+        if case["weights"] is not None:
+            kw["weights"] = case["weights"]
+        got = reciprocal_rank_fusion(case["rankings"], **kw)
+        assert {i: float(s).hex() for i, s in got.items()} == case["scores"]
+        assert list(got.keys()) == list(case["scores"].keys())            # dict in first-seen order
+        ids, sc = fuse_ranked(case["rankings"], **kw)
+        assert ids == case["order"]
+        ids10, _ = fuse_ranked(case["rankings"], top=10, **kw)
+        assert ids10 == case["order"][:10]
+
+
+def test_rrf_batched_vs_oracle():
+    from b200rag import rrf_fuse_rows
+    g = np.random.default_rng(3)
+    Q, R, L = 64, 8, 50
+    ids = np.full((Q, R, L), -1, np.int32)
+    for qi in range(Q):
+        for r in range(R):
+            ln = g.integers(0, L + 1)
+            ids[qi, r, :ln] = g.choice(400, size=ln, replace=False)
+    w = np.array([2.0, 3.0, 1.0, 0.75, 1.0, 0.75, 1.0, 0.75])
+    out_ids, out_sc, counts = rrf_fuse_rows(ids, w, 60, 40)
+    for qi in range(Q):
+        ei, es = c_oracle.rrf(ids[qi], w, 60, 40)
+        assert out_ids[qi, :counts[qi]].tolist() == ei.tolist()
+        assert np.array_equal(out_sc[qi, :counts[qi]], es)
+
+
+# ----------------------------------------------------------------- e2e ----
+def test_hybrid_retrieval_end_to_end_matches_reference(e2e_data, golden_dir):
+    """HybridRetriever around DeviceCollection + DeviceChunkBM25Index + DeviceSummaryBM25Index + device RRF
+    returns exactly what the reference's RAGRetriever returned around the exact CPU collection."""
+    from b200rag import DeviceCollection, DeviceChunkBM25Index, DeviceSummaryBM25Index, HybridRetriever
+    gold, emb, table = e2e_data
+    col = DeviceCollection(dim=emb.shape[1], dtype="f32")
+    helpers.fill(col, gold["chunks"], emb)
+    bm = DeviceChunkBM25Index()
+    bm.build_from_collection(col)
+    sm = DeviceSummaryBM25Index()
+    sm.build(os.path.join(golden_dir, "e2e_summaries.json"))
+    for run in gold["runs"]:
+        cands, docs = helpers.run_e2e_case(HybridRetriever, col, bm, sm, gold, table, run)
+        assert cands == run["candidates"], (run["config"], run["query"])
+        assert docs == run["documents"], (run["config"], run["query"])
+
+
+# ------------------------------------------------------- multi-GPU tail ----
+def test_merge_topk_dev_vs_host_merge():
+    import torch
+    from b200rag import _lib
+    from b200rag.sharded import merge_lists_torch
+    g = torch.Generator().manual_seed(0)
+    for G, B, k in [(2, 5, 10), (8, 33, 100), (3, 1, 1), (8, 4, 224)]:
+        scores = torch.randn(G, B, k, generator=g, dtype=torch.float64).sort(dim=2, descending=True).values
+        scores[:, :, 1] = scores[:, :, 0]                              # ties inside and across lists
+        scores[1:] = torch.where(torch.rand(G - 1, B, k, generator=g) < 0.2, scores[:1], scores[1:])
+        ids = torch.stack([torch.randperm(100000, generator=g)[: B * k].reshape(B, k) + 100000 * r for r in range(G)])
+        ids[-1, :, k // 2:] = -1                                        # a short list
+        want_s, want_i, want_c = merge_lists_torch(scores, ids, k)
+        ds, di = scores.cuda(), ids.cuda()
+        o_s = torch.empty(B, k, dtype=torch.float64, device="cuda")
+        o_i = torch.empty(B, k, dtype=torch.int64, device="cuda")
+        o_c = torch.empty(B, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib().rag_merge_topk_dev(ds.data_ptr(), di.data_ptr(), G, B, k, o_s.data_ptr(), o_i.data_ptr(),
+                                                 o_c.data_ptr()))
+        assert torch.equal(o_i.cpu(), want_i) and torch.equal(o_s.cpu(), want_s) and torch.equal(o_c.cpu(), want_c)
+
+
+# --------------------------------------------------- BASELINE-size cases ----
+def test_dense_config2_full_size_properties():
+    """BASELINE config 2 (1M x 1024 fp32, top-10): size-independent properties + two queries against the oracle."""
+    from b200rag import DeviceCorpus, synth
+    n, d = 1_000_000, 1024
+    c = DeviceCorpus(d, "f32", capacity=n)
+    c.fill_synthetic(seed=1002, nrows=n)
+    q = synth.unit_queries(4, d, 2002)
+    planted = [123456, 999999, 0]
+    rows_p = np.concatenate([c.download(r, 1) for r in planted])
+    qq = np.concatenate([q, rows_p])
+    rows, scores, counts = c.topk(qq, 10)
+    assert (counts == 10).all()
+    assert (np.diff(scores, axis=1) <= 0).all()                        # sorted
+    for j, r in enumerate(planted):                                    # a row is its own nearest neighbour
+        assert rows[4 + j, 0] == r and abs(scores[4 + j, 0] - 1.0) < 1e-6
+    r1, s1, _ = c.topk(qq[:1], 10)                                     # batch-1 == batch-7 row
+    assert r1[0].tolist() == rows[0].tolist() and np.array_equal(s1[0], scores[0])
+    # against the oracle on the regenerated rows (numpy twin of the generator), 2 queries
+    x = synth.synth_rows(1002, 0, n, d)
+    er, es, ec = c_oracle.dense_topk(qq[:2], x, no.DT_F32, 10)
+    assert rows[:2].tolist() == er.tolist() and np.array_equal(scores[:2], es)
+    c.close()
