@@ -328,7 +328,8 @@ def test_merge_topk_dev_vs_host_merge():
     g = torch.Generator().manual_seed(0)
     for G, B, k in [(2, 5, 10), (8, 33, 100), (3, 1, 1), (8, 4, 224)]:
         scores = torch.randn(G, B, k, generator=g, dtype=torch.float64).sort(dim=2, descending=True).values
-        scores[:, :, 1] = scores[:, :, 0]                              # ties inside and across lists
+        if k > 1:
+            scores[:, :, 1] = scores[:, :, 0]                          # ties inside and across lists
         scores[1:] = torch.where(torch.rand(G - 1, B, k, generator=g) < 0.2, scores[:1], scores[1:])
         ids = torch.stack([torch.randperm(100000, generator=g)[: B * k].reshape(B, k) + 100000 * r for r in range(G)])
         ids[-1, :, k // 2:] = -1                                        # a short list
