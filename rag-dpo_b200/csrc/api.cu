@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -75,13 +76,14 @@ struct Ctx {
     size_t pinned_bytes = 0;
     int32_t* pinned_small = nullptr;    // 4 KB for flags / counters read back inside a call
     // scratch (device)
-    DevBuf q, allow, cand, top, flags, tau, nflag, o_rows, o_scores, o_counts;
+    DevBuf q, allow, cand, cand_cnt, q16, q_resid, top, flags, tau, nflag, o_rows, o_scores, o_counts;
     DevBuf fb_q, fb_tau, fb_counts, fb_rows, fb_scores, fb_index;
     DevBuf bm_terms, bm_ranges, bm_cand, bm_rows, bm_scores, bm_counts, bm_allow;
     DevBuf rrf_ids, rrf_w, rrf_oi, rrf_os, rrf_oc;
     DevBuf stage_f32;
 };
 Ctx g;
+int g_tc_min_batch = 5;     // smallest batch served by the tcgen05 path (env B200RAG_TC_MIN_BATCH)
 
 int ensure_pinned(size_t need) {
     if (need <= g.pinned_bytes) return RAG_OK;
@@ -120,6 +122,10 @@ struct rag_corpus {
     size_t row_bytes = 0;
     void* rows = nullptr;
     float* max_norm = nullptr;   // device scalar
+    // bf16 shadow for the tensor-core path (fp32 / fp16 corpora), built lazily, dropped on mutation
+    void* shadow = nullptr;
+    int64_t shadow_cap = 0, shadow_rows = -1;
+    float* shadow_resid = nullptr;
 };
 
 struct rag_bm25 {
@@ -156,6 +162,7 @@ int rag_init(int device) {
     g.stream = g.own_stream;
     for (auto& ev : g.ev) CU_TRY(cudaEventCreate(&ev));
     CU_TRY(cudaMallocHost((void**)&g.pinned_small, 4096));
+    if (const char* e = getenv("B200RAG_TC_MIN_BATCH")) g_tc_min_batch = std::max(1, atoi(e));
     g.inited = true;
     return RAG_OK;
 }
@@ -236,6 +243,8 @@ int rag_corpus_destroy(rag_corpus_t* c) {
         cudaStreamSynchronize(g.stream);
         cudaFree(c->rows);
         cudaFree(c->max_norm);
+        cudaFree(c->shadow);
+        cudaFree(c->shadow_resid);
     }
     delete c;
     return RAG_OK;
@@ -296,6 +305,7 @@ int rag_corpus_upload(rag_corpus_t* c, int64_t row0, int64_t nrows, const float*
         CU_TRY(cudaStreamSynchronize(g.stream));      // the pinned chunk is reused
     }
     c->n = std::max(c->n, row0 + nrows);
+    c->shadow_rows = -1;
     return RAG_OK;
 }
 
@@ -346,6 +356,7 @@ int rag_corpus_compact(rag_corpus_t* c, const int64_t* keep_rows, int64_t nkeep)
     c->rows = nr;
     c->cap = ncap;
     c->n = nkeep;
+    c->shadow_rows = -1;
     // the max norm only ever over-estimates after a delete, which keeps the bound valid
     return RAG_OK;
 }
@@ -369,6 +380,7 @@ int rag_corpus_fill_synthetic(rag_corpus_t* c, uint64_t seed, int64_t gen_row0, 
     g.n_launch += 2;
     CU_TRY(cudaStreamSynchronize(g.stream));
     c->n = std::max(c->n, row0 + nrows);
+    c->shadow_rows = -1;
     return RAG_OK;
 }
 
@@ -385,9 +397,45 @@ int rag_corpus_device_ptr(const rag_corpus_t* c, void** rows_dev) {
 // <= 16 chained FMAs + 2 + 5 tree levels, each 2^-24 -> < 2^-19.
 static const double kEpsScan = 1.0 / 524288.0;
 
+// accumulation error of the tensor-core filter relative to |q|*max|x|: 64 chained K=16 blocks plus the
+// in-block tree, fp32 accumulators (truncating) -> < 70 * 2^-23 < 2^-16.
+static const double kEpsTc = 1.0 / 65536.0;
+
+// bf16 operand of the tensor-core path: the rows themselves, or a lazily built bf16 shadow
+static int ensure_bf16_operand(rag_corpus* c, const void** x16, const float** x_resid) {
+    if (c->dtype == RAG_BF16) {
+        *x16 = c->rows;
+        *x_resid = nullptr;
+        return RAG_OK;
+    }
+    if (c->shadow_rows != c->n) {
+        if (c->shadow_cap < c->n) {
+            if (c->shadow) cudaFree(c->shadow);
+            c->shadow = nullptr;
+            c->shadow_cap = 0;
+            cudaError_t e = cudaMalloc(&c->shadow, (size_t)c->cap * c->dim * 2);
+            if (e != cudaSuccess)
+                return fail(RAG_ENOMEM, "cudaMalloc(%zu) for the bf16 shadow: %s", (size_t)c->cap * c->dim * 2,
+                            cudaGetErrorString(e));
+            c->shadow_cap = c->cap;
+        }
+        if (!c->shadow_resid) {
+            CU_TRY(cudaMalloc((void**)&c->shadow_resid, sizeof(float)));
+        }
+        CU_TRY(cudaMemsetAsync(c->shadow_resid, 0, sizeof(float), g.stream));
+        CU_TRY(shadow_launch(c->rows, c->dtype, c->n, c->dim, c->shadow, c->shadow_resid, g.stream));
+        ++g.n_launch;
+        c->shadow_rows = c->n;
+    }
+    *x16 = c->shadow;
+    *x_resid = c->shadow_resid;
+    return RAG_OK;
+}
+
 static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev, int32_t* o_rows,
                       double* o_scores, int32_t* o_counts) {
-    const int kp = std::max(16, next_pow2(k + 6));
+    const bool use_tc = B >= g_tc_min_batch && c->n > 0;
+    const int kp = use_tc ? std::max(64, next_pow2(2 * k + 1)) : std::max(16, next_pow2(k + 6));
     for (auto& v : g.ev_valid) v = false;
     for (auto& t : g.timings) t = 0.f;
 
@@ -396,11 +444,43 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
     RAG_TRY(g.tau.ensure((size_t)B * 4));
     RAG_TRY(g.nflag.ensure(4));
     CU_TRY(cudaMemsetAsync(g.nflag.p, 0, 4, g.stream));
+    const float* q_resid = nullptr;
+    const float* x_resid = nullptr;
 
     if (c->n == 0) {
         CU_TRY(cudaMemsetAsync(g.top.p, 0, (size_t)B * kp * 8, g.stream));
+    } else if (use_tc) {
+        // ---- tcgen05 contraction + fused top-k (dense_gemm.cu)
+        const void* x16 = nullptr;
+        RAG_TRY(ensure_bf16_operand(c, &x16, &x_resid));
+        GemmParams p{};
+        p.n_rows = c->n;
+        p.dim = c->dim;
+        p.n_queries = B;
+        p.kp = kp;
+        p.allow = allow_dev;
+        int grid = 0;
+        const size_t smem = gemm_plan(p, g.sm_count, g.smem_optin, &grid);
+        if (smem == 0) return fail(RAG_ERANGE, "k=%d does not fit the contraction kernel's shared memory", k);
+        const int bpad = gemm_padded_queries(B);
+        RAG_TRY(g.q16.ensure((size_t)bpad * c->dim * 2));
+        RAG_TRY(g.q_resid.ensure((size_t)bpad * 4));
+        RAG_TRY(g.cand.ensure((size_t)bpad * p.n_lists * 2 * kp * 8));
+        RAG_TRY(g.cand_cnt.ensure((size_t)bpad * p.n_lists * 4));
+        p.cand = g.cand.as<uint64_t>();
+        p.cand_cnt = g.cand_cnt.as<int32_t>();
+        CU_TRY(query_prep_launch(q_dev, B, bpad, c->dim, g.q16.p, g.q_resid.as<float>(), g.stream));
+        ++g.n_launch;
+        q_resid = g.q_resid.as<float>();
+        rec(0);
+        CU_TRY(gemm_launch(p, g.q16.p, x16, grid, smem, g.stream));
+        ++g.n_launch;
+        rec(1);
+        CU_TRY(merge_launch(g.cand.as<uint64_t>(), g.cand_cnt.as<int32_t>(), B, p.n_lists, 2 * kp, kp,
+                            g.top.as<uint64_t>(), g.stream));
+        ++g.n_launch;
     } else {
-        // plan once (geometry does not depend on the group), then one scan launch per <= 4 queries
+        // ---- CUDA-core scan (dense_scan.cu): one launch per <= 4 queries
         ScanParams p{};
         p.rows = c->rows;
         p.n_rows = c->n;
@@ -428,7 +508,7 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
             ++g.n_launch;
         }
         rec(1);
-        CU_TRY(merge_launch(g.cand.as<uint64_t>(), B, n_lists, kp, g.top.as<uint64_t>(), g.stream));
+        CU_TRY(merge_launch(g.cand.as<uint64_t>(), nullptr, B, n_lists, kp, kp, g.top.as<uint64_t>(), g.stream));
         ++g.n_launch;
     }
     rec(2);
@@ -441,7 +521,9 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
     rp.kp = kp;
     rp.k = k;
     rp.B = B;
-    rp.eps_rel = kEpsScan;
+    rp.eps_rel = use_tc ? kEpsTc : kEpsScan;
+    rp.q_resid = q_resid;
+    rp.x_resid = x_resid;
     rp.max_row_norm = c->max_norm;
     rp.out_rows = o_rows;
     rp.out_scores = o_scores;

@@ -1,0 +1,375 @@
+// dense_gemm.cu — batched query x corpus similarity as a tcgen05 tensor-core
+// contraction with a fused running top-k (the score matrix never exists in HBM).
+//
+// Replaces the distance computation + selection inside collection.query(...)
+// (reference call sites: src/rag/retriever.py:215-220, 380-385) for batches of
+// queries (the reference issues them one at a time).
+//
+// Shape of the contraction (per CTA tile):
+//   D[128 queries x 256 rows] (fp32, TMEM) += Q[128 x 64] (bf16, smem) * X[256 x 64]^T (bf16, smem)
+// Queries are the M side so that one TMEM lane == one query: each epilogue
+// thread owns one query and keeps its threshold / candidate count in registers.
+//
+// Warp roles (192 threads, 1 CTA per SM, persistent over row tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B-swizzled boxes) into a 4-stage ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128,N=256,K=16) x 4 per stage;
+//               tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (double-buffered: 2 x 256 TMEM columns, so the
+//               select of tile i overlaps the MMAs of tile i+1), compare against the per-query
+//               threshold, append survivors to the query's candidate list in global memory (L2),
+//               warp-cooperative bitonic prune when a list fills.
+//
+// Both operands are bf16 (the corpus itself, or its bf16 shadow for fp32/fp16 corpora; queries are
+// rounded to bf16 by query_prep_kernel which also returns the exact norm of the rounding residual).
+// The result is only a FILTER: dense_select.cu re-scores the survivors with the canonical fp64 dot
+// product over the stored values and checks the margin against the rigorous filter error bound.
+//
+// Algorithmic work: 2 * B * n * dim flops per call; HBM bytes: ceil(B/128) passes over the bf16 rows.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200rag {
+
+constexpr int GT_M = 128;
+constexpr int GT_N = 256;
+constexpr int GT_K = 64;
+constexpr int GT_A_BYTES = GT_M * GT_K * 2;   // 16 KB
+constexpr int GT_B_BYTES = GT_N * GT_K * 2;   // 32 KB
+constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
+constexpr int GT_THREADS = 192;
+constexpr int GT_EPI_WARPS = 4;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+// bits: [0,14) addr>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 = 64 |
+//       [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile) {
+    uint64_t d = (uint64_t)((smem_u32(smem_tile) >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GT_THREADS, 1)
+dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                       GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // the 128B-swizzled tiles need 1024-byte alignment in the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* stages = smem;                                                    // n_stages * 48 KB
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * GT_STAGE_BYTES);  // 4 warps * 2kp
+    uint64_t* bars = scratch + (size_t)GT_EPI_WARPS * 2 * p.kp;
+    uint64_t* full_bar = bars;                     // [n_stages]
+    uint64_t* empty_bar = bars + 8;                // [n_stages]
+    uint64_t* tfull_bar = bars + 16;               // [2]
+    uint64_t* tempty_bar = bars + 18;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = p.dim / GT_K;
+    const int64_t n_tiles = (p.n_rows + GT_N - 1) / GT_N;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], GT_EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {   // TMEM: all 512 columns (two 128x256 fp32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int qb = 0; qb < p.n_qblocks; ++qb) {
+                for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = stages + (size_t)stage * GT_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], GT_STAGE_BYTES);
+                        tma_load_2d(sa, &map_q, kb * GT_K, qb * GT_M, &full_bar[stage]);
+                        tma_load_2d(sa + GT_A_BYTES, &map_x, kb * GT_K, (int)(t * GT_N), &full_bar[stage]);
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(GT_M, GT_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int qb = 0; qb < p.n_qblocks; ++qb) {
+                for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                    const uint32_t buf = it & 1;
+                    mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * GT_N;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);               // TMA bytes landed
+                        tc_fence_after();
+                        const uint8_t* sa = stages + (size_t)stage * GT_STAGE_BYTES;
+                        const uint64_t a_desc = umma_desc_sw128(sa);
+                        const uint64_t b_desc = umma_desc_sw128(sa + GT_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < GT_K / 16; ++k)               // +32 B per K=16 step inside the swizzle atom
+                            tc_mma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        tc_commit(&empty_bar[stage]);                     // stage reusable once these MMAs retire
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&tfull_bar[buf]);                           // accumulator complete
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: fused running top-k =====================
+        const int ew = warp - 2;                 // scratch slot
+        const int lg = warp & 3;                 // TMEM lane group this warp may read
+        uint64_t* my_scratch = scratch + (size_t)ew * 2 * p.kp;
+        const int cap = 2 * p.kp;
+        const int high_water = cap - 32;
+        uint32_t it = 0;
+        for (int qb = 0; qb < p.n_qblocks; ++qb) {
+            const int q = qb * GT_M + lg * 32 + lane;
+            const bool q_valid = q < p.n_queries;
+            uint64_t* my_list = p.cand + ((size_t)q * p.n_lists + blockIdx.x) * cap;
+            uint64_t thr_key = 0;
+            float thr_f = -INFINITY;
+            int cnt = 0;
+            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const uint32_t buf = it & 1;
+                mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t row0 = (uint32_t)(t * GT_N);
+                for (int c = 0; c < GT_N / 32; ++c) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * GT_N + c * 32, v);
+                    tc_wait_ld();
+                    if (q_valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float s = __uint_as_float(v[j]);
+                            if (s >= thr_f) {
+                                const uint32_t row = row0 + c * 32 + j;
+                                if (row < (uint32_t)p.n_rows && bitmap_test(p.allow, row)) {
+                                    const uint64_t key = make_key(s, row);
+                                    if (key > thr_key) my_list[cnt++] = key;
+                                }
+                            }
+                        }
+                    }
+                    // warp-cooperative prune of every lane whose list is nearly full
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > high_water);
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int n = __shfl_sync(0xffffffffu, cnt, src);
+                        const unsigned long long lp =
+                            __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)my_list, src);
+                        uint64_t* list = reinterpret_cast<uint64_t*>((uintptr_t)lp);
+                        __syncwarp();
+                        for (int i = lane; i < cap; i += 32) my_scratch[i] = i < n ? list[i] : 0ull;
+                        warp_bitonic_desc(my_scratch, cap, lane);
+                        for (int i = lane; i < p.kp; i += 32) list[i] = my_scratch[i];
+                        const uint64_t nt = my_scratch[p.kp - 1];
+                        __syncwarp();
+                        if (lane == src) { cnt = p.kp; thr_key = nt; thr_f = key_score(nt); }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            }
+            if (q_valid) p.cand_cnt[(size_t)q * p.n_lists + blockIdx.x] = cnt;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- query preparation: fp32 -> bf16 (RNE) + exact norm of the rounding residual ---------------------------
+__global__ void query_prep_kernel(const float* __restrict__ q, int n_queries, int n_padded, int dim,
+                                  __nv_bfloat16* __restrict__ q16, float* __restrict__ resid_norm) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_padded) return;
+    double r2 = 0.0;
+    for (int c = lane; c < dim; c += 32) {
+        float v = w < n_queries ? q[(size_t)w * dim + c] : 0.f;
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        q16[(size_t)w * dim + c] = h;
+        double d = (double)v - (double)__bfloat162float(h);
+        r2 += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    if (lane == 0 && w < n_queries) resid_norm[w] = (float)(sqrt(r2) * 1.0000001 + 1e-30);
+}
+
+cudaError_t query_prep_launch(const float* q, int n_queries, int n_padded, int dim, void* q16, float* resid_norm,
+                              cudaStream_t st) {
+    const int warps_per_block = 8;
+    int grid = (n_padded + warps_per_block - 1) / warps_per_block;
+    query_prep_kernel<<<grid, warps_per_block * 32, 0, st>>>(q, n_queries, n_padded, dim,
+                                                             reinterpret_cast<__nv_bfloat16*>(q16), resid_norm);
+    return cudaGetLastError();
+}
+
+// bf16 shadow of an fp32 / fp16 corpus + max over rows of ||x - bf16(x)||_2
+template <int DT>
+__global__ void shadow_kernel(const void* __restrict__ rows, int64_t n_rows, int dim, __nv_bfloat16* __restrict__ out,
+                              float* __restrict__ max_resid) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float best = 0.f;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        float r2 = 0.f;
+        for (int c = lane; c < dim; c += 32) {
+            float v;
+            if constexpr (DT == RAG_F32) v = reinterpret_cast<const float*>(rows)[(size_t)r * dim + c];
+            else v = __half2float(reinterpret_cast<const __half*>(rows)[(size_t)r * dim + c]);
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            out[(size_t)r * dim + c] = h;
+            float d = v - __bfloat162float(h);          // exact in fp32
+            r2 = fmaf(d, d, r2);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        best = fmaxf(best, r2);
+    }
+    if (lane == 0 && best > 0.f)
+        atomicMax(reinterpret_cast<int*>(max_resid), __float_as_int(sqrtf(best) * 1.00001f));
+}
+
+cudaError_t shadow_launch(const void* rows, int dtype, int64_t n_rows, int dim, void* out, float* max_resid,
+                          cudaStream_t st) {
+    int64_t g = (n_rows * 32 + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    if (dtype == RAG_F32)
+        shadow_kernel<RAG_F32><<<(int)g, 256, 0, st>>>(rows, n_rows, dim, reinterpret_cast<__nv_bfloat16*>(out), max_resid);
+    else
+        shadow_kernel<RAG_F16><<<(int)g, 256, 0, st>>>(rows, n_rows, dim, reinterpret_cast<__nv_bfloat16*>(out), max_resid);
+    return cudaGetLastError();
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// row-major [rows][dim] bf16 matrix, box = box_rows x 64 elements, 128B swizzle, OOB rows read as zero
+static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GT_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+int gemm_padded_queries(int n_queries) { return (n_queries + GT_M - 1) / GT_M * GT_M; }
+
+size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
+    const size_t scratch = (size_t)GT_EPI_WARPS * 2 * p.kp * sizeof(uint64_t);
+    const size_t tail = scratch + 256;
+    int stages = (int)((smem_limit - 1024 - (long)tail) / GT_STAGE_BYTES);
+    if (stages > 4) stages = 4;
+    if (stages < 2) return 0;
+    p.n_stages = stages;
+    p.n_qblocks = gemm_padded_queries(p.n_queries) / GT_M;
+    const int64_t n_tiles = (p.n_rows + GT_N - 1) / GT_N;
+    int grid = (int)(n_tiles < sm_count ? (n_tiles > 0 ? n_tiles : 1) : sm_count);
+    *grid_out = grid;
+    p.n_lists = grid;
+    return (size_t)stages * GT_STAGE_BYTES + tail + 1024;   // + slack for the 1024-byte alignment of the ring
+}
+
+cudaError_t gemm_launch(const GemmParams& p, const void* q16, const void* x16, int grid, size_t smem,
+                        cudaStream_t st) {
+    CUtensorMap map_q, map_x;
+    if (!make_map(&map_q, q16, gemm_padded_queries(p.n_queries), p.dim, GT_M)) return cudaErrorNotSupported;
+    if (!make_map(&map_x, x16, p.n_rows, p.dim, GT_N)) return cudaErrorNotSupported;
+    cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dense_gemm_topk_kernel<<<grid, GT_THREADS, smem, st>>>(map_q, map_x, p);
+    return cudaGetLastError();
+}
+
+}  // namespace b200rag

@@ -17,33 +17,40 @@ namespace b200rag {
 // ---------------------------------------------------------------------------
 constexpr int kMergeWarps = 8;
 
-__global__ void __launch_bounds__(kMergeWarps * 32) merge_kernel(const uint64_t* __restrict__ cand, int n_lists,
-                                                                 int kp, uint64_t* __restrict__ top) {
+__global__ void __launch_bounds__(kMergeWarps * 32)
+merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int n_lists, int list_len, int kp,
+             uint64_t* __restrict__ top) {
     extern __shared__ __align__(16) uint64_t sm_keys[];   // kMergeWarps * 2 * kp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x;
-    const uint64_t* src = cand + (size_t)b * n_lists * kp;
-    const int64_t total = (int64_t)n_lists * kp;
+    const uint64_t* src = cand + (size_t)b * n_lists * list_len;
+    const int32_t* cnt = counts ? counts + (size_t)b * n_lists : nullptr;
 
     WarpTopK t;
     t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
-    const int64_t per_iter = (int64_t)kMergeWarps * 32;
-    const int64_t n_iter = (total + per_iter - 1) / per_iter;
-    for (int64_t it = 0; it < n_iter; ++it) {
-        int64_t i = it * per_iter + warp * 32 + lane;
-        uint64_t key = i < total ? src[i] : 0ull;
-        t.offer(key, lane);
+    // each warp walks whole lists (list_len is a multiple of 32): warp w takes lists w, w+8, ...
+    for (int l = warp; l < n_lists; l += kMergeWarps) {
+        const int n = cnt ? min(cnt[l], list_len) : list_len;
+        const uint64_t* lp = src + (size_t)l * list_len;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            t.offer(i < n ? lp[i] : 0ull, lane);
+        }
     }
     t.finish(lane);
     __syncthreads();
-    int n_all = kMergeWarps * 2 * kp;          // power of two
-    block_bitonic_desc(sm_keys, n_all);
+    block_bitonic_desc(sm_keys, kMergeWarps * 2 * kp);      // power of two
     for (int i = threadIdx.x; i < kp; i += blockDim.x) top[(size_t)b * kp + i] = sm_keys[i];
 }
 
-cudaError_t merge_launch(const uint64_t* cand, int B, int n_lists, int kp, uint64_t* top, cudaStream_t st) {
+cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int B, int n_lists, int list_len, int kp,
+                         uint64_t* top, cudaStream_t st) {
     size_t smem = (size_t)kMergeWarps * 2 * kp * sizeof(uint64_t);
-    merge_kernel<<<B, kMergeWarps * 32, smem, st>>>(cand, n_lists, kp, top);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    merge_kernel<<<B, kMergeWarps * 32, smem, st>>>(cand, counts, n_lists, list_len, kp, top);
     return cudaGetLastError();
 }
 
@@ -129,7 +136,9 @@ __global__ void __launch_bounds__(256) refine_kernel(RefineParams p) {
         if (count == p.kp) {
             // the list is full: rows outside it have filter score <= a_min, hence
             // exact score <= a_min + eps.  Safe iff the k-th exact beats that.
-            double eps = p.eps_rel * sqrt(s_qnorm2) * (double)(*p.max_row_norm);
+            const double qn = sqrt(s_qnorm2);
+            double eps = (p.eps_rel * qn + (p.q_resid ? (double)p.q_resid[b] : 0.0)) * (double)(*p.max_row_norm);
+            if (p.x_resid) eps += 1.004 * qn * (double)(*p.x_resid);
             double a_min = (double)key_score(top[p.kp - 1]);
             double e_k = ek[p.k - 1].s;
             if (!(e_k > a_min + eps)) {

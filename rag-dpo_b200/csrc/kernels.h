@@ -33,9 +33,33 @@ int scan_nq_template(int n_queries);
 size_t scan_plan(ScanParams& p, int dtype, int sm_count, int smem_limit, int* grid_out, int* nch_out);
 cudaError_t scan_launch(const ScanParams& p, int dtype, int nch, int grid, size_t smem, cudaStream_t st);
 
+// ---- dense_gemm.cu ---------------------------------------------------------
+struct GemmParams {
+    int64_t n_rows;
+    int dim;
+    int n_queries;           // B (the bf16 query buffer is padded to a multiple of 128 rows)
+    int kp;                  // candidates kept per query (power of two >= 64); lists hold 2*kp
+    const uint8_t* allow;    // nullable row bitmap (device)
+    uint64_t* cand;          // padded_B x n_lists x 2*kp keys
+    int32_t* cand_cnt;       // padded_B x n_lists valid entries per list
+    // derived by gemm_plan
+    int n_lists, n_stages, n_qblocks;
+};
+int gemm_padded_queries(int n_queries);
+size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out);
+cudaError_t gemm_launch(const GemmParams& p, const void* q16, const void* x16, int grid, size_t smem, cudaStream_t st);
+// fp32 queries -> bf16 (padded rows zeroed) + ||q - bf16(q)||_2 per query
+cudaError_t query_prep_launch(const float* q, int n_queries, int n_padded, int dim, void* q16, float* resid_norm,
+                              cudaStream_t st);
+// bf16 shadow of an fp32/fp16 corpus + max_r ||x_r - bf16(x_r)||_2 (atomicMax into *max_resid)
+cudaError_t shadow_launch(const void* rows, int dtype, int64_t n_rows, int dim, void* out, float* max_resid,
+                          cudaStream_t st);
+
 // ---- dense_select.cu -------------------------------------------------------
-// merge: cand (B x n_lists x kp, any order, 0 = empty) -> top (B x kp sorted desc)
-cudaError_t merge_launch(const uint64_t* cand, int B, int n_lists, int kp, uint64_t* top, cudaStream_t st);
+// merge: cand (B x n_lists x list_len keys, any order, 0 = empty; counts nullable = valid entries per
+// list) -> top (B x kp sorted desc)
+cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int B, int n_lists, int list_len, int kp,
+                         uint64_t* top, cudaStream_t st);
 // refine: canonical fp64 score of every candidate in top, sort by (score desc,
 // row asc), write the first k, and raise flag[b] when the margin check fails.
 struct RefineParams {
@@ -43,7 +67,10 @@ struct RefineParams {
     const void* rows;
     const float* q;          // B x dim
     int dtype, dim, kp, k, B;
-    double eps_rel;          // filter error bound / (|q| * max|x|)
+    // filter error bound: eps = (eps_rel*|q| + q_resid[b]) * max_row_norm + 1.004*|q| * x_resid
+    double eps_rel;          // accumulation error / (|q| * max|x|)
+    const float* q_resid;    // nullable, per query: ||q - bf16(q)||_2 (tensor-core path)
+    const float* x_resid;    // nullable device scalar: max_r ||x_r - bf16(x_r)||_2 (bf16 shadow)
     const float* max_row_norm;  // device scalar
     int32_t* out_rows;       // B x k
     double* out_scores;      // B x k

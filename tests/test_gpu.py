@@ -367,3 +367,42 @@ def test_dense_config2_full_size_properties():
     er, es, ec = c_oracle.dense_topk(qq[:2], x, no.DT_F32, 10)
     assert rows[:2].tolist() == er.tolist() and np.array_equal(scores[:2], es)
     c.close()
+
+
+# ------------------------------------------- tensor-core (tcgen05) path ----
+@pytest.mark.parametrize("dtype,n,d,B", [("bf16", 50003, 1024, 300), ("f32", 30000, 1024, 129), ("f16", 8000, 512, 64),
+                                         ("bf16", 700, 64, 9), ("f32", 256, 128, 128), ("bf16", 40000, 2048, 33)])
+def test_dense_batched_tensor_core_path_vs_oracle(dtype, n, d, B):
+    from b200rag import DeviceCorpus, _lib
+    x = helpers.synth_unit(n, d, seed=n + 7)
+    q = helpers.synth_unit(B, d, seed=n + 8)
+    q[1] = x[n // 3]
+    x[n // 5] = x[n // 7]                                  # an exact duplicate pair
+    c = DeviceCorpus(d, dtype)
+    c.append(x)
+    before = _lib.counters()["fallbacks"]
+    for k in (10, 1, 50, 100):
+        check_topk(c, q, min(k, n), DT[dtype])
+    allow = np.random.default_rng(3).random(n) < 0.25
+    check_topk(c, q, 10, DT[dtype], allow)
+    # appended rows invalidate the bf16 shadow
+    c.append(helpers.synth_unit(100, d, seed=99))
+    check_topk(c, q[:16], 10, DT[dtype])
+    assert _lib.counters()["fallbacks"] - before <= 2      # random data: the margin check passes
+    c.close()
+
+
+def test_tensor_core_path_exact_ties_take_the_fallback():
+    from b200rag import DeviceCorpus, _lib
+    n, d, B = 20000, 256, 40
+    x = helpers.synth_unit(n, d, seed=21)
+    q = helpers.synth_unit(B, d, seed=22)
+    dup = np.random.default_rng(4).choice(n, size=900, replace=False)
+    x[dup] = q[3]
+    c = DeviceCorpus(d, "bf16")
+    c.append(x)
+    before = _lib.counters()["fallbacks"]
+    rows, scores, counts = check_topk(c, q, 10, no.DT_BF16)
+    assert rows[3].tolist() == sorted(dup.tolist())[:10]
+    assert _lib.counters()["fallbacks"] == before + 1
+    c.close()
