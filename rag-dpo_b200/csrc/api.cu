@@ -76,7 +76,7 @@ struct Ctx {
     size_t pinned_bytes = 0;
     int32_t* pinned_small = nullptr;    // 4 KB for flags / counters read back inside a call
     // scratch (device)
-    DevBuf q, allow, cand, cand_cnt, q16, q_resid, top, flags, tau, nflag, o_rows, o_scores, o_counts;
+    DevBuf q, allow, cand, cand_cnt, sample_keys, tau_keys, overflow, q16, q_resid, top, flags, tau, nflag, o_rows, o_scores, o_counts;
     DevBuf fb_q, fb_tau, fb_counts, fb_rows, fb_scores, fb_index;
     DevBuf bm_terms, bm_ranges, bm_cand, bm_rows, bm_scores, bm_counts, bm_allow;
     DevBuf rrf_ids, rrf_w, rrf_oi, rrf_os, rrf_oc;
@@ -446,6 +446,8 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
     CU_TRY(cudaMemsetAsync(g.nflag.p, 0, 4, g.stream));
     const float* q_resid = nullptr;
     const float* x_resid = nullptr;
+    const uint64_t* tau_keys = nullptr;
+    const int32_t* overflow = nullptr;
 
     if (c->n == 0) {
         CU_TRY(cudaMemsetAsync(g.top.p, 0, (size_t)B * kp * 8, g.stream));
@@ -465,20 +467,36 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
         const int bpad = gemm_padded_queries(B);
         RAG_TRY(g.q16.ensure((size_t)bpad * c->dim * 2));
         RAG_TRY(g.q_resid.ensure((size_t)bpad * 4));
-        RAG_TRY(g.cand.ensure((size_t)bpad * p.n_lists * 2 * kp * 8));
+        const int sm = gemm_sample_m();
+        RAG_TRY(g.cand.ensure((size_t)bpad * p.n_lists * p.list_cap * 8));
         RAG_TRY(g.cand_cnt.ensure((size_t)bpad * p.n_lists * 4));
+        RAG_TRY(g.sample_keys.ensure((size_t)bpad * p.n_lists * sm * 8));
+        RAG_TRY(g.tau_keys.ensure((size_t)bpad * sm * 8));
+        RAG_TRY(g.overflow.ensure((size_t)bpad * 4));
         p.cand = g.cand.as<uint64_t>();
         p.cand_cnt = g.cand_cnt.as<int32_t>();
+        p.sample_keys = g.sample_keys.as<uint64_t>();
+        p.tau_keys = p.use_sample ? g.tau_keys.as<uint64_t>() : nullptr;
         CU_TRY(query_prep_launch(q_dev, B, bpad, c->dim, g.q16.p, g.q_resid.as<float>(), g.stream));
         ++g.n_launch;
         q_resid = g.q_resid.as<float>();
+        CU_TRY(cudaMemsetAsync(g.cand_cnt.p, 0, (size_t)bpad * p.n_lists * 4, g.stream));
         rec(0);
-        CU_TRY(gemm_launch(p, g.q16.p, x16, grid, smem, g.stream));
+        if (p.use_sample) {
+            // sample pass -> per-query threshold (16th best sample score)
+            CU_TRY(gemm_launch(p, 0, g.q16.p, x16, grid, smem, g.stream));
+            CU_TRY(merge_launch(g.sample_keys.as<uint64_t>(), nullptr, B, p.n_lists, sm, sm,
+                                g.tau_keys.as<uint64_t>(), nullptr, g.stream));
+            g.n_launch += 2;
+        }
+        CU_TRY(gemm_launch(p, 1, g.q16.p, x16, grid, smem, g.stream));
         ++g.n_launch;
         rec(1);
-        CU_TRY(merge_launch(g.cand.as<uint64_t>(), g.cand_cnt.as<int32_t>(), B, p.n_lists, 2 * kp, kp,
-                            g.top.as<uint64_t>(), g.stream));
+        CU_TRY(merge_launch(g.cand.as<uint64_t>(), g.cand_cnt.as<int32_t>(), B, p.n_lists, p.list_cap, kp,
+                            g.top.as<uint64_t>(), g.overflow.as<int32_t>(), g.stream));
         ++g.n_launch;
+        tau_keys = p.tau_keys;
+        overflow = g.overflow.as<int32_t>();
     } else {
         // ---- CUDA-core scan (dense_scan.cu): one launch per <= 4 queries
         ScanParams p{};
@@ -508,7 +526,8 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
             ++g.n_launch;
         }
         rec(1);
-        CU_TRY(merge_launch(g.cand.as<uint64_t>(), nullptr, B, n_lists, kp, kp, g.top.as<uint64_t>(), g.stream));
+        CU_TRY(merge_launch(g.cand.as<uint64_t>(), nullptr, B, n_lists, kp, kp, g.top.as<uint64_t>(), nullptr,
+                            g.stream));
         ++g.n_launch;
     }
     rec(2);
@@ -524,6 +543,9 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
     rp.eps_rel = use_tc ? kEpsTc : kEpsScan;
     rp.q_resid = q_resid;
     rp.x_resid = x_resid;
+    rp.tau_keys = tau_keys;
+    rp.tau_stride = gemm_sample_m();
+    rp.overflow = overflow;
     rp.max_row_norm = c->max_norm;
     rp.out_rows = o_rows;
     rp.out_scores = o_scores;

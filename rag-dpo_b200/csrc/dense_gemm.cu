@@ -15,9 +15,16 @@
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128,N=256,K=16) x 4 per stage;
 //               tcgen05.commit releases the stage / publishes the accumulator
 //   warps 2..5  epilogue: tcgen05.ld the accumulator (double-buffered: 2 x 256 TMEM columns, so the
-//               select of tile i overlaps the MMAs of tile i+1), compare against the per-query
-//               threshold, append survivors to the query's candidate list in global memory (L2),
-//               warp-cooperative bitonic prune when a list fills.
+//               select of tile i overlaps the MMAs of tile i+1) and run the fused select.
+//
+// Fused select, two launches of the same kernel:
+//   SAMPLE pass  over a strided ~4/kp fraction of the row tiles: every thread keeps the 16 best
+//                scores of its query in registers; merged per query, the 16th best sample score
+//                tau_q is a VALID lower bound of the corpus-wide 16th best score.
+//   MAIN pass    over all tiles: one compare per score against tau_q; the (few hundred per query)
+//                survivors are appended to small per-(query, CTA) lists in global memory (L2).
+//                Everything with filter score >= tau_q is captured, so the candidate set provably
+//                contains the top-k unless a list overflows (flagged -> exact fallback pass).
 //
 // Both operands are bf16 (the corpus itself, or its bf16 shadow for fp32/fp16 corpora; queries are
 // rounded to bf16 by query_prep_kernel which also returns the exact norm of the rounding residual).
@@ -94,6 +101,48 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
+constexpr int kSampleM = 16;      // order statistic taken from the sample pass
+
+// Work items of one CTA, identical in all three warp roles.
+//   sample pass (MODE 0): query block outer, the CTA's sample tiles inner (the running top-16 of a
+//                         query lives in registers across tiles)
+//   main pass   (MODE 1): row tile outer, query block inner: a corpus tile is fetched from HBM once
+//                         and re-read from L2 for every query block
+// tiles of this CTA: t = blockIdx.x + i * gridDim.x, i = 0, step, 2*step, ... (at most max_tiles)
+template <int MODE>
+struct WorkIter {
+    int64_t n_tiles, i;
+    int step, max_tiles, n_qblocks;
+    int taken, qb;
+    bool started;
+    __device__ __forceinline__ void init(const GemmParams& p) {
+        n_tiles = (p.n_rows + GT_N - 1) / GT_N;
+        step = MODE == 0 ? p.sample_step : 1;
+        max_tiles = MODE == 0 ? p.sample_tiles : 0x7fffffff;
+        n_qblocks = p.n_qblocks;
+        i = 0; taken = 0; qb = 0; started = false;
+    }
+    __device__ __forceinline__ bool tile_ok() const {
+        return blockIdx.x + i * gridDim.x < n_tiles && taken < max_tiles;
+    }
+    // advances to the next (tile, query block); new_qb tells the epilogue its per-query state changes
+    __device__ __forceinline__ bool next(int64_t& t, int& qblock) {
+        if (!started) {
+            started = true;
+        } else if (MODE == 0) {
+            i += step; ++taken;
+            if (!tile_ok()) { i = 0; taken = 0; ++qb; }
+        } else {
+            if (++qb == n_qblocks) { qb = 0; i += step; ++taken; }
+        }
+        if (qb >= n_qblocks || !tile_ok()) return false;
+        t = blockIdx.x + i * gridDim.x;
+        qblock = qb;
+        return true;
+    }
+};
+
+template <int MODE>     // 0 = sample pass, 1 = main pass
 __global__ void __launch_bounds__(GT_THREADS, 1)
 dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                        GemmParams p) {
@@ -101,8 +150,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     // the 128B-swizzled tiles need 1024-byte alignment in the shared address space
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stages = smem;                                                    // n_stages * 48 KB
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * GT_STAGE_BYTES);  // 4 warps * 2kp
-    uint64_t* bars = scratch + (size_t)GT_EPI_WARPS * 2 * p.kp;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * GT_STAGE_BYTES);
     uint64_t* full_bar = bars;                     // [n_stages]
     uint64_t* empty_bar = bars + 8;                // [n_stages]
     uint64_t* tfull_bar = bars + 16;               // [2]
@@ -111,7 +159,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.dim / GT_K;
-    const int64_t n_tiles = (p.n_rows + GT_N - 1) / GT_N;
+    WorkIter<MODE> work;
+    work.init(p);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -134,16 +183,16 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int qb = 0; qb < p.n_qblocks; ++qb) {
-                for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sa = stages + (size_t)stage * GT_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], GT_STAGE_BYTES);
-                        tma_load_2d(sa, &map_q, kb * GT_K, qb * GT_M, &full_bar[stage]);
-                        tma_load_2d(sa + GT_A_BYTES, &map_x, kb * GT_K, (int)(t * GT_N), &full_bar[stage]);
-                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
-                    }
+            int64_t t;
+            int qb;
+            while (work.next(t, qb)) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = stages + (size_t)stage * GT_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], GT_STAGE_BYTES);
+                    tma_load_2d(sa, &map_q, kb * GT_K, qb * GT_M, &full_bar[stage]);
+                    tma_load_2d(sa + GT_A_BYTES, &map_x, kb * GT_K, (int)(t * GT_N), &full_bar[stage]);
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -154,89 +203,110 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
-            for (int qb = 0; qb < p.n_qblocks; ++qb) {
-                for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-                    const uint32_t buf = it & 1;
-                    mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+            int64_t t;
+            int qb;
+            for (; work.next(t, qb); ++it) {
+                const uint32_t buf = it & 1;
+                mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * GT_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);               // TMA bytes landed
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * GT_N;
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(&full_bar[stage], phase);               // TMA bytes landed
-                        tc_fence_after();
-                        const uint8_t* sa = stages + (size_t)stage * GT_STAGE_BYTES;
-                        const uint64_t a_desc = umma_desc_sw128(sa);
-                        const uint64_t b_desc = umma_desc_sw128(sa + GT_A_BYTES);
+                    const uint8_t* sa = stages + (size_t)stage * GT_STAGE_BYTES;
+                    const uint64_t a_desc = umma_desc_sw128(sa);
+                    const uint64_t b_desc = umma_desc_sw128(sa + GT_A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < GT_K / 16; ++k)               // +32 B per K=16 step inside the swizzle atom
-                            tc_mma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                        tc_commit(&empty_bar[stage]);                     // stage reusable once these MMAs retire
-                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
-                    }
-                    tc_commit(&tfull_bar[buf]);                           // accumulator complete
+                    for (int k = 0; k < GT_K / 16; ++k)               // +32 B per K=16 step inside the swizzle atom
+                        tc_mma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    tc_commit(&empty_bar[stage]);                     // stage reusable once these MMAs retire
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
+                tc_commit(&tfull_bar[buf]);                           // accumulator complete
             }
         }
     } else {
-        // ===================== epilogue: fused running top-k =====================
-        const int ew = warp - 2;                 // scratch slot
+        // ===================== epilogue: fused select =====================
         const int lg = warp & 3;                 // TMEM lane group this warp may read
-        uint64_t* my_scratch = scratch + (size_t)ew * 2 * p.kp;
-        const int cap = 2 * p.kp;
-        const int high_water = cap - 32;
+        const int n_chunks = MODE == 0 ? p.sample_chunks : GT_N / 32;
         uint32_t it = 0;
-        for (int qb = 0; qb < p.n_qblocks; ++qb) {
+        int cur_qb = -1;
+        float best[kSampleM];                    // MODE 0: the 16 best scores of my query, descending
+        int64_t t;
+        int qb;
+        auto flush_sample = [&](int qblock) {
+            const int q = qblock * GT_M + lg * 32 + lane;
+            if (q >= p.n_queries) return;
+            // keys only need to order by score here: a synthetic distinct id keeps them non-zero
+            uint64_t* out = p.sample_keys + ((size_t)q * p.n_lists + blockIdx.x) * kSampleM;
+#pragma unroll
+            for (int i = 0; i < kSampleM; ++i)
+                out[i] = best[i] == -INFINITY ? 0ull : make_key(best[i], (uint32_t)(blockIdx.x * kSampleM + i));
+        };
+        for (; work.next(t, qb); ++it) {
             const int q = qb * GT_M + lg * 32 + lane;
             const bool q_valid = q < p.n_queries;
-            uint64_t* my_list = p.cand + ((size_t)q * p.n_lists + blockIdx.x) * cap;
-            uint64_t thr_key = 0;
-            float thr_f = -INFINITY;
+            // per-(tile, query block) state
+            float tau = -INFINITY;
             int cnt = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-                const uint32_t buf = it & 1;
-                mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
-                tc_fence_after();
-                const uint32_t row0 = (uint32_t)(t * GT_N);
-                for (int c = 0; c < GT_N / 32; ++c) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * GT_N + c * 32, v);
-                    tc_wait_ld();
-                    if (q_valid) {
+            uint64_t* my_list = nullptr;
+            if (MODE == 0) {
+                if (qb != cur_qb) {
+                    if (cur_qb >= 0) flush_sample(cur_qb);
+                    cur_qb = qb;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float s = __uint_as_float(v[j]);
-                            if (s >= thr_f) {
-                                const uint32_t row = row0 + c * 32 + j;
-                                if (row < (uint32_t)p.n_rows && bitmap_test(p.allow, row)) {
-                                    const uint64_t key = make_key(s, row);
-                                    if (key > thr_key) my_list[cnt++] = key;
+                    for (int i = 0; i < kSampleM; ++i) best[i] = -INFINITY;
+                }
+            } else if (q_valid) {
+                if (p.tau_keys) {
+                    const uint64_t tk = p.tau_keys[(size_t)q * kSampleM + (kSampleM - 1)];
+                    if (tk != 0ull) tau = key_score(tk);
+                }
+                cnt = p.cand_cnt[(size_t)q * p.n_lists + blockIdx.x];
+                my_list = p.cand + ((size_t)q * p.n_lists + blockIdx.x) * p.list_cap;
+            }
+            const uint32_t buf = it & 1;
+            mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t row0 = (uint32_t)(t * GT_N);
+            for (int c = 0; c < n_chunks; ++c) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * GT_N + c * 32, v);
+                tc_wait_ld();
+                if (!q_valid) continue;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = __uint_as_float(v[j]);
+                    if (MODE == 0) {
+                        if (s > best[kSampleM - 1]) {
+                            const uint32_t row = row0 + c * 32 + j;
+                            if (row < (uint32_t)p.n_rows && bitmap_test(p.allow, row)) {
+                                float x = s;         // sorted insert: bubble x down the list
+#pragma unroll
+                                for (int i = 0; i < kSampleM; ++i) {
+                                    const float hi = fmaxf(best[i], x);
+                                    x = fminf(best[i], x);
+                                    best[i] = hi;
                                 }
                             }
                         }
-                    }
-                    // warp-cooperative prune of every lane whose list is nearly full
-                    unsigned need = __ballot_sync(0xffffffffu, cnt > high_water);
-                    while (need) {
-                        const int src = __ffs(need) - 1;
-                        need &= need - 1;
-                        const int n = __shfl_sync(0xffffffffu, cnt, src);
-                        const unsigned long long lp =
-                            __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)my_list, src);
-                        uint64_t* list = reinterpret_cast<uint64_t*>((uintptr_t)lp);
-                        __syncwarp();
-                        for (int i = lane; i < cap; i += 32) my_scratch[i] = i < n ? list[i] : 0ull;
-                        warp_bitonic_desc(my_scratch, cap, lane);
-                        for (int i = lane; i < p.kp; i += 32) list[i] = my_scratch[i];
-                        const uint64_t nt = my_scratch[p.kp - 1];
-                        __syncwarp();
-                        if (lane == src) { cnt = p.kp; thr_key = nt; thr_f = key_score(nt); }
+                    } else {
+                        if (s >= tau) {
+                            const uint32_t row = row0 + c * 32 + j;
+                            if (row < (uint32_t)p.n_rows && bitmap_test(p.allow, row)) {
+                                if (cnt < p.list_cap) my_list[cnt] = make_key(s, row);
+                                ++cnt;                // counts past the capacity flag an overflow
+                            }
+                        }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
             }
-            if (q_valid) p.cand_cnt[(size_t)q * p.n_lists + blockIdx.x] = cnt;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (MODE == 1 && q_valid) p.cand_cnt[(size_t)q * p.n_lists + blockIdx.x] = cnt;
         }
+        if (MODE == 0 && cur_qb >= 0) flush_sample(cur_qb);
     }
     tc_fence_before();
     __syncthreads();
@@ -346,10 +416,10 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, 
 
 int gemm_padded_queries(int n_queries) { return (n_queries + GT_M - 1) / GT_M * GT_M; }
 
+int gemm_sample_m() { return kSampleM; }
+
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
-    const size_t scratch = (size_t)GT_EPI_WARPS * 2 * p.kp * sizeof(uint64_t);
-    const size_t tail = scratch + 256;
-    int stages = (int)((smem_limit - 1024 - (long)tail) / GT_STAGE_BYTES);
+    int stages = (int)((smem_limit - 2048) / GT_STAGE_BYTES);
     if (stages > 4) stages = 4;
     if (stages < 2) return 0;
     p.n_stages = stages;
@@ -358,17 +428,42 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     int grid = (int)(n_tiles < sm_count ? (n_tiles > 0 ? n_tiles : 1) : sm_count);
     *grid_out = grid;
     p.n_lists = grid;
-    return (size_t)stages * GT_STAGE_BYTES + tail + 1024;   // + slack for the 1024-byte alignment of the ring
+    // Sample pass: the 16th best of a sample that holds a fraction f of the rows lets ~16/f rows per
+    // query through the main pass; aim for f = 4/kp (about 4*kp survivors), in units of 32 columns.
+    const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
+    const int64_t rows_per_cta = tiles_per_cta * GT_N;
+    if (tiles_per_cta <= 1) {
+        // tiny shard: no threshold at all, every row of the CTA's single tile is captured
+        p.use_sample = 0;
+        p.sample_tiles = 0; p.sample_step = 1; p.sample_chunks = 0;
+        p.list_cap = GT_N;
+    } else {
+        p.use_sample = 1;
+        int64_t want = (rows_per_cta * 4 / p.kp + 31) / 32 * 32;      // sample rows per CTA
+        if (want < 32) want = 32;
+        if (want <= GT_N) {
+            p.sample_tiles = 1;
+            p.sample_chunks = (int)(want / 32);
+            p.sample_step = 1;
+        } else {
+            p.sample_tiles = (int)((want + GT_N - 1) / GT_N);
+            p.sample_chunks = GT_N / 32;
+            p.sample_step = (int)(tiles_per_cta / p.sample_tiles > 0 ? tiles_per_cta / p.sample_tiles : 1);
+        }
+        p.list_cap = 64;
+    }
+    return (size_t)stages * GT_STAGE_BYTES + 256 + 1024;   // + slack for the 1024-byte alignment of the ring
 }
 
-cudaError_t gemm_launch(const GemmParams& p, const void* q16, const void* x16, int grid, size_t smem,
+cudaError_t gemm_launch(const GemmParams& p, int mode, const void* q16, const void* x16, int grid, size_t smem,
                         cudaStream_t st) {
     CUtensorMap map_q, map_x;
     if (!make_map(&map_q, q16, gemm_padded_queries(p.n_queries), p.dim, GT_M)) return cudaErrorNotSupported;
     if (!make_map(&map_x, x16, p.n_rows, p.dim, GT_N)) return cudaErrorNotSupported;
-    cudaError_t e = cudaFuncSetAttribute(dense_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = mode == 0 ? dense_gemm_topk_kernel<0> : dense_gemm_topk_kernel<1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dense_gemm_topk_kernel<<<grid, GT_THREADS, smem, st>>>(map_q, map_x, p);
+    kern<<<grid, GT_THREADS, smem, st>>>(map_q, map_x, p);
     return cudaGetLastError();
 }
 

@@ -19,13 +19,19 @@ constexpr int kMergeWarps = 8;
 
 __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int n_lists, int list_len, int kp,
-             uint64_t* __restrict__ top) {
+             uint64_t* __restrict__ top, int32_t* __restrict__ overflow) {
     extern __shared__ __align__(16) uint64_t sm_keys[];   // kMergeWarps * 2 * kp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     const uint64_t* src = cand + (size_t)b * n_lists * list_len;
     const int32_t* cnt = counts ? counts + (size_t)b * n_lists : nullptr;
 
+    if (overflow && cnt) {
+        int over = 0;
+        for (int l = threadIdx.x; l < n_lists; l += blockDim.x) over |= cnt[l] > list_len;
+        over = __syncthreads_or(over);
+        if (threadIdx.x == 0) overflow[b] = over ? 1 : 0;
+    }
     WarpTopK t;
     t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
     // each warp walks whole lists (list_len is a multiple of 32): warp w takes lists w, w+8, ...
@@ -44,13 +50,13 @@ merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ coun
 }
 
 cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int B, int n_lists, int list_len, int kp,
-                         uint64_t* top, cudaStream_t st) {
+                         uint64_t* top, int32_t* overflow, cudaStream_t st) {
     size_t smem = (size_t)kMergeWarps * 2 * kp * sizeof(uint64_t);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    merge_kernel<<<B, kMergeWarps * 32, smem, st>>>(cand, counts, n_lists, list_len, kp, top);
+    merge_kernel<<<B, kMergeWarps * 32, smem, st>>>(cand, counts, n_lists, list_len, kp, top, overflow);
     return cudaGetLastError();
 }
 
@@ -133,17 +139,27 @@ __global__ void __launch_bounds__(256) refine_kernel(RefineParams p) {
         p.out_counts[b] = nout;
         int flag = 0;
         float tau = 0.f;
-        if (count == p.kp) {
-            // the list is full: rows outside it have filter score <= a_min, hence
-            // exact score <= a_min + eps.  Safe iff the k-th exact beats that.
-            const double qn = sqrt(s_qnorm2);
-            double eps = (p.eps_rel * qn + (p.q_resid ? (double)p.q_resid[b] : 0.0)) * (double)(*p.max_row_norm);
-            if (p.x_resid) eps += 1.004 * qn * (double)(*p.x_resid);
-            double a_min = (double)key_score(top[p.kp - 1]);
-            double e_k = ek[p.k - 1].s;
-            if (!(e_k > a_min + eps)) {
+        const double qn = sqrt(s_qnorm2);
+        double eps = (p.eps_rel * qn + (p.q_resid ? (double)p.q_resid[b] : 0.0)) * (double)(*p.max_row_norm);
+        if (p.x_resid) eps += 1.004 * qn * (double)(*p.x_resid);
+        // upper bound of the filter score of every row that is NOT a candidate
+        bool bounded = false;
+        double outside = 0.0;
+        if (count == p.kp) {                       // list full: the kp-th candidate bounds the rest
+            bounded = true;
+            outside = (double)key_score(top[p.kp - 1]);
+        } else if (p.tau_keys) {                   // threshold capture: everything >= tau_q was kept
+            const uint64_t tk = p.tau_keys[(size_t)b * p.tau_stride + p.tau_stride - 1];
+            if (tk != 0ull) { bounded = true; outside = (double)key_score(tk); }
+        }
+        const bool over = p.overflow && p.overflow[b] != 0;
+        if (bounded || over) {
+            // safe iff the k-th exact score beats (outside + eps); an overflowed list voids the bound
+            const bool have_k = count >= p.k;
+            const double e_k = have_k ? ek[p.k - 1].s : 0.0;
+            if (over || !have_k || !(e_k > outside + eps)) {
                 flag = 1;
-                tau = __double2float_rd(e_k - eps);
+                tau = have_k ? __double2float_rd(e_k - eps) : -3.0e38f;
                 atomicAdd(p.n_flagged, 1);
             }
         }

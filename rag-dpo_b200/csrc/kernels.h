@@ -38,16 +38,24 @@ struct GemmParams {
     int64_t n_rows;
     int dim;
     int n_queries;           // B (the bf16 query buffer is padded to a multiple of 128 rows)
-    int kp;                  // candidates kept per query (power of two >= 64); lists hold 2*kp
+    int kp;                  // candidates kept per query after the merge (power of two >= 64)
     const uint8_t* allow;    // nullable row bitmap (device)
-    uint64_t* cand;          // padded_B x n_lists x 2*kp keys
-    int32_t* cand_cnt;       // padded_B x n_lists valid entries per list
+    // sample pass (mode 0): padded_B x n_lists x 16 keys out
+    uint64_t* sample_keys;
+    // main pass (mode 1): tau_keys = merged sample (padded_B x 16, sorted desc; [15] is the threshold)
+    const uint64_t* tau_keys;
+    uint64_t* cand;          // padded_B x n_lists x list_cap keys
+    int32_t* cand_cnt;       // padded_B x n_lists survivors per list (may exceed list_cap = overflow)
     // derived by gemm_plan
-    int n_lists, n_stages, n_qblocks;
+    int list_cap;            // entries per (query, CTA) list
+    int use_sample;          // 0 = tiny shard: no sample pass, tau_keys = NULL, every row is captured
+    int n_lists, n_stages, n_qblocks, sample_tiles, sample_step, sample_chunks;
 };
+int gemm_sample_m();
 int gemm_padded_queries(int n_queries);
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out);
-cudaError_t gemm_launch(const GemmParams& p, const void* q16, const void* x16, int grid, size_t smem, cudaStream_t st);
+cudaError_t gemm_launch(const GemmParams& p, int mode, const void* q16, const void* x16, int grid, size_t smem,
+                        cudaStream_t st);
 // fp32 queries -> bf16 (padded rows zeroed) + ||q - bf16(q)||_2 per query
 cudaError_t query_prep_launch(const float* q, int n_queries, int n_padded, int dim, void* q16, float* resid_norm,
                               cudaStream_t st);
@@ -58,8 +66,9 @@ cudaError_t shadow_launch(const void* rows, int dtype, int64_t n_rows, int dim, 
 // ---- dense_select.cu -------------------------------------------------------
 // merge: cand (B x n_lists x list_len keys, any order, 0 = empty; counts nullable = valid entries per
 // list) -> top (B x kp sorted desc)
+// overflow (nullable): set to 1 for queries where some counts[] entry exceeds list_len
 cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int B, int n_lists, int list_len, int kp,
-                         uint64_t* top, cudaStream_t st);
+                         uint64_t* top, int32_t* overflow, cudaStream_t st);
 // refine: canonical fp64 score of every candidate in top, sort by (score desc,
 // row asc), write the first k, and raise flag[b] when the margin check fails.
 struct RefineParams {
@@ -72,6 +81,11 @@ struct RefineParams {
     const float* q_resid;    // nullable, per query: ||q - bf16(q)||_2 (tensor-core path)
     const float* x_resid;    // nullable device scalar: max_r ||x_r - bf16(x_r)||_2 (bf16 shadow)
     const float* max_row_norm;  // device scalar
+    // threshold-capture mode (tensor-core path): rows outside the candidate lists have filter score
+    // < tau_q (tau_keys[b*tau_stride + tau_stride-1], 0 = none); overflow[b] != 0 voids that guarantee
+    const uint64_t* tau_keys;
+    int tau_stride;
+    const int32_t* overflow;
     int32_t* out_rows;       // B x k
     double* out_scores;      // B x k
     int32_t* out_counts;     // B
