@@ -432,8 +432,27 @@ static int ensure_bf16_operand(rag_corpus* c, const void** x16, const float** x_
     return RAG_OK;
 }
 
+static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev,
+                            int32_t* o_rows, double* o_scores, int32_t* o_counts);
+
+// batches larger than one contraction launch serves are processed in slices
 static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev, int32_t* o_rows,
                       double* o_scores, int32_t* o_counts) {
+    const int step = gemm_max_batch();
+    if (B <= step) return dense_core_slice(c, q_dev, B, k, allow_dev, o_rows, o_scores, o_counts);
+    float acc[8] = {};
+    for (int off = 0; off < B; off += step) {
+        const int nb = std::min(step, B - off);
+        RAG_TRY(dense_core_slice(c, q_dev + (size_t)off * c->dim, nb, k, allow_dev, o_rows + (size_t)off * k,
+                                 o_scores + (size_t)off * k, o_counts + off));
+        for (int i = 0; i < 8; ++i) acc[i] += g.timings[i];
+    }
+    for (int i = 0; i < 8; ++i) g.timings[i] = acc[i];
+    return RAG_OK;
+}
+
+static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev,
+                            int32_t* o_rows, double* o_scores, int32_t* o_counts) {
     const bool use_tc = B >= g_tc_min_batch && c->n > 0;
     const int kp = use_tc ? std::max(64, next_pow2(2 * k + 1)) : std::max(16, next_pow2(k + 6));
     for (auto& v : g.ev_valid) v = false;

@@ -47,6 +47,7 @@ constexpr int GT_B_BYTES = GT_N * GT_K * 2;   // 32 KB
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
 constexpr int GT_THREADS = 192;
 constexpr int GT_EPI_WARPS = 4;
+constexpr int kMaxQBlocks = 32;   // per launch: 4096 queries (their tau / count live in shared memory)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -83,6 +84,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
         : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
 // bits: [0,14) addr>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 = 64 |
@@ -101,7 +107,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
-constexpr int kSampleM = 16;      // order statistic taken from the sample pass
+constexpr int kSampleM = 8;       // order statistic taken from the sample pass
 
 // Work items of one CTA, identical in all three warp roles.
 //   sample pass (MODE 0): query block outer, the CTA's sample tiles inner (the running top-16 of a
@@ -227,15 +233,36 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
     } else {
         // ===================== epilogue: fused select =====================
+        // Fast path per 32-column chunk: one LDTM.x32 and a branch-free compare mask.  Survivors are rare,
+        // so the slow path is warp-uniform: for every column that passed in ANY lane, re-read that single
+        // column from TMEM (LDTM.x1) and let the lanes that own a survivor handle it.
         const int lg = warp & 3;                 // TMEM lane group this warp may read
+        const int my = lg * 32 + lane;           // my query inside the query block == my TMEM lane
         const int n_chunks = MODE == 0 ? p.sample_chunks : GT_N / 32;
+        float* s_tau = reinterpret_cast<float*>(bars + 24);            // [n_qblocks][128]
+        int* s_cnt = reinterpret_cast<int*>(s_tau + p.n_qblocks * GT_M);
+        if (MODE == 1) {
+            for (int b = 0; b < p.n_qblocks; ++b) {
+                const int q = b * GT_M + my;
+                float tau = INFINITY;                                   // padded queries never pass
+                if (q < p.n_queries) {
+                    tau = -INFINITY;
+                    if (p.tau_keys) {
+                        const uint64_t tk = p.tau_keys[(size_t)q * kSampleM + (kSampleM - 1)];
+                        if (tk != 0ull) tau = key_score(tk);
+                    }
+                }
+                s_tau[b * GT_M + my] = tau;
+                s_cnt[b * GT_M + my] = 0;
+            }
+        }
         uint32_t it = 0;
         int cur_qb = -1;
-        float best[kSampleM];                    // MODE 0: the 16 best scores of my query, descending
+        float best[kSampleM];                    // MODE 0: the best scores of my query, descending
         int64_t t;
         int qb;
         auto flush_sample = [&](int qblock) {
-            const int q = qblock * GT_M + lg * 32 + lane;
+            const int q = qblock * GT_M + my;
             if (q >= p.n_queries) return;
             // keys only need to order by score here: a synthetic distinct id keeps them non-zero
             uint64_t* out = p.sample_keys + ((size_t)q * p.n_lists + blockIdx.x) * kSampleM;
@@ -244,10 +271,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 out[i] = best[i] == -INFINITY ? 0ull : make_key(best[i], (uint32_t)(blockIdx.x * kSampleM + i));
         };
         for (; work.next(t, qb); ++it) {
-            const int q = qb * GT_M + lg * 32 + lane;
-            const bool q_valid = q < p.n_queries;
-            // per-(tile, query block) state
-            float tau = -INFINITY;
+            const int q = qb * GT_M + my;
+            float tau = 0.f;
             int cnt = 0;
             uint64_t* my_list = nullptr;
             if (MODE == 0) {
@@ -257,30 +282,38 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
                     for (int i = 0; i < kSampleM; ++i) best[i] = -INFINITY;
                 }
-            } else if (q_valid) {
-                if (p.tau_keys) {
-                    const uint64_t tk = p.tau_keys[(size_t)q * kSampleM + (kSampleM - 1)];
-                    if (tk != 0ull) tau = key_score(tk);
-                }
-                cnt = p.cand_cnt[(size_t)q * p.n_lists + blockIdx.x];
+            } else {
+                tau = s_tau[qb * GT_M + my];
+                cnt = s_cnt[qb * GT_M + my];
                 my_list = p.cand + ((size_t)q * p.n_lists + blockIdx.x) * p.list_cap;
             }
             const uint32_t buf = it & 1;
             mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t row0 = (uint32_t)(t * GT_N);
+            const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * GT_N;
             for (int c = 0; c < n_chunks; ++c) {
                 uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * GT_N + c * 32, v);
+                tc_ld32(tbase + c * 32, v);
                 tc_wait_ld();
-                if (!q_valid) continue;
+                const float thr = MODE == 0 ? (q < p.n_queries ? best[kSampleM - 1] : INFINITY) : tau;
+                uint32_t m = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float s = __uint_as_float(v[j]);
-                    if (MODE == 0) {
-                        if (s > best[kSampleM - 1]) {
-                            const uint32_t row = row0 + c * 32 + j;
-                            if (row < (uint32_t)p.n_rows && bitmap_test(p.allow, row)) {
+                    const bool pass = MODE == 0 ? (s > thr) : (s >= thr);
+                    m |= pass ? (1u << j) : 0u;
+                }
+                uint32_t um = __reduce_or_sync(0xffffffffu, m);
+                while (um) {
+                    const int j = __ffs(um) - 1;
+                    um &= um - 1;
+                    const float s = __uint_as_float(tc_ld1(tbase + c * 32 + j));
+                    tc_wait_ld();
+                    if ((m >> j) & 1u) {
+                        const uint32_t row = row0 + c * 32 + j;
+                        if (row < (uint32_t)p.n_rows && bitmap_test(p.allow, row)) {
+                            if (MODE == 0) {
                                 float x = s;         // sorted insert: bubble x down the list
 #pragma unroll
                                 for (int i = 0; i < kSampleM; ++i) {
@@ -288,12 +321,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                                     x = fminf(best[i], x);
                                     best[i] = hi;
                                 }
-                            }
-                        }
-                    } else {
-                        if (s >= tau) {
-                            const uint32_t row = row0 + c * 32 + j;
-                            if (row < (uint32_t)p.n_rows && bitmap_test(p.allow, row)) {
+                            } else {
                                 if (cnt < p.list_cap) my_list[cnt] = make_key(s, row);
                                 ++cnt;                // counts past the capacity flag an overflow
                             }
@@ -304,9 +332,15 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-            if (MODE == 1 && q_valid) p.cand_cnt[(size_t)q * p.n_lists + blockIdx.x] = cnt;
+            if (MODE == 1) s_cnt[qb * GT_M + my] = cnt;
         }
         if (MODE == 0 && cur_qb >= 0) flush_sample(cur_qb);
+        if (MODE == 1) {
+            for (int b = 0; b < p.n_qblocks; ++b) {
+                const int q = b * GT_M + my;
+                if (q < p.n_queries) p.cand_cnt[(size_t)q * p.n_lists + blockIdx.x] = s_cnt[b * GT_M + my];
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -417,19 +451,23 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, 
 int gemm_padded_queries(int n_queries) { return (n_queries + GT_M - 1) / GT_M * GT_M; }
 
 int gemm_sample_m() { return kSampleM; }
+int gemm_max_batch() { return kMaxQBlocks * GT_M; }
 
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
-    int stages = (int)((smem_limit - 2048) / GT_STAGE_BYTES);
+    p.n_qblocks = gemm_padded_queries(p.n_queries) / GT_M;
+    if (p.n_qblocks > kMaxQBlocks) return 0;
+    const size_t tail = 256 + (size_t)p.n_qblocks * GT_M * 8;      // barriers + per-query tau / count
+    int stages = (int)((smem_limit - 1024 - (long)tail) / GT_STAGE_BYTES);
     if (stages > 4) stages = 4;
     if (stages < 2) return 0;
     p.n_stages = stages;
-    p.n_qblocks = gemm_padded_queries(p.n_queries) / GT_M;
     const int64_t n_tiles = (p.n_rows + GT_N - 1) / GT_N;
     int grid = (int)(n_tiles < sm_count ? (n_tiles > 0 ? n_tiles : 1) : sm_count);
     *grid_out = grid;
     p.n_lists = grid;
-    // Sample pass: the 16th best of a sample that holds a fraction f of the rows lets ~16/f rows per
-    // query through the main pass; aim for f = 4/kp (about 4*kp survivors), in units of 32 columns.
+    // Sample pass: the m-th best (m = kSampleM) of a sample that holds a fraction f of the rows lets
+    // ~m/f rows per query through the main pass; aim for f = 2/kp (about 4*kp survivors), in units of
+    // 32 columns.
     const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
     const int64_t rows_per_cta = tiles_per_cta * GT_N;
     if (tiles_per_cta <= 1) {
@@ -439,7 +477,7 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
         p.list_cap = GT_N;
     } else {
         p.use_sample = 1;
-        int64_t want = (rows_per_cta * 4 / p.kp + 31) / 32 * 32;      // sample rows per CTA
+        int64_t want = (rows_per_cta * 2 / p.kp + 31) / 32 * 32;      // sample rows per CTA
         if (want < 32) want = 32;
         if (want <= GT_N) {
             p.sample_tiles = 1;
@@ -452,7 +490,7 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
         }
         p.list_cap = 64;
     }
-    return (size_t)stages * GT_STAGE_BYTES + 256 + 1024;   // + slack for the 1024-byte alignment of the ring
+    return (size_t)stages * GT_STAGE_BYTES + tail + 1024;   // + slack for the 1024-byte alignment of the ring
 }
 
 cudaError_t gemm_launch(const GemmParams& p, int mode, const void* q16, const void* x16, int grid, size_t smem,

@@ -40,9 +40,9 @@ struct GemmParams {
     int n_queries;           // B (the bf16 query buffer is padded to a multiple of 128 rows)
     int kp;                  // candidates kept per query after the merge (power of two >= 64)
     const uint8_t* allow;    // nullable row bitmap (device)
-    // sample pass (mode 0): padded_B x n_lists x 16 keys out
+    // sample pass (mode 0): padded_B x n_lists x m keys out (m = gemm_sample_m())
     uint64_t* sample_keys;
-    // main pass (mode 1): tau_keys = merged sample (padded_B x 16, sorted desc; [15] is the threshold)
+    // main pass (mode 1): tau_keys = merged sample (padded_B x m, sorted desc; [m-1] is the threshold)
     const uint64_t* tau_keys;
     uint64_t* cand;          // padded_B x n_lists x list_cap keys
     int32_t* cand_cnt;       // padded_B x n_lists survivors per list (may exceed list_cap = overflow)
@@ -52,6 +52,7 @@ struct GemmParams {
     int n_lists, n_stages, n_qblocks, sample_tiles, sample_step, sample_chunks;
 };
 int gemm_sample_m();
+int gemm_max_batch();
 int gemm_padded_queries(int n_queries);
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out);
 cudaError_t gemm_launch(const GemmParams& p, int mode, const void* q16, const void* x16, int grid, size_t smem,
