@@ -84,10 +84,13 @@ class ShardedDenseIndex:
         t_scores = torch.from_numpy(np.ascontiguousarray(scores)).to(self.device)
         t_ids = torch.from_numpy(np.ascontiguousarray(ids)).to(self.device)
         if self.world > 1:
-            g_scores = torch.empty((self.world, B, kk), dtype=torch.float64, device=self.device)
-            g_ids = torch.empty((self.world, B, kk), dtype=torch.int64, device=self.device)
+            # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
+            g_scores = torch.empty((self.world * B, kk), dtype=torch.float64, device=self.device)
+            g_ids = torch.empty((self.world * B, kk), dtype=torch.int64, device=self.device)
             dist.all_gather_into_tensor(g_scores, t_scores, group=self.group)
             dist.all_gather_into_tensor(g_ids, t_ids, group=self.group)
+            g_scores = g_scores.view(self.world, B, kk)
+            g_ids = g_ids.view(self.world, B, kk)
         else:
             g_scores, g_ids = t_scores[None], t_ids[None]
         if self._merge is not None or self.corpus is None:
