@@ -36,6 +36,7 @@ ROWS_PER_GPU = 1_000_000
 DIM = 1024
 TOPK = 10
 CORPUS_SEED, QUERY_SEED = 1002, 2002
+METRIC = "queries/sec & p50 latency, exact top-10 @ 1024-d, 1/2/4/8 B200; % HBM roofline"
 
 
 def measured_peaks():
@@ -162,7 +163,7 @@ def run_reference(args):
     sample = (f"{done} steps of a {sample_b}-query numpy fp32 GEMM batch (X @ q, argpartition+sort) over the full "
               f"{n}x{d} fp32 corpus on {cores} BLAS threads (os.cpu_count={os.cpu_count()}); chromadb 1.4.1 (HNSW) is "
               f"not installable here, this is the exact search it approximates")
-    line = {"impl": "reference", "metric": "queries/sec, exact top-10 @ 1024-d", "value": qps, "unit": "queries/s",
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"dense exact top-{k}: {n} x {d} fp32 corpus, batch {sample_b} (CPU sample)",
@@ -275,8 +276,9 @@ def run_b200(args):
             torch.cuda.synchronize()
             lat.append(e0.elapsed_time(e1))
             if i == 0:
-                b1_kernel_ms = []
+                b1_kernel_ms, b1_stage_ms = [], []
             b1_kernel_ms.append(float(_lib.last_timings()[0]))
+            b1_stage_ms.append([float(v) for v in _lib.last_timings()[:4]])
         lat_host = []
         for i in range(30):
             t0 = time.perf_counter()
@@ -318,7 +320,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     line = {
-        "metric": "queries/sec, exact top-10 @ 1024-d",
+        "metric": METRIC,
         "value": qps * world, "unit": "queries/s (1M-row-corpus equivalents: corpus = n_gpus x 1M rows)",
         "queries_per_s": qps,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -335,6 +337,9 @@ def run_b200(args):
                        "host_call_ms_p50": float(np.percentile(lat_host, 50)),
                        "host_call_ms_p99": float(np.percentile(lat_host, 99)),
                        "scan_kernel_ms": b1_ms,
+                       "stages_ms": {"scan": float(np.median([v[0] for v in b1_stage_ms])),
+                                     "merge": float(np.median([v[1] for v in b1_stage_ms])),
+                                     "refine": float(np.median([v[2] for v in b1_stage_ms]))},
                        "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved_b1,
                                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_b1 / peaks["hbm_gbs"],
                                     "traffic": 4.096e9, "algorithmic_bytes_per_launch": bytes_per_launch}},
