@@ -841,48 +841,36 @@ int rag_bm25_search(rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr
     RAG_TRY(require_init());
     if (!ix || !q_ptr || !out_rows || !out_scores || !out_counts || Q <= 0) return fail(RAG_EINVAL, "NULL argument");
     if (k <= 0 || k > RAG_MAX_K) return fail(RAG_ERANGE, "k=%d outside 1..%d", k, RAG_MAX_K);
+    if (q_ptr[0] != 0 || q_ptr[Q] < 0 || (q_ptr[Q] > 0 && !q_terms)) return fail(RAG_EINVAL, "bad q_ptr / q_terms");
     const int kp = std::max(16, next_pow2(k));
     for (auto& v : g.ev_valid) v = false;
     for (auto& t : g.timings) t = 0.f;
-    const uint8_t* allow_dev = nullptr;
-    if (allow_bitmap) {
-        const size_t ab = (size_t)((ix->d.n_docs + 7) / 8);
-        RAG_TRY(g.bm_allow.ensure(ab + 16));
-        CU_TRY(cudaMemcpyAsync(g.bm_allow.p, allow_bitmap, ab, cudaMemcpyHostToDevice, g.stream));
-        allow_dev = g.bm_allow.as<uint8_t>();
-    }
-    RAG_TRY(g.bm_rows.ensure((size_t)Q * k * 4));
-    RAG_TRY(g.bm_scores.ensure((size_t)Q * k * 8));
-    RAG_TRY(g.bm_counts.ensure((size_t)Q * 4));
-    const int max_grid = g.sm_count * 2;
-    RAG_TRY(g.bm_cand.ensure((size_t)max_grid * 8 * kp * bm25_key_bytes()));
-    std::vector<int64_t> ranges;
-    rec(0);
-    for (int qi = 0; qi < Q; ++qi) {
-        const int32_t* terms = q_terms + q_ptr[qi];
-        const int nt = q_ptr[qi + 1] - q_ptr[qi];
-        int64_t total = 0;
-        RAG_TRY(bm25_accumulate_query(ix, terms, nt, ranges, &total));
-        int32_t* o_r = g.bm_rows.as<int32_t>() + (size_t)qi * k;
-        double* o_s = g.bm_scores.as<double>() + (size_t)qi * k;
-        int32_t* o_c = g.bm_counts.as<int32_t>() + qi;
-        const int n_ranges = (int)ranges.size() / 2;
-        const int grid = bm25_harvest_grid(total, g.sm_count);
-        RAG_TRY(g.bm_ranges.ensure(std::max<size_t>(16, ranges.size() * 8)));
-        if (n_ranges > 0) {
-            // pageable -> device copy of a few bytes: synchronous w.r.t. the host buffer
-            CU_TRY(cudaMemcpyAsync(g.bm_ranges.p, ranges.data(), ranges.size() * 8, cudaMemcpyHostToDevice, g.stream));
-            CU_TRY(cudaStreamSynchronize(g.stream));
-        }
-        CU_TRY(bm25_harvest_launch(ix->d, g.bm_ranges.as<int64_t>(), n_ranges, allow_dev, kp, grid, g.bm_cand.p,
-                                   g.stream));
-        CU_TRY(bm25_select_launch(g.bm_cand.p, grid * 8, kp, k, o_r, o_s, o_c, g.stream));
-        g.n_launch += 2;
-    }
-    rec(1);
+    const int n_tok = q_ptr[Q];
+    const size_t tb = (size_t)std::max(n_tok, 1) * 4, pb = (size_t)(Q + 1) * 4;
+    const size_t ab = allow_bitmap ? (size_t)((ix->d.n_docs + 7) / 8) : 0;
     const size_t rb = (size_t)Q * k * 4, sb = (size_t)Q * k * 8, cb = (size_t)Q * 4;
-    RAG_TRY(ensure_pinned(sb + rb + cb));
+    const int n_lists = bm25_range_lists(ix->d.n_docs);
+    RAG_TRY(g.bm_terms.ensure(tb));
+    RAG_TRY(g.bm_ranges.ensure(pb));
+    if (ab) RAG_TRY(g.bm_allow.ensure(ab + 16));
+    RAG_TRY(g.bm_rows.ensure(rb));
+    RAG_TRY(g.bm_scores.ensure(sb));
+    RAG_TRY(g.bm_counts.ensure(cb));
+    RAG_TRY(g.bm_cand.ensure((size_t)Q * n_lists * kp * bm25_key_bytes()));
+    RAG_TRY(ensure_pinned(std::max(tb + pb + ab, sb + rb + cb)));
     uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
+    if (n_tok > 0) memcpy(pin, q_terms, (size_t)n_tok * 4);
+    memcpy(pin + tb, q_ptr, pb);
+    if (ab) memcpy(pin + tb + pb, allow_bitmap, ab);
+    CU_TRY(cudaMemcpyAsync(g.bm_terms.p, pin, tb, cudaMemcpyHostToDevice, g.stream));
+    CU_TRY(cudaMemcpyAsync(g.bm_ranges.p, pin + tb, pb, cudaMemcpyHostToDevice, g.stream));
+    if (ab) CU_TRY(cudaMemcpyAsync(g.bm_allow.p, pin + tb + pb, ab, cudaMemcpyHostToDevice, g.stream));
+    rec(0);
+    CU_TRY(bm25_range_launch(ix->d, g.bm_terms.as<int32_t>(), g.bm_ranges.as<int32_t>(), Q,
+                             ab ? g.bm_allow.as<uint8_t>() : nullptr, kp, k, g.bm_cand.p, g.bm_rows.as<int32_t>(),
+                             g.bm_scores.as<double>(), g.bm_counts.as<int32_t>(), g.stream));
+    g.n_launch += 2;
+    rec(1);
     CU_TRY(cudaMemcpyAsync(pin, g.bm_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
     CU_TRY(cudaMemcpyAsync(pin + sb, g.bm_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
     CU_TRY(cudaMemcpyAsync(pin + sb + rb, g.bm_counts.p, cb, cudaMemcpyDeviceToHost, g.stream));

@@ -196,6 +196,155 @@ cudaError_t bm25_reset_launch(const Bm25Device& ix, const int64_t* d_ranges, int
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Fused per-query kernel: every CTA owns a contiguous range of kBmRange rows and
+// keeps their fp64 scores in SHARED memory.  For each query token in order it adds
+// the postings that fall inside its range (postings are sorted by row, so the range
+// is found by binary search) with a __syncthreads() between tokens: the summation
+// order per row is exactly numpy's, with no global accumulator, no atomics and no
+// grid-wide barrier.  The CTA then selects its local top-kp; bm25_select_kernel
+// merges the per-range lists.  grid = (row ranges, queries).
+// ---------------------------------------------------------------------------
+constexpr int kBmRange = 4096;        // rows per CTA: 32 KB of fp64 accumulators
+constexpr int kBmMaxTokens = 128;     // query tokens handled per pass
+constexpr int kBmThreads = 256;
+
+__global__ void __launch_bounds__(kBmThreads)
+bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_row,
+                  const double* __restrict__ impact, const double* __restrict__ idf, int64_t n_docs, int64_t n_terms,
+                  const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
+                  const uint8_t* __restrict__ allow, int kp, Bm25Key* __restrict__ cand) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    double* acc = reinterpret_cast<double*>(sm_raw);                              // kBmRange
+    Bm25Key* bufs = reinterpret_cast<Bm25Key*>(sm_raw + kBmRange * sizeof(double));  // 8 warps * 2 * kp
+    __shared__ int64_t s_lo[kBmMaxTokens], s_hi[kBmMaxTokens];
+    __shared__ double s_w[kBmMaxTokens];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.y;
+    const int64_t r0 = (int64_t)blockIdx.x * kBmRange;
+    const int64_t r1 = r0 + kBmRange < n_docs ? r0 + kBmRange : n_docs;
+    const int32_t* terms = q_terms + q_ptr[qi];
+    const int nt = q_ptr[qi + 1] - q_ptr[qi];
+
+    for (int i = threadIdx.x; i < kBmRange; i += kBmThreads) acc[i] = 0.0;
+    for (int t0 = 0; t0 < nt; t0 += kBmMaxTokens) {
+        const int tn = nt - t0 < kBmMaxTokens ? nt - t0 : kBmMaxTokens;
+        // posting sub-range of every token inside [r0, r1): one binary search per (token, bound)
+        for (int j = threadIdx.x; j < 2 * tn; j += kBmThreads) {
+            const int i = j >> 1;
+            const int32_t t = terms[t0 + i];
+            int64_t pos = 0;
+            double w = 0.0;
+            if (t >= 0 && t < n_terms) {
+                w = idf[t];
+                int64_t lo = term_ptr[t], hi = term_ptr[t + 1];
+                const int64_t target = (j & 1) ? r1 : r0;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if ((int64_t)post_row[mid] < target) lo = mid + 1; else hi = mid;
+                }
+                pos = lo;
+            }
+            if (j & 1) s_hi[i] = pos; else { s_lo[i] = pos; s_w[i] = w; }
+        }
+        __syncthreads();
+        for (int i = 0; i < tn; ++i) {           // token order == numpy's `score +=` order
+            const double w = s_w[i];
+            if (w != 0.0) {
+                for (int64_t p = s_lo[i] + threadIdx.x; p < s_hi[i]; p += kBmThreads) {
+                    const int r = (int)(post_row[p] - r0);
+                    acc[r] = __dadd_rn(acc[r], __dmul_rn(w, impact[p]));
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // local select: score > 0, allowed rows, (score desc, row asc)
+    WarpTopKT<Bm25Key> t;
+    t.init(bufs + (size_t)warp * 2 * kp, kp, lane);
+    const int n_local = (int)(r1 - r0);
+    for (int i0 = warp * 32; i0 < n_local; i0 += kBmThreads) {
+        const int i = i0 + lane;
+        Bm25Key key{0ull, 0u, 0u};
+        if (i < n_local) {
+            const double sc = acc[i];
+            const uint32_t r = (uint32_t)(r0 + i);
+            if (sc > 0.0 && bitmap_test(allow, r)) { key.s = (uint64_t)__double_as_longlong(sc); key.nrow = ~r; }
+        }
+        t.offer(key, lane);
+    }
+    t.finish(lane);
+    __syncthreads();
+    block_bitonic_desc(bufs, 8 * 2 * kp);
+    Bm25Key* out = cand + ((size_t)qi * gridDim.x + blockIdx.x) * kp;
+    for (int i = threadIdx.x; i < kp; i += kBmThreads) out[i] = bufs[i];
+}
+
+// per-query merge of the range lists (grid = queries)
+__global__ void __launch_bounds__(256)
+bm25_select_batch_kernel(const Bm25Key* __restrict__ cand, int n_lists, int kp, int k, int32_t* out_rows,
+                         double* out_scores, int32_t* out_counts) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    Bm25Key* bufs = reinterpret_cast<Bm25Key*>(sm_raw);      // 8 * 2 * kp
+    __shared__ int s_count;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x;
+    const Bm25Key* src = cand + (size_t)qi * n_lists * kp;
+    WarpTopKT<Bm25Key> t;
+    t.init(bufs + (size_t)warp * 2 * kp, kp, lane);
+    const int64_t total = (int64_t)n_lists * kp;
+    const int64_t n_iter = (total + 255) / 256;
+    for (int64_t it = 0; it < n_iter; ++it) {
+        const int64_t i = it * 256 + threadIdx.x;
+        Bm25Key key{0ull, 0u, 0u};
+        if (i < total) key = src[i];
+        t.offer(key, lane);
+    }
+    t.finish(lane);
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    block_bitonic_desc(bufs, 8 * 2 * kp);
+    int local = 0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) local += (bufs[i].s != 0ull);
+    if (local) atomicAdd(&s_count, local);
+    __syncthreads();
+    const int nout = s_count;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool ok = i < nout;
+        out_rows[(size_t)qi * k + i] = ok ? (int32_t)(~bufs[i].nrow) : -1;
+        out_scores[(size_t)qi * k + i] = ok ? __longlong_as_double((long long)bufs[i].s) : 0.0;
+    }
+    if (threadIdx.x == 0) out_counts[qi] = nout;
+}
+
+int bm25_range_lists(int64_t n_docs) { return (int)((n_docs + kBmRange - 1) / kBmRange); }
+
+cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int Q,
+                              const uint8_t* allow, int kp, int k, void* cand, int32_t* out_rows, double* out_scores,
+                              int32_t* out_counts, cudaStream_t st) {
+    const int n_ranges = bm25_range_lists(ix.n_docs);
+    size_t smem = (size_t)kBmRange * sizeof(double) + (size_t)8 * 2 * kp * sizeof(Bm25Key);
+    cudaError_t e = cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    for (int q0 = 0; q0 < Q; q0 += 32768) {            // gridDim.y limit
+        const int nq = Q - q0 < 32768 ? Q - q0 : 32768;
+        dim3 grid(n_ranges, nq);
+        bm25_range_kernel<<<grid, kBmThreads, smem, st>>>(ix.term_ptr, ix.post_row, ix.post_impact, ix.idf, ix.n_docs,
+                                                          ix.n_terms, d_q_terms, d_q_ptr + q0, allow, kp,
+                                                          reinterpret_cast<Bm25Key*>(cand) + (size_t)q0 * n_ranges * kp);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    size_t smem2 = (size_t)8 * 2 * kp * sizeof(Bm25Key);
+    if (smem2 > 48 * 1024) {
+        e = cudaFuncSetAttribute(bm25_select_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return e;
+    }
+    bm25_select_batch_kernel<<<Q, 256, smem2, st>>>(reinterpret_cast<const Bm25Key*>(cand), n_ranges, kp, k, out_rows,
+                                                    out_scores, out_counts);
+    return cudaGetLastError();
+}
+
 size_t bm25_key_bytes() { return sizeof(Bm25Key); }
 
 }  // namespace b200rag

@@ -146,6 +146,11 @@ cudaError_t bm25_select_launch(const void* cand, int n_lists, int kp, int k, int
                                int32_t* out_count, cudaStream_t st);
 cudaError_t bm25_reset_launch(const Bm25Device& ix, const int64_t* d_ranges, int n_ranges, int grid, cudaStream_t st);
 size_t bm25_key_bytes();
+// fused search: grid (row ranges of 4096, queries); fp64 accumulators in shared memory, tokens in order
+int bm25_range_lists(int64_t n_docs);
+cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int Q,
+                              const uint8_t* allow, int kp, int k, void* cand, int32_t* out_rows, double* out_scores,
+                              int32_t* out_counts, cudaStream_t st);
 
 // ---- rrf.cu ----------------------------------------------------------------
 int rrf_max_entries();
