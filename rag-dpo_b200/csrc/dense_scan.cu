@@ -179,14 +179,27 @@ dense_scan_kernel(ScanParams p) {
     }
 
     if constexpr (MODE == 0) {
-        // final prune, then publish this warp's KP best keys (sorted desc, 0-padded)
-        const int list = blockIdx.x * CW + cw;
+        // per-CTA merge: every consumer warp finishes its list, then consumer warp 0 folds the other
+        // warps' KP best keys into its own and publishes ONE list per (query, CTA)
 #pragma unroll
-        for (int qi = 0; qi < NQ; ++qi) {
-            if (qi >= p.n_queries) break;
-            top[qi].finish(lane);
-            uint64_t* out = p.cand + ((size_t)qi * p.n_lists + list) * p.kp;
-            for (int i = lane; i < p.kp; i += kWarp) out[i] = i < top[qi].n ? top[qi].buf[i] : 0ull;
+        for (int qi = 0; qi < NQ; ++qi)
+            if (qi < p.n_queries) top[qi].finish(lane);
+        asm volatile("bar.sync 1, %0;" ::"r"(CW * 32) : "memory");       // consumer warps only
+        if (cw == 0) {
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+                if (qi >= p.n_queries) break;
+                for (int w = 1; w < CW; ++w) {
+                    const uint64_t* other = cand_base + ((size_t)w * NQ + qi) * 2 * p.kp;
+                    for (int i0 = 0; i0 < p.kp; i0 += kWarp) {
+                        const int i = i0 + lane;
+                        top[qi].offer(i < p.kp ? other[i] : 0ull, lane);
+                    }
+                }
+                top[qi].finish(lane);
+                uint64_t* out = p.cand + ((size_t)qi * p.n_lists + blockIdx.x) * p.kp;
+                for (int i = lane; i < p.kp; i += kWarp) out[i] = i < top[qi].n ? top[qi].buf[i] : 0ull;
+            }
         }
     }
 }
@@ -227,7 +240,7 @@ static int scan_consumer_warps(int nq_t) { return nq_t <= 2 ? 16 : 8; }
 int scan_nq_template(int n_queries) { return n_queries <= 1 ? 1 : (n_queries <= 2 ? 2 : 4); }
 
 // Fills the derived fields of p (tile geometry, stages) and returns the dynamic
-// shared-memory size; n_lists = grid * consumer warps.
+// shared-memory size; n_lists = grid (the CTA merges its warps' lists).
 size_t scan_plan(ScanParams& p, int dtype, int sm_count, int smem_limit, int* grid_out, int* nch_out) {
     const int esz = dtype == RAG_F32 ? 4 : 2;
     p.row_bytes = p.dim * esz;
@@ -248,7 +261,7 @@ size_t scan_plan(ScanParams& p, int dtype, int sm_count, int smem_limit, int* gr
     int64_t n_tiles = (p.n_rows + tile_rows - 1) / tile_rows;
     int grid = (int)(n_tiles < sm_count ? (n_tiles > 0 ? n_tiles : 1) : sm_count);
     *grid_out = grid;
-    p.n_lists = grid * cw;
+    p.n_lists = grid;            // one merged list per (query, CTA)
     return 128 + (size_t)stages * p.tile_bytes + cand_bytes;
 }
 
