@@ -50,27 +50,64 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled through NVML
+    (nvidia_ml_py) every 20 ms; falls back to polling nvidia-smi when NVML is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
         self.gpu = gpu_index
-        self.samples = []
+        self.sm, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        try:
+            self.power.append(n.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+        except Exception:
+            pass
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            self.sm.append(float(c[1]))
+            self.max_mhz = float(c[2])
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.samples.append([c.strip() for c in line.split(",")])
+                self._sample_nvml() if self._nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02 if self._nvml else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -82,20 +119,13 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for s in self.samples:
-            try:
-                sm.append(float(s[1])); mx.append(float(s[2]))
-            except Exception:
-                continue
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for name, v in zip(names, s[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        out = {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(min(self.sm)), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self._nvml else "nvidia-smi"}
+        if self.power:
+            out["power_w_max"] = float(max(self.power))
+        return out
 
 
 # ---------------------------------------------------------------------------
@@ -194,8 +224,12 @@ def run_b200(args):
     index = ShardedDenseIndex(d, n_total, dtype="f32", device=dev)
     index.fill_synthetic(CORPUS_SEED)
     corpus = index.corpus
-    q_host = synth.unit_queries(B, d, QUERY_SEED)
-    q_dev = torch.from_numpy(q_host).to(dev)
+    # host-side query / result buffers live in page-locked memory (what a serving process would do)
+    q_host = _lib.pinned_empty((B, d), np.float32)
+    q_host[:] = synth.unit_queries(B, d, QUERY_SEED)
+    out_host = (_lib.pinned_empty((B, k), np.int32), _lib.pinned_empty((B, k), np.float64),
+                _lib.pinned_empty((B,), np.int32))
+    q_dev = torch.from_numpy(np.array(q_host)).to(dev)
     L = _lib.lib()
     # one non-default stream for torch's collectives AND the library's kernels, so that
     # stream order is the only synchronisation and torch.cuda.Event sees everything
@@ -232,7 +266,7 @@ def run_b200(args):
         """the call a user makes: host buffers in, host results out"""
         if world > 1:
             return index.topk(q_host, k)
-        return corpus.topk(q_host, k)
+        return corpus.topk(q_host, k, out=out_host)
 
     def barrier():
         if world > 1:
@@ -363,7 +397,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -51,6 +51,10 @@ int rag_set_stream(void* cuda_stream);    /* run on the caller's stream (e.g. to
 const char* rag_last_error(void);
 int rag_abi_version(void);
 int rag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
+/* page-locked host memory: buffers allocated here are DMA'd directly by the host-pointer entry points
+ * (no staging copy); any other host pointer is staged through an internal pinned block. */
+int rag_host_alloc(void** out, size_t bytes);
+int rag_host_free(void* p);
 /* per-stage device time (ms, CUDA events on the launching stream) of the last
  * dense / bm25 call: [0] main scan or contraction kernel, [1] candidate merge,
  * [2] fp64 refine + select, [3] fallback pass (0 if not taken), rest 0. */

@@ -25,6 +25,8 @@ SYMBOLS = {
     "rag_last_error": (C.c_char_p, []),
     "rag_abi_version": (_i, []),
     "rag_device_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "rag_host_alloc": (_i, [_vp, C.c_size_t]),
+    "rag_host_free": (_i, [_vp]),
     "rag_last_timings": (_i, [_vp, _i]),
     "rag_counters": (_i, [_vp, _i]),
     "rag_corpus_create": (_i, [_vp, _i64, _i, _i]),
@@ -96,6 +98,35 @@ def ptr(a):
         return None
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib().rag_host_alloc(C.byref(self.ptr), max(int(nbytes), 1)))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                load().rag_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory: the host-pointer entry points DMA it directly."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    block = _PinnedBlock(n)
+    buf = (C.c_uint8 * max(n, 1)).from_address(block.ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED_KEEPALIVE[id(buf)] = block
+    import weakref
+    weakref.finalize(buf, _PINNED_KEEPALIVE.pop, id(buf), None)
+    return arr
+
+
+_PINNED_KEEPALIVE = {}
 
 
 def device_info():

@@ -95,16 +95,19 @@ class DeviceCorpus:
         _lib.check(self._L.rag_corpus_device_ptr(self._h, C.byref(p)))
         return p.value
 
-    def topk(self, q32, k, allow_bitmap=None):
+    def topk(self, q32, k, allow_bitmap=None, out=None):
         """q32 (B,dim) fp32 host array (already normalised). Returns rows int32
         (B,k) [-1 padded], canonical fp64 scores (B,k), counts int32 (B,)."""
         q32 = np.ascontiguousarray(np.atleast_2d(q32), dtype=np.float32)
         B = q32.shape[0]
         if q32.shape[1] != self.dim:
             raise ValueError(f"query dim {q32.shape[1]} != collection dim {self.dim}")
-        rows = np.empty((B, k), dtype=np.int32)
-        scores = np.empty((B, k), dtype=np.float64)
-        counts = np.empty(B, dtype=np.int32)
+        if out is not None:
+            rows, scores, counts = out              # caller-provided (e.g. pinned) result buffers
+        else:
+            rows = np.empty((B, k), dtype=np.int32)
+            scores = np.empty((B, k), dtype=np.float64)
+            counts = np.empty(B, dtype=np.int32)
         ab = np.ascontiguousarray(allow_bitmap, dtype=np.uint8) if allow_bitmap is not None else None
         _lib.check(self._L.rag_dense_topk(self._h, _lib.ptr(q32), B, int(k), _lib.ptr(ab), _lib.ptr(rows),
                                           _lib.ptr(scores), _lib.ptr(counts)))

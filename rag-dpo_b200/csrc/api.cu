@@ -187,6 +187,29 @@ int rag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_by
     return RAG_OK;
 }
 
+int rag_host_alloc(void** out, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!out || bytes == 0) return fail(RAG_EINVAL, "bad host allocation request");
+    CU_TRY(cudaMallocHost(out, bytes));
+    return RAG_OK;
+}
+
+int rag_host_free(void* p) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (p && g.inited) cudaFreeHost(p);
+    return RAG_OK;
+}
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int rag_last_timings(float* ms, int n) {
     std::lock_guard<std::mutex> lk(g.mu);
     for (int i = 0; i < n; ++i) ms[i] = i < 8 ? g.timings[i] : 0.f;
@@ -704,17 +727,30 @@ int rag_dense_topk(rag_corpus_t* c, const float* q, int B, int k, const uint8_t*
     RAG_TRY(g.o_scores.ensure(sb));
     RAG_TRY(g.o_counts.ensure(cb));
     if (ab) RAG_TRY(g.allow.ensure(ab + 16));
-    // inputs -> pinned -> device
+    // inputs: DMA straight from page-locked caller memory, otherwise stage through the pinned block
+    const bool q_pinned = is_pinned(q);
+    const bool out_pinned = is_pinned(out_scores) && is_pinned(out_rows) && is_pinned(out_counts);
     RAG_TRY(ensure_pinned(std::max(qb + ab, sb + rb + cb)));
     uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
-    memcpy(pin, q, qb);
-    CU_TRY(cudaMemcpyAsync(g.q.p, pin, qb, cudaMemcpyHostToDevice, g.stream));
+    if (q_pinned) {
+        CU_TRY(cudaMemcpyAsync(g.q.p, q, qb, cudaMemcpyHostToDevice, g.stream));
+    } else {
+        memcpy(pin, q, qb);
+        CU_TRY(cudaMemcpyAsync(g.q.p, pin, qb, cudaMemcpyHostToDevice, g.stream));
+    }
     if (ab) {
         memcpy(pin + qb, allow_bitmap, ab);
         CU_TRY(cudaMemcpyAsync(g.allow.p, pin + qb, ab, cudaMemcpyHostToDevice, g.stream));
     }
     RAG_TRY(dense_core(c, g.q.as<float>(), B, k, ab ? g.allow.as<uint8_t>() : nullptr, g.o_rows.as<int32_t>(),
                        g.o_scores.as<double>(), g.o_counts.as<int32_t>()));
+    if (out_pinned) {
+        CU_TRY(cudaMemcpyAsync(out_scores, g.o_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
+        CU_TRY(cudaMemcpyAsync(out_rows, g.o_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
+        CU_TRY(cudaMemcpyAsync(out_counts, g.o_counts.p, cb, cudaMemcpyDeviceToHost, g.stream));
+        CU_TRY(cudaStreamSynchronize(g.stream));
+        return RAG_OK;
+    }
     CU_TRY(cudaMemcpyAsync(pin, g.o_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
     CU_TRY(cudaMemcpyAsync(pin + sb, g.o_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
     CU_TRY(cudaMemcpyAsync(pin + sb + rb, g.o_counts.p, cb, cudaMemcpyDeviceToHost, g.stream));

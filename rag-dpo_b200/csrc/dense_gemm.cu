@@ -465,9 +465,9 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     int grid = (int)(n_tiles < sm_count ? (n_tiles > 0 ? n_tiles : 1) : sm_count);
     *grid_out = grid;
     p.n_lists = grid;
-    // Sample pass: the m-th best (m = kSampleM) of a sample that holds a fraction f of the rows lets
-    // ~m/f rows per query through the main pass; aim for f = 2/kp (about 4*kp survivors), in units of
-    // 32 columns.
+    // Sample pass: the m-th best (m = kSampleM = 8) of a sample that holds a fraction f of the rows lets
+    // ~m/f rows per query through the main pass; aim for f = 1/kp (about 8*kp survivors, ~8*kp/148 per
+    // (query, CTA) list), in units of 32 columns.
     const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
     const int64_t rows_per_cta = tiles_per_cta * GT_N;
     if (tiles_per_cta <= 1) {
@@ -477,7 +477,7 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
         p.list_cap = GT_N;
     } else {
         p.use_sample = 1;
-        int64_t want = (rows_per_cta * 2 / p.kp + 31) / 32 * 32;      // sample rows per CTA
+        int64_t want = (rows_per_cta / p.kp + 31) / 32 * 32;          // sample rows per CTA
         if (want < 32) want = 32;
         if (want <= GT_N) {
             p.sample_tiles = 1;
