@@ -184,3 +184,121 @@ class HybridRetriever:
             docs.append(RetrievedDocument(document_path=path, chunks=best, avg_similarity=0.0, primary_nature=""))
         docs.sort(key=lambda d: d.avg_similarity, reverse=True)
         return docs[:n_documents]
+
+
+# --------------------------------------------------------------------------------------------------
+# Batched front-end.  The reference issues, per question, 4 dense + 4 BM25 calls
+# one query at a time (src/rag/retriever.py:372-452).  retrieve_candidates_batch answers many questions
+# with ONE dense call (all query variants of all questions), ONE BM25 call per distinct doc_filter and
+# ONE device RRF call, and only materialises RetrievedChunk objects for the final candidates.  Results
+# are identical to calling retrieve_candidates() question by question.
+# --------------------------------------------------------------------------------------------------
+def _retrieve_candidates_batch(self, queries, n_candidates: int = 100, where_filter=None):
+    import numpy as np
+    from .collection import distance_from_score
+    from .rrf import rrf_fuse_rows
+
+    col, bm = self.collection, self.chunk_bm25
+    use_bm25 = self.enable_hybrid and bm is not None and bm.is_built
+    if not hasattr(col, "query_rows") or (use_bm25 and not hasattr(bm, "search_rows")):
+        return [self.retrieve_candidates(q, n_candidates, where_filter) for q in queries]
+    n_fetch = max(n_candidates, 50)
+    # 1. query variants + summary pre-filter per question
+    variants, filters = [], []
+    for q in queries:
+        expanded = self.acronym_expander(q)
+        variants.append(self.query_expander.expand(expanded) if self.query_expander is not None else [expanded])
+        f = None
+        if self.enable_summary_prefilter and self.summary_bm25 is not None and self.summary_bm25._is_built:
+            f = self.summary_bm25.get_relevant_doc_paths(expanded, top_k=self.summary_prefilter_k)
+        filters.append(f)
+    flat = [v for vs in variants for v in vs]
+    owner = [qi for qi, vs in enumerate(variants) for _ in vs]
+    # 2. one dense call for every variant of every question
+    emb = np.asarray(self._embed(flat), dtype=np.float32)
+    d_rows, d_scores, d_counts = col.query_rows(emb, n_fetch, where_filter)
+    # 3. BM25: one call per distinct doc_filter (the filter applies BEFORE the top-k, bm25_index.py:272-275)
+    b_rows = b_scores = b_counts = None
+    if use_bm25:
+        k_b = min(n_fetch, len(bm.chunk_ids))
+        tokens = [bm.tokenizer(v) for v in flat]
+        b_rows = np.full((len(flat), max(k_b, 1)), -1, np.int32)
+        b_scores = np.zeros((len(flat), max(k_b, 1)), np.float64)
+        b_counts = np.zeros(len(flat), np.int32)
+        groups = {}
+        for vi, qi in enumerate(owner):
+            key = frozenset(filters[qi]) if filters[qi] is not None else None
+            groups.setdefault(key, []).append(vi)
+        for key, idx in groups.items():
+            live = [vi for vi in idx if tokens[vi]]
+            if not live or k_b == 0:
+                continue
+            r, s, c = bm.search_rows([tokens[vi] for vi in live], n_fetch, set(key) if key is not None else None)
+            b_rows[live, :r.shape[1]], b_scores[live, :r.shape[1]], b_counts[live] = r, s, c
+        if not hasattr(bm, "_to_col") or len(bm._to_col) != len(bm.chunk_ids):
+            bm._to_col = np.array([col._pos[cid] for cid in bm.chunk_ids], dtype=np.int32)
+    # 4. rankings in the reference's order: dense v0, bm25 v0, dense v1, bm25 v1, ...
+    Q = len(queries)
+    vmax = max(len(vs) for vs in variants)
+    R = vmax * (2 if use_bm25 else 1)
+    ids = np.full((Q, R, n_fetch), -1, np.int32)
+    weights = np.zeros((Q, R), np.float64)
+    dense_lists = {}
+    paths = None
+    vi = 0
+    for qi in range(Q):
+        for v in range(len(variants[qi])):
+            rows = d_rows[vi, :d_counts[vi]].tolist()
+            if filters[qi]:
+                if paths is None:
+                    paths = [(m or {}).get("document_path", "") for m in col._metas]
+                kept = [r for r in rows if paths[r] in filters[qi]]
+                if len(kept) < 10:
+                    ks = set(kept)
+                    kept.extend([r for r in rows if r not in ks][:10 - len(kept)])
+                rows = kept
+            dense_lists[(qi, v)] = (rows, vi)
+            slot = v * 2 if use_bm25 else v
+            ids[qi, slot, :len(rows)] = rows
+            q_weight = 2.0 if v == 0 else 1.0
+            weights[qi, slot] = q_weight
+            if use_bm25:
+                ids[qi, slot + 1, :b_counts[vi]] = bm._to_col[b_rows[vi, :b_counts[vi]]]
+                weights[qi, slot + 1] = q_weight * 1.5 if v == 0 else q_weight * 0.75
+            vi += 1
+    # 5. one device RRF call for all questions
+    f_ids, f_scores, f_counts = rrf_fuse_rows(ids, weights, 60, n_candidates)
+    # 6. materialise only the final candidates
+    out = []
+    for qi in range(Q):
+        nv = len(variants[qi])
+        best_dist, best_bm25 = {}, {}
+        for v in range(nv):
+            rows, vi = dense_lists[(qi, v)]
+            pos = {r: j for j, r in enumerate(d_rows[vi, :d_counts[vi]].tolist())}
+            for r in rows:
+                dist = distance_from_score(d_scores[vi, pos[r]])
+                if r not in best_dist or dist < best_dist[r]:
+                    best_dist[r] = dist
+            if use_bm25:
+                for j in range(b_counts[vi]):
+                    r = int(bm._to_col[b_rows[vi, j]])
+                    best_bm25[r] = max(best_bm25.get(r, 0.0), float(b_scores[vi, j]))
+        single = (nv * (2 if use_bm25 else 1)) <= 1
+        chunks = []
+        for j in range(f_counts[qi]):
+            r = int(f_ids[qi, j])
+            meta = col._metas[r] or {}
+            dist = best_dist.get(r, 1.0)
+            c = _chunk_from_meta(col._ids[r], col._docs[r], meta if r in best_dist else dict(meta), dist)
+            c.semantic_score = c.similarity_score if r in best_dist else 0.0
+            c.bm25_score = best_bm25.get(r, 0.0)
+            c.hybrid_score = c.semantic_score if single else float(f_scores[qi, j])
+            chunks.append(c)
+        if single:
+            chunks.sort(key=lambda c: c.hybrid_score, reverse=True)
+        out.append(chunks)
+    return out
+
+
+HybridRetriever.retrieve_candidates_batch = _retrieve_candidates_batch

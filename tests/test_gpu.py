@@ -406,3 +406,31 @@ def test_tensor_core_path_exact_ties_take_the_fallback():
     assert rows[3].tolist() == sorted(dup.tolist())[:10]
     assert _lib.counters()["fallbacks"] == before + 1
     c.close()
+
+
+def test_batched_front_end_equals_per_question_path(e2e_data, golden_dir):
+    """retrieve_candidates_batch (one dense call + one BM25 call per filter + one device RRF call for many
+    questions) returns what the reference returned question by question."""
+    from b200rag import DeviceCollection, DeviceChunkBM25Index, DeviceSummaryBM25Index, HybridRetriever
+    gold, emb, table = e2e_data
+    col = DeviceCollection(dim=emb.shape[1], dtype="f32")
+    helpers.fill(col, gold["chunks"], emb)
+    bm = DeviceChunkBM25Index()
+    bm.build_from_collection(col)
+    sm = DeviceSummaryBM25Index()
+    sm.build(os.path.join(golden_dir, "e2e_summaries.json"))
+    groups = {}
+    for run in gold["runs"]:
+        key = (str(run["config"]), str(run["where"]))
+        groups.setdefault(key, []).append(run)
+    assert any(len(v) > 1 for v in groups.values())
+    for runs in groups.values():
+        cfg, where = runs[0]["config"], runs[0]["where"]
+        r = HybridRetriever(collection=col, embedding_provider=helpers.FixedEmbeddingProvider(table),
+                            summary_bm25_index=sm if cfg["prefilter"] else None, chunk_bm25_index=bm,
+                            query_expander=helpers.FixedQueryExpander(gold["expansions"]) if cfg["expander"] else None,
+                            summary_prefilter_k=8, enable_hybrid=cfg["hybrid"], enable_summary_prefilter=cfg["prefilter"],
+                            acronym_expander=helpers.acronym_expander_for_golden(gold))
+        got = r.retrieve_candidates_batch([run["query"] for run in runs], n_candidates=40, where_filter=where)
+        for run, chunks in zip(runs, got):
+            assert [helpers.chunk_dump(c) for c in chunks] == run["candidates"], (cfg, run["query"])
