@@ -51,6 +51,9 @@ int rag_set_stream(void* cuda_stream);    /* run on the caller's stream (e.g. to
 const char* rag_last_error(void);
 int rag_abi_version(void);
 int rag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
+/* runtime knobs: "tc_min_batch" (smallest batch served by the tcgen05 contraction path, default 2),
+ * "tc_b1_shadow" (1 = a single query on an fp32/fp16 corpus is filtered through the bf16 shadow, default 1) */
+int rag_set_option(const char* key, int64_t value);
 /* page-locked host memory: buffers allocated here are DMA'd directly by the host-pointer entry points
  * (no staging copy); any other host pointer is staged through an internal pinned block. */
 int rag_host_alloc(void** out, size_t bytes);

@@ -25,6 +25,7 @@ SYMBOLS = {
     "rag_last_error": (C.c_char_p, []),
     "rag_abi_version": (_i, []),
     "rag_device_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "rag_set_option": (_i, [C.c_char_p, _i64]),
     "rag_host_alloc": (_i, [_vp, C.c_size_t]),
     "rag_host_free": (_i, [_vp]),
     "rag_last_timings": (_i, [_vp, _i]),
@@ -147,6 +148,10 @@ def counters():
     out = np.zeros(4, dtype=np.int64)
     check(lib().rag_counters(ptr(out), 4))
     return {"launches": int(out[0]), "fallbacks": int(out[1])}
+
+
+def set_option(key, value):
+    check(lib().rag_set_option(key.encode(), int(value)))
 
 
 def set_stream(cuda_stream_ptr):

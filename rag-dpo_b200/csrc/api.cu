@@ -83,7 +83,8 @@ struct Ctx {
     DevBuf stage_f32;
 };
 Ctx g;
-int g_tc_min_batch = 5;     // smallest batch served by the tcgen05 path (env B200RAG_TC_MIN_BATCH)
+int g_tc_min_batch = 2;     // smallest batch served by the tcgen05 path (env B200RAG_TC_MIN_BATCH)
+int g_tc_b1_shadow = 1;     // batch-1 on fp32/fp16 corpora goes through the bf16 shadow (env B200RAG_TC_B1_SHADOW)
 
 int ensure_pinned(size_t need) {
     if (need <= g.pinned_bytes) return RAG_OK;
@@ -163,6 +164,7 @@ int rag_init(int device) {
     for (auto& ev : g.ev) CU_TRY(cudaEventCreate(&ev));
     CU_TRY(cudaMallocHost((void**)&g.pinned_small, 4096));
     if (const char* e = getenv("B200RAG_TC_MIN_BATCH")) g_tc_min_batch = std::max(1, atoi(e));
+    if (const char* e = getenv("B200RAG_TC_B1_SHADOW")) g_tc_b1_shadow = atoi(e) != 0;
     g.inited = true;
     return RAG_OK;
 }
@@ -184,6 +186,15 @@ int rag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_by
     CU_TRY(cudaMemGetInfo(&f, &t));
     if (free_bytes) *free_bytes = f;
     if (total_bytes) *total_bytes = t;
+    return RAG_OK;
+}
+
+int rag_set_option(const char* key, int64_t value) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!key) return fail(RAG_EINVAL, "key is NULL");
+    if (!strcmp(key, "tc_min_batch")) g_tc_min_batch = (int)std::max<int64_t>(1, value);
+    else if (!strcmp(key, "tc_b1_shadow")) g_tc_b1_shadow = value != 0;
+    else return fail(RAG_EINVAL, "unknown option %s", key);
     return RAG_OK;
 }
 
@@ -476,7 +487,9 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
 
 static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev,
                             int32_t* o_rows, double* o_scores, int32_t* o_counts) {
-    const bool use_tc = B >= g_tc_min_batch && c->n > 0;
+    // tensor-core path: every batch >= g_tc_min_batch (default 2); a single query only when the corpus is not
+    // bf16 (the filter then streams the bf16 shadow: half the bytes of the fp32 rows) and large enough to matter
+    const bool use_tc = c->n > 0 && (B >= g_tc_min_batch || (g_tc_b1_shadow && c->dtype != RAG_BF16 && c->n >= 262144));
     const int kp = use_tc ? std::max(64, next_pow2(2 * k + 1)) : std::max(16, next_pow2(k + 6));
     for (auto& v : g.ev_valid) v = false;
     for (auto& t : g.timings) t = 0.f;

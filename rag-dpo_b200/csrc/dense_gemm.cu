@@ -304,6 +304,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     const bool pass = MODE == 0 ? (s > thr) : (s >= thr);
                     m |= pass ? (1u << j) : 0u;
                 }
+                if (MODE == 0 && c == n_chunks - 1) m &= p.sample_last_mask;   // column-granular sample size
                 uint32_t um = __reduce_or_sync(0xffffffffu, m);
                 while (um) {
                     const int j = __ffs(um) - 1;
@@ -473,19 +474,22 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     if (tiles_per_cta <= 1) {
         // tiny shard: no threshold at all, every row of the CTA's single tile is captured
         p.use_sample = 0;
-        p.sample_tiles = 0; p.sample_step = 1; p.sample_chunks = 0;
+        p.sample_tiles = 0; p.sample_step = 1; p.sample_chunks = 0; p.sample_last_mask = 0;
         p.list_cap = GT_N;
     } else {
         p.use_sample = 1;
-        int64_t want = (rows_per_cta / p.kp + 31) / 32 * 32;          // sample rows per CTA
-        if (want < 32) want = 32;
+        int64_t want = (rows_per_cta + p.kp - 1) / p.kp;               // sample rows per CTA
+        if (want < 2) want = 2;
         if (want <= GT_N) {
             p.sample_tiles = 1;
-            p.sample_chunks = (int)(want / 32);
+            p.sample_chunks = (int)((want + 31) / 32);
+            const int last = (int)(want - (int64_t)(p.sample_chunks - 1) * 32);
+            p.sample_last_mask = last >= 32 ? 0xffffffffu : ((1u << last) - 1u);
             p.sample_step = 1;
         } else {
             p.sample_tiles = (int)((want + GT_N - 1) / GT_N);
             p.sample_chunks = GT_N / 32;
+            p.sample_last_mask = 0xffffffffu;
             p.sample_step = (int)(tiles_per_cta / p.sample_tiles > 0 ? tiles_per_cta / p.sample_tiles : 1);
         }
         p.list_cap = 64;

@@ -50,6 +50,7 @@ struct GemmParams {
     int list_cap;            // entries per (query, CTA) list
     int use_sample;          // 0 = tiny shard: no sample pass, tau_keys = NULL, every row is captured
     int n_lists, n_stages, n_qblocks, sample_tiles, sample_step, sample_chunks;
+    uint32_t sample_last_mask;   // columns of the last sample chunk that count
 };
 int gemm_sample_m();
 int gemm_max_batch();

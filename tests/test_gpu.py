@@ -434,3 +434,37 @@ def test_batched_front_end_equals_per_question_path(e2e_data, golden_dir):
         got = r.retrieve_candidates_batch([run["query"] for run in runs], n_candidates=40, where_filter=where)
         for run, chunks in zip(runs, got):
             assert [helpers.chunk_dump(c) for c in chunks] == run["candidates"], (cfg, run["query"])
+
+
+def test_scan_kernel_multi_query_variants_forced():
+    """B = 2..7 through the CUDA-core scan kernel (NQ = 2 and 4 templates, several launches) by raising the
+    tensor-core threshold; the default dispatch sends B >= 2 to the contraction kernel."""
+    from b200rag import DeviceCorpus, _lib
+    _lib.set_option("tc_min_batch", 1 << 20)
+    _lib.set_option("tc_b1_shadow", 0)
+    try:
+        for dtype, n, d in [("bf16", 9000, 1024), ("f32", 5000, 512), ("f16", 3000, 256)]:
+            x = helpers.synth_unit(n, d, seed=n)
+            q = helpers.synth_unit(7, d, seed=n + 1)
+            c = DeviceCorpus(d, dtype)
+            c.append(x)
+            for B, k in [(2, 10), (3, 50), (4, 100), (7, 10)]:
+                check_topk(c, q[:B], k, DT[dtype])
+            c.close()
+    finally:
+        _lib.set_option("tc_min_batch", 2)
+        _lib.set_option("tc_b1_shadow", 1)
+
+
+def test_single_query_on_fp32_corpus_uses_the_bf16_shadow_and_stays_exact():
+    from b200rag import DeviceCorpus, _lib
+    n, d = 300_000, 1024                      # >= 262144 rows: batch-1 goes through the contraction kernel
+    c = DeviceCorpus(d, "f32")
+    c.fill_synthetic(seed=5, nrows=n)
+    q = helpers.synth_unit(3, d, seed=6)
+    q[1] = c.download(12345, 1)[0]
+    launches = _lib.counters()["launches"]
+    for i in range(3):
+        check_topk(c, q[i:i + 1], 10, no.DT_F32)
+    check_topk(c, q[:1], 50, no.DT_F32)
+    c.close()

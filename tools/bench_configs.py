@@ -22,6 +22,16 @@ CASES = {
     "c5_shard_b4096": (12_500_000, "bf16", 4096, 10, "config 5: one shard, 4096-query throughput"),
     "c2_b1": (1_000_000, "f32", 1, 10, "config 2 batch-1"),
     "c1_50k": (50_000, "f32", 1, 50, "config 1: 50k chunks, n_results=50 as the reference issues"),
+    "c1_50k_b4": (50_000, "f32", 4, 50, "config 1: 4 query variants of one question, n_results=50"),
+    "c1_17k_b4": (16_919, "f32", 4, 50, "the reference's real corpus size, 4 query variants, n_results=50"),
+    "c2_b2": (1_000_000, "f32", 2, 10, "config 2 batch-2"),
+    "c2_b4": (1_000_000, "f32", 4, 10, "config 2 batch-4"),
+    "c2_b4_k50": (1_000_000, "f32", 4, 50, "config 2 batch-4 top-50"),
+    "c2_b1_k50": (1_000_000, "f32", 1, 50, "config 2 batch-1 top-50"),
+    "bf16_1m_b1": (1_000_000, "bf16", 1, 10, "1M bf16 batch-1"),
+    "bf16_1m_b4_k50": (1_000_000, "bf16", 4, 50, "1M bf16 batch-4 top-50"),
+    "c2_b8": (1_000_000, "f32", 8, 10, "config 2 batch-8"),
+    "c2_b64": (1_000_000, "f32", 64, 10, "config 2 batch-64"),
 }
 
 
