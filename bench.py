@@ -240,10 +240,12 @@ def run_b200(args):
     def make_device_step(nq):
         """whole hot path with HBM-resident queries: local top-k (+ exchange + merge when sharded)"""
         o_rows = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        o_scores = torch.empty((nq, k), dtype=torch.float64, device=dev)
         o_counts = torch.empty((nq,), dtype=torch.int32, device=dev)
-        g_scores = torch.empty((world, nq, k), dtype=torch.float64, device=dev)
-        g_ids = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+        # one packed buffer per rank: [scores (nq x k f64) | global ids (nq x k i64)] -> ONE all-gather
+        mine = torch.empty((2, nq, k), dtype=torch.float64, device=dev)
+        o_scores = mine[0]
+        my_ids = mine[1].view(torch.int64)
+        gathered = torch.empty((world, 2, nq, k), dtype=torch.float64, device=dev)
         m_scores = torch.empty((nq, k), dtype=torch.float64, device=dev)
         m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         m_counts = torch.empty((nq,), dtype=torch.int32, device=dev)
@@ -251,11 +253,11 @@ def run_b200(args):
         def step():
             corpus.topk_dev(q_dev.data_ptr(), nq, k, o_rows.data_ptr(), o_scores.data_ptr(), o_counts.data_ptr())
             if world > 1:
-                ids = torch.where(o_rows >= 0, o_rows.to(torch.int64) + index.row_lo, -1)
-                dist.all_gather_into_tensor(g_scores, o_scores)
-                dist.all_gather_into_tensor(g_ids, ids)
-                _lib.check(L.rag_merge_topk_dev(g_scores.data_ptr(), g_ids.data_ptr(), world, nq, k,
-                                                m_scores.data_ptr(), m_ids.data_ptr(), m_counts.data_ptr()))
+                my_ids.copy_(o_rows)                       # int32 -> int64
+                my_ids.add_(index.row_lo)                  # local row -> global id (k <= rows per shard: no padding)
+                dist.all_gather_into_tensor(gathered, mine)
+                _lib.check(L.rag_merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + nq * k * 8, world, nq, k,
+                                                2 * nq * k, m_scores.data_ptr(), m_ids.data_ptr(), m_counts.data_ptr()))
             return (m_ids, m_scores) if world > 1 else (o_rows, o_scores)
         return step
 

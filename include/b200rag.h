@@ -104,8 +104,11 @@ int rag_dense_topk_dev(rag_corpus_t* c, const float* q_dev, int B, int k, const 
                        int32_t* out_rows_dev, double* out_scores_dev, int32_t* out_counts_dev);
 /* multi-GPU exchange step (one process per GPU): after an all-gather of the G
  * ranks' (score, global id) lists, keep the global top-k per query, order
- * (score desc, id asc).  Device pointers: scores/ids are G x B x k. */
-int rag_merge_topk_dev(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k,
+ * (score desc, id asc).  Device pointers: rank g's B x k block of scores / ids
+ * starts at element g * rank_stride (0 = B*k, i.e. dense G x B x k arrays), so one
+ * packed all-gather buffer can carry both.  STREAM-ORDERED: returns after the
+ * launch; the result is ready when the stream (rag_set_stream) reaches it. */
+int rag_merge_topk_dev(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k, int64_t rank_stride,
                        double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev);
 
 /* ---- BM25 keyword scoring over CSR postings -------------------------------

@@ -41,7 +41,7 @@ SYMBOLS = {
     "rag_corpus_device_ptr": (_i, [_vp, _vp]),
     "rag_dense_topk": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "rag_dense_topk_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
-    "rag_merge_topk_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rag_merge_topk_dev": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp, _vp]),
     "rag_bm25_create": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _d, _d, _d]),
     "rag_bm25_destroy": (_i, [_vp]),
     "rag_bm25_search": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
@@ -148,6 +148,11 @@ def counters():
     out = np.zeros(4, dtype=np.int64)
     check(lib().rag_counters(ptr(out), 4))
     return {"launches": int(out[0]), "fallbacks": int(out[1])}
+
+
+def sync_stream_of(torch, device):
+    """rag_merge_topk_dev is stream-ordered: wait for the library's stream before reading its output"""
+    torch.cuda.synchronize(device)
 
 
 def set_option(key, value):

@@ -102,6 +102,7 @@ class ShardedDenseIndex:
             o_s = torch.empty((B, kk), dtype=torch.float64, device=self.device)
             o_i = torch.empty((B, kk), dtype=torch.int64, device=self.device)
             o_c = torch.empty((B,), dtype=torch.int32, device=self.device)
-            _lib.check(_lib.lib().rag_merge_topk_dev(g_scores.data_ptr(), g_ids.data_ptr(), self.world, B, kk,
+            _lib.check(_lib.lib().rag_merge_topk_dev(g_scores.data_ptr(), g_ids.data_ptr(), self.world, B, kk, 0,
                                                      o_s.data_ptr(), o_i.data_ptr(), o_c.data_ptr()))
+            _lib.sync_stream_of(torch, self.device)
         return o_i.cpu().numpy(), o_s.cpu().numpy(), o_c.cpu().numpy()

@@ -774,17 +774,18 @@ int rag_dense_topk(rag_corpus_t* c, const float* q, int B, int k, const uint8_t*
     return RAG_OK;
 }
 
-int rag_merge_topk_dev(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k, double* out_scores_dev,
-                       int64_t* out_ids_dev, int32_t* out_counts_dev) {
+int rag_merge_topk_dev(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k, int64_t rank_stride,
+                       double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev) {
     std::lock_guard<std::mutex> lk(g.mu);
     RAG_TRY(require_init());
     if (!scores_dev || !ids_dev || !out_scores_dev || !out_ids_dev || !out_counts_dev)
         return fail(RAG_EINVAL, "NULL argument");
     if (G <= 0 || B <= 0 || k <= 0 || k > RAG_MAX_K || (int64_t)G * k > 8192)
         return fail(RAG_ERANGE, "G=%d B=%d k=%d outside the supported range", G, B, k);
-    CU_TRY(merge_exact_launch(scores_dev, ids_dev, G, B, k, out_scores_dev, out_ids_dev, out_counts_dev, g.stream));
+    if (rank_stride == 0) rank_stride = (int64_t)B * k;
+    CU_TRY(merge_exact_launch(scores_dev, ids_dev, G, B, k, rank_stride, out_scores_dev, out_ids_dev, out_counts_dev,
+                              g.stream));
     ++g.n_launch;
-    CU_TRY(cudaStreamSynchronize(g.stream));
     return RAG_OK;
 }
 

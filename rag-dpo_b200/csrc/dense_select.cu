@@ -236,8 +236,8 @@ struct ExactKey64 {
 
 __global__ void __launch_bounds__(256) merge_exact_kernel(const double* __restrict__ scores,
                                                           const int64_t* __restrict__ ids, int G, int B, int k,
-                                                          int nsort, double* out_scores, int64_t* out_ids,
-                                                          int32_t* out_counts) {
+                                                          int64_t rank_stride, int nsort, double* out_scores,
+                                                          int64_t* out_ids, int32_t* out_counts) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     ExactKey64* ek = reinterpret_cast<ExactKey64*>(sm_raw);
     __shared__ int s_count;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) merge_exact_kernel(const double* __restri
         e.s = -INFINITY; e.id = INT64_MAX;
         if (i < G * k) {
             int g = i / k, j = i % k;
-            size_t src = ((size_t)g * B + b) * k + j;
+            size_t src = (size_t)g * rank_stride + (size_t)b * k + j;
             int64_t id = ids[src];
             if (id >= 0) { e.s = scores[src]; e.id = id; ++local; }
         }
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(256) merge_exact_kernel(const double* __restri
     if (threadIdx.x == 0) out_counts[b] = nout;
 }
 
-cudaError_t merge_exact_launch(const double* scores, const int64_t* ids, int G, int B, int k, double* out_scores,
-                               int64_t* out_ids, int32_t* out_counts, cudaStream_t st) {
+cudaError_t merge_exact_launch(const double* scores, const int64_t* ids, int G, int B, int k, int64_t rank_stride,
+                               double* out_scores, int64_t* out_ids, int32_t* out_counts, cudaStream_t st) {
     int nsort = 32;
     while (nsort < G * k) nsort <<= 1;
     size_t smem = (size_t)nsort * sizeof(ExactKey64);
@@ -275,7 +275,7 @@ cudaError_t merge_exact_launch(const double* scores, const int64_t* ids, int G, 
         cudaError_t e = cudaFuncSetAttribute(merge_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    merge_exact_kernel<<<B, 256, smem, st>>>(scores, ids, G, B, k, nsort, out_scores, out_ids, out_counts);
+    merge_exact_kernel<<<B, 256, smem, st>>>(scores, ids, G, B, k, rank_stride, nsort, out_scores, out_ids, out_counts);
     return cudaGetLastError();
 }
 

@@ -112,8 +112,8 @@ struct CollectSelectParams {
 };
 cudaError_t collect_select_launch(const CollectSelectParams& p, cudaStream_t st);
 // G sorted (score,id) lists per query -> global top-k
-cudaError_t merge_exact_launch(const double* scores, const int64_t* ids, int G, int B, int k, double* out_scores,
-                               int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
+cudaError_t merge_exact_launch(const double* scores, const int64_t* ids, int G, int B, int k, int64_t rank_stride,
+                               double* out_scores, int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
 
 // ---- corpus.cu -------------------------------------------------------------
 cudaError_t convert_rows_launch(const float* src, void* dst, int dtype, int64_t n_elems, cudaStream_t st);

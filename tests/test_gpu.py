@@ -339,8 +339,19 @@ def test_merge_topk_dev_vs_host_merge():
         o_i = torch.empty(B, k, dtype=torch.int64, device="cuda")
         o_c = torch.empty(B, dtype=torch.int32, device="cuda")
         torch.cuda.synchronize()
-        _lib.check(_lib.lib().rag_merge_topk_dev(ds.data_ptr(), di.data_ptr(), G, B, k, o_s.data_ptr(), o_i.data_ptr(),
-                                                 o_c.data_ptr()))
+        _lib.check(_lib.lib().rag_merge_topk_dev(ds.data_ptr(), di.data_ptr(), G, B, k, 0, o_s.data_ptr(),
+                                                 o_i.data_ptr(), o_c.data_ptr()))
+        torch.cuda.synchronize()
+        # packed layout: one buffer per rank holding [scores | ids], as bench.py all-gathers it
+        packed = torch.empty((G, 2, B, k), dtype=torch.float64, device="cuda")
+        packed[:, 0] = ds
+        packed[:, 1].view(torch.int64).copy_(di)
+        o_s2, o_i2, o_c2 = torch.empty_like(o_s), torch.empty_like(o_i), torch.empty_like(o_c)
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib().rag_merge_topk_dev(packed.data_ptr(), packed.data_ptr() + B * k * 8, G, B, k, 2 * B * k,
+                                                 o_s2.data_ptr(), o_i2.data_ptr(), o_c2.data_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(o_i2, o_i) and torch.equal(o_s2, o_s) and torch.equal(o_c2, o_c)
         assert torch.equal(o_i.cpu(), want_i) and torch.equal(o_s.cpu(), want_s) and torch.equal(o_c.cpu(), want_c)
 
 
