@@ -479,3 +479,75 @@ def test_single_query_on_fp32_corpus_uses_the_bf16_shadow_and_stays_exact():
         check_topk(c, q[i:i + 1], 10, no.DT_F32)
     check_topk(c, q[:1], 50, no.DT_F32)
     c.close()
+
+
+# ------------------------------------------------- BASELINE full-size shapes ----
+def _slice_exactness(c, q, rows, scores, lo, hi, dt):
+    """Exactness restricted to the row slice [lo, hi): the rows of the slice whose oracle score reaches our k-th
+    score must be exactly our returned rows that fall in the slice, with identical fp64 scores."""
+    x = c.download(lo, hi - lo)
+    raw = raw_rows(x, dt)
+    for b in range(len(q)):
+        osc = c_oracle.dense_scores(q[b], raw, dt)
+        kth = scores[b, -1]
+        kth_row = rows[b, -1]
+        want = {int(lo + i): float(osc[i]) for i in np.nonzero(osc >= kth)[0]
+                if osc[i] > kth or lo + i <= kth_row}
+        got = {int(r): float(s) for r, s in zip(rows[b], scores[b]) if lo <= r < hi}
+        assert got == want, (b, lo, hi)
+
+
+def test_config5_shard_full_size():
+    """BASELINE config 5, one of the 8 shards: 12.5M x 1024 bf16 (25.6 GB), top-10, batch 1 (scan kernel) and a
+    batch through the tcgen05 kernel; both paths must agree and be exact on sampled row slices."""
+    from b200rag import DeviceCorpus, synth
+    n, d, k = 12_500_000, 1024, 10
+    c = DeviceCorpus(d, "bf16", capacity=n)
+    c.fill_synthetic(seed=1005, nrows=n)
+    q = synth.unit_queries(6, d, 2005)
+    planted = [7_654_321, n - 1]
+    q[4:] = np.concatenate([c.download(r, 1) for r in planted])
+    r1 = [c.topk(q[i:i + 1], k) for i in range(6)]                 # batch-1: CUDA-core scan
+    rows = np.concatenate([r[0] for r in r1]); scores = np.concatenate([r[1] for r in r1])
+    rows_b, scores_b, counts_b = c.topk(q, k)                      # batch-6: tcgen05 contraction
+    assert np.array_equal(rows, rows_b) and np.array_equal(scores, scores_b)
+    assert (counts_b == k).all() and (np.diff(scores, axis=1) <= 0).all()
+    for j, r in enumerate(planted):
+        assert rows[4 + j, 0] == r
+    for b in range(6):                                             # slices that contain returned rows + a random one
+        lo = int(rows[b, 0]) // 200_000 * 200_000
+        _slice_exactness(c, q[b:b + 1], rows[b:b + 1], scores[b:b + 1], lo, min(n, lo + 200_000), no.DT_BF16)
+    _slice_exactness(c, q[:3], rows[:3], scores[:3], 3_000_000, 3_300_000, no.DT_BF16)
+    c.close()
+
+
+def test_config3_shard_shape_batch4096_top100():
+    """BASELINE config 3 shape per GPU at G=8: 1.25M x 1024 bf16, 4096-query batch, top-100."""
+    from b200rag import DeviceCorpus, synth, _lib
+    n, d, k, B = 1_250_000, 1024, 100, 4096
+    c = DeviceCorpus(d, "bf16", capacity=n)
+    c.fill_synthetic(seed=1003, nrows=n)
+    q = synth.unit_queries(B, d, 2003)
+    f0 = _lib.counters()["fallbacks"]
+    rows, scores, counts = c.topk(q, k)
+    assert (counts == k).all() and (np.diff(scores, axis=1) <= 0).all()
+    assert _lib.counters()["fallbacks"] - f0 <= 1
+    pick = [0, 1, 2047, 4095]
+    raw = raw_rows(c.download(), no.DT_BF16)
+    er, es, ec = c_oracle.dense_topk(q[pick], raw, no.DT_BF16, k)
+    assert rows[pick].tolist() == er.tolist() and np.array_equal(scores[pick], es)
+    c.close()
+
+
+def test_batch_larger_than_one_launch_is_sliced():
+    from b200rag import DeviceCorpus
+    n, d, B = 3000, 128, 4100
+    x = helpers.synth_unit(n, d, seed=1)
+    q = helpers.synth_unit(B, d, seed=2)
+    c = DeviceCorpus(d, "bf16")
+    c.append(x)
+    rows, scores, counts = c.topk(q, 5)
+    pick = [0, 4095, 4096, 4099]
+    er, es, ec = c_oracle.dense_topk(q[pick], raw_rows(c.download(), no.DT_BF16), no.DT_BF16, 5)
+    assert rows[pick].tolist() == er.tolist() and np.array_equal(scores[pick], es)
+    c.close()
