@@ -14,6 +14,8 @@
 // (row id + fp64 impact) + 16 * touched rows (accumulator read-modify-write).
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -209,6 +211,9 @@ constexpr int kBmRange = 4096;        // rows per CTA: 32 KB of fp64 accumulator
 constexpr int kBmMaxTokens = 128;     // query tokens handled per pass
 constexpr int kBmThreads = 256;
 
+constexpr int kBmWarps = kBmThreads / 32;
+constexpr int kBmSeg = kBmRange / kBmWarps;      // rows owned by one warp: 512
+
 __global__ void __launch_bounds__(kBmThreads)
 bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_row,
                   const double* __restrict__ impact, const double* __restrict__ idf, int64_t n_docs, int64_t n_terms,
@@ -217,7 +222,8 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
     extern __shared__ __align__(16) uint8_t sm_raw[];
     double* acc = reinterpret_cast<double*>(sm_raw);                              // kBmRange
     Bm25Key* bufs = reinterpret_cast<Bm25Key*>(sm_raw + kBmRange * sizeof(double));  // 8 warps * 2 * kp
-    __shared__ int64_t s_lo[kBmMaxTokens], s_hi[kBmMaxTokens];
+    // posting offsets of every token at the 9 warp-segment boundaries of this CTA's row range
+    __shared__ int64_t s_bound[kBmMaxTokens][kBmWarps + 1];
     __shared__ double s_w[kBmMaxTokens];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.y;
@@ -229,44 +235,63 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
     for (int i = threadIdx.x; i < kBmRange; i += kBmThreads) acc[i] = 0.0;
     for (int t0 = 0; t0 < nt; t0 += kBmMaxTokens) {
         const int tn = nt - t0 < kBmMaxTokens ? nt - t0 : kBmMaxTokens;
-        // posting sub-range of every token inside [r0, r1): one binary search per (token, bound)
-        for (int j = threadIdx.x; j < 2 * tn; j += kBmThreads) {
-            const int i = j >> 1;
+        __syncthreads();                             // previous pass done with s_bound / acc zeroed
+        // one binary search per (token, boundary): postings of a term are sorted by row
+        for (int j = threadIdx.x; j < tn * (kBmWarps + 1); j += kBmThreads) {
+            const int i = j / (kBmWarps + 1), bnd = j % (kBmWarps + 1);
             const int32_t t = terms[t0 + i];
             int64_t pos = 0;
             double w = 0.0;
             if (t >= 0 && t < n_terms) {
                 w = idf[t];
                 int64_t lo = term_ptr[t], hi = term_ptr[t + 1];
-                const int64_t target = (j & 1) ? r1 : r0;
+                int64_t target = r0 + (int64_t)bnd * kBmSeg;
+                if (target > r1) target = r1;
                 while (lo < hi) {
                     const int64_t mid = (lo + hi) >> 1;
                     if ((int64_t)post_row[mid] < target) lo = mid + 1; else hi = mid;
                 }
                 pos = lo;
             }
-            if (j & 1) s_hi[i] = pos; else { s_lo[i] = pos; s_w[i] = w; }
+            s_bound[i][bnd] = pos;
+            if (bnd == 0) s_w[i] = w;
         }
         __syncthreads();
-        for (int i = 0; i < tn; ++i) {           // token order == numpy's `score +=` order
+        // every warp accumulates ITS 512 rows token by token (numpy's `score +=` order) with no block-wide
+        // barrier; the first chunk of the next token is prefetched while the current one is added
+        int64_t p_next = s_bound[0][warp] + lane;
+        int32_t row_n = 0;
+        double imp_n = 0.0;
+        if (p_next < s_bound[0][warp + 1]) { row_n = post_row[p_next]; imp_n = impact[p_next]; }
+        for (int i = 0; i < tn; ++i) {
             const double w = s_w[i];
+            const int64_t hi = s_bound[i][warp + 1];
+            int64_t p = p_next;
+            int32_t row = row_n;
+            double imp = imp_n;
+            if (i + 1 < tn) {
+                p_next = s_bound[i + 1][warp] + lane;
+                if (p_next < s_bound[i + 1][warp + 1]) { row_n = post_row[p_next]; imp_n = impact[p_next]; }
+            }
             if (w != 0.0) {
-                for (int64_t p = s_lo[i] + threadIdx.x; p < s_hi[i]; p += kBmThreads) {
-                    const int r = (int)(post_row[p] - r0);
-                    acc[r] = __dadd_rn(acc[r], __dmul_rn(w, impact[p]));
+                while (p < hi) {
+                    const int r = (int)(row - r0);
+                    acc[r] = __dadd_rn(acc[r], __dmul_rn(w, imp));
+                    p += 32;
+                    if (p < hi) { row = post_row[p]; imp = impact[p]; }
                 }
             }
-            __syncthreads();
+            __syncwarp();                            // two tokens may hit the same row from different lanes
         }
     }
-    // local select: score > 0, allowed rows, (score desc, row asc)
+    // local select over this warp's rows: score > 0, allowed, (score desc, row asc)
     WarpTopKT<Bm25Key> t;
     t.init(bufs + (size_t)warp * 2 * kp, kp, lane);
-    const int n_local = (int)(r1 - r0);
-    for (int i0 = warp * 32; i0 < n_local; i0 += kBmThreads) {
-        const int i = i0 + lane;
+    const int seg0 = warp * kBmSeg;
+    for (int i0 = 0; i0 < kBmSeg; i0 += 32) {
+        const int i = seg0 + i0 + lane;
         Bm25Key key{0ull, 0u, 0u};
-        if (i < n_local) {
+        if (r0 + i < r1) {
             const double sc = acc[i];
             const uint32_t r = (uint32_t)(r0 + i);
             if (sc > 0.0 && bitmap_test(allow, r)) { key.s = (uint64_t)__double_as_longlong(sc); key.nrow = ~r; }
@@ -275,44 +300,105 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
     }
     t.finish(lane);
     __syncthreads();
-    block_bitonic_desc(bufs, 8 * 2 * kp);
-    Bm25Key* out = cand + ((size_t)qi * gridDim.x + blockIdx.x) * kp;
-    for (int i = threadIdx.x; i < kp; i += kBmThreads) out[i] = bufs[i];
+    if (warp == 0) {                                 // fold the other warps' lists into warp 0's
+        for (int w = 1; w < kBmWarps; ++w) {
+            const Bm25Key* other = bufs + (size_t)w * 2 * kp;
+            for (int i0 = 0; i0 < kp; i0 += 32) {
+                const int i = i0 + lane;
+                Bm25Key key{0ull, 0u, 0u};
+                if (i < kp) key = other[i];
+                t.offer(key, lane);
+            }
+        }
+        t.finish(lane);
+        Bm25Key* out = cand + ((size_t)qi * gridDim.x + blockIdx.x) * kp;
+        for (int i = lane; i < kp; i += 32) out[i] = t.buf[i];
+    }
 }
 
-// per-query merge of the range lists (grid = queries)
+// per-query merge of the range lists (grid = queries).  Every list is sorted descending, so the k-th
+// largest list HEAD is a valid lower bound of the global k-th score (k distinct rows reach it): only list
+// prefixes >= that bound can matter, which is k + a handful of entries instead of n_lists * kp.
+constexpr int kBmMaxHeads = 2048;
+constexpr int kBmCollect = 1024;
+
 __global__ void __launch_bounds__(256)
 bm25_select_batch_kernel(const Bm25Key* __restrict__ cand, int n_lists, int kp, int k, int32_t* out_rows,
                          double* out_scores, int32_t* out_counts) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
-    Bm25Key* bufs = reinterpret_cast<Bm25Key*>(sm_raw);      // 8 * 2 * kp
-    __shared__ int s_count;
+    Bm25Key* s_keys = reinterpret_cast<Bm25Key*>(sm_raw);     // max(kBmMaxHeads, 16 * kp) entries
+    __shared__ int s_n;
+    __shared__ Bm25Key s_thr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x;
     const Bm25Key* src = cand + (size_t)qi * n_lists * kp;
-    WarpTopKT<Bm25Key> t;
-    t.init(bufs + (size_t)warp * 2 * kp, kp, lane);
-    const int64_t total = (int64_t)n_lists * kp;
-    const int64_t n_iter = (total + 255) / 256;
-    for (int64_t it = 0; it < n_iter; ++it) {
-        const int64_t i = it * 256 + threadIdx.x;
-        Bm25Key key{0ull, 0u, 0u};
-        if (i < total) key = src[i];
-        t.offer(key, lane);
+    bool exhaustive = n_lists > kBmMaxHeads;
+    int n = 0;
+    if (!exhaustive) {
+        int nsort = 32;
+        while (nsort < n_lists) nsort <<= 1;
+        for (int l = threadIdx.x; l < nsort; l += blockDim.x) {
+            Bm25Key h{0ull, 0u, 0u};
+            if (l < n_lists) h = src[(size_t)l * kp];
+            s_keys[l] = h;
+        }
+        block_bitonic_desc(s_keys, nsort);
+        if (threadIdx.x == 0) {
+            s_thr = k <= nsort ? s_keys[k - 1] : Bm25Key{0ull, 0u, 0u};     // empty key == no bound
+            s_n = 0;
+        }
+        __syncthreads();
+        const Bm25Key thr = s_thr;
+        __syncthreads();
+        // walk every list while its entries reach the bound
+        for (int l = threadIdx.x; l < n_lists; l += blockDim.x) {
+            const Bm25Key* lp = src + (size_t)l * kp;
+            for (int i = 0; i < kp; ++i) {
+                const Bm25Key e = lp[i];
+                if (e.s == 0ull || e < thr) break;
+                const int slot = atomicAdd(&s_n, 1);
+                if (slot < kBmCollect) s_keys[slot] = e;
+            }
+        }
+        __syncthreads();
+        n = s_n;
+        if (n > kBmCollect) {
+            exhaustive = true;                 // > 1024 entries at the bound (mass ties): take the full merge
+        } else {
+            int ns2 = 32;
+            while (ns2 < n) ns2 <<= 1;
+            for (int i = n + threadIdx.x; i < ns2; i += blockDim.x) s_keys[i] = Bm25Key{0ull, 0u, 0u};
+            block_bitonic_desc(s_keys, ns2);
+        }
     }
-    t.finish(lane);
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    block_bitonic_desc(bufs, 8 * 2 * kp);
-    int local = 0;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) local += (bufs[i].s != 0ull);
-    if (local) atomicAdd(&s_count, local);
-    __syncthreads();
-    const int nout = s_count;
+    if (exhaustive) {
+        __syncthreads();
+        WarpTopKT<Bm25Key> t;
+        t.init(s_keys + (size_t)warp * 2 * kp, kp, lane);
+        const int64_t total = (int64_t)n_lists * kp;
+        const int64_t n_iter = (total + 255) / 256;
+        for (int64_t it = 0; it < n_iter; ++it) {
+            const int64_t i = it * 256 + threadIdx.x;
+            Bm25Key key{0ull, 0u, 0u};
+            if (i < total) key = src[i];
+            t.offer(key, lane);
+        }
+        t.finish(lane);
+        __syncthreads();
+        block_bitonic_desc(s_keys, 8 * 2 * kp);
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        int local = 0;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) local += (s_keys[i].s != 0ull);
+        if (local) atomicAdd(&s_n, local);
+        __syncthreads();
+        n = s_n;
+    }
+    const int nout = n < k ? n : k;
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
         const bool ok = i < nout;
-        out_rows[(size_t)qi * k + i] = ok ? (int32_t)(~bufs[i].nrow) : -1;
-        out_scores[(size_t)qi * k + i] = ok ? __longlong_as_double((long long)bufs[i].s) : 0.0;
+        out_rows[(size_t)qi * k + i] = ok ? (int32_t)(~s_keys[i].nrow) : -1;
+        out_scores[(size_t)qi * k + i] = ok ? __longlong_as_double((long long)s_keys[i].s) : 0.0;
     }
     if (threadIdx.x == 0) out_counts[qi] = nout;
 }
@@ -335,7 +421,8 @@ cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, co
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    size_t smem2 = (size_t)8 * 2 * kp * sizeof(Bm25Key);
+    const size_t entries = (size_t)std::max(kBmMaxHeads, 16 * kp);
+    const size_t smem2 = entries * sizeof(Bm25Key);
     if (smem2 > 48 * 1024) {
         e = cudaFuncSetAttribute(bm25_select_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e != cudaSuccess) return e;

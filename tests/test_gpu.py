@@ -551,3 +551,33 @@ def test_batch_larger_than_one_launch_is_sliced():
     er, es, ec = c_oracle.dense_topk(q[pick], raw_rows(c.download(), no.DT_BF16), no.DT_BF16, 5)
     assert rows[pick].tolist() == er.tolist() and np.array_equal(scores[pick], es)
     c.close()
+
+
+def test_bm25_mass_ties_and_many_ranges():
+    """> 1024 documents tie for the best BM25 score (identical documents): ties must resolve to the lowest rows;
+    also exercises a corpus with many 4096-row ranges."""
+    from b200rag.bm25 import DeviceBM25, Postings
+    n_docs = 30000
+    g = np.random.default_rng(8)
+    docs = [g.integers(10, 400, size=g.integers(5, 30)) for _ in range(n_docs)]
+    same = np.array([1, 2, 3, 3, 7], dtype=np.int64)
+    dup = np.sort(g.choice(n_docs, size=2500, replace=False))
+    for r in dup:
+        docs[r] = same.copy()
+    # relabel to first-seen order
+    flat = np.concatenate(docs)
+    uniq, first = np.unique(flat, return_index=True)
+    remap = np.full(int(flat.max()) + 1, -1, dtype=np.int64)
+    remap[uniq[np.argsort(first)]] = np.arange(len(uniq))
+    docs = [remap[d] for d in docs]
+    p = Postings.from_term_ids(docs, n_terms=len(uniq))
+    o = no.CsrBM25(docs)
+    ix = DeviceBM25(p)
+    q = remap[np.array([3, 7, 1])].astype(np.int32)
+    for k in (10, 50, 224):
+        rows, scores, counts = ix.search_ids([q, q[:1]], k)
+        for i, qt in enumerate([q, q[:1]]):
+            er, es = o.search(qt.tolist(), k)
+            assert rows[i, :counts[i]].tolist() == er.tolist() and np.array_equal(scores[i, :counts[i]], es)
+    assert rows[0, :10].tolist() == dup[:10].tolist()
+    ix.close()
