@@ -18,11 +18,13 @@
 //               select of tile i overlaps the MMAs of tile i+1) and run the fused select.
 //
 // Fused select, two launches of the same kernel:
-//   SAMPLE pass  over a strided ~4/kp fraction of the row tiles: every thread keeps the 16 best
-//                scores of its query in registers; merged per query, the 16th best sample score
-//                tau_q is a VALID lower bound of the corpus-wide 16th best score.
-//   MAIN pass    over all tiles: one compare per score against tau_q; the (few hundred per query)
-//                survivors are appended to small per-(query, CTA) lists in global memory (L2).
+//   SAMPLE pass  over a ~1/kp fraction of the rows (strided tiles, column-granular): every thread keeps
+//                the 8 best scores of its query in registers; merged per query, the 8th best sample
+//                score tau_q is a VALID lower bound of the corpus-wide 8th best score.
+//   MAIN pass    over all tiles (row tile outer, query block inner: a corpus tile is fetched from HBM
+//                once and re-read from L2 by the other query blocks): a branch-free compare mask per
+//                32-column chunk against tau_q; the ~8*kp survivors per query are appended to small
+//                per-(query, CTA) lists in global memory (L2).
 //                Everything with filter score >= tau_q is captured, so the candidate set provably
 //                contains the top-k unless a list overflows (flagged -> exact fallback pass).
 //
@@ -31,7 +33,7 @@
 // The result is only a FILTER: dense_select.cu re-scores the survivors with the canonical fp64 dot
 // product over the stored values and checks the margin against the rigorous filter error bound.
 //
-// Algorithmic work: 2 * B * n * dim flops per call; HBM bytes: ceil(B/128) passes over the bf16 rows.
+// Algorithmic work: 2 * B * n * dim flops per call; HBM bytes: ONE pass over the bf16 rows (+ the sample).
 #include <cuda.h>
 
 #include "common.cuh"
