@@ -187,6 +187,40 @@ class DeviceCollection:
                     self.corpus.overwrite(r, l2_normalize_rows(np.asarray(embeddings[j], dtype=np.float32)))
             self._where.invalidate()
 
+    # ---- persistence: flat export / import of the device-resident store -----------
+    def save(self, directory):
+        """rows.npy (stored values widened to fp32 — exact for bf16/fp16), ids.json, documents.json,
+        metadatas.json, manifest.json"""
+        import json
+        import os
+        with self._lock:
+            os.makedirs(directory, exist_ok=True)
+            np.save(os.path.join(directory, "rows.npy"), self.corpus.download())
+            for name, obj in (("ids", self._ids), ("documents", self._docs), ("metadatas", self._metas)):
+                with open(os.path.join(directory, f"{name}.json"), "w", encoding="utf-8") as f:
+                    json.dump(obj, f, ensure_ascii=False)
+            with open(os.path.join(directory, "manifest.json"), "w", encoding="utf-8") as f:
+                json.dump({"name": self.name, "dim": self.dim, "dtype": self.corpus.dtype, "count": len(self._ids),
+                           "metadata": self.metadata, "format": 1}, f)
+
+    @classmethod
+    def load(cls, directory, dtype=None):
+        import json
+        import os
+        with open(os.path.join(directory, "manifest.json"), "r", encoding="utf-8") as f:
+            man = json.load(f)
+        col = cls(name=man["name"], dim=man["dim"], dtype=man["dtype"] if dtype is None else dtype,
+                  metadata=man.get("metadata"), capacity=man["count"])
+        rows = np.load(os.path.join(directory, "rows.npy"), mmap_mode="r")
+        step = 65536
+        for s in range(0, rows.shape[0], step):          # stored values: already normalised and quantised
+            col.corpus.append(np.ascontiguousarray(rows[s:s + step], dtype=np.float32))
+        for name, attr in (("ids", "_ids"), ("documents", "_docs"), ("metadatas", "_metas")):
+            with open(os.path.join(directory, f"{name}.json"), "r", encoding="utf-8") as f:
+                setattr(col, attr, json.load(f))
+        col._pos = {i: r for r, i in enumerate(col._ids)}
+        return col
+
     # ---- read path --------------------------------------------------------
     def count(self):
         return len(self._ids)

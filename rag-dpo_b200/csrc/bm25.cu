@@ -6,9 +6,11 @@
 //
 // Bit-parity rules: fp64 throughout, numpy's evaluation order,
 // no FMA contraction (explicit __dmul_rn/__ddiv_rn/__dadd_rn), and the score of
-// a row is accumulated token by token in query order (one launch per token, so
-// the order is the stream order).  Within a token every posting hits a
-// distinct row, so no atomics are needed for the accumulation.
+// a row is accumulated token by token in query order.  Within a token every
+// posting hits a distinct row, so no atomics are needed for the accumulation.
+// rag_bm25_search uses the fused bm25_range_kernel (scores of a 4096-row range in
+// shared memory); rag_bm25_scores (full get_scores vector) uses one
+// bm25_accumulate_kernel launch per token over a global accumulator.
 //
 // Algorithmic bytes per query: sum over query tokens of df(t) * (4 + 8)
 // (row id + fp64 impact) + 16 * touched rows (accumulator read-modify-write).
@@ -77,110 +79,11 @@ struct Bm25Key {
     __device__ __forceinline__ bool operator>(const Bm25Key& o) const { return o < *this; }
 };
 
-constexpr int kHarvestWarps = 8;
-
-// Walk the postings of the query's distinct tokens; the first thread to reach a
-// row claims its final score with an atomic exchange (which also zeroes the
-// accumulator for the next query), keeps it if > 0 and allowed, and offers it
-// to the warp's running top-KP.
-__global__ void __launch_bounds__(kHarvestWarps * 32)
-bm25_harvest_kernel(const int32_t* __restrict__ post_row, const int64_t* __restrict__ ranges, int n_ranges,
-                    const uint8_t* __restrict__ allow, unsigned long long* __restrict__ score_bits, int kp,
-                    Bm25Key* __restrict__ cand) {
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    Bm25Key* bufs = reinterpret_cast<Bm25Key*>(sm_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpTopKT<Bm25Key> t;
-    t.init(bufs + (size_t)warp * 2 * kp, kp, lane);
-    const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    for (int ri = 0; ri < n_ranges; ++ri) {
-        const int64_t lo = ranges[2 * ri], hi = ranges[2 * ri + 1];
-        const int64_t n_iter = (hi - lo + nthreads - 1) / nthreads;
-        for (int64_t it = 0; it < n_iter; ++it) {
-            const int64_t p = lo + it * nthreads + gthread;
-            Bm25Key key{0ull, 0u, 0u};
-            if (p < hi) {
-                const uint32_t r = (uint32_t)post_row[p];
-                const unsigned long long old = atomicExch(&score_bits[r], 0ull);
-                if (old != 0ull && __longlong_as_double((long long)old) > 0.0 && bitmap_test(allow, r)) {
-                    key.s = old;
-                    key.nrow = ~r;
-                }
-            }
-            t.offer(key, lane);
-        }
-    }
-    t.finish(lane);
-    Bm25Key* out = cand + ((size_t)blockIdx.x * kHarvestWarps + warp) * kp;
-    for (int i = lane; i < kp; i += 32) out[i] = t.buf[i];
-}
-
-__global__ void __launch_bounds__(256)
-bm25_select_kernel(const Bm25Key* __restrict__ cand, int n_lists, int kp, int k, int32_t* out_rows, double* out_scores,
-                   int32_t* out_count) {
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    Bm25Key* bufs = reinterpret_cast<Bm25Key*>(sm_raw);      // 8 * 2 * kp
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpTopKT<Bm25Key> t;
-    t.init(bufs + (size_t)warp * 2 * kp, kp, lane);
-    const int64_t total = (int64_t)n_lists * kp;
-    const int64_t n_iter = (total + 255) / 256;
-    for (int64_t it = 0; it < n_iter; ++it) {
-        const int64_t i = it * 256 + threadIdx.x;
-        Bm25Key key{0ull, 0u, 0u};
-        if (i < total) key = cand[i];
-        t.offer(key, lane);
-    }
-    t.finish(lane);
-    __syncthreads();
-    block_bitonic_desc(bufs, 8 * 2 * kp);
-    __shared__ int s_count;
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    int local = 0;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) local += (bufs[i].s != 0ull);
-    if (local) atomicAdd(&s_count, local);
-    __syncthreads();
-    const int nout = s_count;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const bool ok = i < nout;
-        out_rows[i] = ok ? (int32_t)(~bufs[i].nrow) : -1;
-        out_scores[i] = ok ? __longlong_as_double((long long)bufs[i].s) : 0.0;
-    }
-    if (threadIdx.x == 0) *out_count = nout;
-}
-
 int bm25_harvest_grid(int64_t total_postings, int sm_count) {
-    int64_t g = (total_postings + kHarvestWarps * 32 * 8 - 1) / (kHarvestWarps * 32 * 8);
+    int64_t g = (total_postings + 2047) / 2048;
     if (g > sm_count * 2) g = sm_count * 2;
     if (g < 1) g = 1;
     return (int)g;
-}
-
-cudaError_t bm25_harvest_launch(const Bm25Device& ix, const int64_t* d_ranges, int n_ranges, const uint8_t* allow,
-                                int kp, int grid, void* cand, cudaStream_t st) {
-    size_t smem = (size_t)kHarvestWarps * 2 * kp * sizeof(Bm25Key);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(bm25_harvest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    bm25_harvest_kernel<<<grid, kHarvestWarps * 32, smem, st>>>(ix.post_row, d_ranges, n_ranges, allow,
-                                                               reinterpret_cast<unsigned long long*>(ix.score), kp,
-                                                               reinterpret_cast<Bm25Key*>(cand));
-    return cudaGetLastError();
-}
-
-cudaError_t bm25_select_launch(const void* cand, int n_lists, int kp, int k, int32_t* out_rows, double* out_scores,
-                               int32_t* out_count, cudaStream_t st) {
-    size_t smem = (size_t)8 * 2 * kp * sizeof(Bm25Key);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(bm25_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    bm25_select_kernel<<<1, 256, smem, st>>>(reinterpret_cast<const Bm25Key*>(cand), n_lists, kp, k, out_rows,
-                                             out_scores, out_count);
-    return cudaGetLastError();
 }
 
 // zero the accumulator on the rows a query touched (used after rag_bm25_scores,

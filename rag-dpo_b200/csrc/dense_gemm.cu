@@ -119,7 +119,7 @@ constexpr int kSampleM = 8;       // order statistic taken from the sample pass
 // tiles of this CTA: t = blockIdx.x + i * gridDim.x, i = 0, step, 2*step, ... (at most max_tiles)
 template <int MODE>
 struct WorkIter {
-    int64_t n_tiles, i;
+    int64_t n_tiles, i, i_first;
     int step, max_tiles, n_qblocks;
     int taken, qb;
     bool started;
@@ -128,7 +128,14 @@ struct WorkIter {
         step = MODE == 0 ? p.sample_step : 1;
         max_tiles = MODE == 0 ? p.sample_tiles : 0x7fffffff;
         n_qblocks = p.n_qblocks;
-        i = 0; taken = 0; qb = 0; started = false;
+        // the sample of CTA c starts at a pseudo-random one of its tiles, so that the union of the CTAs'
+        // samples is spread over the whole corpus instead of being its first rows
+        i_first = 0;
+        if (MODE == 0) {
+            const int64_t span = n_tiles / gridDim.x - (int64_t)(max_tiles - 1) * step;   // tiles every CTA has
+            if (span > 1) i_first = (int64_t)((blockIdx.x * 2654435761u) % (uint32_t)span);
+        }
+        i = i_first; taken = 0; qb = 0; started = false;
     }
     __device__ __forceinline__ bool tile_ok() const {
         return blockIdx.x + i * gridDim.x < n_tiles && taken < max_tiles;
@@ -139,7 +146,7 @@ struct WorkIter {
             started = true;
         } else if (MODE == 0) {
             i += step; ++taken;
-            if (!tile_ok()) { i = 0; taken = 0; ++qb; }
+            if (!tile_ok()) { i = i_first; taken = 0; ++qb; }
         } else {
             if (++qb == n_qblocks) { qb = 0; i += step; ++taken; }
         }

@@ -138,13 +138,7 @@ cudaError_t bm25_impact_launch(const int32_t* post_row, const int32_t* post_tf, 
                                double avgdl, double k1, double b, double* impact, cudaStream_t st);
 // one token of one query: score[row] += w * impact[p] over postings [lo, hi)
 cudaError_t bm25_accumulate_launch(const Bm25Device& ix, int64_t lo, int64_t hi, double w, cudaStream_t st);
-// harvest the touched rows (ranges = [lo,hi) pairs of the query's distinct tokens):
-// claim + zero the accumulator, keep score > 0 and allowed rows, per-warp top-kp.
-int bm25_harvest_grid(int64_t total_postings, int sm_count);     // lists = grid * 8
-cudaError_t bm25_harvest_launch(const Bm25Device& ix, const int64_t* d_ranges, int n_ranges, const uint8_t* allow,
-                                int kp, int grid, void* cand, cudaStream_t st);
-cudaError_t bm25_select_launch(const void* cand, int n_lists, int kp, int k, int32_t* out_rows, double* out_scores,
-                               int32_t* out_count, cudaStream_t st);
+int bm25_harvest_grid(int64_t total_postings, int sm_count);     // grid for the reset pass
 cudaError_t bm25_reset_launch(const Bm25Device& ix, const int64_t* d_ranges, int n_ranges, int grid, cudaStream_t st);
 size_t bm25_key_bytes();
 // fused search: grid (row ranges of 4096, queries); fp64 accumulators in shared memory, tokens in order

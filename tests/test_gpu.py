@@ -195,6 +195,36 @@ def test_synthetic_fill_matches_numpy_twin():
         c.close()
 
 
+def test_collection_save_load_roundtrip(e2e_data, tmp_path):
+    from b200rag import DeviceCollection
+    gold, emb, table = e2e_data
+    for dtype in ("bf16", "f32"):
+        a = DeviceCollection(dim=emb.shape[1], dtype=dtype)
+        helpers.fill(a, gold["chunks"], emb)
+        a.save(str(tmp_path / dtype))
+        b = DeviceCollection.load(str(tmp_path / dtype))
+        assert b.count() == a.count() and np.array_equal(a.corpus.download(), b.corpus.download())
+        qs = [list(map(float, v)) for v in list(table.values())[:3]]
+        assert a.query(query_embeddings=qs, n_results=20, where={"source": "CNIL"}) == \
+            b.query(query_embeddings=qs, n_results=20, where={"source": "CNIL"})
+
+
+def test_selective_where_filters_through_the_tensor_core_path():
+    from b200rag import DeviceCorpus
+    n, d = 300_000, 256
+    c = DeviceCorpus(d, "bf16")
+    c.fill_synthetic(seed=9, nrows=n)
+    q = helpers.synth_unit(9, d, seed=10)
+    g = np.random.default_rng(0)
+    for frac in (0.0005, 0.02, 0.5):
+        allow = g.random(n) < frac
+        check_topk(c, q, 10, no.DT_BF16, allow)
+    allow = np.zeros(n, bool)
+    allow[250_000:250_300] = True                       # a contiguous island of allowed rows
+    check_topk(c, q, 50, no.DT_BF16, allow)
+    c.close()
+
+
 # ---------------------------------------------------------------- BM25 ----
 def test_bm25_golden_from_reference_index():
     from b200rag import DeviceCollection, DeviceChunkBM25Index
