@@ -218,10 +218,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from b200rag import _lib, synth
     from b200rag.sharded import ShardedDenseIndex
-    n_local, d, k, B = ROWS_PER_GPU, DIM, TOPK, args.batch
+    n_local, d, k, B = args.rows_per_gpu, DIM, args.k, args.batch
+    esz = 4 if args.dtype == "f32" else 2
     n_total = n_local * world
     dev = torch.device("cuda", local)
-    index = ShardedDenseIndex(d, n_total, dtype="f32", device=dev)
+    index = ShardedDenseIndex(d, n_total, dtype=args.dtype, device=dev)
     index.fill_synthetic(CORPUS_SEED)
     corpus = index.corpus
     # host-side query / result buffers live in page-locked memory (what a serving process would do)
@@ -335,13 +336,15 @@ def run_b200(args):
     # HBM-bound: algorithmic bytes = rows * dim * sizeof(dtype) per launch (the shard is read once).
     tc_min = int(os.environ.get("B200RAG_TC_MIN_BATCH", "2"))
     main_ms = float(np.mean(kern_ms))
-    bytes_per_launch = n_local * d * 4
+    bytes_per_launch = n_local * d * esz
     if B >= tc_min:
         flops = 2.0 * B * n_local * d
         ach = flops / (main_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "dense_gemm_topk_kernel (tcgen05 bf16 contraction + fused top-k)",
                 "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                "frac_of_sustained": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac_of_sustained": ach / peaks["bf16_tflops_sustained"],
+                # dram__bytes_read + write of the main pass, ncu --set full (profiles/r1_final_ncu_full_raw.csv)
+                "traffic": 2.40e9 if (B == 1024 and n_local == 1_000_000 and args.dtype == "f32") else None,
                 "peak_source": peaks["source"] + " (burst cuBLAS bf16; kernel timed alone)",
                 "launches_per_step": 1, "avg_launch_ms": main_ms, "algorithmic_flops_per_launch": flops}
     else:
@@ -353,7 +356,7 @@ def run_b200(args):
                 "launches_per_step": n_scan_launches, "avg_launch_ms": scan_ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch}
     b1_ms = float(np.median([v[0] for v in b1_stage_ms]))
-    shadow_bytes = n_local * d * 2
+    shadow_bytes = n_local * d * 2           # batch-1 default path: bf16 rows (the corpus itself or its shadow)
     achieved_b1 = shadow_bytes / (b1_ms / 1e3) / 1e9
     scan_ms = float(np.median([v[0] for v in scan_stage_ms]))
     achieved_scan = bytes_per_launch / (scan_ms / 1e3) / 1e9
@@ -364,16 +367,18 @@ def run_b200(args):
         return
     line = {
         "metric": METRIC,
-        "value": qps * world, "unit": "queries/s (1M-row-corpus equivalents: corpus = n_gpus x 1M rows)",
+        "value": qps * world * (n_local / 1e6), "unit": "queries/s (1M-row-corpus equivalents: corpus = n_gpus x 1M rows)",
         "queries_per_s": qps,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"dense exact top-{k}: {n_local} x {d} fp32 rows per GPU ({n_total} total), "
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"dense exact top-{k}: {n_local} x {d} {args.dtype} rows per GPU ({n_total} total), "
                                f"batch {B} queries per step",
                    "corpus_rows": n_total, "rows_per_gpu": n_local, "dim": d, "k": k, "batch": B,
                    "parallelism": f"row-shard x{world} + all-gather merge" if world > 1 else "single GPU",
-                   "l2": "corpus shard (4.1 GB) is larger than L2 (126 MB): every step re-streams it from HBM"},
-        "e2e": {"value": qps_e2e * world, "unit": "queries/s (1M-row-corpus equivalents)", "queries_per_s": qps_e2e,
+                   "l2": f"corpus shard ({n_local * d * esz / 1e9:.1f} GB) is larger than L2 (126 MB): every step "
+                         f"re-streams it from HBM"},
+        "e2e": {"value": qps_e2e * world * (n_local / 1e6), "unit": "queries/s (1M-row-corpus equivalents)",
+                "queries_per_s": qps_e2e,
                 "h2d_bytes_per_step": int(B * d * 4), "d2h_bytes_per_step": int(B * k * 12 + B * 4)},
         "gpu_launches": int(launches),
         "latency_b1": {"device_ms_p50": float(np.percentile(lat, 50)), "device_ms_p99": float(np.percentile(lat, 99)),
@@ -381,19 +386,22 @@ def run_b200(args):
                        "host_call_ms_p99": float(np.percentile(lat_host, 99)),
                        "stages_ms": {"filter": b1_ms, "merge": float(np.median([v[1] for v in b1_stage_ms])),
                                      "refine": float(np.median([v[2] for v in b1_stage_ms]))},
-                       "roofline": {"bound": "hbm", "kernel": "dense_gemm_topk_kernel over the bf16 shadow (sample + main)",
+                       "roofline": {"bound": "hbm",
+                                    "kernel": ("dense_scan_kernel over the bf16 rows" if args.dtype == "bf16" else
+                                               "dense_gemm_topk_kernel over the bf16 shadow (sample + main)"),
                                     "achieved": achieved_b1, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": achieved_b1 / peaks["hbm_gbs"], "traffic": None,
                                     "algorithmic_bytes_per_launch": shadow_bytes},
-                       "scan_fp32_rows": {"device_ms_p50": float(np.percentile(lat_scan, 50)), "scan_kernel_ms": scan_ms,
-                                          "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel over the fp32 rows",
+                       "scan_path": {"device_ms_p50": float(np.percentile(lat_scan, 50)), "scan_kernel_ms": scan_ms,
+                                          "roofline": {"bound": "hbm", "kernel": f"dense_scan_kernel over the {args.dtype} rows",
                                                        "achieved": achieved_scan, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                       "frac": achieved_scan / peaks["hbm_gbs"], "traffic": 4.096e9,
+                                                       "frac": achieved_scan / peaks["hbm_gbs"],
+                                                       "traffic": 4.096e9 if (args.dtype == "f32" and n_local == 1_000_000) else None,
                                                        "algorithmic_bytes_per_launch": bytes_per_launch}}},
         "roofline": roof,
         "clocks": clock_summary,
     }
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and n_local <= 2_000_000:
         x = corpus.download()
         sample_b = min(B, 64)
         cqps, cms, cdone = time_cpu(x, q_host, k, sample_b, 6, 1, budget_s=25.0)
@@ -413,6 +421,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU,
+                    help="rows per GPU shard (default: BASELINE config 2; 12500000 with --dtype bf16 = config 5)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
+    ap.add_argument("--k", type=int, default=TOPK)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
