@@ -523,8 +523,8 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
         RAG_TRY(g.q16.ensure((size_t)bpad * c->dim * 2));
         RAG_TRY(g.q_resid.ensure((size_t)bpad * 4));
         const int sm = gemm_sample_m();
-        RAG_TRY(g.cand.ensure((size_t)bpad * p.n_lists * p.list_cap * 8));
-        RAG_TRY(g.cand_cnt.ensure((size_t)bpad * p.n_lists * 4));
+        RAG_TRY(g.cand.ensure((size_t)bpad * p.list_cap * 8));
+        RAG_TRY(g.cand_cnt.ensure((size_t)bpad * 4));
         RAG_TRY(g.sample_keys.ensure((size_t)bpad * p.n_lists * sm * 8));
         RAG_TRY(g.tau_keys.ensure((size_t)bpad * sm * 8));
         RAG_TRY(g.overflow.ensure((size_t)bpad * 4));
@@ -535,19 +535,20 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
         CU_TRY(query_prep_launch(q_dev, B, bpad, c->dim, g.q16.p, g.q_resid.as<float>(), g.stream));
         ++g.n_launch;
         q_resid = g.q_resid.as<float>();
-        CU_TRY(cudaMemsetAsync(g.cand_cnt.p, 0, (size_t)bpad * p.n_lists * 4, g.stream));
+        CU_TRY(cudaMemsetAsync(g.cand_cnt.p, 0, (size_t)bpad * 4, g.stream));
         rec(0);
         if (p.use_sample) {
             // sample pass -> per-query threshold (16th best sample score)
             CU_TRY(gemm_launch(p, 0, g.q16.p, x16, grid, smem, g.stream));
-            CU_TRY(merge_launch(g.sample_keys.as<uint64_t>(), nullptr, B, p.n_lists, sm, sm,
+            CU_TRY(merge_launch(g.sample_keys.as<uint64_t>(), nullptr, 0, B, p.n_lists, sm, sm,
                                 g.tau_keys.as<uint64_t>(), nullptr, g.stream));
             g.n_launch += 2;
         }
         CU_TRY(gemm_launch(p, 1, g.q16.p, x16, grid, smem, g.stream));
         ++g.n_launch;
         rec(1);
-        CU_TRY(merge_launch(g.cand.as<uint64_t>(), g.cand_cnt.as<int32_t>(), B, p.n_lists, p.list_cap, kp,
+        // the per-query list is one contiguous block: let the 8 merge warps split it
+        CU_TRY(merge_launch(g.cand.as<uint64_t>(), g.cand_cnt.as<int32_t>(), 1, B, 8, p.list_cap / 8, kp,
                             g.top.as<uint64_t>(), g.overflow.as<int32_t>(), g.stream));
         ++g.n_launch;
         tau_keys = p.tau_keys;
@@ -581,7 +582,7 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
             ++g.n_launch;
         }
         rec(1);
-        CU_TRY(merge_launch(g.cand.as<uint64_t>(), nullptr, B, n_lists, kp, kp, g.top.as<uint64_t>(), nullptr,
+        CU_TRY(merge_launch(g.cand.as<uint64_t>(), nullptr, 0, B, n_lists, kp, kp, g.top.as<uint64_t>(), nullptr,
                             g.stream));
         ++g.n_launch;
     }

@@ -23,10 +23,10 @@
 //                score tau_q is a VALID lower bound of the corpus-wide 8th best score.
 //   MAIN pass    over all tiles (row tile outer, query block inner: a corpus tile is fetched from HBM
 //                once and re-read from L2 by the other query blocks): a branch-free compare mask per
-//                32-column chunk against tau_q; the ~8*kp survivors per query are appended to small
-//                per-(query, CTA) lists in global memory (L2).
+//                32-column chunk against tau_q; the ~8*kp survivors per query are appended (one atomic
+//                slot claim each) to that query's candidate list in global memory (L2).
 //                Everything with filter score >= tau_q is captured, so the candidate set provably
-//                contains the top-k unless a list overflows (flagged -> exact fallback pass).
+//                contains the top-k unless the list overflows (flagged -> exact fallback pass).
 //
 // Both operands are bf16 (the corpus itself, or its bf16 shadow for fp32/fp16 corpora; queries are
 // rounded to bf16 by query_prep_kernel which also returns the exact norm of the rounding residual).
@@ -249,7 +249,6 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int my = lg * 32 + lane;           // my query inside the query block == my TMEM lane
         const int n_chunks = MODE == 0 ? p.sample_chunks : GT_N / 32;
         float* s_tau = reinterpret_cast<float*>(bars + 24);            // [n_qblocks][128]
-        int* s_cnt = reinterpret_cast<int*>(s_tau + p.n_qblocks * GT_M);
         if (MODE == 1) {
             for (int b = 0; b < p.n_qblocks; ++b) {
                 const int q = b * GT_M + my;
@@ -262,7 +261,6 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     }
                 }
                 s_tau[b * GT_M + my] = tau;
-                s_cnt[b * GT_M + my] = 0;
             }
         }
         uint32_t it = 0;
@@ -282,8 +280,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         for (; work.next(t, qb); ++it) {
             const int q = qb * GT_M + my;
             float tau = 0.f;
-            int cnt = 0;
             uint64_t* my_list = nullptr;
+            int* my_cnt = nullptr;
             if (MODE == 0) {
                 if (qb != cur_qb) {
                     if (cur_qb >= 0) flush_sample(cur_qb);
@@ -293,8 +291,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
             } else {
                 tau = s_tau[qb * GT_M + my];
-                cnt = s_cnt[qb * GT_M + my];
-                my_list = p.cand + ((size_t)q * p.n_lists + blockIdx.x) * p.list_cap;
+                my_list = p.cand + (size_t)q * p.list_cap;      // ONE list per query, shared by all CTAs
+                my_cnt = p.cand_cnt + q;
             }
             const uint32_t buf = it & 1;
             mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
@@ -332,8 +330,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                                     best[i] = hi;
                                 }
                             } else {
-                                if (cnt < p.list_cap) my_list[cnt] = make_key(s, row);
-                                ++cnt;                // counts past the capacity flag an overflow
+                                const int slot = atomicAdd(my_cnt, 1);      // counts past the capacity flag an overflow
+                                if (slot < p.list_cap) my_list[slot] = make_key(s, row);
                             }
                         }
                     }
@@ -342,15 +340,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-            if (MODE == 1) s_cnt[qb * GT_M + my] = cnt;
         }
         if (MODE == 0 && cur_qb >= 0) flush_sample(cur_qb);
-        if (MODE == 1) {
-            for (int b = 0; b < p.n_qblocks; ++b) {
-                const int q = b * GT_M + my;
-                if (q < p.n_queries) p.cand_cnt[(size_t)q * p.n_lists + blockIdx.x] = s_cnt[b * GT_M + my];
-            }
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -466,7 +457,7 @@ int gemm_max_batch() { return kMaxQBlocks * GT_M; }
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     p.n_qblocks = gemm_padded_queries(p.n_queries) / GT_M;
     if (p.n_qblocks > kMaxQBlocks) return 0;
-    const size_t tail = 256 + (size_t)p.n_qblocks * GT_M * 8;      // barriers + per-query tau / count
+    const size_t tail = 256 + (size_t)p.n_qblocks * GT_M * 4;      // barriers + per-query tau
     int stages = (int)((smem_limit - 1024 - (long)tail) / GT_STAGE_BYTES);
     if (stages > 4) stages = 4;
     if (stages < 2) return 0;
@@ -476,16 +467,11 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     *grid_out = grid;
     p.n_lists = grid;
     // Sample pass: the m-th best (m = kSampleM = 8) of a sample that holds a fraction f of the rows lets
-    // ~m/f rows per query through the main pass; aim for f = 1/kp (about 8*kp survivors, ~8*kp/148 per
-    // (query, CTA) list), in units of 32 columns.
+    // ~m/f rows per query through the main pass; aim for f = 1/kp (about 8*kp survivors per query),
+    // column-granular.
     const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
     const int64_t rows_per_cta = tiles_per_cta * GT_N;
-    if (tiles_per_cta <= 1) {
-        // tiny shard: no threshold at all, every row of the CTA's single tile is captured
-        p.use_sample = 0;
-        p.sample_tiles = 0; p.sample_step = 1; p.sample_chunks = 0; p.sample_last_mask = 0;
-        p.list_cap = GT_N;
-    } else {
+    {
         p.use_sample = 1;
         int64_t want = (rows_per_cta + p.kp - 1) / p.kp;               // sample rows per CTA
         if (want < 2) want = 2;
@@ -501,8 +487,9 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
             p.sample_last_mask = 0xffffffffu;
             p.sample_step = (int)(tiles_per_cta / p.sample_tiles > 0 ? tiles_per_cta / p.sample_tiles : 1);
         }
-        p.list_cap = 64;
     }
+    // one candidate list per query, filled by all CTAs: <= ~8*kp survivors expected, >= 4x head-room
+    p.list_cap = 32 * p.kp > 4096 ? 32 * p.kp : 4096;
     return (size_t)stages * GT_STAGE_BYTES + tail + 1024;   // + slack for the 1024-byte alignment of the ring
 }
 

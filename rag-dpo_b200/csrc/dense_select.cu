@@ -18,25 +18,32 @@ namespace b200rag {
 constexpr int kMergeWarps = 8;
 
 __global__ void __launch_bounds__(kMergeWarps * 32)
-merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int n_lists, int list_len, int kp,
-             uint64_t* __restrict__ top, int32_t* __restrict__ overflow) {
+merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
+             int list_len, int kp, uint64_t* __restrict__ top, int32_t* __restrict__ overflow) {
     extern __shared__ __align__(16) uint64_t sm_keys[];   // kMergeWarps * 2 * kp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     const uint64_t* src = cand + (size_t)b * n_lists * list_len;
-    const int32_t* cnt = counts ? counts + (size_t)b * n_lists : nullptr;
+    const int32_t* cnt = (counts && !flat_counts) ? counts + (size_t)b * n_lists : nullptr;
+    const int flat_total = (counts && flat_counts) ? counts[b] : 0;
 
-    if (overflow && cnt) {
+    if (overflow && counts) {
         int over = 0;
-        for (int l = threadIdx.x; l < n_lists; l += blockDim.x) over |= cnt[l] > list_len;
-        over = __syncthreads_or(over);
+        if (flat_counts) {
+            over = flat_total > n_lists * list_len;
+        } else {
+            for (int l = threadIdx.x; l < n_lists; l += blockDim.x) over |= cnt[l] > list_len;
+            over = __syncthreads_or(over);
+        }
         if (threadIdx.x == 0) overflow[b] = over ? 1 : 0;
     }
     WarpTopK t;
     t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
     // each warp walks whole lists (list_len is a multiple of 32): warp w takes lists w, w+8, ...
     for (int l = warp; l < n_lists; l += kMergeWarps) {
-        const int n = cnt ? min(cnt[l], list_len) : list_len;
+        int n = list_len;
+        if (cnt) n = min(cnt[l], list_len);
+        else if (flat_counts) n = max(0, min(flat_total - l * list_len, list_len));
         const uint64_t* lp = src + (size_t)l * list_len;
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + lane;
@@ -49,14 +56,14 @@ merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ coun
     for (int i = threadIdx.x; i < kp; i += blockDim.x) top[(size_t)b * kp + i] = sm_keys[i];
 }
 
-cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int B, int n_lists, int list_len, int kp,
-                         uint64_t* top, int32_t* overflow, cudaStream_t st) {
+cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int B, int n_lists, int list_len,
+                         int kp, uint64_t* top, int32_t* overflow, cudaStream_t st) {
     size_t smem = (size_t)kMergeWarps * 2 * kp * sizeof(uint64_t);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    merge_kernel<<<B, kMergeWarps * 32, smem, st>>>(cand, counts, n_lists, list_len, kp, top, overflow);
+    merge_kernel<<<B, kMergeWarps * 32, smem, st>>>(cand, counts, flat_counts, n_lists, list_len, kp, top, overflow);
     return cudaGetLastError();
 }
 

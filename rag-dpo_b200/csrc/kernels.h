@@ -44,11 +44,11 @@ struct GemmParams {
     uint64_t* sample_keys;
     // main pass (mode 1): tau_keys = merged sample (padded_B x m, sorted desc; [m-1] is the threshold)
     const uint64_t* tau_keys;
-    uint64_t* cand;          // padded_B x n_lists x list_cap keys
-    int32_t* cand_cnt;       // padded_B x n_lists survivors per list (may exceed list_cap = overflow)
+    uint64_t* cand;          // padded_B x list_cap keys: one list per query, appended to by every CTA
+    int32_t* cand_cnt;       // padded_B survivors per query (may exceed list_cap = overflow), zeroed by the caller
     // derived by gemm_plan
-    int list_cap;            // entries per (query, CTA) list
-    int use_sample;          // 0 = tiny shard: no sample pass, tau_keys = NULL, every row is captured
+    int list_cap;            // entries per query list
+    int use_sample;          // always 1 (kept for the launcher)
     int n_lists, n_stages, n_qblocks, sample_tiles, sample_step, sample_chunks;
     uint32_t sample_last_mask;   // columns of the last sample chunk that count
 };
@@ -66,11 +66,12 @@ cudaError_t shadow_launch(const void* rows, int dtype, int64_t n_rows, int dim, 
                           cudaStream_t st);
 
 // ---- dense_select.cu -------------------------------------------------------
-// merge: cand (B x n_lists x list_len keys, any order, 0 = empty; counts nullable = valid entries per
-// list) -> top (B x kp sorted desc)
-// overflow (nullable): set to 1 for queries where some counts[] entry exceeds list_len
-cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int B, int n_lists, int list_len, int kp,
-                         uint64_t* top, int32_t* overflow, cudaStream_t st);
+// merge: cand (B x n_lists x list_len keys, any order, 0 = empty) -> top (B x kp sorted desc).
+// counts: NULL (all entries valid), or per (query, list) valid entries, or — flat_counts != 0 — ONE count
+// per query for the whole contiguous n_lists*list_len block.  overflow (nullable): set to 1 for queries
+// whose count exceeds the capacity.
+cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int B, int n_lists, int list_len,
+                         int kp, uint64_t* top, int32_t* overflow, cudaStream_t st);
 // refine: canonical fp64 score of every candidate in top, sort by (score desc,
 // row asc), write the first k, and raise flag[b] when the margin check fails.
 struct RefineParams {

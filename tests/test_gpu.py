@@ -611,3 +611,25 @@ def test_bm25_mass_ties_and_many_ranges():
             assert rows[i, :counts[i]].tolist() == er.tolist() and np.array_equal(scores[i, :counts[i]], es)
     assert rows[0, :10].tolist() == dup[:10].tolist()
     ix.close()
+
+
+def test_clustered_corpus_through_the_tensor_core_path():
+    """Rows sorted by cluster (adjacent rows are near-duplicates, as chunks of one document are): every query's
+    neighbours sit in one or two row tiles, and the sample may miss the query's cluster entirely."""
+    from b200rag import DeviceCorpus, _lib
+    n_clusters, per, d = 600, 250, 256
+    g = np.random.default_rng(3)
+    centers = helpers.synth_unit(n_clusters, d, seed=4)
+    x = np.repeat(centers, per, axis=0) + 0.08 * g.standard_normal((n_clusters * per, d)).astype(np.float32)
+    x = no.l2_normalize_rows(x)
+    q = no.l2_normalize_rows(centers[g.choice(n_clusters, size=40, replace=False)] +
+                             0.05 * g.standard_normal((40, d)).astype(np.float32))
+    for dtype in ("bf16", "f32"):
+        c = DeviceCorpus(d, dtype)
+        c.append(x)
+        f0 = _lib.counters()["fallbacks"]
+        check_topk(c, q, 10, DT[dtype])
+        check_topk(c, q, 100, DT[dtype])
+        check_topk(c, q[:1], 10, DT[dtype])
+        assert _lib.counters()["fallbacks"] - f0 <= 1, "clustered rows should not push queries into the fallback pass"
+        c.close()
