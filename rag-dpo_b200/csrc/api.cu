@@ -78,7 +78,7 @@ struct Ctx {
     // scratch (device)
     DevBuf q, allow, cand, cand_cnt, sample_keys, tau_keys, overflow, q16, q_resid, top, flags, tau, nflag, o_rows, o_scores, o_counts;
     DevBuf fb_q, fb_tau, fb_counts, fb_rows, fb_scores, fb_index;
-    DevBuf bm_terms, bm_ranges, bm_cand, bm_rows, bm_scores, bm_counts, bm_allow;
+    DevBuf bm_terms, bm_ranges, bm_cand, bm_rows, bm_scores, bm_counts, bm_allow, bm_scratch, bm_index;
     DevBuf rrf_ids, rrf_w, rrf_oi, rrf_os, rrf_oc;
     DevBuf stage_f32;
 };
@@ -907,7 +907,6 @@ int rag_bm25_search(rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr
     RAG_TRY(g.bm_rows.ensure(rb));
     RAG_TRY(g.bm_scores.ensure(sb));
     RAG_TRY(g.bm_counts.ensure(cb));
-    RAG_TRY(g.bm_cand.ensure((size_t)Q * n_lists * kp * bm25_key_bytes()));
     RAG_TRY(ensure_pinned(std::max(tb + pb + ab, sb + rb + cb)));
     uint8_t* pin = reinterpret_cast<uint8_t*>(g.pinned);
     if (n_tok > 0) memcpy(pin, q_terms, (size_t)n_tok * 4);
@@ -916,11 +915,27 @@ int rag_bm25_search(rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr
     CU_TRY(cudaMemcpyAsync(g.bm_terms.p, pin, tb, cudaMemcpyHostToDevice, g.stream));
     CU_TRY(cudaMemcpyAsync(g.bm_ranges.p, pin + tb, pb, cudaMemcpyHostToDevice, g.stream));
     if (ab) CU_TRY(cudaMemcpyAsync(g.bm_allow.p, pin + tb + pb, ab, cudaMemcpyHostToDevice, g.stream));
+    const uint8_t* allow_dev = ab ? g.bm_allow.as<uint8_t>() : nullptr;
     rec(0);
-    CU_TRY(bm25_range_launch(ix->d, g.bm_terms.as<int32_t>(), g.bm_ranges.as<int32_t>(), Q,
-                             ab ? g.bm_allow.as<uint8_t>() : nullptr, kp, k, g.bm_cand.p, g.bm_rows.as<int32_t>(),
-                             g.bm_scores.as<double>(), g.bm_counts.as<int32_t>(), g.stream));
-    g.n_launch += 2;
+    const bool fast = bm25_fast_supported(ix->d.n_docs, k);
+    if (fast) {
+        // fast path in chunks that keep the fp64 score scratch under ~1.5 GB
+        int qc = (int)std::max<int64_t>(1, std::min<int64_t>(Q, (int64_t)1500000000 / (ix->d.n_docs * 8)));
+        RAG_TRY(g.bm_scratch.ensure(bm25_fast_scratch_bytes(ix->d.n_docs, k, qc)));
+        for (int q0 = 0; q0 < Q; q0 += qc) {
+            const int nq = std::min(qc, Q - q0);
+            CU_TRY(bm25_fast_launch(ix->d, g.bm_terms.as<int32_t>(), g.bm_ranges.as<int32_t>(), q0, nq, allow_dev, k,
+                                    g.bm_scratch.p, g.bm_rows.as<int32_t>(), g.bm_scores.as<double>(),
+                                    g.bm_counts.as<int32_t>(), g.stream));
+            g.n_launch += 4;
+        }
+    } else {
+        RAG_TRY(g.bm_cand.ensure((size_t)Q * n_lists * kp * bm25_key_bytes()));
+        CU_TRY(bm25_range_launch(ix->d, g.bm_terms.as<int32_t>(), g.bm_ranges.as<int32_t>(), nullptr, Q, allow_dev, kp, k,
+                                 g.bm_cand.p, g.bm_rows.as<int32_t>(), g.bm_scores.as<double>(),
+                                 g.bm_counts.as<int32_t>(), g.stream));
+        g.n_launch += 2;
+    }
     rec(1);
     CU_TRY(cudaMemcpyAsync(pin, g.bm_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
     CU_TRY(cudaMemcpyAsync(pin + sb, g.bm_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
@@ -929,6 +944,34 @@ int rag_bm25_search(rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr
     memcpy(out_scores, pin, sb);
     memcpy(out_rows, pin + sb, rb);
     memcpy(out_counts, pin + sb + rb, cb);
+    if (fast) {
+        // queries whose survivor list overflowed (mass ties at the bound) are redone on the robust path
+        std::vector<int32_t> redo;
+        for (int q = 0; q < Q; ++q)
+            if (out_counts[q] < 0) redo.push_back(q);
+        if (!redo.empty()) {
+            ++g.n_fallback;
+            const int nr = (int)redo.size();
+            RAG_TRY(g.bm_index.ensure((size_t)nr * 4));
+            RAG_TRY(g.bm_cand.ensure((size_t)nr * n_lists * kp * bm25_key_bytes()));
+            CU_TRY(cudaMemcpyAsync(g.bm_index.p, redo.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, g.stream));
+            // outputs of the redo land in the first nr slots of the result buffers
+            CU_TRY(bm25_range_launch(ix->d, g.bm_terms.as<int32_t>(), g.bm_ranges.as<int32_t>(), g.bm_index.as<int32_t>(),
+                                     nr, allow_dev, kp, k, g.bm_cand.p, g.bm_rows.as<int32_t>(),
+                                     g.bm_scores.as<double>(), g.bm_counts.as<int32_t>(), g.stream));
+            g.n_launch += 2;
+            CU_TRY(cudaMemcpyAsync(pin, g.bm_scores.p, (size_t)nr * k * 8, cudaMemcpyDeviceToHost, g.stream));
+            CU_TRY(cudaMemcpyAsync(pin + sb, g.bm_rows.p, (size_t)nr * k * 4, cudaMemcpyDeviceToHost, g.stream));
+            CU_TRY(cudaMemcpyAsync(pin + sb + rb, g.bm_counts.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, g.stream));
+            CU_TRY(cudaStreamSynchronize(g.stream));
+            for (int i = 0; i < nr; ++i) {
+                const int q = redo[i];
+                memcpy(out_scores + (size_t)q * k, pin + (size_t)i * k * 8, (size_t)k * 8);
+                memcpy(out_rows + (size_t)q * k, pin + sb + (size_t)i * k * 4, (size_t)k * 4);
+                out_counts[q] = reinterpret_cast<int32_t*>(pin + sb + rb)[i];
+            }
+        }
+    }
     float ms = 0.f;
     if (g.ev_valid[0] && g.ev_valid[1] && cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]) == cudaSuccess) g.timings[0] = ms;
     return RAG_OK;

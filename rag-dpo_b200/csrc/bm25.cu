@@ -117,24 +117,14 @@ constexpr int kBmThreads = 256;
 constexpr int kBmWarps = kBmThreads / 32;
 constexpr int kBmSeg = kBmRange / kBmWarps;      // rows owned by one warp: 512
 
-__global__ void __launch_bounds__(kBmThreads)
-bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_row,
-                  const double* __restrict__ impact, const double* __restrict__ idf, int64_t n_docs, int64_t n_terms,
-                  const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
-                  const uint8_t* __restrict__ allow, int kp, Bm25Key* __restrict__ cand) {
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    double* acc = reinterpret_cast<double*>(sm_raw);                              // kBmRange
-    Bm25Key* bufs = reinterpret_cast<Bm25Key*>(sm_raw + kBmRange * sizeof(double));  // 8 warps * 2 * kp
-    // posting offsets of every token at the 9 warp-segment boundaries of this CTA's row range
-    __shared__ int64_t s_bound[kBmMaxTokens][kBmWarps + 1];
-    __shared__ double s_w[kBmMaxTokens];
+// accumulate the scores of the CTA's row range [r0, r1) for query qi into acc (shared memory)
+__device__ __forceinline__ void bm25_accumulate_range(const int64_t* __restrict__ term_ptr,
+                                                      const int32_t* __restrict__ post_row,
+                                                      const double* __restrict__ impact,
+                                                      const double* __restrict__ idf, int64_t n_terms,
+                                                      const int32_t* __restrict__ terms, int nt, int64_t r0, int64_t r1,
+                                                      double* acc, int64_t (*s_bound)[kBmWarps + 1], double* s_w) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qi = blockIdx.y;
-    const int64_t r0 = (int64_t)blockIdx.x * kBmRange;
-    const int64_t r1 = r0 + kBmRange < n_docs ? r0 + kBmRange : n_docs;
-    const int32_t* terms = q_terms + q_ptr[qi];
-    const int nt = q_ptr[qi + 1] - q_ptr[qi];
-
     for (int i = threadIdx.x; i < kBmRange; i += kBmThreads) acc[i] = 0.0;
     for (int t0 = 0; t0 < nt; t0 += kBmMaxTokens) {
         const int tn = nt - t0 < kBmMaxTokens ? nt - t0 : kBmMaxTokens;
@@ -187,6 +177,27 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
             __syncwarp();                            // two tokens may hit the same row from different lanes
         }
     }
+    __syncwarp();
+}
+
+// ROBUST path: per-range sorted top-kp lists (any k, any tie structure)
+__global__ void __launch_bounds__(kBmThreads)
+bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_row,
+                  const double* __restrict__ impact, const double* __restrict__ idf, int64_t n_docs, int64_t n_terms,
+                  const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
+                  const int32_t* __restrict__ q_index, const uint8_t* __restrict__ allow, int kp,
+                  Bm25Key* __restrict__ cand) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    double* acc = reinterpret_cast<double*>(sm_raw);                              // kBmRange
+    Bm25Key* bufs = reinterpret_cast<Bm25Key*>(sm_raw + kBmRange * sizeof(double));  // 8 warps * 2 * kp
+    __shared__ int64_t s_bound[kBmMaxTokens][kBmWarps + 1];
+    __shared__ double s_w[kBmMaxTokens];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = q_index ? q_index[blockIdx.y] : blockIdx.y;      // which query this grid row serves
+    const int64_t r0 = (int64_t)blockIdx.x * kBmRange;
+    const int64_t r1 = r0 + kBmRange < n_docs ? r0 + kBmRange : n_docs;
+    bm25_accumulate_range(term_ptr, post_row, impact, idf, n_terms, q_terms + q_ptr[qi], q_ptr[qi + 1] - q_ptr[qi], r0,
+                          r1, acc, s_bound, s_w);
     // local select over this warp's rows: score > 0, allowed, (score desc, row asc)
     WarpTopKT<Bm25Key> t;
     t.init(bufs + (size_t)warp * 2 * kp, kp, lane);
@@ -214,9 +225,213 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
             }
         }
         t.finish(lane);
-        Bm25Key* out = cand + ((size_t)qi * gridDim.x + blockIdx.x) * kp;
+        Bm25Key* out = cand + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kp;
         for (int i = lane; i < kp; i += 32) out[i] = t.buf[i];
     }
+}
+
+// ---------------------------------------------------------------------------
+// FAST path (4 launches for a batch of queries):
+//   A  bm25_scores_heads_kernel  accumulate as above, write the range's fp64 scores to global memory and
+//                                its H best (score > 0, allowed) keys as "heads", H = ceil(k / n_ranges)
+//   B  bm25_tau_kernel           tau = k-th largest head: k distinct rows reach it, so it is a valid lower
+//                                bound of the global k-th score
+//   C  bm25_filter_kernel        every row with key >= tau is appended to the query's survivor list
+//   D  bm25_final_kernel         sort the (k + few) survivors; more than kBmSurvivors of them (mass ties)
+//                                flags the query (count = -1) and the caller re-runs it on the robust path
+// ---------------------------------------------------------------------------
+constexpr int kBmSurvivors = 2048;
+constexpr int kBmMaxH = 32;       // heads per range the fast path supports (static shared memory budget)
+
+__device__ __forceinline__ Bm25Key warp_max_key(Bm25Key k) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        Bm25Key other;
+        other.s = __shfl_xor_sync(0xffffffffu, (unsigned long long)k.s, o);
+        other.nrow = __shfl_xor_sync(0xffffffffu, k.nrow, o);
+        other.pad = 0;
+        if (k < other) k = other;
+    }
+    return k;
+}
+
+__global__ void __launch_bounds__(kBmThreads)
+bm25_scores_heads_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_row,
+                         const double* __restrict__ impact, const double* __restrict__ idf, int64_t n_docs,
+                         int64_t n_terms, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
+                         int q0, const uint8_t* __restrict__ allow, int H, double* __restrict__ scores_out,
+                         Bm25Key* __restrict__ heads) {
+    __shared__ __align__(16) double acc[kBmRange];
+    __shared__ int64_t s_bound[kBmMaxTokens][kBmWarps + 1];
+    __shared__ double s_w[kBmMaxTokens];
+    __shared__ Bm25Key s_heads[kBmWarps][kBmMaxH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = q0 + blockIdx.y;
+    const int64_t r0 = (int64_t)blockIdx.x * kBmRange;
+    const int64_t r1 = r0 + kBmRange < n_docs ? r0 + kBmRange : n_docs;
+    bm25_accumulate_range(term_ptr, post_row, impact, idf, n_terms, q_terms + q_ptr[qi], q_ptr[qi + 1] - q_ptr[qi], r0,
+                          r1, acc, s_bound, s_w);
+    // my 16 rows of the warp's segment: write the scores out, keep the selectable ones as keys in registers
+    Bm25Key mine[kBmSeg / 32];
+    double* out = scores_out + (size_t)blockIdx.y * n_docs;
+#pragma unroll
+    for (int j = 0; j < kBmSeg / 32; ++j) {
+        const int i = warp * kBmSeg + j * 32 + lane;
+        Bm25Key key{0ull, 0u, 0u};
+        if (r0 + i < r1) {
+            const double sc = acc[i];
+            out[r0 + i] = sc;
+            const uint32_t r = (uint32_t)(r0 + i);
+            if (sc > 0.0 && bitmap_test(allow, r)) { key.s = (uint64_t)__double_as_longlong(sc); key.nrow = ~r; }
+        }
+        mine[j] = key;
+    }
+    // H rounds of warp arg-max: the warp's H best keys, descending
+    for (int h = 0; h < H; ++h) {
+        Bm25Key best{0ull, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < kBmSeg / 32; ++j)
+            if (best < mine[j]) best = mine[j];
+        const Bm25Key top = warp_max_key(best);
+#pragma unroll
+        for (int j = 0; j < kBmSeg / 32; ++j)
+            if (mine[j].s == top.s && mine[j].nrow == top.nrow) mine[j] = Bm25Key{0ull, 0u, 0u};
+        if (lane == 0) s_heads[warp][h] = top;
+    }
+    __syncthreads();
+    // warp 0: the range's H best among the 8 * H warp heads
+    if (warp == 0) {
+        Bm25Key* dst = heads + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * H;
+        const int n = kBmWarps * H;                 // <= 512
+        for (int h = 0; h < H; ++h) {
+            Bm25Key best{0ull, 0u, 0u};
+            int where = -1;
+            for (int i = lane; i < n; i += 32) {
+                const Bm25Key c = s_heads[i / H][i % H];
+                if (best < c) { best = c; where = i; }
+            }
+            const Bm25Key top = warp_max_key(best);
+            if (where >= 0 && best.s == top.s && best.nrow == top.nrow) s_heads[where / H][where % H] = Bm25Key{0ull, 0u, 0u};
+            __syncwarp();
+            if (lane == 0) dst[h] = top;
+        }
+    }
+}
+
+// tau[q] = k-th largest head (empty key when fewer than k heads exist: no bound)
+__global__ void __launch_bounds__(256)
+bm25_tau_kernel(const Bm25Key* __restrict__ heads, int n_heads, int k, Bm25Key* __restrict__ tau, int32_t* counts) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    Bm25Key* s_keys = reinterpret_cast<Bm25Key*>(sm_raw);
+    const int q = blockIdx.x;
+    int nsort = 32;
+    while (nsort < n_heads) nsort <<= 1;
+    for (int i = threadIdx.x; i < nsort; i += blockDim.x)
+        s_keys[i] = i < n_heads ? heads[(size_t)q * n_heads + i] : Bm25Key{0ull, 0u, 0u};
+    block_bitonic_desc(s_keys, nsort);
+    if (threadIdx.x == 0) {
+        tau[q] = k <= n_heads ? s_keys[k - 1] : Bm25Key{0ull, 0u, 0u};
+        counts[q] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bm25_filter_kernel(const double* __restrict__ scores, int64_t n_docs, const uint8_t* __restrict__ allow,
+                   const Bm25Key* __restrict__ tau, Bm25Key* __restrict__ surv, int32_t* __restrict__ counts) {
+    const int q = blockIdx.y;
+    const Bm25Key thr = tau[q];
+    const double* sc = scores + (size_t)q * n_docs;
+    const double thr_s = thr.s ? __longlong_as_double((long long)thr.s) : 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_docs; r += (int64_t)gridDim.x * blockDim.x) {
+        const double v = sc[r];
+        if (v > 0.0 && v >= thr_s) {
+            Bm25Key key{(uint64_t)__double_as_longlong(v), ~(uint32_t)r, 0u};
+            if (!(key < thr) && bitmap_test(allow, (uint32_t)r)) {
+                const int slot = atomicAdd(&counts[q], 1);
+                if (slot < kBmSurvivors) surv[(size_t)q * kBmSurvivors + slot] = key;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bm25_final_kernel(const Bm25Key* __restrict__ surv, const int32_t* __restrict__ counts, int k, int32_t* out_rows,
+                  double* out_scores, int32_t* out_counts) {
+    __shared__ Bm25Key s_keys[kBmSurvivors];
+    const int q = blockIdx.x;
+    const int n = counts[q];
+    if (n > kBmSurvivors) {                         // mass ties at the bound: robust path must redo this query
+        if (threadIdx.x == 0) out_counts[q] = -1;
+        return;
+    }
+    int nsort = 32;
+    while (nsort < n) nsort <<= 1;
+    for (int i = threadIdx.x; i < nsort; i += blockDim.x)
+        s_keys[i] = i < n ? surv[(size_t)q * kBmSurvivors + i] : Bm25Key{0ull, 0u, 0u};
+    block_bitonic_desc(s_keys, nsort);
+    const int nout = n < k ? n : k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool ok = i < nout;
+        out_rows[(size_t)q * k + i] = ok ? (int32_t)(~s_keys[i].nrow) : -1;
+        out_scores[(size_t)q * k + i] = ok ? __longlong_as_double((long long)s_keys[i].s) : 0.0;
+    }
+    if (threadIdx.x == 0) out_counts[q] = nout;
+}
+
+int bm25_fast_heads_per_range(int64_t n_docs, int k) {
+    const int n_ranges = (int)((n_docs + kBmRange - 1) / kBmRange);
+    return (k + n_ranges - 1) / n_ranges;
+}
+bool bm25_fast_supported(int64_t n_docs, int k) {
+    const int n_ranges = (int)((n_docs + kBmRange - 1) / kBmRange);
+    const int H = bm25_fast_heads_per_range(n_docs, k);
+    return H <= kBmMaxH && (int64_t)n_ranges * H <= 4096;
+}
+size_t bm25_fast_scratch_bytes(int64_t n_docs, int k, int Q) {
+    const int n_ranges = (int)((n_docs + kBmRange - 1) / kBmRange);
+    const int H = bm25_fast_heads_per_range(n_docs, k);
+    return (size_t)Q * n_docs * 8 + (size_t)Q * n_ranges * H * sizeof(Bm25Key) + (size_t)Q * sizeof(Bm25Key) +
+           (size_t)Q * kBmSurvivors * sizeof(Bm25Key) + (size_t)Q * 4 + 1024;
+}
+
+// queries [q0, q0+Q) of the uploaded batch; outputs written at out_* + q0 (counts = -1: redo on the robust path)
+cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int q0, int Q,
+                             const uint8_t* allow, int k, void* scratch, int32_t* out_rows, double* out_scores,
+                             int32_t* out_counts, cudaStream_t st) {
+    const int n_ranges = (int)((ix.n_docs + kBmRange - 1) / kBmRange);
+    const int H = bm25_fast_heads_per_range(ix.n_docs, k);
+    uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
+    double* scores = reinterpret_cast<double*>(base);
+    base += (size_t)Q * ix.n_docs * 8;
+    Bm25Key* heads = reinterpret_cast<Bm25Key*>(base);
+    base += (size_t)Q * n_ranges * H * sizeof(Bm25Key);
+    Bm25Key* tau = reinterpret_cast<Bm25Key*>(base);
+    base += (size_t)Q * sizeof(Bm25Key);
+    Bm25Key* surv = reinterpret_cast<Bm25Key*>(base);
+    base += (size_t)Q * kBmSurvivors * sizeof(Bm25Key);
+    int32_t* counts = reinterpret_cast<int32_t*>(base);
+    dim3 grid_a(n_ranges, Q);
+    bm25_scores_heads_kernel<<<grid_a, kBmThreads, 0, st>>>(ix.term_ptr, ix.post_row, ix.post_impact, ix.idf, ix.n_docs,
+                                                           ix.n_terms, d_q_terms, d_q_ptr, q0, allow, H, scores, heads);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int n_heads = n_ranges * H;
+    int nsort = 32;
+    while (nsort < n_heads) nsort <<= 1;
+    const size_t smem_b = (size_t)nsort * sizeof(Bm25Key);
+    if (smem_b > 48 * 1024) {
+        e = cudaFuncSetAttribute(bm25_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+        if (e != cudaSuccess) return e;
+    }
+    bm25_tau_kernel<<<Q, 256, smem_b, st>>>(heads, n_heads, k, tau, counts);
+    int gx = (int)((ix.n_docs + 256 * 8 - 1) / (256 * 8));
+    if (gx > 148 * 4) gx = 148 * 4;
+    if (gx < 1) gx = 1;
+    dim3 grid_c(gx, Q);
+    bm25_filter_kernel<<<grid_c, 256, 0, st>>>(scores, ix.n_docs, allow, tau, surv, counts);
+    bm25_final_kernel<<<Q, 256, 0, st>>>(surv, counts, k, out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k,
+                                         out_counts + q0);
+    return cudaGetLastError();
 }
 
 // per-query merge of the range lists (grid = queries).  Every list is sorted descending, so the k-th
@@ -308,9 +523,10 @@ bm25_select_batch_kernel(const Bm25Key* __restrict__ cand, int n_lists, int kp, 
 
 int bm25_range_lists(int64_t n_docs) { return (int)((n_docs + kBmRange - 1) / kBmRange); }
 
-cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int Q,
-                              const uint8_t* allow, int kp, int k, void* cand, int32_t* out_rows, double* out_scores,
-                              int32_t* out_counts, cudaStream_t st) {
+// robust path for Q queries; q_index (device, nullable) lists which uploaded queries they are
+cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr,
+                              const int32_t* d_q_index, int Q, const uint8_t* allow, int kp, int k, void* cand,
+                              int32_t* out_rows, double* out_scores, int32_t* out_counts, cudaStream_t st) {
     const int n_ranges = bm25_range_lists(ix.n_docs);
     size_t smem = (size_t)kBmRange * sizeof(double) + (size_t)8 * 2 * kp * sizeof(Bm25Key);
     cudaError_t e = cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -319,7 +535,8 @@ cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, co
         const int nq = Q - q0 < 32768 ? Q - q0 : 32768;
         dim3 grid(n_ranges, nq);
         bm25_range_kernel<<<grid, kBmThreads, smem, st>>>(ix.term_ptr, ix.post_row, ix.post_impact, ix.idf, ix.n_docs,
-                                                          ix.n_terms, d_q_terms, d_q_ptr + q0, allow, kp,
+                                                          ix.n_terms, d_q_terms, d_q_ptr + (d_q_index ? 0 : q0),
+                                                          d_q_index ? d_q_index + q0 : nullptr, allow, kp,
                                                           reinterpret_cast<Bm25Key*>(cand) + (size_t)q0 * n_ranges * kp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

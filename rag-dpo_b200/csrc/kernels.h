@@ -144,9 +144,15 @@ cudaError_t bm25_reset_launch(const Bm25Device& ix, const int64_t* d_ranges, int
 size_t bm25_key_bytes();
 // fused search: grid (row ranges of 4096, queries); fp64 accumulators in shared memory, tokens in order
 int bm25_range_lists(int64_t n_docs);
-cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int Q,
-                              const uint8_t* allow, int kp, int k, void* cand, int32_t* out_rows, double* out_scores,
-                              int32_t* out_counts, cudaStream_t st);
+cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr,
+                              const int32_t* d_q_index, int Q, const uint8_t* allow, int kp, int k, void* cand,
+                              int32_t* out_rows, double* out_scores, int32_t* out_counts, cudaStream_t st);
+// fast path: scores + range heads -> tau -> filter -> final sort (counts = -1: redo on the robust path)
+bool bm25_fast_supported(int64_t n_docs, int k);
+size_t bm25_fast_scratch_bytes(int64_t n_docs, int k, int Q);
+cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int q0, int Q,
+                             const uint8_t* allow, int k, void* scratch, int32_t* out_rows, double* out_scores,
+                             int32_t* out_counts, cudaStream_t st);
 
 // ---- rrf.cu ----------------------------------------------------------------
 int rrf_max_entries();
