@@ -370,7 +370,9 @@ def run_b200(args):
         "value": qps * world * (n_local / 1e6), "unit": "queries/s (1M-row-corpus equivalents: corpus = n_gpus x 1M rows)",
         "queries_per_s": qps,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (tcgen05 filter, fp32 accumulate) + f64 (exact refine of the candidates)",
+        "storage_dtype": args.dtype, "data": "synthetic",
         "config": {"workload": f"dense exact top-{k}: {n_local} x {d} {args.dtype} rows per GPU ({n_total} total), "
                                f"batch {B} queries per step",
                    "corpus_rows": n_total, "rows_per_gpu": n_local, "dim": d, "k": k, "batch": B,

@@ -467,18 +467,20 @@ static int ensure_bf16_operand(rag_corpus* c, const void** x16, const float** x_
 }
 
 static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev,
-                            int32_t* o_rows, double* o_scores, int32_t* o_counts);
+                            int32_t* o_rows, double* o_scores, int32_t* o_counts, bool defer);
+static int dense_finish(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev, int32_t* o_rows,
+                        double* o_scores, int32_t* o_counts, bool* redone);
 
 // batches larger than one contraction launch serves are processed in slices
 static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev, int32_t* o_rows,
                       double* o_scores, int32_t* o_counts) {
     const int step = gemm_max_batch();
-    if (B <= step) return dense_core_slice(c, q_dev, B, k, allow_dev, o_rows, o_scores, o_counts);
+    if (B <= step) return dense_core_slice(c, q_dev, B, k, allow_dev, o_rows, o_scores, o_counts, false);
     float acc[8] = {};
     for (int off = 0; off < B; off += step) {
         const int nb = std::min(step, B - off);
         RAG_TRY(dense_core_slice(c, q_dev + (size_t)off * c->dim, nb, k, allow_dev, o_rows + (size_t)off * k,
-                                 o_scores + (size_t)off * k, o_counts + off));
+                                 o_scores + (size_t)off * k, o_counts + off, false));
         for (int i = 0; i < 8; ++i) acc[i] += g.timings[i];
     }
     for (int i = 0; i < 8; ++i) g.timings[i] = acc[i];
@@ -486,7 +488,7 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
 }
 
 static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev,
-                            int32_t* o_rows, double* o_scores, int32_t* o_counts) {
+                            int32_t* o_rows, double* o_scores, int32_t* o_counts, bool defer) {
     // tensor-core path: every batch >= g_tc_min_batch (default 2); a single query only when the corpus is not
     // bf16 (the filter then streams the bf16 shadow: half the bytes of the fp32 rows) and large enough to matter
     const bool use_tc = c->n > 0 && (B >= g_tc_min_batch || (g_tc_b1_shadow && c->dtype != RAG_BF16 && c->n >= 262144));
@@ -502,7 +504,10 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
     const float* q_resid = nullptr;
     const float* x_resid = nullptr;
     const uint64_t* tau_keys = nullptr;
-    const int32_t* overflow = nullptr;
+    int32_t* overflow = nullptr;
+    // inputs of the fused merge + refine launch
+    const int32_t* m_counts = nullptr;
+    int m_flat = 0, m_lists = 0, m_len = 0;
 
     if (c->n == 0) {
         CU_TRY(cudaMemsetAsync(g.top.p, 0, (size_t)B * kp * 8, g.stream));
@@ -547,10 +552,11 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
         CU_TRY(gemm_launch(p, 1, g.q16.p, x16, grid, smem, g.stream));
         ++g.n_launch;
         rec(1);
-        // the per-query list is one contiguous block: let the 8 merge warps split it
-        CU_TRY(merge_launch(g.cand.as<uint64_t>(), g.cand_cnt.as<int32_t>(), 1, B, 8, p.list_cap / 8, kp,
-                            g.top.as<uint64_t>(), g.overflow.as<int32_t>(), g.stream));
-        ++g.n_launch;
+        // the per-query list is one contiguous block: the 8 merge warps split it (flat count per query)
+        m_counts = g.cand_cnt.as<int32_t>();
+        m_flat = 1;
+        m_lists = 8;
+        m_len = p.list_cap / 8;
         tau_keys = p.tau_keys;
         overflow = g.overflow.as<int32_t>();
     } else {
@@ -582,9 +588,8 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
             ++g.n_launch;
         }
         rec(1);
-        CU_TRY(merge_launch(g.cand.as<uint64_t>(), nullptr, 0, B, n_lists, kp, kp, g.top.as<uint64_t>(), nullptr,
-                            g.stream));
-        ++g.n_launch;
+        m_lists = n_lists;
+        m_len = kp;
     }
     rec(2);
     RefineParams rp{};
@@ -609,14 +614,26 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
     rp.flags = g.flags.as<int32_t>();
     rp.tau = g.tau.as<float>();
     rp.n_flagged = g.nflag.as<int32_t>();
-    CU_TRY(refine_launch(rp, g.stream));
+    if (c->n == 0) {
+        CU_TRY(refine_launch(rp, g.stream));
+    } else {
+        CU_TRY(merge_refine_launch(g.cand.as<uint64_t>(), m_counts, m_flat, m_lists, m_len, overflow, rp, g.stream));
+    }
     ++g.n_launch;
     rec(3);
 
-    int32_t* h_nflag = g.pinned_small;
-    CU_TRY(cudaMemcpyAsync(h_nflag, g.nflag.p, 4, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaMemcpyAsync(g.pinned_small, g.nflag.p, 4, cudaMemcpyDeviceToHost, g.stream));
+    if (defer) return RAG_OK;          // the caller syncs once (results + flag) and then calls dense_finish
     CU_TRY(cudaStreamSynchronize(g.stream));
-    const int n_flagged = *h_nflag;
+    return dense_finish(c, q_dev, B, k, allow_dev, o_rows, o_scores, o_counts, nullptr);
+}
+
+// after the stream was synchronised: run the exact fallback pass for flagged queries (rare), fill the timings.
+// *redone is set when the fallback rewrote some results.
+static int dense_finish(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev, int32_t* o_rows,
+                        double* o_scores, int32_t* o_counts, bool* redone) {
+    const int n_flagged = *g.pinned_small;
+    if (redone) *redone = n_flagged > 0;
 
     if (n_flagged > 0) {
         // ---- fallback: the margin check failed for some queries (near-ties deeper than
@@ -756,22 +773,35 @@ int rag_dense_topk(rag_corpus_t* c, const float* q, int B, int k, const uint8_t*
         memcpy(pin + qb, allow_bitmap, ab);
         CU_TRY(cudaMemcpyAsync(g.allow.p, pin + qb, ab, cudaMemcpyHostToDevice, g.stream));
     }
-    RAG_TRY(dense_core(c, g.q.as<float>(), B, k, ab ? g.allow.as<uint8_t>() : nullptr, g.o_rows.as<int32_t>(),
-                       g.o_scores.as<double>(), g.o_counts.as<int32_t>()));
-    if (out_pinned) {
-        CU_TRY(cudaMemcpyAsync(out_scores, g.o_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
-        CU_TRY(cudaMemcpyAsync(out_rows, g.o_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
-        CU_TRY(cudaMemcpyAsync(out_counts, g.o_counts.p, cb, cudaMemcpyDeviceToHost, g.stream));
-        CU_TRY(cudaStreamSynchronize(g.stream));
-        return RAG_OK;
+    const uint8_t* allow_dev = ab ? g.allow.as<uint8_t>() : nullptr;
+    const bool one_sync = B <= gemm_max_batch();
+    if (one_sync) {
+        // launch everything, read results and the fallback flag back with ONE synchronisation
+        RAG_TRY(dense_core_slice(c, g.q.as<float>(), B, k, allow_dev, g.o_rows.as<int32_t>(), g.o_scores.as<double>(),
+                                 g.o_counts.as<int32_t>(), true));
+    } else {
+        RAG_TRY(dense_core(c, g.q.as<float>(), B, k, allow_dev, g.o_rows.as<int32_t>(), g.o_scores.as<double>(),
+                           g.o_counts.as<int32_t>()));
     }
-    CU_TRY(cudaMemcpyAsync(pin, g.o_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
-    CU_TRY(cudaMemcpyAsync(pin + sb, g.o_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
-    CU_TRY(cudaMemcpyAsync(pin + sb + rb, g.o_counts.p, cb, cudaMemcpyDeviceToHost, g.stream));
-    CU_TRY(cudaStreamSynchronize(g.stream));
-    memcpy(out_scores, pin, sb);
-    memcpy(out_rows, pin + sb, rb);
-    memcpy(out_counts, pin + sb + rb, cb);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        uint8_t* ds = out_pinned ? reinterpret_cast<uint8_t*>(out_scores) : pin;
+        uint8_t* dr = out_pinned ? reinterpret_cast<uint8_t*>(out_rows) : pin + sb;
+        uint8_t* dc = out_pinned ? reinterpret_cast<uint8_t*>(out_counts) : pin + sb + rb;
+        CU_TRY(cudaMemcpyAsync(ds, g.o_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
+        CU_TRY(cudaMemcpyAsync(dr, g.o_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
+        CU_TRY(cudaMemcpyAsync(dc, g.o_counts.p, cb, cudaMemcpyDeviceToHost, g.stream));
+        CU_TRY(cudaStreamSynchronize(g.stream));
+        bool redone = false;
+        if (one_sync && attempt == 0)
+            RAG_TRY(dense_finish(c, g.q.as<float>(), B, k, allow_dev, g.o_rows.as<int32_t>(), g.o_scores.as<double>(),
+                                 g.o_counts.as<int32_t>(), &redone));
+        if (!redone) break;            // otherwise copy the rewritten results once more
+    }
+    if (!out_pinned) {
+        memcpy(out_scores, pin, sb);
+        memcpy(out_rows, pin + sb, rb);
+        memcpy(out_counts, pin + sb + rb, cb);
+    }
     return RAG_OK;
 }
 

@@ -17,12 +17,11 @@ namespace b200rag {
 // ---------------------------------------------------------------------------
 constexpr int kMergeWarps = 8;
 
-__global__ void __launch_bounds__(kMergeWarps * 32)
-merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
-             int list_len, int kp, uint64_t* __restrict__ top, int32_t* __restrict__ overflow) {
-    extern __shared__ __align__(16) uint64_t sm_keys[];   // kMergeWarps * 2 * kp
+// leaves the query's kp best keys, sorted descending, in sm_keys[0..kp) (all threads synchronised)
+__device__ __forceinline__ void merge_body(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts,
+                                           int flat_counts, int n_lists, int list_len, int kp, int b,
+                                           uint64_t* sm_keys, int32_t* __restrict__ overflow) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x;
     const uint64_t* src = cand + (size_t)b * n_lists * list_len;
     const int32_t* cnt = (counts && !flat_counts) ? counts + (size_t)b * n_lists : nullptr;
     const int flat_total = (counts && flat_counts) ? counts[b] : 0;
@@ -39,7 +38,7 @@ merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ coun
     }
     WarpTopK t;
     t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
-    // each warp walks whole lists (list_len is a multiple of 32): warp w takes lists w, w+8, ...
+    // each warp walks whole lists: warp w takes lists w, w+8, ...
     for (int l = warp; l < n_lists; l += kMergeWarps) {
         int n = list_len;
         if (cnt) n = min(cnt[l], list_len);
@@ -53,6 +52,14 @@ merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ coun
     t.finish(lane);
     __syncthreads();
     block_bitonic_desc(sm_keys, kMergeWarps * 2 * kp);      // power of two
+}
+
+__global__ void __launch_bounds__(kMergeWarps * 32)
+merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
+             int list_len, int kp, uint64_t* __restrict__ top, int32_t* __restrict__ overflow) {
+    extern __shared__ __align__(16) uint64_t sm_keys[];   // kMergeWarps * 2 * kp
+    const int b = blockIdx.x;
+    merge_body(cand, counts, flat_counts, n_lists, list_len, kp, b, sm_keys, overflow);
     for (int i = threadIdx.x; i < kp; i += blockDim.x) top[(size_t)b * kp + i] = sm_keys[i];
 }
 
@@ -100,14 +107,11 @@ struct ExactKey {
     }
 };
 
-__global__ void __launch_bounds__(256) refine_kernel(RefineParams p) {
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    ExactKey* ek = reinterpret_cast<ExactKey*>(sm_raw);          // max(kp,32)
+// canonical re-score of the kp candidates in `top` (shared or global memory), final order, margin check
+__device__ __forceinline__ void refine_body(const RefineParams& p, int b, const uint64_t* top, ExactKey* ek) {
     __shared__ double s_qnorm2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x;
     const float* q = p.q + (size_t)b * p.dim;
-    const uint64_t* top = p.top + (size_t)b * p.kp;
     const int nsort = p.kp < 32 ? 32 : p.kp;
 
     for (int j = warp; j < nsort; j += 8) {
@@ -175,9 +179,37 @@ __global__ void __launch_bounds__(256) refine_kernel(RefineParams p) {
     }
 }
 
+__global__ void __launch_bounds__(256) refine_kernel(RefineParams p) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    refine_body(p, blockIdx.x, p.top + (size_t)blockIdx.x * p.kp, reinterpret_cast<ExactKey*>(sm_raw));
+}
+
 cudaError_t refine_launch(const RefineParams& p, cudaStream_t st) {
     int nsort = p.kp < 32 ? 32 : p.kp;
     refine_kernel<<<p.B, 256, (size_t)nsort * sizeof(ExactKey), st>>>(p);
+    return cudaGetLastError();
+}
+
+// merge + refine in one launch: the merged candidates never leave shared memory
+__global__ void __launch_bounds__(256)
+merge_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
+                    int list_len, int32_t* __restrict__ overflow, RefineParams p) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    uint64_t* sm_keys = reinterpret_cast<uint64_t*>(sm_raw);                        // kMergeWarps * 2 * kp
+    ExactKey* ek = reinterpret_cast<ExactKey*>(sm_raw + (size_t)kMergeWarps * 2 * p.kp * sizeof(uint64_t));
+    merge_body(cand, counts, flat_counts, n_lists, list_len, p.kp, blockIdx.x, sm_keys, overflow);
+    refine_body(p, blockIdx.x, sm_keys, ek);
+}
+
+cudaError_t merge_refine_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int n_lists, int list_len,
+                                int32_t* overflow, const RefineParams& p, cudaStream_t st) {
+    const int nsort = p.kp < 32 ? 32 : p.kp;
+    const size_t smem = (size_t)kMergeWarps * 2 * p.kp * sizeof(uint64_t) + (size_t)nsort * sizeof(ExactKey);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    merge_refine_kernel<<<p.B, 256, smem, st>>>(cand, counts, flat_counts, n_lists, list_len, overflow, p);
     return cudaGetLastError();
 }
 

@@ -97,6 +97,9 @@ struct RefineParams {
     int32_t* n_flagged;      // scalar counter
 };
 cudaError_t refine_launch(const RefineParams& p, cudaStream_t st);
+// merge + refine fused: the merged top-kp never leaves shared memory (p.top is not used)
+cudaError_t merge_refine_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int n_lists, int list_len,
+                                int32_t* overflow, const RefineParams& p, cudaStream_t st);
 // fallback tail: exact scores of the collected rows + top-k select, one CTA per query
 struct CollectSelectParams {
     const uint32_t* rows_list;   // nq x cap
