@@ -633,3 +633,40 @@ def test_clustered_corpus_through_the_tensor_core_path():
         check_topk(c, q[:1], 10, DT[dtype])
         assert _lib.counters()["fallbacks"] - f0 <= 1, "clustered rows should not push queries into the fallback pass"
         c.close()
+
+
+def test_more_edges_k224_dim2048_zero_vectors_pinned_buffers():
+    from b200rag import DeviceCorpus, DeviceCollection, pinned_empty, _lib
+    # largest k on both paths, dim 2048
+    n, d = 5000, 2048
+    x = helpers.synth_unit(n, d, seed=31)
+    q = helpers.synth_unit(6, d, seed=32)
+    c = DeviceCorpus(d, "bf16")
+    c.append(x)
+    check_topk(c, q[:1], 224, no.DT_BF16)          # scan kernel, kp = 256
+    check_topk(c, q, 224, no.DT_BF16)              # contraction kernel, kp = 512
+    # caller-provided page-locked buffers are DMA'd directly and give the same answer
+    qp = pinned_empty((6, d), np.float32)
+    qp[:] = q
+    out = (pinned_empty((6, 10), np.int32), pinned_empty((6, 10), np.float64), pinned_empty((6,), np.int32))
+    r1, s1, c1 = c.topk(qp, 10, out=out)
+    r2, s2, c2 = c.topk(q, 10)
+    assert np.array_equal(r1, r2) and np.array_equal(s1, s2) and np.array_equal(c1, c2)
+    c.close()
+    # all-zero embedding rows / queries: cosine space normalises with a floor, scores are exactly 0
+    col = DeviceCollection(dim=64, dtype="f32")
+    emb = helpers.synth_unit(10, 64, seed=1)
+    emb[3] = 0.0
+    col.add(ids=[f"i{j}" for j in range(10)], documents=["t"] * 10, embeddings=emb, metadatas=[{"a": j} for j in range(10)])
+    ora = no.ExactCollection(dim=64)
+    ora.add(ids=[f"i{j}" for j in range(10)], documents=["t"] * 10, embeddings=emb, metadatas=[{"a": j} for j in range(10)])
+    for qv in (emb[1].tolist(), [0.0] * 64):
+        assert col.query(query_embeddings=[qv], n_results=10) == ora.query(query_embeddings=[qv], n_results=10)
+    # update with a new embedding, get by ids / where
+    col.update(ids=["i2"], embeddings=[emb[7].tolist()], metadatas=[{"a": 99}])
+    ora.update(ids=["i2"], embeddings=[emb[7].tolist()], metadatas=[{"a": 99}])
+    assert col.query(query_embeddings=[emb[7].tolist()], n_results=3) == ora.query(query_embeddings=[emb[7].tolist()], n_results=3)
+    assert col.get(ids=["i5", "i2", "nope"])["ids"] == ora.get(ids=["i5", "i2", "nope"])["ids"]
+    assert col.get(where={"a": {"$gte": 8}})["ids"] == ora.get(where={"a": {"$gte": 8}})["ids"]
+    with pytest.raises(_lib.B200RagError):
+        _lib.set_option("no_such_option", 1)
