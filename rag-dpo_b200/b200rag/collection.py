@@ -248,12 +248,25 @@ class DeviceCollection:
                                          if rows else np.zeros((0, self.dim), np.float32))
             return out
 
-    def query_rows(self, query_embeddings, n_results=10, where=None):
-        """Batched array-level query: rows int32 (B,k), fp64 cosine (B,k), counts (B,)."""
+    def doc_filter_bitmap(self, doc_paths):
+        """row bitmap of the chunks whose metadata document_path is in doc_paths"""
+        key = frozenset(doc_paths)
+        mask = np.fromiter(((m or {}).get("document_path", "") in key for m in self._metas), dtype=bool,
+                           count=len(self._metas))
+        return np.packbits(mask, bitorder="little"), int(mask.sum())
+
+    def query_rows(self, query_embeddings, n_results=10, where=None, doc_filter=None):
+        """Batched array-level query: rows int32 (B,k), fp64 cosine (B,k), counts (B,).
+        doc_filter (opt-in, NOT what the reference does): restrict the search to the chunks of these documents
+        BEFORE the top-k, instead of post-filtering the results (src/rag/retriever.py:393-398)."""
         with self._lock:
             q = l2_normalize_rows(np.asarray(query_embeddings, dtype=np.float32))
             n = len(self._ids)
             bitmap, allowed = self._where.compile(self._metas, where)
+            if doc_filter is not None:
+                fb, fa = self.doc_filter_bitmap(doc_filter)
+                bitmap = fb if bitmap is None else np.bitwise_and(bitmap, fb)
+                allowed = int(np.unpackbits(bitmap, bitorder="little")[:n].sum())
             k = min(int(n_results), n)
             if k <= 0 or allowed == 0:
                 B = q.shape[0]

@@ -670,3 +670,21 @@ def test_more_edges_k224_dim2048_zero_vectors_pinned_buffers():
     assert col.get(where={"a": {"$gte": 8}})["ids"] == ora.get(where={"a": {"$gte": 8}})["ids"]
     with pytest.raises(_lib.B200RagError):
         _lib.set_option("no_such_option", 1)
+
+
+def test_opt_in_dense_doc_filter_prefilter(e2e_data):
+    """N4: restricting the dense search to a set of documents BEFORE the top-k equals the exact search over only
+    those rows (and differs from the reference's post-filter, which is why it is opt-in)."""
+    from b200rag import DeviceCollection
+    gold, emb, table = e2e_data
+    col = DeviceCollection(dim=emb.shape[1], dtype="f32")
+    helpers.fill(col, gold["chunks"], emb)
+    docs = sorted({c["metadata"]["document_path"] for c in gold["chunks"]})[::4]
+    q = np.array(list(table.values())[:3], dtype=np.float32)
+    rows, scores, counts = col.query_rows(q, 25, where={"source": "CNIL"}, doc_filter=docs)
+    allow = np.array([(c["metadata"]["document_path"] in set(docs)) and c["metadata"]["source"] == "CNIL"
+                      for c in gold["chunks"]])
+    stored = col.corpus.download()
+    er, es, ec = c_oracle.dense_topk(no.l2_normalize_rows(q), stored, no.DT_F32, 25, np.packbits(allow, bitorder="little"))
+    for b in range(3):
+        assert rows[b, :counts[b]].tolist() == er[b, :ec[b]].tolist() and np.array_equal(scores[b, :counts[b]], es[b, :ec[b]])
