@@ -67,9 +67,53 @@ class ShardedDenseIndex:
     def topk(self, q32, k):
         """q32: numpy (B,dim) fp32, identical on every rank.  Returns numpy
         (ids int64 (B,k) [-1 pad], scores f64 (B,k), counts int32 (B,))."""
+        if self._local_topk is None and self.corpus is not None:
+            return self._topk_device(q32, int(k))
+        return self._topk_host(q32, int(k))
+
+    def _topk_device(self, q32, kk):
+        """GPU path: queries H2D once, local top-k with device-resident outputs, ONE packed all-gather
+        ([scores | global ids] per rank), stream-ordered merge, one D2H of the merged result."""
+        torch, dist = self.torch, self.dist
+        from . import _lib
+        L = _lib.lib()
+        B = q32.shape[0]
+        dev = self.device
+        n_local = self.row_hi - self.row_lo
+        kl = min(kk, n_local)
+        stream = torch.cuda.current_stream(dev)
+        if stream.cuda_stream != 0:
+            _lib.set_stream(stream.cuda_stream)       # library kernels and NCCL on the same stream
+        q_dev = torch.from_numpy(np.ascontiguousarray(q32, dtype=np.float32)).to(dev, non_blocking=True)
+        mine = torch.zeros((2, B, kk), dtype=torch.float64, device=dev)
+        my_ids = mine[1].view(torch.int64)
+        my_ids.fill_(-1)
+        if kl > 0:
+            o_rows = torch.empty((B, kl), dtype=torch.int32, device=dev)
+            o_scores = torch.empty((B, kl), dtype=torch.float64, device=dev)
+            o_counts = torch.empty((B,), dtype=torch.int32, device=dev)
+            stream.synchronize()                      # inputs are in place before the library's stream reads them
+            self.corpus.topk_dev(q_dev.data_ptr(), B, kl, o_rows.data_ptr(), o_scores.data_ptr(), o_counts.data_ptr())
+            mine[0, :, :kl] = o_scores
+            gid = o_rows.to(torch.int64)
+            my_ids[:, :kl] = torch.where(gid >= 0, gid + self.row_lo, gid)
+        if self.world > 1:
+            gathered = torch.empty((self.world, 2, B, kk), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        else:
+            gathered = mine[None]
+        o_s = torch.empty((B, kk), dtype=torch.float64, device=dev)
+        o_i = torch.empty((B, kk), dtype=torch.int64, device=dev)
+        o_c = torch.empty((B,), dtype=torch.int32, device=dev)
+        stream.synchronize()                          # the gather has landed (no-op wait when streams are shared)
+        _lib.check(L.rag_merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + B * kk * 8, self.world, B, kk,
+                                        2 * B * kk, o_s.data_ptr(), o_i.data_ptr(), o_c.data_ptr()))
+        _lib.sync_stream_of(torch, dev)
+        return o_i.cpu().numpy(), o_s.cpu().numpy(), o_c.cpu().numpy()
+
+    def _topk_host(self, q32, kk):
         torch, dist = self.torch, self.dist
         B = q32.shape[0]
-        kk = int(k)
         if self._local_topk is not None:
             rows, scores, counts = self._local_topk(q32, kk)
         else:

@@ -87,10 +87,23 @@ __device__ __forceinline__ double canonical_dot(const float* __restrict__ q, con
                                                 size_t row, int dim, int lane) {
     double p = 0.0;
     const size_t base = row * (size_t)dim;
-    for (int j = 0; j < dim / 32; ++j) {
-        double a = (double)q[32 * j + lane];
-        double x = load_elem_f64(rows, dtype, base + 32 * j + lane);
-        p = __fma_rn(a, x, p);      // the product is exact in fp64, so this is one rounding: p + a*x
+    const int steps = dim / 32;
+    // the summation ORDER is fixed (j ascending); the loads are issued 8 at a time so that their latencies overlap
+    int j = 0;
+    for (; j + 8 <= steps; j += 8) {
+        double a[8], x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a[u] = (double)q[32 * (j + u) + lane];
+            x[u] = load_elem_f64(rows, dtype, base + 32 * (j + u) + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p = __fma_rn(a[u], x[u], p);   // exact product: one rounding, p + a*x
+    }
+    for (; j < steps; ++j) {
+        const double a = (double)q[32 * j + lane];
+        const double x = load_elem_f64(rows, dtype, base + 32 * j + lane);
+        p = __fma_rn(a, x, p);
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) p = __dadd_rn(p, __shfl_down_sync(0xffffffffu, p, off));

@@ -688,3 +688,16 @@ def test_opt_in_dense_doc_filter_prefilter(e2e_data):
     er, es, ec = c_oracle.dense_topk(no.l2_normalize_rows(q), stored, no.DT_F32, 25, np.packbits(allow, bitorder="little"))
     for b in range(3):
         assert rows[b, :counts[b]].tolist() == er[b, :ec[b]].tolist() and np.array_equal(scores[b, :counts[b]], es[b, :ec[b]])
+
+
+def test_sharded_index_single_rank_device_path():
+    """ShardedDenseIndex on one rank (no process group): device-resident local top-k + packed merge == corpus.topk"""
+    from b200rag.sharded import ShardedDenseIndex
+    n, d = 40000, 256
+    idx = ShardedDenseIndex(d, n, dtype="bf16")
+    idx.fill_synthetic(seed=3)
+    q = helpers.synth_unit(9, d, seed=4)
+    for B, k in [(1, 10), (9, 50)]:
+        ids, scores, counts = idx.topk(q[:B], k)
+        r, s, c = idx.corpus.topk(q[:B], k)
+        assert ids.tolist() == r.astype(np.int64).tolist() and np.array_equal(scores, s) and counts.tolist() == c.tolist()
