@@ -84,32 +84,64 @@ class ShardedDenseIndex:
         stream = torch.cuda.current_stream(dev)
         if stream.cuda_stream != 0:
             _lib.set_stream(stream.cuda_stream)       # library kernels and NCCL on the same stream
-        q_dev = torch.from_numpy(np.ascontiguousarray(q32, dtype=np.float32)).to(dev, non_blocking=True)
-        mine = torch.zeros((2, B, kk), dtype=torch.float64, device=dev)
-        my_ids = mine[1].view(torch.int64)
-        my_ids.fill_(-1)
+        buf = self._buffers(B, kk, kl)
+        buf["q_host"].copy_(torch.from_numpy(np.ascontiguousarray(q32, dtype=np.float32)))
+        buf["q_dev"].copy_(buf["q_host"], non_blocking=True)
+        mine, my_ids = buf["mine"], buf["my_ids"]
+        if kl < kk:
+            mine[0].zero_()
+            my_ids.fill_(-1)
         if kl > 0:
-            o_rows = torch.empty((B, kl), dtype=torch.int32, device=dev)
-            o_scores = torch.empty((B, kl), dtype=torch.float64, device=dev)
-            o_counts = torch.empty((B,), dtype=torch.int32, device=dev)
             stream.synchronize()                      # inputs are in place before the library's stream reads them
-            self.corpus.topk_dev(q_dev.data_ptr(), B, kl, o_rows.data_ptr(), o_scores.data_ptr(), o_counts.data_ptr())
-            mine[0, :, :kl] = o_scores
-            gid = o_rows.to(torch.int64)
+            self.corpus.topk_dev(buf["q_dev"].data_ptr(), B, kl, buf["o_rows"].data_ptr(), buf["o_scores"].data_ptr(),
+                                 buf["o_counts"].data_ptr())
+            mine[0, :, :kl] = buf["o_scores"]
+            gid = buf["o_rows"].to(torch.int64)
             my_ids[:, :kl] = torch.where(gid >= 0, gid + self.row_lo, gid)
         if self.world > 1:
-            gathered = torch.empty((self.world, 2, B, kk), dtype=torch.float64, device=dev)
+            gathered = buf["gathered"]
             dist.all_gather_into_tensor(gathered, mine, group=self.group)
         else:
             gathered = mine[None]
-        o_s = torch.empty((B, kk), dtype=torch.float64, device=dev)
-        o_i = torch.empty((B, kk), dtype=torch.int64, device=dev)
-        o_c = torch.empty((B,), dtype=torch.int32, device=dev)
         stream.synchronize()                          # the gather has landed (no-op wait when streams are shared)
         _lib.check(L.rag_merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + B * kk * 8, self.world, B, kk,
-                                        2 * B * kk, o_s.data_ptr(), o_i.data_ptr(), o_c.data_ptr()))
+                                        2 * B * kk, buf["m_scores"].data_ptr(), buf["m_ids"].data_ptr(),
+                                        buf["m_counts"].data_ptr()))
+        h = buf["host_out"]
         _lib.sync_stream_of(torch, dev)
-        return o_i.cpu().numpy(), o_s.cpu().numpy(), o_c.cpu().numpy()
+        h[0].copy_(buf["m_ids"]); h[1].copy_(buf["m_scores"]); h[2].copy_(buf["m_counts"])
+        return h[0].numpy().copy(), h[1].numpy().copy(), h[2].numpy().copy()
+
+    def _buffers(self, B, kk, kl):
+        """device / pinned buffers reused across calls of the same shape"""
+        torch = self.torch
+        key = (B, kk, kl)
+        cache = self.__dict__.setdefault("_buf_cache", {})
+        buf = cache.get(key)
+        if buf is None:
+            dev = self.device
+            mine = torch.zeros((2, B, kk), dtype=torch.float64, device=dev)
+            my_ids = mine[1].view(torch.int64)
+            my_ids.fill_(-1)
+            buf = {
+                "q_host": torch.empty((B, self.dim), dtype=torch.float32).pin_memory(),
+                "q_dev": torch.empty((B, self.dim), dtype=torch.float32, device=dev),
+                "mine": mine, "my_ids": my_ids,
+                "o_rows": torch.empty((B, max(kl, 1)), dtype=torch.int32, device=dev),
+                "o_scores": torch.empty((B, max(kl, 1)), dtype=torch.float64, device=dev),
+                "o_counts": torch.empty((B,), dtype=torch.int32, device=dev),
+                "gathered": torch.empty((self.world, 2, B, kk), dtype=torch.float64, device=dev),
+                "m_scores": torch.empty((B, kk), dtype=torch.float64, device=dev),
+                "m_ids": torch.empty((B, kk), dtype=torch.int64, device=dev),
+                "m_counts": torch.empty((B,), dtype=torch.int32, device=dev),
+                "host_out": (torch.empty((B, kk), dtype=torch.int64).pin_memory(),
+                             torch.empty((B, kk), dtype=torch.float64).pin_memory(),
+                             torch.empty((B,), dtype=torch.int32).pin_memory()),
+            }
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = buf
+        return buf
 
     def _topk_host(self, q32, kk):
         torch, dist = self.torch, self.dist
