@@ -204,7 +204,7 @@ cudaError_t refine_launch(const RefineParams& p, cudaStream_t st) {
 }
 
 // merge + refine in one launch: the merged candidates never leave shared memory
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 7)      // 7 CTAs/SM: a 1024-query batch is a single wave on 148 SMs
 merge_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
                     int list_len, int32_t* __restrict__ overflow, RefineParams p) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
