@@ -701,3 +701,36 @@ def test_sharded_index_single_rank_device_path():
         ids, scores, counts = idx.topk(q[:B], k)
         r, s, c = idx.corpus.topk(q[:B], k)
         assert ids.tolist() == r.astype(np.int64).tolist() and np.array_equal(scores, s) and counts.tolist() == c.tolist()
+
+
+def test_concurrent_callers_share_one_collection(e2e_data):
+    """Streamlit script threads share one cached instance (app.py:42): concurrent query() / search() calls must be
+    serialised correctly."""
+    import threading
+    from b200rag import DeviceCollection, DeviceChunkBM25Index
+    gold, emb, table = e2e_data
+    col = DeviceCollection(dim=emb.shape[1], dtype="bf16")
+    helpers.fill(col, gold["chunks"], emb)
+    bm = DeviceChunkBM25Index()
+    bm.build_from_collection(col)
+    qs = [list(map(float, v)) for v in list(table.values())[:12]]
+    texts = [c["text"][:60] for c in gold["chunks"][:12]]
+    want_d = [col.query(query_embeddings=[q], n_results=20) for q in qs]
+    want_b = [[(r.doc_key, r.score) for r in bm.search(t, top_k=20)] for t in texts]
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(5):
+                for i in range(tid, 12, 4):
+                    assert col.query(query_embeddings=[qs[i]], n_results=20) == want_d[i]
+                    assert [(r.doc_key, r.score) for r in bm.search(texts[i], top_k=20)] == want_b[i]
+        except Exception as e:     # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:2]
