@@ -19,8 +19,8 @@
 //
 // Fused select, two launches of the same kernel:
 //   SAMPLE pass  over a ~1/kp fraction of the rows (strided tiles, column-granular): every thread keeps
-//                the 4 best scores of its query in registers; merged per query, the 4th best sample
-//                score tau_q is a VALID lower bound of the corpus-wide 4th best score.
+//                the 8 best scores of its query in registers; merged per query, the 8th best sample
+//                score tau_q is a VALID lower bound of the corpus-wide 8th best score.
 //   MAIN pass    over all tiles (row tile outer, query block inner: a corpus tile is fetched from HBM
 //                once and re-read from L2 by the other query blocks): a branch-free compare mask per
 //                32-column chunk against tau_q; the ~8*kp survivors per query are appended (one atomic
@@ -109,7 +109,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
-constexpr int kSampleM = 4;       // order statistic taken from the sample pass
+constexpr int kSampleM = 8;       // order statistic taken from the sample pass
 
 // Work items of one CTA, identical in all three warp roles.
 //   sample pass (MODE 0): query block outer, the CTA's sample tiles inner (the running top-16 of a
@@ -466,14 +466,15 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     int grid = (int)(n_tiles < sm_count ? (n_tiles > 0 ? n_tiles : 1) : sm_count);
     *grid_out = grid;
     p.n_lists = grid;
-    // Sample pass: the m-th best (m = kSampleM = 4) of a sample that holds a fraction f of the rows lets
-    // ~m/f rows per query through the main pass; aim for f = 1/(2*kp) (about 8*kp survivors per query),
-    // column-granular.
+    // Sample pass: the m-th best (m = kSampleM = 8) of a sample that holds a fraction f of the rows lets
+    // ~(1/f) * Gamma(m) rows per query through the main pass; f = 1/kp gives 8*kp survivors on average and
+    // fewer than kp of them with probability P(Gamma(8) < 1) ~ 1e-5 (m = 4 made that 2e-3: too many
+    // fallback passes at k = 100).  Column-granular.
     const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
     const int64_t rows_per_cta = tiles_per_cta * GT_N;
     {
         p.use_sample = 1;
-        int64_t want = (rows_per_cta + 2 * p.kp - 1) / (2 * p.kp);     // sample rows per CTA
+        int64_t want = (rows_per_cta + p.kp - 1) / p.kp;               // sample rows per CTA
         if (want < 2) want = 2;
         if (want <= GT_N) {
             p.sample_tiles = 1;

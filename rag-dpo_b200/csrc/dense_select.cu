@@ -204,7 +204,10 @@ cudaError_t refine_launch(const RefineParams& p, cudaStream_t st) {
 }
 
 // merge + refine in one launch: the merged candidates never leave shared memory
-__global__ void __launch_bounds__(256, 7)      // 7 CTAs/SM: a 1024-query batch is a single wave on 148 SMs
+// MIN_BLOCKS = 7 (32 registers): a 1024-query batch is a single wave on 148 SMs; MIN_BLOCKS = 2 keeps the
+// registers that let the refine loads overlap, which is what matters for a handful of queries
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
 merge_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
                     int list_len, int32_t* __restrict__ overflow, RefineParams p) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -218,11 +221,12 @@ cudaError_t merge_refine_launch(const uint64_t* cand, const int32_t* counts, int
                                 int32_t* overflow, const RefineParams& p, cudaStream_t st) {
     const int nsort = p.kp < 32 ? 32 : p.kp;
     const size_t smem = (size_t)kMergeWarps * 2 * p.kp * sizeof(uint64_t) + (size_t)nsort * sizeof(ExactKey);
+    auto kern = p.B >= 512 ? merge_refine_kernel<7> : merge_refine_kernel<2>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(merge_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    merge_refine_kernel<<<p.B, 256, smem, st>>>(cand, counts, flat_counts, n_lists, list_len, overflow, p);
+    kern<<<p.B, 256, smem, st>>>(cand, counts, flat_counts, n_lists, list_len, overflow, p);
     return cudaGetLastError();
 }
 
