@@ -18,13 +18,13 @@
 //               select of tile i overlaps the MMAs of tile i+1) and run the fused select.
 //
 // Fused select, two launches of the same kernel:
-//   SAMPLE pass  over a ~1/kp fraction of the rows (strided tiles, column-granular): every thread keeps
+//   SAMPLE pass  over a fraction 8/E of the rows, E = max(1024, 4*kp) (column-granular): every thread keeps
 //                the 8 best scores of its query in registers; merged per query, the 8th best sample
 //                score tau_q is a VALID lower bound of the corpus-wide 8th best score.
 //   MAIN pass    over all tiles (row tile outer, query block inner: a corpus tile is fetched from HBM
 //                once and re-read from L2 by the other query blocks): a branch-free compare mask per
-//                32-column chunk against tau_q; the ~8*kp survivors per query are appended (one atomic
-//                slot claim each) to that query's candidate list in global memory (L2).
+//                32-column chunk against tau_q; the ~E survivors per query are parked per thread and
+//                flushed once per tile (one atomic slot reservation) into that query's candidate list.
 //                Everything with filter score >= tau_q is captured, so the candidate set provably
 //                contains the top-k unless the list overflows (flagged -> exact fallback pass).
 //
@@ -49,6 +49,7 @@ constexpr int GT_B_BYTES = GT_N * GT_K * 2;   // 32 KB
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
 constexpr int GT_THREADS = 192;
 constexpr int GT_EPI_WARPS = 4;
+constexpr int kPend = 4;           // survivors a thread parks per tile before it must flush
 constexpr int kMaxQBlocks = 32;   // per launch: 4096 queries (their tau / count live in shared memory)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -249,6 +250,9 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int my = lg * 32 + lane;           // my query inside the query block == my TMEM lane
         const int n_chunks = MODE == 0 ? p.sample_chunks : GT_N / 32;
         float* s_tau = reinterpret_cast<float*>(bars + 24);            // [n_qblocks][128]
+        // survivors of the current tile are parked here (per thread) and flushed with ONE atomic slot
+        // reservation per thread and tile, so a warp waits for the atomic round trip once per tile
+        uint64_t* s_pend = reinterpret_cast<uint64_t*>(s_tau + p.n_qblocks * GT_M) + (size_t)((warp - 2) * 32 + lane) * kPend;
         if (MODE == 1) {
             for (int b = 0; b < p.n_qblocks; ++b) {
                 const int q = b * GT_M + my;
@@ -282,6 +286,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             float tau = 0.f;
             uint64_t* my_list = nullptr;
             int* my_cnt = nullptr;
+            int npend = 0;
             if (MODE == 0) {
                 if (qb != cur_qb) {
                     if (cur_qb >= 0) flush_sample(cur_qb);
@@ -330,8 +335,13 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                                     best[i] = hi;
                                 }
                             } else {
-                                const int slot = atomicAdd(my_cnt, 1);      // counts past the capacity flag an overflow
-                                if (slot < p.list_cap) my_list[slot] = make_key(s, row);
+                                s_pend[npend++] = make_key(s, row);
+                                if (npend == kPend) {                       // rare: many survivors in one tile
+                                    const int slot = atomicAdd(my_cnt, kPend);
+                                    for (int i = 0; i < kPend; ++i)
+                                        if (slot + i < p.list_cap) my_list[slot + i] = s_pend[i];
+                                    npend = 0;
+                                }
                             }
                         }
                     }
@@ -340,6 +350,11 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (MODE == 1 && npend > 0) {              // counts past the capacity flag an overflow
+                const int slot = atomicAdd(my_cnt, npend);
+                for (int i = 0; i < npend; ++i)
+                    if (slot + i < p.list_cap) my_list[slot + i] = s_pend[i];
+            }
         }
         if (MODE == 0 && cur_qb >= 0) flush_sample(cur_qb);
     }
@@ -451,13 +466,15 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, 
 
 int gemm_padded_queries(int n_queries) { return (n_queries + GT_M - 1) / GT_M * GT_M; }
 
+int g_sample_div = 1;     // multiplies the survivor target of the sample pass (option "sample_div", experiments)
+void gemm_set_sample_div(int v) { g_sample_div = v < 1 ? 1 : (v > 8 ? 8 : v); }
 int gemm_sample_m() { return kSampleM; }
 int gemm_max_batch() { return kMaxQBlocks * GT_M; }
 
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     p.n_qblocks = gemm_padded_queries(p.n_queries) / GT_M;
     if (p.n_qblocks > kMaxQBlocks) return 0;
-    const size_t tail = 256 + (size_t)p.n_qblocks * GT_M * 4;      // barriers + per-query tau
+    const size_t tail = 256 + (size_t)p.n_qblocks * GT_M * 4 + (size_t)GT_M * kPend * 8;   // barriers, tau, parked keys
     int stages = (int)((smem_limit - 1024 - (long)tail) / GT_STAGE_BYTES);
     if (stages > 4) stages = 4;
     if (stages < 2) return 0;
@@ -467,14 +484,17 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     *grid_out = grid;
     p.n_lists = grid;
     // Sample pass: the m-th best (m = kSampleM = 8) of a sample that holds a fraction f of the rows lets
-    // ~(1/f) * Gamma(m) rows per query through the main pass; f = 1/kp gives 8*kp survivors on average and
-    // fewer than kp of them with probability P(Gamma(8) < 1) ~ 1e-5 (m = 4 made that 2e-3: too many
-    // fallback passes at k = 100).  Column-granular.
+    // ~(1/f) * Gamma(m) rows per query through the main pass.  Every survivor costs the main pass a slow-path
+    // visit, a larger sample costs the sample pass: aim for E = max(1024, 4*kp) survivors per query
+    // (measured sweet spot for k = 10 and k = 100), i.e. f = 8 / E.  Fewer than ~1.5*k survivors (which
+    // would flag the query for the fallback pass) then has probability P(Gamma(8) < 12*k/E) < 1e-4.
+    // Column-granular.
     const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
     const int64_t rows_per_cta = tiles_per_cta * GT_N;
+    const int64_t e_target = (int64_t)(4 * p.kp > 1024 ? 4 * p.kp : 1024) * (g_sample_div > 0 ? g_sample_div : 1);
     {
         p.use_sample = 1;
-        int64_t want = (rows_per_cta + p.kp - 1) / p.kp;               // sample rows per CTA
+        int64_t want = (rows_per_cta * kSampleM + e_target - 1) / e_target;   // sample rows per CTA
         if (want < 2) want = 2;
         if (want <= GT_N) {
             p.sample_tiles = 1;
@@ -489,8 +509,8 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
             p.sample_step = (int)(tiles_per_cta / p.sample_tiles > 0 ? tiles_per_cta / p.sample_tiles : 1);
         }
     }
-    // one candidate list per query, filled by all CTAs: <= ~8*kp survivors expected, >= 4x head-room
-    p.list_cap = 32 * p.kp > 4096 ? 32 * p.kp : 4096;
+    // one candidate list per query, filled by all CTAs: E survivors expected, 4x head-room
+    p.list_cap = (int)(4 * e_target);
     return (size_t)stages * GT_STAGE_BYTES + tail + 1024;   // + slack for the 1024-byte alignment of the ring
 }
 

@@ -53,6 +53,7 @@ struct GemmParams {
     uint32_t sample_last_mask;   // columns of the last sample chunk that count
 };
 int gemm_sample_m();
+void gemm_set_sample_div(int v);
 int gemm_max_batch();
 int gemm_padded_queries(int n_queries);
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out);
