@@ -195,6 +195,7 @@ int rag_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "tc_min_batch")) g_tc_min_batch = (int)std::max<int64_t>(1, value);
     else if (!strcmp(key, "tc_b1_shadow")) g_tc_b1_shadow = value != 0;
     else if (!strcmp(key, "sample_div")) gemm_set_sample_div((int)value);
+    else if (!strcmp(key, "balance_tail")) gemm_set_balance_tail((int)value);
     else return fail(RAG_EINVAL, "unknown option %s", key);
     return RAG_OK;
 }

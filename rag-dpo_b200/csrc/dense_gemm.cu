@@ -124,6 +124,10 @@ struct WorkIter {
     int step, max_tiles, n_qblocks;
     int taken, qb;
     bool started;
+    // MODE 1 tail: the n_tiles % gridDim.x leftover tiles are split by (tile, query block) ITEMS over all
+    // CTAs, so that the CTAs finish within a few items of each other instead of a whole tile apart
+    int64_t full_rounds, tail_item, tail_end;
+    bool in_tail;
     __device__ __forceinline__ void init(const GemmParams& p) {
         n_tiles = (p.n_rows + GT_N - 1) / GT_N;
         step = MODE == 0 ? p.sample_step : 1;
@@ -137,23 +141,40 @@ struct WorkIter {
             if (span > 1) i_first = (int64_t)((blockIdx.x * 2654435761u) % (uint32_t)span);
         }
         i = i_first; taken = 0; qb = 0; started = false;
+        in_tail = false;
+        full_rounds = n_tiles / gridDim.x;
+        const int64_t tail_items = (n_tiles - full_rounds * gridDim.x) * n_qblocks;
+        tail_item = tail_items * blockIdx.x / gridDim.x;
+        tail_end = tail_items * (blockIdx.x + 1) / gridDim.x;
+        if (MODE == 1 && p.balance_tail) max_tiles = (int)full_rounds; else tail_end = tail_item;
     }
     __device__ __forceinline__ bool tile_ok() const {
         return blockIdx.x + i * gridDim.x < n_tiles && taken < max_tiles;
     }
-    // advances to the next (tile, query block); new_qb tells the epilogue its per-query state changes
+    // advances to the next (tile, query block)
     __device__ __forceinline__ bool next(int64_t& t, int& qblock) {
-        if (!started) {
-            started = true;
-        } else if (MODE == 0) {
-            i += step; ++taken;
-            if (!tile_ok()) { i = i_first; taken = 0; ++qb; }
+        if (!in_tail) {
+            if (!started) {
+                started = true;
+            } else if (MODE == 0) {
+                i += step; ++taken;
+                if (!tile_ok()) { i = i_first; taken = 0; ++qb; }
+            } else {
+                if (++qb == n_qblocks) { qb = 0; i += step; ++taken; }
+            }
+            if (qb < n_qblocks && tile_ok()) {
+                t = blockIdx.x + i * gridDim.x;
+                qblock = qb;
+                return true;
+            }
+            if (MODE == 0) return false;
+            in_tail = true;
         } else {
-            if (++qb == n_qblocks) { qb = 0; i += step; ++taken; }
+            ++tail_item;
         }
-        if (qb >= n_qblocks || !tile_ok()) return false;
-        t = blockIdx.x + i * gridDim.x;
-        qblock = qb;
+        if (tail_item >= tail_end) return false;
+        t = full_rounds * gridDim.x + tail_item / n_qblocks;
+        qblock = (int)(tail_item % n_qblocks);
         return true;
     }
 };
@@ -466,6 +487,8 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, 
 
 int gemm_padded_queries(int n_queries) { return (n_queries + GT_M - 1) / GT_M * GT_M; }
 
+int g_balance_tail = 1;   // split the leftover tiles of the main pass by items (option "balance_tail")
+void gemm_set_balance_tail(int v) { g_balance_tail = v != 0; }
 int g_sample_div = 1;     // multiplies the survivor target of the sample pass (option "sample_div", experiments)
 void gemm_set_sample_div(int v) { g_sample_div = v < 1 ? 1 : (v > 8 ? 8 : v); }
 int gemm_sample_m() { return kSampleM; }
@@ -483,6 +506,7 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     int grid = (int)(n_tiles < sm_count ? (n_tiles > 0 ? n_tiles : 1) : sm_count);
     *grid_out = grid;
     p.n_lists = grid;
+    p.balance_tail = g_balance_tail;
     // Sample pass: the m-th best (m = kSampleM = 8) of a sample that holds a fraction f of the rows lets
     // ~(1/f) * Gamma(m) rows per query through the main pass.  Every survivor costs the main pass a slow-path
     // visit, a larger sample costs the sample pass: aim for E = max(1024, 4*kp) survivors per query

@@ -51,9 +51,11 @@ struct GemmParams {
     int use_sample;          // always 1 (kept for the launcher)
     int n_lists, n_stages, n_qblocks, sample_tiles, sample_step, sample_chunks;
     uint32_t sample_last_mask;   // columns of the last sample chunk that count
+    int balance_tail;            // main pass: split the leftover tiles by (tile, query block) items
 };
 int gemm_sample_m();
 void gemm_set_sample_div(int v);
+void gemm_set_balance_tail(int v);
 int gemm_max_batch();
 int gemm_padded_queries(int n_queries);
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out);

@@ -18,7 +18,7 @@ def run(rows, dtype, B, k, divs, reps=6):
     res = {d: [] for d in divs}
     for rep in range(reps):
         for d in divs:
-            _lib.set_option("sample_div", d)
+            _lib.set_option(KNOB, d)
             for _ in range(2):
                 c.topk_dev(qd.data_ptr(), B, k, o_r.data_ptr(), o_s.data_ptr(), o_c.data_ptr())
             t = []
@@ -27,11 +27,13 @@ def run(rows, dtype, B, k, divs, reps=6):
                 c.topk_dev(qd.data_ptr(), B, k, o_r.data_ptr(), o_s.data_ptr(), o_c.data_ptr())
                 t.append((1e3 * (time.perf_counter() - t0), float(_lib.last_timings()[0])))
             res[d].append(min(t))
-    _lib.set_option("sample_div", 1)
+    _lib.set_option(KNOB, 1)
     out = {d: (round(float(np.median([x[0] for x in v])), 4), round(float(np.median([x[1] for x in v])), 4)) for d, v in res.items()}
-    print(json.dumps({"rows": rows, "dtype": dtype, "B": B, "k": k, "call_ms,contraction_ms by sample_div": out, "fallbacks": _lib.counters()["fallbacks"]}), flush=True)
+    print(json.dumps({"rows": rows, "dtype": dtype, "B": B, "k": k, "call_ms,contraction_ms by knob value": out, "fallbacks": _lib.counters()["fallbacks"]}), flush=True)
     c.close()
 
-run(1_000_000, "f32", 1024, 10, [1, 2, 4])
-run(1_250_000, "bf16", 4096, 100, [1, 2, 4])
-run(1_000_000, "f32", 128, 10, [1, 2, 4])
+KNOB = sys.argv[1] if len(sys.argv) > 1 else "sample_div"
+VALS = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 4]
+run(1_000_000, "f32", 1024, 10, VALS)
+run(1_250_000, "bf16", 4096, 100, VALS)
+run(1_000_000, "f32", 256, 10, VALS)
