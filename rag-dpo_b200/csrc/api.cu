@@ -437,9 +437,9 @@ static const double kEpsScan = 1.0 / 524288.0;
 // in-block tree, fp32 accumulators (truncating) -> < 70 * 2^-23 < 2^-16.
 static const double kEpsTc = 1.0 / 65536.0;
 
-// bf16 operand of the tensor-core path: the rows themselves, or a lazily built bf16 shadow
+// 16-bit operand of the tensor-core path: bf16 / fp16 rows as stored, or a lazily built bf16 shadow of fp32 rows
 static int ensure_bf16_operand(rag_corpus* c, const void** x16, const float** x_resid) {
-    if (c->dtype == RAG_BF16) {
+    if (c->dtype == RAG_BF16 || c->dtype == RAG_F16) {
         *x16 = c->rows;
         *x_resid = nullptr;
         return RAG_OK;
@@ -491,9 +491,9 @@ static int dense_core(rag_corpus* c, const float* q_dev, int B, int k, const uin
 
 static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, const uint8_t* allow_dev,
                             int32_t* o_rows, double* o_scores, int32_t* o_counts, bool defer) {
-    // tensor-core path: every batch >= g_tc_min_batch (default 2); a single query only when the corpus is not
-    // bf16 (the filter then streams the bf16 shadow: half the bytes of the fp32 rows) and large enough to matter
-    const bool use_tc = c->n > 0 && (B >= g_tc_min_batch || (g_tc_b1_shadow && c->dtype != RAG_BF16 && c->n >= 262144));
+    // tensor-core path: every batch >= g_tc_min_batch (default 2); a single query only on an fp32 corpus (the
+    // filter then streams the bf16 shadow: half the bytes of the fp32 rows) that is large enough to matter
+    const bool use_tc = c->n > 0 && (B >= g_tc_min_batch || (g_tc_b1_shadow && c->dtype == RAG_F32 && c->n >= 262144));
     const int kp = use_tc ? std::max(64, next_pow2(2 * k + 1)) : std::max(16, next_pow2(k + 6));
     for (auto& v : g.ev_valid) v = false;
     for (auto& t : g.timings) t = 0.f;
@@ -523,6 +523,7 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
         p.n_queries = B;
         p.kp = kp;
         p.allow = allow_dev;
+        p.fp16_operands = c->dtype == RAG_F16;
         int grid = 0;
         const size_t smem = gemm_plan(p, g.sm_count, g.smem_optin, &grid);
         if (smem == 0) return fail(RAG_ERANGE, "k=%d does not fit the contraction kernel's shared memory", k);
@@ -539,7 +540,7 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
         p.cand_cnt = g.cand_cnt.as<int32_t>();
         p.sample_keys = g.sample_keys.as<uint64_t>();
         p.tau_keys = p.use_sample ? g.tau_keys.as<uint64_t>() : nullptr;
-        CU_TRY(query_prep_launch(q_dev, B, bpad, c->dim, g.q16.p, g.q_resid.as<float>(), g.stream));
+        CU_TRY(query_prep_launch(q_dev, B, bpad, c->dim, g.q16.p, g.q_resid.as<float>(), p.fp16_operands, g.stream));
         ++g.n_launch;
         q_resid = g.q_resid.as<float>();
         CU_TRY(cudaMemsetAsync(g.cand_cnt.p, 0, (size_t)bpad * 4, g.stream));

@@ -28,13 +28,16 @@
 //                Everything with filter score >= tau_q is captured, so the candidate set provably
 //                contains the top-k unless the list overflows (flagged -> exact fallback pass).
 //
-// Both operands are bf16 (the corpus itself, or its bf16 shadow for fp32/fp16 corpora; queries are
-// rounded to bf16 by query_prep_kernel which also returns the exact norm of the rounding residual).
+// Both operands are 16-bit: bf16 (a bf16 corpus, or the bf16 shadow of an fp32 corpus) or fp16 (an fp16 corpus,
+// used as stored); queries are rounded to the same format by query_prep_kernel, which also returns the exact
+// norm of the rounding residual.
 // The result is only a FILTER: dense_select.cu re-scores the survivors with the canonical fp64 dot
 // product over the stored values and checks the margin against the rigorous filter error bound.
 //
 // Algorithmic work: 2 * B * n * dim flops per call; HBM bytes: ONE pass over the bf16 rows (+ the sample).
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -104,9 +107,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 at [4,6), A format at [7,10), B format at [10,13) (0 = f16, 1 = bf16),
+// both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_16bit(int m, int n, uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
@@ -236,7 +240,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(GT_M, GT_N);
+            const uint32_t idesc = umma_idesc_16bit(GT_M, GT_N, p.fp16_operands ? 0u : 1u);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
@@ -388,17 +392,26 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 }
 
 // ---- query preparation: fp32 -> bf16 (RNE) + exact norm of the rounding residual ---------------------------
+template <typename T16>
 __global__ void query_prep_kernel(const float* __restrict__ q, int n_queries, int n_padded, int dim,
-                                  __nv_bfloat16* __restrict__ q16, float* __restrict__ resid_norm) {
+                                  T16* __restrict__ q16, float* __restrict__ resid_norm) {
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_padded) return;
     double r2 = 0.0;
     for (int c = lane; c < dim; c += 32) {
         float v = w < n_queries ? q[(size_t)w * dim + c] : 0.f;
-        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        T16 h;
+        float back;
+        if constexpr (sizeof(T16) == sizeof(__nv_bfloat16) && std::is_same<T16, __nv_bfloat16>::value) {
+            h = __float2bfloat16_rn(v);
+            back = __bfloat162float(h);
+        } else {
+            h = __float2half_rn(v);
+            back = __half2float(h);
+        }
         q16[(size_t)w * dim + c] = h;
-        double d = (double)v - (double)__bfloat162float(h);
+        double d = (double)v - (double)back;
         r2 += d * d;
     }
 #pragma unroll
@@ -407,11 +420,15 @@ __global__ void query_prep_kernel(const float* __restrict__ q, int n_queries, in
 }
 
 cudaError_t query_prep_launch(const float* q, int n_queries, int n_padded, int dim, void* q16, float* resid_norm,
-                              cudaStream_t st) {
+                              int fp16, cudaStream_t st) {
     const int warps_per_block = 8;
     int grid = (n_padded + warps_per_block - 1) / warps_per_block;
-    query_prep_kernel<<<grid, warps_per_block * 32, 0, st>>>(q, n_queries, n_padded, dim,
-                                                             reinterpret_cast<__nv_bfloat16*>(q16), resid_norm);
+    if (fp16)
+        query_prep_kernel<__half><<<grid, warps_per_block * 32, 0, st>>>(q, n_queries, n_padded, dim,
+                                                                        reinterpret_cast<__half*>(q16), resid_norm);
+    else
+        query_prep_kernel<__nv_bfloat16><<<grid, warps_per_block * 32, 0, st>>>(
+            q, n_queries, n_padded, dim, reinterpret_cast<__nv_bfloat16*>(q16), resid_norm);
     return cudaGetLastError();
 }
 
@@ -472,14 +489,14 @@ static EncodeTiledFn encode_fn() {
 }
 
 // row-major [rows][dim] bf16 matrix, box = box_rows x 64 elements, 128B swizzle, OOB rows read as zero
-static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows) {
+static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows, int fp16) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
     cuuint32_t box[2] = {(cuuint32_t)GT_K, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+    CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -541,8 +558,9 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
 cudaError_t gemm_launch(const GemmParams& p, int mode, const void* q16, const void* x16, int grid, size_t smem,
                         cudaStream_t st) {
     CUtensorMap map_q, map_x;
-    if (!make_map(&map_q, q16, gemm_padded_queries(p.n_queries), p.dim, GT_M)) return cudaErrorNotSupported;
-    if (!make_map(&map_x, x16, p.n_rows, p.dim, GT_N)) return cudaErrorNotSupported;
+    if (!make_map(&map_q, q16, gemm_padded_queries(p.n_queries), p.dim, GT_M, p.fp16_operands))
+        return cudaErrorNotSupported;
+    if (!make_map(&map_x, x16, p.n_rows, p.dim, GT_N, p.fp16_operands)) return cudaErrorNotSupported;
     auto kern = mode == 0 ? dense_gemm_topk_kernel<0> : dense_gemm_topk_kernel<1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

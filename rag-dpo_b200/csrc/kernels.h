@@ -52,6 +52,7 @@ struct GemmParams {
     int n_lists, n_stages, n_qblocks, sample_tiles, sample_step, sample_chunks;
     uint32_t sample_last_mask;   // columns of the last sample chunk that count
     int balance_tail;            // main pass: split the leftover tiles by (tile, query block) items
+    int fp16_operands;           // 1: both operands are fp16 (fp16 corpus used as stored), 0: bf16
 };
 int gemm_sample_m();
 void gemm_set_sample_div(int v);
@@ -63,7 +64,7 @@ cudaError_t gemm_launch(const GemmParams& p, int mode, const void* q16, const vo
                         cudaStream_t st);
 // fp32 queries -> bf16 (padded rows zeroed) + ||q - bf16(q)||_2 per query
 cudaError_t query_prep_launch(const float* q, int n_queries, int n_padded, int dim, void* q16, float* resid_norm,
-                              cudaStream_t st);
+                              int fp16, cudaStream_t st);
 // bf16 shadow of an fp32/fp16 corpus + max_r ||x_r - bf16(x_r)||_2 (atomicMax into *max_resid)
 cudaError_t shadow_launch(const void* rows, int dtype, int64_t n_rows, int dim, void* out, float* max_resid,
                           cudaStream_t st);
