@@ -16,8 +16,10 @@ MatJoss/RAG-DPO (citations relative to /root/reference):
 
 The canonical dense score is the fp64 sum of the exact
 products of the stored values in a FIXED order, so GPU and oracle agree
-bit-for-bit:  32 interleaved partial sums p[l] += q[32j+l]*x[32j+l] for
-j = 0..D/32-1, then p[l] += p[l+off] for off = 16,8,4,2,1.
+bit-for-bit:  32 partial sums; p[l] owns the 8-element groups g = l, l+32,
+l+64, ... (elements 8g..8g+7) and adds their products in ascending element
+order; then p[l] += p[l+off] for off = 16,8,4,2,1.  (A group is one 16-byte
+vector of a bf16/fp16 row, two of an fp32 row: the order a GPU warp reads in.)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 ``--impl reference`` leg may import anything under oracle/.
@@ -74,10 +76,14 @@ def canonical_scores(q32, x_stored32):
     q = np.asarray(q32, dtype=np.float32).astype(np.float64)
     x = np.atleast_2d(x_stored32)
     n, d = x.shape
-    assert d % 32 == 0
+    assert d % 8 == 0
+    groups = d // 8
     p = np.zeros((n, 32), dtype=np.float64)
-    for j in range(d // 32):
-        p += x[:, 32 * j:32 * j + 32].astype(np.float64) * q[32 * j:32 * j + 32]
+    for c in range((groups + 31) // 32):            # lane l takes group 32c + l of this chunk
+        w = min(32, groups - 32 * c)
+        for i in range(8):
+            cols = slice(256 * c + i, 256 * c + 8 * w, 8)
+            p[:, :w] += x[:, cols].astype(np.float64) * q[cols]
     off = 16
     while off >= 1:
         p[:, :off] += p[:, off:2 * off]

@@ -68,14 +68,15 @@ static inline double load_elem(const void* rows, int dtype, int64_t idx) {
     }
 }
 
-/* Canonical score: 32 interleaved fp64 partial sums, then a
- * fixed halving tree.  The products are exact in fp64 (24-bit x <=24-bit). */
+/* Canonical score: 32 fp64 partial sums — p[l] owns the 8-element
+ * groups l, l+32, l+64, ... and adds their products in ascending element order —
+ * then a fixed halving tree.  The products are exact in fp64 (24-bit x <=24-bit). */
 double orc_dense_score(const float* q, const void* rows, int dtype, int64_t row, int d) {
     double p[32];
     for (int l = 0; l < 32; ++l) p[l] = 0.0;
-    for (int j = 0; j < d / 32; ++j)
-        for (int l = 0; l < 32; ++l)
-            p[l] += (double)q[32 * j + l] * load_elem(rows, dtype, row * (int64_t)d + 32 * j + l);
+    for (int g = 0; g < d / 8; ++g)
+        for (int i = 0; i < 8; ++i)
+            p[g & 31] += (double)q[8 * g + i] * load_elem(rows, dtype, row * (int64_t)d + 8 * g + i);
     for (int off = 16; off >= 1; off >>= 1)
         for (int l = 0; l < off; ++l) p[l] += p[l + off];
     return p[0];

@@ -150,7 +150,10 @@ struct WarpTopKT {
         __syncwarp();
     }
     __device__ __forceinline__ void prune(int lane) {
-        const int cap = 2 * kp;
+        // sort the smallest power of two that covers the n live entries (entries past it are never read
+        // before they are overwritten by later appends or cleared by finish())
+        int cap = kWarp < 2 * kp ? kWarp : 2 * kp;
+        while (cap < n) cap <<= 1;
         for (int i = n + lane; i < cap; i += kWarp) buf[i] = K{};
         warp_bitonic_desc(buf, cap, lane);
         if (n > kp) n = kp;

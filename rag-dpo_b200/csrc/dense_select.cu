@@ -75,35 +75,93 @@ cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int flat_c
 }
 
 // ---------------------------------------------------------------------------
-// canonical fp64 score (warp-cooperative).  Valid in lane 0.
+// canonical fp64 score, warp-cooperative.  Lane l owns the 8-element groups l, l+32, l+64,
+// ... of the row — one 16-byte vector of a bf16/fp16 row, two of an fp32 row — and adds their products in
+// ascending element order; then the fixed lane tree.  Valid in lane 0.
+// The query sits in SHARED memory as doubles in a lane-major layout (q64_index) so that a lane's two
+// doubles of every 16-byte read are conflict-free.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double load_elem_f64(const void* rows, int dtype, size_t idx) {
-    if (dtype == RAG_F32) return (double)reinterpret_cast<const float*>(rows)[idx];
-    if (dtype == RAG_BF16) return (double)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[idx]);
-    return (double)__half2float(reinterpret_cast<const __half*>(rows)[idx]);
+__host__ __device__ __forceinline__ int q64_index(int e) {   // element e -> slot in the staged query
+    const int g = e >> 3, i = e & 7;
+    return ((((g >> 5) * 4 + (i >> 1)) * 32 + (g & 31)) << 1) + (i & 1);
+}
+__host__ __device__ __forceinline__ int q64_slots(int dim) { return ((dim / 8 + 31) / 32) * 256; }
+
+// stages q (fp32, global) as doubles into q64s; returns |q|^2 (valid in every thread).  All threads of a
+// 256-thread CTA call it; s_red: 8 doubles of shared memory.  Ends with __syncthreads().
+__device__ __forceinline__ double stage_query(const float* __restrict__ q, int dim, double* q64s, double* s_red) {
+    double sq = 0.0;
+    for (int v = threadIdx.x; v < dim / 4; v += blockDim.x) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(q) + v);
+        const int e = 4 * v;
+        double2 a = make_double2((double)f.x, (double)f.y), b = make_double2((double)f.z, (double)f.w);
+        *reinterpret_cast<double2*>(q64s + q64_index(e)) = a;
+        *reinterpret_cast<double2*>(q64s + q64_index(e + 2)) = b;
+        sq += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
+    return tot;
 }
 
-__device__ __forceinline__ double canonical_dot(const float* __restrict__ q, const void* __restrict__ rows, int dtype,
-                                                size_t row, int dim, int lane) {
-    double p = 0.0;
-    const size_t base = row * (size_t)dim;
-    const int steps = dim / 32;
-    // the summation ORDER is fixed (j ascending); the loads are issued 8 at a time so that their latencies overlap
-    int j = 0;
-    for (; j + 8 <= steps; j += 8) {
-        double a[8], x[8];
+template <int DT>
+__device__ __forceinline__ void unpack8_f64(const uint4* v, double* x) {
+    if constexpr (DT == RAG_F32) {
+        x[0] = (double)__uint_as_float(v[0].x); x[1] = (double)__uint_as_float(v[0].y);
+        x[2] = (double)__uint_as_float(v[0].z); x[3] = (double)__uint_as_float(v[0].w);
+        x[4] = (double)__uint_as_float(v[1].x); x[5] = (double)__uint_as_float(v[1].y);
+        x[6] = (double)__uint_as_float(v[1].z); x[7] = (double)__uint_as_float(v[1].w);
+    } else {
+        const uint32_t w[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            a[u] = (double)q[32 * (j + u) + lane];
-            x[u] = load_elem_f64(rows, dtype, base + 32 * (j + u) + lane);
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (DT == RAG_BF16) {
+                x[2 * i] = (double)__uint_as_float(w[i] << 16);
+                x[2 * i + 1] = (double)__uint_as_float(w[i] & 0xFFFF0000u);
+            } else {
+                x[2 * i] = (double)__half2float(__ushort_as_half((unsigned short)(w[i] & 0xFFFFu)));
+                x[2 * i + 1] = (double)__half2float(__ushort_as_half((unsigned short)(w[i] >> 16)));
+            }
+        }
+    }
+}
+
+template <int DT>
+__device__ __forceinline__ double canonical_dot(const double* __restrict__ q64s, const void* __restrict__ rows,
+                                                size_t row, int dim, int lane) {
+    constexpr int VPG = DT == RAG_F32 ? 2 : 1;       // 16-byte vectors per 8-element group
+    constexpr int CH = DT == RAG_F32 ? 2 : 4;        // chunks (of 32 groups) whose loads are in flight together
+    const int groups = dim >> 3;
+    const uint4* base = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(rows) +
+                                                       row * (size_t)dim * (DT == RAG_F32 ? 4 : 2));
+    double p = 0.0;
+    for (int c0 = 0; c0 * 32 < groups; c0 += CH) {
+        uint4 v[CH][VPG];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int g = (c0 + u) * 32 + lane;
+#pragma unroll
+            for (int h = 0; h < VPG; ++h) v[u][h] = g < groups ? __ldg(base + g * VPG + h) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) p = __fma_rn(a[u], x[u], p);   // exact product: one rounding, p + a*x
-    }
-    for (; j < steps; ++j) {
-        const double a = (double)q[32 * j + lane];
-        const double x = load_elem_f64(rows, dtype, base + 32 * j + lane);
-        p = __fma_rn(a, x, p);
+        for (int u = 0; u < CH; ++u) {
+            const int g = (c0 + u) * 32 + lane;
+            if (g < groups) {
+                double x[8];
+                unpack8_f64<DT>(v[u], x);
+                const double2* qq = reinterpret_cast<const double2*>(q64s) + (size_t)(c0 + u) * 4 * 32 + lane;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {       // exact products: one rounding per addition
+                    const double2 a = qq[h * 32];
+                    p = __fma_rn(a.x, x[2 * h], p);
+                    p = __fma_rn(a.y, x[2 * h + 1], p);
+                }
+            }
+        }
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) p = __dadd_rn(p, __shfl_down_sync(0xffffffffu, p, off));
@@ -120,67 +178,185 @@ struct ExactKey {
     }
 };
 
-// canonical re-score of the kp candidates in `top` (shared or global memory), final order, margin check
-__device__ __forceinline__ void refine_body(const RefineParams& p, int b, const uint64_t* top, ExactKey* ek) {
-    __shared__ double s_qnorm2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* q = p.q + (size_t)b * p.dim;
-    const int nsort = p.kp < 32 ? 32 : p.kp;
+// ---------------------------------------------------------------------------
+// fused select + refine: one CTA (8 warps) per query.
+//   1. merge: every warp runs a top-kp over its share of the query's candidate keys; the 8 sorted lists
+//      (even warps descending, odd ascending) are merged pairwise — elementwise max of a descending and an
+//      ascending list is the bitonic top half of their union — down to ONE list of the kp best filter keys.
+//   2. refine, adaptive: re-score the first m1 = k + a few candidates with the canonical fp64 dot product,
+//      take the k-th exact score E_k, and re-score exactly those further candidates whose filter score can
+//      still reach it (filter >= E_k - eps; the list is sorted, so they are a prefix).  Candidates past that
+//      prefix provably cannot enter the top-k, so they are never fetched.
+//   3. final order by rank counting over the re-scored candidates, margin check against the rows that are
+//      not in the list at all (the same rigorous bound as before).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int first_round(int k) {
+    const int m = (k + 6 + 7) & ~7;
+    return m < 16 ? 16 : m;
+}
 
-    for (int j = warp; j < nsort; j += 8) {
-        uint64_t key = j < p.kp ? top[j] : 0ull;
-        ExactKey e;
-        e.pad = 0;
-        if (key == 0ull) {
-            e.s = -INFINITY; e.row = 0xFFFFFFFFu;
-        } else {
-            e.row = key_row(key);
-            e.s = canonical_dot(q, p.rows, p.dtype, e.row, p.dim, lane);
+template <int DT, int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
+select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
+                     int list_len, int32_t* __restrict__ overflow, RefineParams p) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    __shared__ double s_red[8];
+    __shared__ double s_ek;
+    const int kp = p.kp, b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* sm_keys = reinterpret_cast<uint64_t*>(sm_raw);                      // kMergeWarps * 2 * kp
+    ExactKey* ek = reinterpret_cast<ExactKey*>(sm_raw + (size_t)kMergeWarps * 2 * kp * sizeof(uint64_t));   // kp
+    double* q64s = reinterpret_cast<double*>(ek + kp);
+
+    const double qnorm2 = stage_query(p.q + (size_t)b * p.dim, p.dim, q64s, s_red);
+
+    // ---- 1. merge ----------------------------------------------------------------------------------
+    if (cand == nullptr) {          // already merged (empty corpus): p.top holds kp keys per query
+        for (int i = threadIdx.x; i < kp; i += blockDim.x) sm_keys[i] = p.top[(size_t)b * kp + i];
+    } else {
+        const uint64_t* src = cand + (size_t)b * n_lists * list_len;
+        const int capacity = n_lists * list_len;
+        WarpTopK t;
+        t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
+        if (flat_counts) {          // ONE contiguous list with a count: 32-key blocks dealt round-robin to the warps
+            const int raw = counts[b];
+            const int total = raw < capacity ? raw : capacity;
+            if (overflow && threadIdx.x == 0) overflow[b] = raw > capacity ? 1 : 0;
+            for (int i0 = warp * 32; i0 < total; i0 += kMergeWarps * 32) {
+                const int i = i0 + lane;
+                t.offer(i < total ? src[i] : 0ull, lane);
+            }
+        } else {                    // n_lists lists of list_len keys (0 = empty): warp w takes lists w, w+8, ...
+            const int32_t* cnt = counts ? counts + (size_t)b * n_lists : nullptr;
+            if (overflow && counts) {
+                int over = 0;
+                for (int l = threadIdx.x; l < n_lists; l += blockDim.x) over |= cnt[l] > list_len;
+                over = __syncthreads_or(over);
+                if (threadIdx.x == 0) overflow[b] = over ? 1 : 0;
+            }
+            for (int l = warp; l < n_lists; l += kMergeWarps) {
+                const int n = cnt ? min(cnt[l], list_len) : list_len;
+                const uint64_t* lp = src + (size_t)l * list_len;
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const int i = i0 + lane;
+                    t.offer(i < n ? lp[i] : 0ull, lane);
+                }
+            }
         }
-        if (lane == 0) ek[j] = e;
-    }
-    if (warp == 0) {
-        double s = 0.0;
-        for (int i = lane; i < p.dim; i += 32) s += (double)q[i] * (double)q[i];
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) s_qnorm2 = s;
+        t.finish(lane);             // buf[0..n) sorted descending, the rest empty
+        if (warp & 1) {             // odd warps: ascending, so that (even, odd) pairs are bitonic
+            for (int j = lane; j < kp / 2; j += 32) {
+                const uint64_t a = t.buf[j], c = t.buf[kp - 1 - j];
+                t.buf[j] = c; t.buf[kp - 1 - j] = a;
+            }
+        }
+        // pairwise reduction 8 -> 4 -> 2 -> 1 lists; list i of a round lives at slot i * span
+        for (int span = 1; span < kMergeWarps; span <<= 1) {
+            const int npairs = kMergeWarps / (2 * span);
+            __syncthreads();
+            for (int tt = threadIdx.x; tt < kp * npairs; tt += blockDim.x) {
+                const int pr = tt / kp, j = tt - pr * kp;
+                uint64_t* A = sm_keys + (size_t)pr * 2 * span * 2 * kp;
+                const uint64_t c = A[(size_t)span * 2 * kp + j];
+                if (c > A[j]) A[j] = c;                      // top half of (descending A, ascending B): bitonic
+            }
+            for (int stride = kp >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int tt = threadIdx.x; tt < (kp >> 1) * npairs; tt += blockDim.x) {
+                    const int pr = tt / (kp >> 1), u = tt - pr * (kp >> 1);
+                    uint64_t* A = sm_keys + (size_t)pr * 2 * span * 2 * kp;
+                    const int lo = 2 * u - (u & (stride - 1)), hi = lo + stride;
+                    const uint64_t x = A[lo], y = A[hi];
+                    const bool swap = (pr & 1) ? (y < x) : (x < y);     // list pr of the next round: even -> descending
+                    if (swap) { A[lo] = y; A[hi] = x; }
+                }
+            }
+        }
     }
     __syncthreads();
-    if (warp != 0) return;
-    warp_bitonic_desc(ek, nsort, lane);
+    const uint64_t* top = sm_keys;                  // kp best filter keys, descending, empties (0) last
 
-    int count = 0;
-    for (int i = lane; i < p.kp; i += 32) count += (ek[i].row != 0xFFFFFFFFu);
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) count += __shfl_xor_sync(0xffffffffu, count, off);
-    const int nout = count < p.k ? count : p.k;
-    for (int i = lane; i < p.k; i += 32) {
-        p.out_rows[(size_t)b * p.k + i] = i < nout ? (int32_t)ek[i].row : -1;
-        p.out_scores[(size_t)b * p.k + i] = i < nout ? ek[i].s : 0.0;
+    // ---- 2. adaptive refine ------------------------------------------------------------------------
+    int nc = 0;                                     // candidates in the list
+    for (int i0 = 0; i0 < kp; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        nc += __syncthreads_count(i < kp && top[i] != 0ull);
     }
-    if (lane == 0) {
+    const double qn = sqrt(qnorm2);
+    double eps = (p.eps_rel * qn + (p.q_resid ? (double)p.q_resid[b] : 0.0)) * (double)(*p.max_row_norm);
+    if (p.x_resid) eps += 1.004 * qn * (double)(*p.x_resid);
+
+    const int m1 = min(nc, first_round(p.k));
+    for (int j = warp; j < m1; j += kMergeWarps) {
+        const uint32_t row = key_row(top[j]);
+        const double s = canonical_dot<DT>(q64s, p.rows, row, p.dim, lane);
+        if (lane == 0) { ek[j].s = s; ek[j].row = row; ek[j].pad = 0; }
+    }
+    __syncthreads();
+    int m2 = m1;
+    if (m1 >= p.k && m1 < nc) {                     // block-uniform
+        if (threadIdx.x < m1) {
+            const ExactKey me = ek[threadIdx.x];
+            int rank = 0;
+            for (int i = 0; i < m1; ++i) rank += me < ek[i];
+            if (rank == p.k - 1) s_ek = me.s;
+        }
+        __syncthreads();
+        const double e_k = s_ek;
+        // candidates whose filter score can still reach the k-th exact score: a prefix of the sorted list
+        for (int i0 = m1; i0 < nc; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x;
+            const int need = __syncthreads_count(i < nc && !(e_k > (double)key_score(top[i]) + eps));
+            m2 += need;
+            if (need < (int)blockDim.x) break;      // block-uniform
+        }
+        for (int j = m1 + warp; j < m2; j += kMergeWarps) {
+            const uint32_t row = key_row(top[j]);
+            const double s = canonical_dot<DT>(q64s, p.rows, row, p.dim, lane);
+            if (lane == 0) { ek[j].s = s; ek[j].row = row; ek[j].pad = 0; }
+        }
+        __syncthreads();
+    }
+
+    // ---- 3. final order (rank counting), outputs, margin check -------------------------------------
+    const int nout = m2 < p.k ? m2 : p.k;
+    for (int j = threadIdx.x; j < m2; j += blockDim.x) {
+        const ExactKey me = ek[j];
+        int rank = 0;
+        for (int i = 0; i < m2; ++i) rank += me < ek[i];
+        if (rank < p.k) {
+            p.out_rows[(size_t)b * p.k + rank] = (int32_t)me.row;
+            p.out_scores[(size_t)b * p.k + rank] = me.s;
+            if (rank == p.k - 1) s_ek = me.s;
+        }
+    }
+    for (int i = nout + threadIdx.x; i < p.k; i += blockDim.x) {
+        p.out_rows[(size_t)b * p.k + i] = -1;
+        p.out_scores[(size_t)b * p.k + i] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         p.out_counts[b] = nout;
         int flag = 0;
         float tau = 0.f;
-        const double qn = sqrt(s_qnorm2);
-        double eps = (p.eps_rel * qn + (p.q_resid ? (double)p.q_resid[b] : 0.0)) * (double)(*p.max_row_norm);
-        if (p.x_resid) eps += 1.004 * qn * (double)(*p.x_resid);
-        // upper bound of the filter score of every row that is NOT a candidate
+        const bool have_k = m2 >= p.k;
+        const double e_k = have_k ? s_ek : 0.0;
+        // upper bound of the filter score of every row that was NOT re-scored
         bool bounded = false;
         double outside = 0.0;
-        if (count == p.kp) {                       // list full: the kp-th candidate bounds the rest
+        if (m2 < nc) {                              // next candidate of the sorted list (safe by construction)
             bounded = true;
-            outside = (double)key_score(top[p.kp - 1]);
-        } else if (p.tau_keys) {                   // threshold capture: everything >= tau_q was kept
+            outside = (double)key_score(top[m2]);
+        } else if (nc == kp) {                      // list full: its last key bounds everything that was dropped
+            bounded = true;
+            outside = (double)key_score(top[kp - 1]);
+        } else if (p.tau_keys) {                    // threshold capture: everything >= tau_q is in the list
             const uint64_t tk = p.tau_keys[(size_t)b * p.tau_stride + p.tau_stride - 1];
             if (tk != 0ull) { bounded = true; outside = (double)key_score(tk); }
         }
-        const bool over = p.overflow && p.overflow[b] != 0;
+        const bool over = overflow && cand && overflow[b] != 0;
         if (bounded || over) {
             // safe iff the k-th exact score beats (outside + eps); an overflowed list voids the bound
-            const bool have_k = count >= p.k;
-            const double e_k = have_k ? ek[p.k - 1].s : 0.0;
             if (over || !have_k || !(e_k > outside + eps)) {
                 flag = 1;
                 tau = have_k ? __double2float_rd(e_k - eps) : -3.0e38f;
@@ -192,36 +368,19 @@ __device__ __forceinline__ void refine_body(const RefineParams& p, int b, const 
     }
 }
 
-__global__ void __launch_bounds__(256) refine_kernel(RefineParams p) {
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    refine_body(p, blockIdx.x, p.top + (size_t)blockIdx.x * p.kp, reinterpret_cast<ExactKey*>(sm_raw));
+static size_t select_refine_smem(int kp, int dim) {
+    return (size_t)kMergeWarps * 2 * kp * sizeof(uint64_t) + (size_t)kp * sizeof(ExactKey) +
+           (size_t)q64_slots(dim) * sizeof(double);
 }
 
-cudaError_t refine_launch(const RefineParams& p, cudaStream_t st) {
-    int nsort = p.kp < 32 ? 32 : p.kp;
-    refine_kernel<<<p.B, 256, (size_t)nsort * sizeof(ExactKey), st>>>(p);
-    return cudaGetLastError();
-}
-
-// merge + refine in one launch: the merged candidates never leave shared memory
-// MIN_BLOCKS = 7 (32 registers): a 1024-query batch is a single wave on 148 SMs; MIN_BLOCKS = 2 keeps the
-// registers that let the refine loads overlap, which is what matters for a handful of queries
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(256, MIN_BLOCKS)
-merge_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
-                    int list_len, int32_t* __restrict__ overflow, RefineParams p) {
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    uint64_t* sm_keys = reinterpret_cast<uint64_t*>(sm_raw);                        // kMergeWarps * 2 * kp
-    ExactKey* ek = reinterpret_cast<ExactKey*>(sm_raw + (size_t)kMergeWarps * 2 * p.kp * sizeof(uint64_t));
-    merge_body(cand, counts, flat_counts, n_lists, list_len, p.kp, blockIdx.x, sm_keys, overflow);
-    refine_body(p, blockIdx.x, sm_keys, ek);
-}
-
-cudaError_t merge_refine_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int n_lists, int list_len,
-                                int32_t* overflow, const RefineParams& p, cudaStream_t st) {
-    const int nsort = p.kp < 32 ? 32 : p.kp;
-    const size_t smem = (size_t)kMergeWarps * 2 * p.kp * sizeof(uint64_t) + (size_t)nsort * sizeof(ExactKey);
-    auto kern = p.B >= 512 ? merge_refine_kernel<7> : merge_refine_kernel<2>;
+template <int DT>
+static cudaError_t select_refine_dt(const uint64_t* cand, const int32_t* counts, int flat_counts, int n_lists,
+                                    int list_len, int32_t* overflow, const RefineParams& p, cudaStream_t st) {
+    const size_t smem = select_refine_smem(p.kp, p.dim);
+    // big batches: 6 (fp32 rows: 5, the registers of the wider loads) CTAs per SM; MIN_BLOCKS = 2 keeps the
+    // registers that let the refine loads overlap, which is what matters for a handful of queries
+    constexpr int kBig = DT == RAG_F32 ? 5 : 6;
+    auto kern = p.B >= 512 ? select_refine_kernel<DT, kBig> : select_refine_kernel<DT, 2>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -230,23 +389,39 @@ cudaError_t merge_refine_launch(const uint64_t* cand, const int32_t* counts, int
     return cudaGetLastError();
 }
 
+cudaError_t merge_refine_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int n_lists, int list_len,
+                                int32_t* overflow, const RefineParams& p, cudaStream_t st) {
+    if (p.dtype == RAG_F32) return select_refine_dt<RAG_F32>(cand, counts, flat_counts, n_lists, list_len, overflow, p, st);
+    if (p.dtype == RAG_BF16) return select_refine_dt<RAG_BF16>(cand, counts, flat_counts, n_lists, list_len, overflow, p, st);
+    return select_refine_dt<RAG_F16>(cand, counts, flat_counts, n_lists, list_len, overflow, p, st);
+}
+
+// p.top already holds the merged kp keys per query (used for an empty corpus: all keys 0)
+cudaError_t refine_launch(const RefineParams& p, cudaStream_t st) {
+    return merge_refine_launch(nullptr, nullptr, 0, 0, 0, nullptr, p, st);
+}
+
 // ---------------------------------------------------------------------------
 // fallback tail: exact scores of every collected row, then a streaming
 // best-k select (sort 2048 at a time, keep the head).
 // ---------------------------------------------------------------------------
 constexpr int kSelN = 2048;
 
+template <int DT>
 __global__ void __launch_bounds__(256) collect_select_kernel(CollectSelectParams p) {
     __shared__ ExactKey ek[kSelN];
+    __shared__ double s_red[8];
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    double* q64s = reinterpret_cast<double*>(sm_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x;
-    const float* q = p.q + (size_t)qi * p.dim;
     const uint32_t* list = p.rows_list + (size_t)qi * p.cap;
     double* sc = p.scratch_scores + (size_t)qi * p.cap;
     const int cnt = (int)(p.counts[qi] < (unsigned)p.cap ? p.counts[qi] : (unsigned)p.cap);
+    stage_query(p.q + (size_t)qi * p.dim, p.dim, q64s, s_red);
 
     for (int j = warp; j < cnt; j += 8) {
-        double s = canonical_dot(q, p.rows, p.dtype, list[j], p.dim, lane);
+        double s = canonical_dot<DT>(q64s, p.rows, list[j], p.dim, lane);
         if (lane == 0) sc[j] = s;
     }
     __syncthreads();
@@ -275,7 +450,10 @@ __global__ void __launch_bounds__(256) collect_select_kernel(CollectSelectParams
 }
 
 cudaError_t collect_select_launch(const CollectSelectParams& p, cudaStream_t st) {
-    collect_select_kernel<<<p.nq, 256, 0, st>>>(p);
+    const size_t smem = (size_t)q64_slots(p.dim) * sizeof(double);
+    if (p.dtype == RAG_F32) collect_select_kernel<RAG_F32><<<p.nq, 256, smem, st>>>(p);
+    else if (p.dtype == RAG_BF16) collect_select_kernel<RAG_BF16><<<p.nq, 256, smem, st>>>(p);
+    else collect_select_kernel<RAG_F16><<<p.nq, 256, smem, st>>>(p);
     return cudaGetLastError();
 }
 
