@@ -196,6 +196,7 @@ int rag_set_option(const char* key, int64_t value) {
     else if (!strcmp(key, "tc_b1_shadow")) g_tc_b1_shadow = value != 0;
     else if (!strcmp(key, "sample_div")) gemm_set_sample_div((int)value);
     else if (!strcmp(key, "balance_tail")) gemm_set_balance_tail((int)value);
+    else if (!strcmp(key, "pair_mode")) gemm_set_pair_mode((int)value);
     else return fail(RAG_EINVAL, "unknown option %s", key);
     return RAG_OK;
 }

@@ -28,6 +28,12 @@
 //                Everything with filter score >= tau_q is captured, so the candidate set provably
 //                contains the top-k unless the list overflows (flagged -> exact fallback pass).
 //
+// Pair mode (NCTA = 2, main pass with an even number of query blocks): two CTAs of a cluster — the two SMs of
+// one TPC — work on ONE 256-query x 256-row tile with tcgen05.mma.cta_group::2.  Each CTA stages its own 128
+// queries and HALF of the row tile (16 KB + 16 KB per stage instead of 16 + 32), the leader CTA issues the
+// MMAs, each CTA's TMEM receives its own 128 x 256 accumulator and runs the same fused select.  Operand
+// traffic from L2 and shared-memory reads per SM drop by a third.
+//
 // Both operands are 16-bit: bf16 (a bf16 corpus, or the bf16 shadow of an fp32 corpus) or fp16 (an fp16 corpus,
 // used as stored); queries are rounded to the same format by query_prep_kernel, which also returns the exact
 // norm of the rounding residual.
@@ -96,6 +102,51 @@ __device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {
     return v;
 }
 
+// ---- cluster (CTA pair) helpers ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a location in this CTA's shared memory) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a pair: data lands in THIS CTA's shared memory, the bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                                 uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// the MMAs issued so far by this thread are complete -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
 // bits: [0,14) addr>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 = 64 |
 //       [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
@@ -116,47 +167,50 @@ __host__ __device__ constexpr uint32_t umma_idesc_16bit(int m, int n, uint32_t f
 // ---- the kernel ---------------------------------------------------------------------------------
 constexpr int kSampleM = 8;       // order statistic taken from the sample pass
 
-// Work items of one CTA, identical in all three warp roles.
-//   sample pass (MODE 0): query block outer, the CTA's sample tiles inner (the running top-16 of a
+// Work items of one worker (a CTA, or a CTA pair in pair mode), identical in all three warp roles.
+//   sample pass (MODE 0): query block outer, the CTA's sample tiles inner (the running top-m of a
 //                         query lives in registers across tiles)
-//   main pass   (MODE 1): row tile outer, query block inner: a corpus tile is fetched from HBM once
-//                         and re-read from L2 for every query block
-// tiles of this CTA: t = blockIdx.x + i * gridDim.x, i = 0, step, 2*step, ... (at most max_tiles)
-template <int MODE>
+//   main pass   (MODE 1): row tile outer, query item inner: a corpus tile is fetched from HBM once
+//                         and re-read from L2 for every query item (a query block; a PAIR of blocks in pair mode)
+// tiles of this worker: t = worker + i * n_workers, i = 0, step, 2*step, ... (at most max_tiles)
+template <int MODE, int NCTA>
 struct WorkIter {
     int64_t n_tiles, i, i_first;
-    int step, max_tiles, n_qblocks;
+    int step, max_tiles, n_qitems;
+    int worker, n_workers;
     int taken, qb;
     bool started;
-    // MODE 1 tail: the n_tiles % gridDim.x leftover tiles are split by (tile, query block) ITEMS over all
-    // CTAs, so that the CTAs finish within a few items of each other instead of a whole tile apart
+    // MODE 1 tail: the n_tiles % n_workers leftover tiles are split by (tile, query item) ITEMS over all
+    // workers, so that they finish within a few items of each other instead of a whole tile apart
     int64_t full_rounds, tail_item, tail_end;
     bool in_tail;
     __device__ __forceinline__ void init(const GemmParams& p) {
         n_tiles = (p.n_rows + GT_N - 1) / GT_N;
         step = MODE == 0 ? p.sample_step : 1;
         max_tiles = MODE == 0 ? p.sample_tiles : 0x7fffffff;
-        n_qblocks = p.n_qblocks;
+        n_qitems = (p.n_qblocks + NCTA - 1) / NCTA;
+        worker = blockIdx.x / NCTA;
+        n_workers = gridDim.x / NCTA;
         // the sample of CTA c starts at a pseudo-random one of its tiles, so that the union of the CTAs'
         // samples is spread over the whole corpus instead of being its first rows
         i_first = 0;
         if (MODE == 0) {
-            const int64_t span = n_tiles / gridDim.x - (int64_t)(max_tiles - 1) * step;   // tiles every CTA has
-            if (span > 1) i_first = (int64_t)((blockIdx.x * 2654435761u) % (uint32_t)span);
+            const int64_t span = n_tiles / n_workers - (int64_t)(max_tiles - 1) * step;   // tiles every CTA has
+            if (span > 1) i_first = (int64_t)((worker * 2654435761u) % (uint32_t)span);
         }
         i = i_first; taken = 0; qb = 0; started = false;
         in_tail = false;
-        full_rounds = n_tiles / gridDim.x;
-        const int64_t tail_items = (n_tiles - full_rounds * gridDim.x) * n_qblocks;
-        tail_item = tail_items * blockIdx.x / gridDim.x;
-        tail_end = tail_items * (blockIdx.x + 1) / gridDim.x;
+        full_rounds = n_tiles / n_workers;
+        const int64_t tail_items = (n_tiles - full_rounds * n_workers) * n_qitems;
+        tail_item = tail_items * worker / n_workers;
+        tail_end = tail_items * (worker + 1) / n_workers;
         if (MODE == 1 && p.balance_tail) max_tiles = (int)full_rounds; else tail_end = tail_item;
     }
     __device__ __forceinline__ bool tile_ok() const {
-        return blockIdx.x + i * gridDim.x < n_tiles && taken < max_tiles;
+        return worker + i * n_workers < n_tiles && taken < max_tiles;
     }
-    // advances to the next (tile, query block)
-    __device__ __forceinline__ bool next(int64_t& t, int& qblock) {
+    // advances to the next (tile, query item)
+    __device__ __forceinline__ bool next(int64_t& t, int& qitem) {
         if (!in_tail) {
             if (!started) {
                 started = true;
@@ -164,11 +218,11 @@ struct WorkIter {
                 i += step; ++taken;
                 if (!tile_ok()) { i = i_first; taken = 0; ++qb; }
             } else {
-                if (++qb == n_qblocks) { qb = 0; i += step; ++taken; }
+                if (++qb == n_qitems) { qb = 0; i += step; ++taken; }
             }
-            if (qb < n_qblocks && tile_ok()) {
-                t = blockIdx.x + i * gridDim.x;
-                qblock = qb;
+            if (qb < n_qitems && tile_ok()) {
+                t = worker + i * n_workers;
+                qitem = qb;
                 return true;
             }
             if (MODE == 0) return false;
@@ -177,42 +231,54 @@ struct WorkIter {
             ++tail_item;
         }
         if (tail_item >= tail_end) return false;
-        t = full_rounds * gridDim.x + tail_item / n_qblocks;
-        qblock = (int)(tail_item % n_qblocks);
+        t = full_rounds * n_workers + tail_item / n_qitems;
+        qitem = (int)(tail_item % n_qitems);
         return true;
     }
 };
 
-template <int MODE>     // 0 = sample pass, 1 = main pass
+template <int MODE, int NCTA>     // MODE 0 = sample pass, 1 = main pass; NCTA 2 = CTA-pair MMA (main pass only)
 __global__ void __launch_bounds__(GT_THREADS, 1)
 dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                        GemmParams p) {
+    constexpr int B_ROWS = GT_N / NCTA;                   // rows of the tile this CTA stages
+    constexpr int B_BYTES = B_ROWS * GT_K * 2;
+    constexpr int STAGE_BYTES = GT_A_BYTES + B_BYTES;     // 48 KB, pair mode 32 KB
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the 128B-swizzled tiles need 1024-byte alignment in the shared address space
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* stages = smem;                                                    // n_stages * 48 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * GT_STAGE_BYTES);
-    uint64_t* full_bar = bars;                     // [n_stages]
+    uint8_t* stages = smem;                                                    // n_stages * STAGE_BYTES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * STAGE_BYTES);
+    uint64_t* full_bar = bars;                     // [n_stages]   (pair mode: the leader's are used)
     uint64_t* empty_bar = bars + 8;                // [n_stages]
     uint64_t* tfull_bar = bars + 16;               // [2]
-    uint64_t* tempty_bar = bars + 18;              // [2]
+    uint64_t* tempty_bar = bars + 18;              // [2]          (pair mode: the leader's are used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.dim / GT_K;
-    WorkIter<MODE> work;
+    const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair
+    WorkIter<MODE, NCTA> work;
     work.init(p);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], GT_EPI_WARPS); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], GT_EPI_WARPS * NCTA); }
         mbar_fence_init();
     }
-    if (warp == 1) {   // TMEM: all 512 columns (two 128x256 fp32 accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (NCTA == 2) cluster_sync_all();             // the peer's barriers exist before anything can signal them
+    if (warp == 1) {   // TMEM: all 512 columns (two 128x256 fp32 accumulators); pair mode: in both CTAs at once
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -225,45 +291,56 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             int64_t t;
-            int qb;
-            while (work.next(t, qb)) {
+            int qi;
+            while (work.next(t, qi)) {
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = stages + (size_t)stage * GT_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], GT_STAGE_BYTES);
-                    tma_load_2d(sa, &map_q, kb * GT_K, qb * GT_M, &full_bar[stage]);
-                    tma_load_2d(sa + GT_A_BYTES, &map_x, kb * GT_K, (int)(t * GT_N), &full_bar[stage]);
+                    uint8_t* sa = stages + (size_t)stage * STAGE_BYTES;
+                    if (NCTA == 2) {
+                        // both CTAs' bytes are counted on the leader's barrier, which only the leader arms
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                        const uint32_t lbar = mapa_u32(&full_bar[stage], 0);
+                        tma_load_2d_pair(sa, &map_q, kb * GT_K, (qi * 2 + (int)rank) * GT_M, lbar);
+                        tma_load_2d_pair(sa + GT_A_BYTES, &map_x, kb * GT_K, (int)(t * GT_N) + (int)rank * B_ROWS, lbar);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(sa, &map_q, kb * GT_K, qi * GT_M, &full_bar[stage]);
+                        tma_load_2d(sa + GT_A_BYTES, &map_x, kb * GT_K, (int)(t * GT_N), &full_bar[stage]);
+                    }
                     if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_16bit(GT_M, GT_N, p.fp16_operands ? 0u : 1u);
+        // ===================== MMA issuer (pair mode: the leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = umma_idesc_16bit(GT_M * NCTA, GT_N, p.fp16_operands ? 0u : 1u);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
             int64_t t;
-            int qb;
-            for (; work.next(t, qb); ++it) {
+            int qi;
+            for (; work.next(t, qi); ++it) {
                 const uint32_t buf = it & 1;
-                mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+                mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue(s) drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * GT_N;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);               // TMA bytes landed
+                    mbar_wait(&full_bar[stage], phase);               // TMA bytes landed (in both CTAs)
                     tc_fence_after();
-                    const uint8_t* sa = stages + (size_t)stage * GT_STAGE_BYTES;
+                    const uint8_t* sa = stages + (size_t)stage * STAGE_BYTES;
                     const uint64_t a_desc = umma_desc_sw128(sa);
                     const uint64_t b_desc = umma_desc_sw128(sa + GT_A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < GT_K / 16; ++k)               // +32 B per K=16 step inside the swizzle atom
-                        tc_mma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                    tc_commit(&empty_bar[stage]);                     // stage reusable once these MMAs retire
+                    for (int k = 0; k < GT_K / 16; ++k) {             // +32 B per K=16 step inside the swizzle atom
+                        if (NCTA == 2) tc_mma_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        else tc_mma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    // stage reusable (in both CTAs) once these MMAs retire
+                    if (NCTA == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
                     if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[buf]);                           // accumulator complete
+                if (NCTA == 2) tc_commit_pair(&tfull_bar[buf]); else tc_commit(&tfull_bar[buf]);   // accumulator complete
             }
         }
     } else {
@@ -274,12 +351,15 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int lg = warp & 3;                 // TMEM lane group this warp may read
         const int my = lg * 32 + lane;           // my query inside the query block == my TMEM lane
         const int n_chunks = MODE == 0 ? p.sample_chunks : GT_N / 32;
-        float* s_tau = reinterpret_cast<float*>(bars + 24);            // [n_qblocks][128]
+        const int n_tau_blocks = (p.n_qblocks + NCTA - 1) / NCTA * NCTA;
+        float* s_tau = reinterpret_cast<float*>(bars + 24);            // [n_tau_blocks][128]
         // survivors of the current tile are parked here (per thread) and flushed with ONE atomic slot
         // reservation per thread and tile, so a warp waits for the atomic round trip once per tile
-        uint64_t* s_pend = reinterpret_cast<uint64_t*>(s_tau + p.n_qblocks * GT_M) + (size_t)((warp - 2) * 32 + lane) * kPend;
+        uint64_t* s_pend = reinterpret_cast<uint64_t*>(s_tau + n_tau_blocks * GT_M) + (size_t)((warp - 2) * 32 + lane) * kPend;
+        const uint32_t tempty_leader0 = NCTA == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u;
+        const uint32_t tempty_leader1 = NCTA == 2 ? mapa_u32(&tempty_bar[1], 0) : 0u;
         if (MODE == 1) {
-            for (int b = 0; b < p.n_qblocks; ++b) {
+            for (int b = (int)rank; b < n_tau_blocks; b += NCTA) {      // the query blocks this CTA serves
                 const int q = b * GT_M + my;
                 float tau = INFINITY;                                   // padded queries never pass
                 if (q < p.n_queries) {
@@ -296,7 +376,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         int cur_qb = -1;
         float best[kSampleM];                    // MODE 0: the best scores of my query, descending
         int64_t t;
-        int qb;
+        int qi;
         auto flush_sample = [&](int qblock) {
             const int q = qblock * GT_M + my;
             if (q >= p.n_queries) return;
@@ -306,7 +386,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             for (int i = 0; i < kSampleM; ++i)
                 out[i] = best[i] == -INFINITY ? 0ull : make_key(best[i], (uint32_t)(blockIdx.x * kSampleM + i));
         };
-        for (; work.next(t, qb); ++it) {
+        for (; work.next(t, qi); ++it) {
+            const int qb = qi * NCTA + (int)rank;                // the query block of THIS CTA
             const int q = qb * GT_M + my;
             float tau = 0.f;
             uint64_t* my_list = nullptr;
@@ -374,7 +455,10 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (lane == 0) {
+                if (NCTA == 2) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+                else mbar_arrive(&tempty_bar[buf]);
+            }
             if (MODE == 1 && npend > 0) {              // counts past the capacity flag an overflow
                 const int slot = atomicAdd(my_cnt, npend);
                 for (int i = 0; i < npend; ++i)
@@ -385,9 +469,13 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) cluster_sync_all();     // the peer is done with this CTA's barriers / operands / TMEM
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (NCTA == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -506,6 +594,8 @@ int gemm_padded_queries(int n_queries) { return (n_queries + GT_M - 1) / GT_M * 
 
 int g_balance_tail = 1;   // split the leftover tiles of the main pass by items (option "balance_tail")
 void gemm_set_balance_tail(int v) { g_balance_tail = v != 0; }
+int g_pair_mode = 1;      // main pass as CTA pairs (tcgen05 cta_group::2) when the query blocks pair up (option "pair_mode")
+void gemm_set_pair_mode(int v) { g_pair_mode = v != 0; }
 int g_sample_div = 1;     // multiplies the survivor target of the sample pass (option "sample_div", experiments)
 void gemm_set_sample_div(int v) { g_sample_div = v < 1 ? 1 : (v > 8 ? 8 : v); }
 int gemm_sample_m() { return kSampleM; }
@@ -514,7 +604,8 @@ int gemm_max_batch() { return kMaxQBlocks * GT_M; }
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     p.n_qblocks = gemm_padded_queries(p.n_queries) / GT_M;
     if (p.n_qblocks > kMaxQBlocks) return 0;
-    const size_t tail = 256 + (size_t)p.n_qblocks * GT_M * 4 + (size_t)GT_M * kPend * 8;   // barriers, tau, parked keys
+    // barriers, tau (query blocks rounded up to a pair), parked keys
+    const size_t tail = 256 + (size_t)((p.n_qblocks + 1) / 2 * 2) * GT_M * 4 + (size_t)GT_M * kPend * 8;
     int stages = (int)((smem_limit - 1024 - (long)tail) / GT_STAGE_BYTES);
     if (stages > 4) stages = 4;
     if (stages < 2) return 0;
@@ -524,6 +615,16 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     *grid_out = grid;
     p.n_lists = grid;
     p.balance_tail = g_balance_tail;
+    // pair mode (main pass): 32 KB stages, one CTA pair per row tile; only when the query blocks pair up
+    // (an odd block count would leave one CTA of the last pair multiplying padding) and every pair has work
+    {
+        const int pair_stage = GT_A_BYTES + GT_B_BYTES / 2;
+        int ps = (int)((smem_limit - 1024 - (long)tail) / pair_stage);
+        if (ps > 6) ps = 6;
+        p.n_stages_pair = ps;
+        p.pair = g_pair_mode && p.n_qblocks % 2 == 0 && ps >= 2 && n_tiles >= sm_count && sm_count >= 2;
+        p.smem_pair = (size_t)ps * pair_stage + tail + 1024;
+    }
     // Sample pass: the m-th best (m = kSampleM = 8) of a sample that holds a fraction f of the rows lets
     // ~(1/f) * Gamma(m) rows per query through the main pass.  Every survivor costs the main pass a slow-path
     // visit, a larger sample costs the sample pass: aim for E = max(1024, 4*kp) survivors per query
@@ -555,13 +656,52 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     return (size_t)stages * GT_STAGE_BYTES + tail + 1024;   // + slack for the 1024-byte alignment of the ring
 }
 
+// main pass as CTA pairs: cluster launch, one pair per SM pair that can be co-resident
+static cudaError_t gemm_launch_pair(const GemmParams& p, const void* q16, const void* x16, int sm_count, cudaStream_t st) {
+    CUtensorMap map_q, map_x;
+    if (!make_map(&map_q, q16, gemm_padded_queries(p.n_queries), p.dim, GT_M, p.fp16_operands))
+        return cudaErrorNotSupported;
+    if (!make_map(&map_x, x16, p.n_rows, p.dim, GT_N / 2, p.fp16_operands)) return cudaErrorNotSupported;
+    auto kern = dense_gemm_topk_kernel<1, 2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_pair);
+    if (e != cudaSuccess) return e;
+    GemmParams pp = p;
+    pp.n_stages = p.n_stages_pair;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(GT_THREADS);
+    cfg.dynamicSmemBytes = p.smem_pair;
+    cfg.stream = st;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    static int max_pairs = -1;            // CTA pairs that are resident together (persistent kernel: one wave)
+    if (max_pairs < 0) {
+        cfg.gridDim = dim3(sm_count / 2 * 2);
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess) return e;
+        max_pairs = n;
+    }
+    const int64_t n_tiles = (p.n_rows + GT_N - 1) / GT_N;
+    int pairs = max_pairs < sm_count / 2 ? max_pairs : sm_count / 2;
+    if (n_tiles < pairs) pairs = (int)n_tiles;
+    if (pairs < 1) return cudaErrorLaunchOutOfResources;
+    cfg.gridDim = dim3(2 * pairs);
+    return cudaLaunchKernelEx(&cfg, kern, map_q, map_x, pp);
+}
+
 cudaError_t gemm_launch(const GemmParams& p, int mode, const void* q16, const void* x16, int grid, size_t smem,
                         cudaStream_t st) {
+    if (mode == 1 && p.pair) return gemm_launch_pair(p, q16, x16, grid, st);
     CUtensorMap map_q, map_x;
     if (!make_map(&map_q, q16, gemm_padded_queries(p.n_queries), p.dim, GT_M, p.fp16_operands))
         return cudaErrorNotSupported;
     if (!make_map(&map_x, x16, p.n_rows, p.dim, GT_N, p.fp16_operands)) return cudaErrorNotSupported;
-    auto kern = mode == 0 ? dense_gemm_topk_kernel<0> : dense_gemm_topk_kernel<1>;
+    auto kern = mode == 0 ? dense_gemm_topk_kernel<0, 1> : dense_gemm_topk_kernel<1, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, GT_THREADS, smem, st>>>(map_q, map_x, p);

@@ -53,10 +53,14 @@ struct GemmParams {
     uint32_t sample_last_mask;   // columns of the last sample chunk that count
     int balance_tail;            // main pass: split the leftover tiles by (tile, query block) items
     int fp16_operands;           // 1: both operands are fp16 (fp16 corpus used as stored), 0: bf16
+    // pair mode of the main pass (tcgen05 cta_group::2): decided by gemm_plan
+    int pair, n_stages_pair;
+    size_t smem_pair;
 };
 int gemm_sample_m();
 void gemm_set_sample_div(int v);
 void gemm_set_balance_tail(int v);
+void gemm_set_pair_mode(int v);
 int gemm_max_batch();
 int gemm_padded_queries(int n_queries);
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out);

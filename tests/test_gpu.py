@@ -433,6 +433,29 @@ def test_dense_batched_tensor_core_path_vs_oracle(dtype, n, d, B):
     c.close()
 
 
+@pytest.mark.parametrize("dtype,n,d,B", [("bf16", 50003, 1024, 512), ("f32", 40000, 512, 256), ("f16", 38000, 1024, 300)])
+def test_pair_mode_cta_group2_vs_oracle_and_single_cta(dtype, n, d, B):
+    """Main pass as CTA pairs (tcgen05 cta_group::2): needs >= 148 row tiles and an even number of 128-query
+    blocks (B = 300 -> 3 blocks: stays single-CTA).  Same results as the oracle and as the single-CTA kernel."""
+    from b200rag import DeviceCorpus, _lib
+    x = helpers.synth_unit(n, d, seed=n + 17)
+    q = helpers.synth_unit(B, d, seed=n + 18)
+    q[3] = x[n // 2]
+    x[n - 1] = x[5]                                        # duplicate pair across the first and the last tile
+    c = DeviceCorpus(d, dtype)
+    c.append(x)
+    allow = np.random.default_rng(4).random(n) < 0.5
+    try:
+        r2, s2, _ = check_topk(c, q, 10, DT[dtype])
+        ra2, sa2, _ = check_topk(c, q, 37, DT[dtype], allow)
+        _lib.set_option("pair_mode", 0)
+        r1, s1, _ = c.topk(q, 10)
+        assert r1.tolist() == r2.tolist() and np.array_equal(s1, s2)
+    finally:
+        _lib.set_option("pair_mode", 1)
+    c.close()
+
+
 def test_tensor_core_path_exact_ties_take_the_fallback():
     from b200rag import DeviceCorpus, _lib
     n, d, B = 20000, 256, 40
