@@ -276,14 +276,20 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    call_ms = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0 = _lib.counters()["launches"]
+        walls = []
         e0.record(torch.cuda.current_stream())
         for _ in range(steps):
+            t0 = time.perf_counter()
             fn()
+            walls.append(1e3 * (time.perf_counter() - t0))
         e1.record(torch.cuda.current_stream())
+        call_ms[fn.__name__] = walls
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -381,7 +387,9 @@ def run_b200(args):
                          f"re-streams it from HBM"},
         "e2e": {"value": qps_e2e * world * (n_local / 1e6), "unit": "queries/s (1M-row-corpus equivalents)",
                 "queries_per_s": qps_e2e,
-                "h2d_bytes_per_step": int(B * d * 4), "d2h_bytes_per_step": int(B * k * 12 + B * 4)},
+                "h2d_bytes_per_step": int(B * d * 4), "d2h_bytes_per_step": int(B * k * 12 + B * 4),
+                "call_ms_p50": float(np.median(call_ms["step_host"])), "call_ms_max": float(max(call_ms["step_host"]))},
+        "step_call_ms": {"p50": float(np.median(call_ms["step"])), "max": float(max(call_ms["step"]))},
         "gpu_launches": int(launches),
         "latency_b1": {"device_ms_p50": float(np.percentile(lat, 50)), "device_ms_p99": float(np.percentile(lat, 99)),
                        "host_call_ms_p50": float(np.percentile(lat_host, 50)),

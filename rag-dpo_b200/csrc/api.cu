@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -197,6 +198,7 @@ int rag_set_option(const char* key, int64_t value) {
     else if (!strcmp(key, "sample_div")) gemm_set_sample_div((int)value);
     else if (!strcmp(key, "balance_tail")) gemm_set_balance_tail((int)value);
     else if (!strcmp(key, "pair_mode")) gemm_set_pair_mode((int)value);
+    else if (!strcmp(key, "sample_resident")) gemm_set_sample_resident((int)value);
     else return fail(RAG_EINVAL, "unknown option %s", key);
     return RAG_OK;
 }
@@ -549,8 +551,8 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
         if (p.use_sample) {
             // sample pass -> per-query threshold (16th best sample score)
             CU_TRY(gemm_launch(p, 0, g.q16.p, x16, grid, smem, g.stream));
-            CU_TRY(merge_launch(g.sample_keys.as<uint64_t>(), nullptr, 0, B, p.n_lists, sm, sm,
-                                g.tau_keys.as<uint64_t>(), nullptr, g.stream));
+            CU_TRY(sample_tau_launch(g.sample_keys.as<uint64_t>(), B, p.n_lists * sm, sm, g.tau_keys.as<uint64_t>(),
+                                     g.stream));
             g.n_launch += 2;
         }
         CU_TRY(gemm_launch(p, 1, g.q16.p, x16, grid, smem, g.stream));
@@ -754,6 +756,8 @@ int rag_dense_topk(rag_corpus_t* c, const float* q, int B, int k, const uint8_t*
     std::lock_guard<std::mutex> lk(g.mu);
     RAG_TRY(require_init());
     RAG_TRY(dense_check(c, q, B, k, out_rows, out_scores, out_counts));
+    const auto t_enter = std::chrono::steady_clock::now();
+    float ms_queued = 0.f;
     const size_t qb = (size_t)B * c->dim * 4;
     const size_t ab = allow_bitmap ? (size_t)((c->n + 7) / 8) : 0;
     const size_t rb = (size_t)B * k * 4, sb = (size_t)B * k * 8, cb = (size_t)B * 4;
@@ -794,6 +798,8 @@ int rag_dense_topk(rag_corpus_t* c, const float* q, int B, int k, const uint8_t*
         CU_TRY(cudaMemcpyAsync(ds, g.o_scores.p, sb, cudaMemcpyDeviceToHost, g.stream));
         CU_TRY(cudaMemcpyAsync(dr, g.o_rows.p, rb, cudaMemcpyDeviceToHost, g.stream));
         CU_TRY(cudaMemcpyAsync(dc, g.o_counts.p, cb, cudaMemcpyDeviceToHost, g.stream));
+        if (attempt == 0)
+            ms_queued = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
         CU_TRY(cudaStreamSynchronize(g.stream));
         bool redone = false;
         if (one_sync && attempt == 0)
@@ -806,6 +812,9 @@ int rag_dense_topk(rag_corpus_t* c, const float* q, int B, int k, const uint8_t*
         memcpy(out_rows, pin + sb, rb);
         memcpy(out_counts, pin + sb + rb, cb);
     }
+    // host-side view of the call: time spent queueing work (before the one synchronisation) and in total
+    g.timings[4] = ms_queued;
+    g.timings[5] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
     return RAG_OK;
 }
 

@@ -248,12 +248,18 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     // the 128B-swizzled tiles need 1024-byte alignment in the shared address space
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stages = smem;                                                    // n_stages * STAGE_BYTES
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.n_stages * STAGE_BYTES);
+    // resident sample (MODE 0, small samples): the CTA's <= 64 sample rows stay in shared memory for all query
+    // blocks (dim/64 blocks of 8 KB) and only the queries stream through a ring of 16 KB stages
+    const bool resident = MODE == 0 && p.sample_resident;
+    constexpr int RES_B_BYTES = 64 * GT_K * 2;                                 // 64 rows x 64 columns
+    uint8_t* a_ring = stages + (size_t)(p.dim / GT_K) * RES_B_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.ring_bytes);
     uint64_t* full_bar = bars;                     // [n_stages]   (pair mode: the leader's are used)
     uint64_t* empty_bar = bars + 8;                // [n_stages]
     uint64_t* tfull_bar = bars + 16;               // [2]
     uint64_t* tempty_bar = bars + 18;              // [2]          (pair mode: the leader's are used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* bres_bar = bars + 22;                // resident sample rows landed
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.dim / GT_K;
@@ -264,6 +270,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], GT_EPI_WARPS * NCTA); }
+        mbar_init(bres_bar, 1);
         mbar_fence_init();
     }
     if (NCTA == 2) cluster_sync_all();             // the peer's barriers exist before anything can signal them
@@ -292,9 +299,24 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             uint32_t phase = 0;
             int64_t t;
             int qi;
+            if (resident) {
+                WorkIter<MODE, NCTA> peek = work;
+                if (peek.next(t, qi)) {            // the one sample tile of this CTA: its first 64 rows, all of K
+                    mbar_arrive_expect_tx(bres_bar, num_kb * RES_B_BYTES);
+                    for (int kb = 0; kb < num_kb; ++kb)
+                        tma_load_2d(stages + (size_t)kb * RES_B_BYTES, &map_x, kb * GT_K, (int)(t * GT_N), bres_bar);
+                }
+            }
             while (work.next(t, qi)) {
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (resident) {
+                        uint8_t* sa = a_ring + (size_t)stage * GT_A_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], GT_A_BYTES);
+                        tma_load_2d(sa, &map_q, kb * GT_K, qi * GT_M, &full_bar[stage]);
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     uint8_t* sa = stages + (size_t)stage * STAGE_BYTES;
                     if (NCTA == 2) {
                         // both CTAs' bytes are counted on the leader's barrier, which only the leader arms
@@ -314,13 +336,15 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     } else if (warp == 1) {
         // ===================== MMA issuer (pair mode: the leader CTA only) =====================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = umma_idesc_16bit(GT_M * NCTA, GT_N, p.fp16_operands ? 0u : 1u);
+            const uint32_t idesc = umma_idesc_16bit(GT_M * NCTA, resident ? 64 : GT_N, p.fp16_operands ? 0u : 1u);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
             int64_t t;
             int qi;
+            bool rows_ready = !resident;
             for (; work.next(t, qi); ++it) {
+                if (!rows_ready) { mbar_wait(bres_bar, 0); tc_fence_after(); rows_ready = true; }
                 const uint32_t buf = it & 1;
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);      // epilogue(s) drained this accumulator
                 tc_fence_after();
@@ -328,9 +352,9 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);               // TMA bytes landed (in both CTAs)
                     tc_fence_after();
-                    const uint8_t* sa = stages + (size_t)stage * STAGE_BYTES;
+                    const uint8_t* sa = resident ? a_ring + (size_t)stage * GT_A_BYTES : stages + (size_t)stage * STAGE_BYTES;
                     const uint64_t a_desc = umma_desc_sw128(sa);
-                    const uint64_t b_desc = umma_desc_sw128(sa + GT_A_BYTES);
+                    const uint64_t b_desc = umma_desc_sw128(resident ? stages + (size_t)kb * RES_B_BYTES : sa + GT_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < GT_K / 16; ++k) {             // +32 B per K=16 step inside the swizzle atom
                         if (NCTA == 2) tc_mma_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
@@ -596,6 +620,8 @@ int g_balance_tail = 1;   // split the leftover tiles of the main pass by items 
 void gemm_set_balance_tail(int v) { g_balance_tail = v != 0; }
 int g_pair_mode = 1;      // main pass as CTA pairs (tcgen05 cta_group::2) when the query blocks pair up (option "pair_mode")
 void gemm_set_pair_mode(int v) { g_pair_mode = v != 0; }
+int g_sample_resident = 1;   // small samples keep their rows resident in shared memory (option "sample_resident")
+void gemm_set_sample_resident(int v) { g_sample_resident = v != 0; }
 int g_sample_div = 1;     // multiplies the survivor target of the sample pass (option "sample_div", experiments)
 void gemm_set_sample_div(int v) { g_sample_div = v < 1 ? 1 : (v > 8 ? 8 : v); }
 int gemm_sample_m() { return kSampleM; }
@@ -610,6 +636,7 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     if (stages > 4) stages = 4;
     if (stages < 2) return 0;
     p.n_stages = stages;
+    p.ring_bytes = stages * GT_STAGE_BYTES;
     const int64_t n_tiles = (p.n_rows + GT_N - 1) / GT_N;
     int grid = (int)(n_tiles < sm_count ? (n_tiles > 0 ? n_tiles : 1) : sm_count);
     *grid_out = grid;
@@ -624,6 +651,7 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
         p.n_stages_pair = ps;
         p.pair = g_pair_mode && p.n_qblocks % 2 == 0 && ps >= 2 && n_tiles >= sm_count && sm_count >= 2;
         p.smem_pair = (size_t)ps * pair_stage + tail + 1024;
+        p.ring_bytes_pair = ps * pair_stage;
     }
     // Sample pass: the m-th best (m = kSampleM = 8) of a sample that holds a fraction f of the rows lets
     // ~(1/f) * Gamma(m) rows per query through the main pass.  Every survivor costs the main pass a slow-path
@@ -651,6 +679,20 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
             p.sample_step = (int)(tiles_per_cta / p.sample_tiles > 0 ? tiles_per_cta / p.sample_tiles : 1);
         }
     }
+    // small sample (one tile, <= 64 columns): the sample rows stay resident in shared memory (dim/64 x 8 KB) and
+    // the MMA is 64 columns wide; the queries stream through a ring of 16 KB stages
+    p.sample_resident = 0;
+    if (g_sample_resident && p.sample_tiles == 1 && p.sample_chunks <= 2) {
+        const long res = (long)(p.dim / GT_K) * 64 * GT_K * 2;
+        int sa = (int)((smem_limit - 1024 - (long)tail - res) / GT_A_BYTES);
+        if (sa > 6) sa = 6;
+        if (sa >= 3) {
+            p.sample_resident = 1;
+            p.n_stages_sample = sa;
+            p.ring_bytes_sample = (int)(res + (long)sa * GT_A_BYTES);
+            p.smem_sample = (size_t)p.ring_bytes_sample + tail + 1024;
+        }
+    }
     // one candidate list per query, filled by all CTAs: E survivors expected, 4x head-room
     p.list_cap = (int)(4 * e_target);
     return (size_t)stages * GT_STAGE_BYTES + tail + 1024;   // + slack for the 1024-byte alignment of the ring
@@ -667,6 +709,7 @@ static cudaError_t gemm_launch_pair(const GemmParams& p, const void* q16, const 
     if (e != cudaSuccess) return e;
     GemmParams pp = p;
     pp.n_stages = p.n_stages_pair;
+    pp.ring_bytes = p.ring_bytes_pair;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -697,14 +740,23 @@ static cudaError_t gemm_launch_pair(const GemmParams& p, const void* q16, const 
 cudaError_t gemm_launch(const GemmParams& p, int mode, const void* q16, const void* x16, int grid, size_t smem,
                         cudaStream_t st) {
     if (mode == 1 && p.pair) return gemm_launch_pair(p, q16, x16, grid, st);
+    const bool resident = mode == 0 && p.sample_resident;
+    GemmParams pp = p;
+    if (resident) {
+        pp.n_stages = p.n_stages_sample;
+        pp.ring_bytes = p.ring_bytes_sample;
+        smem = p.smem_sample;
+    } else {
+        pp.sample_resident = 0;
+    }
     CUtensorMap map_q, map_x;
     if (!make_map(&map_q, q16, gemm_padded_queries(p.n_queries), p.dim, GT_M, p.fp16_operands))
         return cudaErrorNotSupported;
-    if (!make_map(&map_x, x16, p.n_rows, p.dim, GT_N, p.fp16_operands)) return cudaErrorNotSupported;
+    if (!make_map(&map_x, x16, p.n_rows, p.dim, resident ? 64 : GT_N, p.fp16_operands)) return cudaErrorNotSupported;
     auto kern = mode == 0 ? dense_gemm_topk_kernel<0, 1> : dense_gemm_topk_kernel<1, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, GT_THREADS, smem, st>>>(map_q, map_x, p);
+    kern<<<grid, GT_THREADS, smem, st>>>(map_q, map_x, pp);
     return cudaGetLastError();
 }
 

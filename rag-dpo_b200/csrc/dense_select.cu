@@ -12,65 +12,62 @@
 
 namespace b200rag {
 
-// ---------------------------------------------------------------------------
-// merge: one CTA per query, 8 warps each scanning a strided share of the keys
-// ---------------------------------------------------------------------------
 constexpr int kMergeWarps = 8;
 
-// leaves the query's kp best keys, sorted descending, in sm_keys[0..kp) (all threads synchronised)
-__device__ __forceinline__ void merge_body(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts,
-                                           int flat_counts, int n_lists, int list_len, int kp, int b,
-                                           uint64_t* sm_keys, int32_t* __restrict__ overflow) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t* src = cand + (size_t)b * n_lists * list_len;
-    const int32_t* cnt = (counts && !flat_counts) ? counts + (size_t)b * n_lists : nullptr;
-    const int flat_total = (counts && flat_counts) ? counts[b] : 0;
-
-    if (overflow && counts) {
-        int over = 0;
-        if (flat_counts) {
-            over = flat_total > n_lists * list_len;
-        } else {
-            for (int l = threadIdx.x; l < n_lists; l += blockDim.x) over |= cnt[l] > list_len;
-            over = __syncthreads_or(over);
+// ---------------------------------------------------------------------------
+// sample threshold: the M best of the n_keys sample keys of a query (the contraction kernel's sample pass
+// leaves M per CTA), one WARP per query, registers only: every lane keeps the M best of its share, then M
+// rounds of "warp-wide maximum of the lanes' heads, the owner pops".  top[q*M + M-1] is the query's threshold.
+// ---------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(256) sample_tau_kernel(const uint64_t* __restrict__ keys, int n_queries, int n_keys,
+                                                         uint64_t* __restrict__ top) {
+    const int lane = threadIdx.x & 31;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= n_queries) return;                       // warp-uniform
+    const uint64_t* src = keys + (size_t)q * n_keys;
+    uint64_t best[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) best[i] = 0ull;
+    for (int i0 = 0; i0 < n_keys; i0 += 32 * 4) {
+        uint64_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            v[u] = i < n_keys ? src[i] : 0ull;
         }
-        if (threadIdx.x == 0) overflow[b] = over ? 1 : 0;
-    }
-    WarpTopK t;
-    t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
-    // each warp walks whole lists: warp w takes lists w, w+8, ...
-    for (int l = warp; l < n_lists; l += kMergeWarps) {
-        int n = list_len;
-        if (cnt) n = min(cnt[l], list_len);
-        else if (flat_counts) n = max(0, min(flat_total - l * list_len, list_len));
-        const uint64_t* lp = src + (size_t)l * list_len;
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            t.offer(i < n ? lp[i] : 0ull, lane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint64_t x = v[u];
+            if (x > best[M - 1]) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) {             // sorted insert: bubble x down the list
+                    const uint64_t hi = best[i] > x ? best[i] : x;
+                    x = best[i] > x ? x : best[i];
+                    best[i] = hi;
+                }
+            }
         }
     }
-    t.finish(lane);
-    __syncthreads();
-    block_bitonic_desc(sm_keys, kMergeWarps * 2 * kp);      // power of two
+    for (int r = 0; r < M; ++r) {
+        uint64_t mx = best[0];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const uint64_t o = __shfl_xor_sync(0xffffffffu, mx, off);
+            mx = o > mx ? o : mx;
+        }
+        if (lane == 0) top[(size_t)q * M + r] = mx;
+        if (mx != 0ull && best[0] == mx) {                // keys are distinct: exactly one owner pops
+#pragma unroll
+            for (int i = 0; i + 1 < M; ++i) best[i] = best[i + 1];
+            best[M - 1] = 0ull;
+        }
+    }
 }
 
-__global__ void __launch_bounds__(kMergeWarps * 32)
-merge_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
-             int list_len, int kp, uint64_t* __restrict__ top, int32_t* __restrict__ overflow) {
-    extern __shared__ __align__(16) uint64_t sm_keys[];   // kMergeWarps * 2 * kp
-    const int b = blockIdx.x;
-    merge_body(cand, counts, flat_counts, n_lists, list_len, kp, b, sm_keys, overflow);
-    for (int i = threadIdx.x; i < kp; i += blockDim.x) top[(size_t)b * kp + i] = sm_keys[i];
-}
-
-cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int B, int n_lists, int list_len,
-                         int kp, uint64_t* top, int32_t* overflow, cudaStream_t st) {
-    size_t smem = (size_t)kMergeWarps * 2 * kp * sizeof(uint64_t);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    merge_kernel<<<B, kMergeWarps * 32, smem, st>>>(cand, counts, flat_counts, n_lists, list_len, kp, top, overflow);
+cudaError_t sample_tau_launch(const uint64_t* keys, int n_queries, int n_keys, int m, uint64_t* top, cudaStream_t st) {
+    if (m != 8) return cudaErrorInvalidValue;
+    sample_tau_kernel<8><<<(n_queries + 7) / 8, 256, 0, st>>>(keys, n_queries, n_keys, top);
     return cudaGetLastError();
 }
 

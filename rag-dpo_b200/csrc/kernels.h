@@ -54,13 +54,18 @@ struct GemmParams {
     int balance_tail;            // main pass: split the leftover tiles by (tile, query block) items
     int fp16_operands;           // 1: both operands are fp16 (fp16 corpus used as stored), 0: bf16
     // pair mode of the main pass (tcgen05 cta_group::2): decided by gemm_plan
-    int pair, n_stages_pair;
+    int pair, n_stages_pair, ring_bytes_pair;
     size_t smem_pair;
+    int ring_bytes;              // bytes of the operand ring in front of the barriers (set per launch)
+    // resident sample (small samples): decided by gemm_plan
+    int sample_resident, n_stages_sample, ring_bytes_sample;
+    size_t smem_sample;
 };
 int gemm_sample_m();
 void gemm_set_sample_div(int v);
 void gemm_set_balance_tail(int v);
 void gemm_set_pair_mode(int v);
+void gemm_set_sample_resident(int v);
 int gemm_max_batch();
 int gemm_padded_queries(int n_queries);
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out);
@@ -74,12 +79,8 @@ cudaError_t shadow_launch(const void* rows, int dtype, int64_t n_rows, int dim, 
                           cudaStream_t st);
 
 // ---- dense_select.cu -------------------------------------------------------
-// merge: cand (B x n_lists x list_len keys, any order, 0 = empty) -> top (B x kp sorted desc).
-// counts: NULL (all entries valid), or per (query, list) valid entries, or — flat_counts != 0 — ONE count
-// per query for the whole contiguous n_lists*list_len block.  overflow (nullable): set to 1 for queries
-// whose count exceeds the capacity.
-cudaError_t merge_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int B, int n_lists, int list_len,
-                         int kp, uint64_t* top, int32_t* overflow, cudaStream_t st);
+// sample threshold: the m (= 8) best of each query's n_keys sample keys -> top (B x m, descending)
+cudaError_t sample_tau_launch(const uint64_t* keys, int n_queries, int n_keys, int m, uint64_t* top, cudaStream_t st);
 // refine: canonical fp64 score of every candidate in top, sort by (score desc,
 // row asc), write the first k, and raise flag[b] when the margin check fails.
 struct RefineParams {
@@ -105,7 +106,10 @@ struct RefineParams {
     int32_t* n_flagged;      // scalar counter
 };
 cudaError_t refine_launch(const RefineParams& p, cudaStream_t st);
-// merge + refine fused: the merged top-kp never leaves shared memory (p.top is not used)
+// merge + refine fused: cand = B x n_lists x list_len keys (any order, 0 = empty); counts: NULL (all entries
+// valid), or per (query, list) valid entries, or — flat_counts != 0 — ONE count per query for the whole
+// contiguous n_lists*list_len block; overflow (nullable): set to 1 for queries whose count exceeds the
+// capacity.  The merged top-kp never leaves shared memory (p.top is not used).
 cudaError_t merge_refine_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int n_lists, int list_len,
                                 int32_t* overflow, const RefineParams& p, cudaStream_t st);
 // fallback tail: exact scores of the collected rows + top-k select, one CTA per query
