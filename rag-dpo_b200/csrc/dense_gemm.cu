@@ -674,8 +674,10 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
             p.sample_step = 1;
         } else {
             p.sample_tiles = (int)((want + GT_N - 1) / GT_N);
-            p.sample_chunks = GT_N / 32;
-            p.sample_last_mask = 0xffffffffu;
+            const int per_tile = (int)((want + p.sample_tiles - 1) / p.sample_tiles);   // columns of every sample tile
+            p.sample_chunks = (per_tile + 31) / 32;
+            const int last = per_tile - (p.sample_chunks - 1) * 32;
+            p.sample_last_mask = last >= 32 ? 0xffffffffu : ((1u << last) - 1u);
             p.sample_step = (int)(tiles_per_cta / p.sample_tiles > 0 ? tiles_per_cta / p.sample_tiles : 1);
         }
     }
