@@ -52,15 +52,19 @@ const char* rag_last_error(void);
 int rag_abi_version(void);
 int rag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
 /* runtime knobs: "tc_min_batch" (smallest batch served by the tcgen05 contraction path, default 2),
- * "tc_b1_shadow" (1 = a single query on an fp32/fp16 corpus is filtered through the bf16 shadow, default 1) */
+ * "tc_b1_shadow" (1 = a single query on an fp32/fp16 corpus is filtered through the bf16 shadow, default 1),
+ * "pair_mode" (1 = main pass as CTA pairs with tcgen05 cta_group::2 when the query blocks pair up, default 1),
+ * "sample_resident" (1 = small sample passes keep their rows in shared memory, default 1),
+ * "balance_tail", "sample_div" (experiments; defaults 1) */
 int rag_set_option(const char* key, int64_t value);
 /* page-locked host memory: buffers allocated here are DMA'd directly by the host-pointer entry points
  * (no staging copy); any other host pointer is staged through an internal pinned block. */
 int rag_host_alloc(void** out, size_t bytes);
 int rag_host_free(void* p);
-/* per-stage device time (ms, CUDA events on the launching stream) of the last
- * dense / bm25 call: [0] main scan or contraction kernel, [1] candidate merge,
- * [2] fp64 refine + select, [3] fallback pass (0 if not taken), rest 0. */
+/* per-stage time (ms) of the last dense / bm25 call.  CUDA events on the launching stream: [0] filter stage
+ * (scan kernel, or query prep + sample + threshold + contraction), [1] unused gap, [2] select + fp64 refine,
+ * [3] fallback pass (0 if not taken), [6] the contraction's main pass alone.  Host clock, host-buffer dense
+ * call only: [4] time spent queueing work before the one synchronisation, [5] whole call. */
 int rag_last_timings(float* ms, int n);
 /* counters since rag_init: [0] kernels launched, [1] fallback passes taken */
 int rag_counters(int64_t* out, int n);

@@ -29,15 +29,15 @@ __global__ void __launch_bounds__(256) sample_tau_kernel(const uint64_t* __restr
     uint64_t best[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) best[i] = 0ull;
-    for (int i0 = 0; i0 < n_keys; i0 += 32 * 4) {
-        uint64_t v[4];
+    for (int i0 = 0; i0 < n_keys; i0 += 32 * 8) {
+        uint64_t v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * 32 + lane;
             v[u] = i < n_keys ? src[i] : 0ull;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             uint64_t x = v[u];
             if (x > best[M - 1]) {
 #pragma unroll

@@ -442,11 +442,15 @@ def test_pair_mode_cta_group2_vs_oracle_and_single_cta(dtype, n, d, B):
     q = helpers.synth_unit(B, d, seed=n + 18)
     q[3] = x[n // 2]
     x[n - 1] = x[5]                                        # duplicate pair across the first and the last tile
+    dup = np.random.default_rng(5).choice(n, size=700, replace=False)
+    x[dup] = q[7]                                          # 700 exact ties: query 7 overflows into the fallback pass
     c = DeviceCorpus(d, dtype)
     c.append(x)
     allow = np.random.default_rng(4).random(n) < 0.5
     try:
+        f0 = _lib.counters()["fallbacks"]
         r2, s2, _ = check_topk(c, q, 10, DT[dtype])
+        assert r2[7].tolist() == sorted(dup.tolist())[:10] and _lib.counters()["fallbacks"] == f0 + 1
         ra2, sa2, _ = check_topk(c, q, 37, DT[dtype], allow)
         _lib.set_option("pair_mode", 0)
         r1, s1, _ = c.topk(q, 10)
