@@ -391,7 +391,9 @@ def run_b200(args):
                          f"re-streams it from HBM"},
         "e2e": {"value": qps_e2e * world * (n_local / 1e6), "unit": "queries/s (1M-row-corpus equivalents)",
                 "queries_per_s": qps_e2e,
-                "h2d_bytes_per_step": int(B * d * 4), "d2h_bytes_per_step": int(B * k * 12 + B * 4),
+                "h2d_bytes_per_step": int(B * d * 4),
+                # single GPU: int32 rows + f64 scores + counts; sharded: int64 global ids + f64 scores + counts
+                "d2h_bytes_per_step": int(B * k * (16 if world > 1 else 12) + B * 4),
                 "call_ms_p50": float(np.median(call_ms["step_host"])), "call_ms_max": float(max(call_ms["step_host"]))},
         "step_call_ms": {"p50": float(np.median(call_ms["step"])), "max": float(max(call_ms["step"]))},
         "gpu_launches": int(launches),

@@ -84,32 +84,49 @@ class ShardedDenseIndex:
         stream = torch.cuda.current_stream(dev)
         if stream.cuda_stream != 0:
             _lib.set_stream(stream.cuda_stream)       # library kernels and NCCL on the same stream
+        shared = stream.cuda_stream != 0              # library kernels and NCCL run on this very stream
         buf = self._buffers(B, kk, kl)
-        buf["q_host"].copy_(torch.from_numpy(np.ascontiguousarray(q32, dtype=np.float32)))
-        buf["q_dev"].copy_(buf["q_host"], non_blocking=True)
+        qt = torch.from_numpy(np.ascontiguousarray(q32, dtype=np.float32))
+        if qt.is_pinned():                            # page-locked caller memory (rag_host_alloc): DMA it directly
+            buf["q_dev"].copy_(qt, non_blocking=True)
+        else:
+            buf["q_host"].copy_(qt)
+            buf["q_dev"].copy_(buf["q_host"], non_blocking=True)
         mine, my_ids = buf["mine"], buf["my_ids"]
-        if kl < kk:
+        if not shared:
+            stream.synchronize()                      # inputs are in place before the library's own stream reads them
+        if kl == kk:
+            # the local scores land directly in the packed exchange buffer; k <= rows per shard: no padding
+            self.corpus.topk_dev(buf["q_dev"].data_ptr(), B, kl, buf["o_rows"].data_ptr(), mine[0].data_ptr(),
+                                 buf["o_counts"].data_ptr())
+            my_ids.copy_(buf["o_rows"])               # int32 -> int64
+            my_ids.add_(self.row_lo)                  # local row -> global id
+        else:
             mine[0].zero_()
             my_ids.fill_(-1)
-        if kl > 0:
-            stream.synchronize()                      # inputs are in place before the library's stream reads them
-            self.corpus.topk_dev(buf["q_dev"].data_ptr(), B, kl, buf["o_rows"].data_ptr(), buf["o_scores"].data_ptr(),
-                                 buf["o_counts"].data_ptr())
-            mine[0, :, :kl] = buf["o_scores"]
-            gid = buf["o_rows"].to(torch.int64)
-            my_ids[:, :kl] = torch.where(gid >= 0, gid + self.row_lo, gid)
+            if kl > 0:
+                self.corpus.topk_dev(buf["q_dev"].data_ptr(), B, kl, buf["o_rows"].data_ptr(),
+                                     buf["o_scores"].data_ptr(), buf["o_counts"].data_ptr())
+                mine[0, :, :kl] = buf["o_scores"]
+                gid = buf["o_rows"].to(torch.int64)
+                my_ids[:, :kl] = torch.where(gid >= 0, gid + self.row_lo, gid)
         if self.world > 1:
             gathered = buf["gathered"]
             dist.all_gather_into_tensor(gathered, mine, group=self.group)
         else:
             gathered = mine[None]
-        stream.synchronize()                          # the gather has landed (no-op wait when streams are shared)
+        if not shared:
+            stream.synchronize()                      # the gather has landed before the library's stream merges
         _lib.check(L.rag_merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + B * kk * 8, self.world, B, kk,
                                         2 * B * kk, buf["m_scores"].data_ptr(), buf["m_ids"].data_ptr(),
                                         buf["m_counts"].data_ptr()))
         h = buf["host_out"]
-        _lib.sync_stream_of(torch, dev)
-        h[0].copy_(buf["m_ids"]); h[1].copy_(buf["m_scores"]); h[2].copy_(buf["m_counts"])
+        if not shared:
+            _lib.sync_stream_of(torch, dev)
+        h[0].copy_(buf["m_ids"], non_blocking=True)
+        h[1].copy_(buf["m_scores"], non_blocking=True)
+        h[2].copy_(buf["m_counts"], non_blocking=True)
+        stream.synchronize()
         return h[0].numpy().copy(), h[1].numpy().copy(), h[2].numpy().copy()
 
     def _buffers(self, B, kk, kl):
