@@ -23,10 +23,10 @@ _LIB = None
 
 
 def build(force=False):
-    """Compile oracle.c -> liboracle.so with gcc (no reference sources involved)."""
+    """Compile oracle.c + hnsw.c -> liboracle.so with gcc (no reference sources involved)."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("oracle.c", "hnsw.c", "Makefile"))
+    if force or not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
     return so
 
@@ -52,5 +52,11 @@ def lib():
         L.orc_bm25_select.argtypes = [c.c_void_p, c.c_int64, c.c_void_p, c.c_int, c.c_void_p, c.c_void_p]
         L.orc_rrf.restype = c.c_int
         L.orc_rrf.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p]
+        L.hnsw_build.restype = c.c_void_p
+        L.hnsw_build.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_uint64]
+        L.hnsw_search.restype = c.c_int
+        L.hnsw_search.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_void_p]
+        L.hnsw_free.restype = None
+        L.hnsw_free.argtypes = [c.c_void_p]
         _LIB = L
     return _LIB

@@ -66,3 +66,34 @@ def rrf(ids, weights, rrf_k=60, top=None):
     out_s = np.empty(max(top, 1), dtype=np.float64)
     c = lib().orc_rrf(_p(ids), _p(weights), R, L, rrf_k, top, _p(out_i), _p(out_s))
     return out_i[:c].copy(), out_s[:c].copy()
+
+
+class HnswIndex:
+    """Restated hnswlib-style index (oracle/hnsw.c): what chromadb 1.4.1 builds for a cosine collection with its
+    defaults M=16, ef_construction=100, ef_search=100.  PARITY UNPINNED (statistical twin); used only to report
+    recall@k of the approximate store against the exact search."""
+
+    def __init__(self, x_unit, M=16, ef_construction=100, seed=100):
+        self.x = np.ascontiguousarray(x_unit, dtype=np.float32)
+        n, d = self.x.shape
+        assert d % 16 == 0
+        self._h = lib().hnsw_build(_p(self.x), n, d, M, ef_construction, seed)
+
+    def query(self, q_unit, k, ef_search=100):
+        q = np.ascontiguousarray(np.atleast_2d(q_unit), dtype=np.float32)
+        ids = np.full((len(q), k), -1, dtype=np.int32)
+        dist = np.zeros((len(q), k), dtype=np.float32)
+        for i in range(len(q)):
+            lib().hnsw_search(self._h, _p(q[i]), k, ef_search, _p(ids[i]), _p(dist[i]))
+        return ids, dist
+
+    def close(self):
+        if self._h:
+            lib().hnsw_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -183,3 +183,22 @@ def test_reference_retriever_runs_around_the_oracle(e2e_data):
                                       enable_hybrid=run["config"]["hybrid"], enable_summary_prefilter=False)
     got = r.retrieve_candidates(run["query"], n_candidates=40, where_filter=run["where"])
     assert [helpers.chunk_dump(c) for c in got] == run["candidates"]
+
+
+def test_restated_hnsw_index_recall_against_exact_search():
+    """The approximate store the reference queries (chromadb -> HNSW), restated in oracle/hnsw.c: on a clustered
+    corpus (what document chunks look like) it finds almost all of the exact top-10; its distances are exact."""
+    g = np.random.default_rng(5)
+    n_clusters, per, d = 80, 50, 64
+    centers = no.l2_normalize_rows(g.standard_normal((n_clusters, d)).astype(np.float32))
+    x = no.l2_normalize_rows(np.repeat(centers, per, axis=0) + 0.25 * g.standard_normal((n_clusters * per, d)).astype(np.float32))
+    q = no.l2_normalize_rows(centers[:20] + 0.2 * g.standard_normal((20, d)).astype(np.float32))
+    ix = c_oracle.HnswIndex(x, M=16, ef_construction=100)
+    ids, dist = ix.query(q, 10, ef_search=100)
+    er, es, ec = c_oracle.dense_topk(q, x, no.DT_F32, 10)
+    hits = sum(len(set(ids[i].tolist()) & set(er[i].tolist())) for i in range(len(q)))
+    assert hits / (10 * len(q)) >= 0.9
+    for i in range(len(q)):
+        assert (np.diff(dist[i]) >= 0).all()
+        np.testing.assert_allclose(dist[i], 1.0 - (x[ids[i]] @ q[i]), atol=2e-6)
+    ix.close()
