@@ -613,7 +613,6 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
     rp.x_resid = x_resid;
     rp.tau_keys = tau_keys;
     rp.tau_stride = gemm_sample_m();
-    rp.overflow = overflow;
     rp.max_row_norm = c->max_norm;
     rp.out_rows = o_rows;
     rp.out_scores = o_scores;

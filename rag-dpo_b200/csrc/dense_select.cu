@@ -1,6 +1,7 @@
-// dense_select.cu — the exact tail of the dense path: merge the per-warp
-// candidate lists, re-score the survivors with the CANONICAL fp64 dot product
-// (DESIGN.md §3), sort by (score desc, row asc) and check the filter margin.
+// dense_select.cu — the exact tail of the dense path: keep the best candidates by
+// filter score, re-score those that can still reach the top-k with the CANONICAL
+// fp64 dot product, order them by (score desc, row asc) and check
+// the filter margin.
 //
 // Together with dense_scan.cu / dense_gemm.cu this replaces the selection done
 // inside collection.query(...) (src/rag/retriever.py:215-220, 380-385): the

@@ -94,10 +94,10 @@ struct RefineParams {
     const float* x_resid;    // nullable device scalar: max_r ||x_r - bf16(x_r)||_2 (bf16 shadow)
     const float* max_row_norm;  // device scalar
     // threshold-capture mode (tensor-core path): rows outside the candidate lists have filter score
-    // < tau_q (tau_keys[b*tau_stride + tau_stride-1], 0 = none); overflow[b] != 0 voids that guarantee
+    // < tau_q (tau_keys[b*tau_stride + tau_stride-1], 0 = none); an overflowed list (merge_refine_launch's
+    // `overflow`) voids that guarantee
     const uint64_t* tau_keys;
     int tau_stride;
-    const int32_t* overflow;
     int32_t* out_rows;       // B x k
     double* out_scores;      // B x k
     int32_t* out_counts;     // B
