@@ -343,7 +343,7 @@ def run_b200(args):
     # fused select), tensor-bound: algorithmic flops = 2 * B * rows * dim per launch.  B <= 4: dense_scan_kernel,
     # HBM-bound: algorithmic bytes = rows * dim * sizeof(dtype) per launch (the shard is read once).
     tc_min = int(os.environ.get("B200RAG_TC_MIN_BATCH", "2"))
-    main_ms = float(np.mean(kern_ms))
+    main_ms = float(np.median(kern_ms))      # median: one NVML / driver hiccup must not skew the kernel figure
     bytes_per_launch = n_local * d * esz
     if B >= tc_min:
         flops = 2.0 * B * n_local * d
@@ -356,7 +356,7 @@ def run_b200(args):
                 "peak_source": peaks["source"] + " (burst cuBLAS bf16; kernel timed alone)",
                 "launches_per_step": 1, "avg_launch_ms": main_ms, "algorithmic_flops_per_launch": flops,
                 # the whole filter stage around it: query prep, sample pass, threshold kernel, main pass
-                "filter_stage_ms": float(np.mean(stage_ms))}
+                "filter_stage_ms": float(np.median(stage_ms))}
     else:
         n_scan_launches = (B + 3) // 4
         scan_ms = main_ms / n_scan_launches

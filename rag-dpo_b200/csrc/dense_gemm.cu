@@ -446,7 +446,37 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     const bool pass = MODE == 0 ? (s > thr) : (s >= thr);
                     m |= pass ? (1u << j) : 0u;
                 }
-                if (MODE == 0 && c == n_chunks - 1) m &= p.sample_last_mask;   // column-granular sample size
+                if constexpr (MODE == 0) {
+                    // sample pass: early on every column beats the (still empty) list of every query, so the
+                    // values are inserted straight from the registers of the LDTM.x32, branch-free: a column that
+                    // does not count (outside the sample, past the last row, filtered out, or below my current
+                    // 8th best) is replaced by -inf, which falls through the bubble
+                    uint32_t valid = c == n_chunks - 1 ? p.sample_last_mask : 0xffffffffu;   // column-granular sample
+                    const int64_t left = p.n_rows - (int64_t)row0 - c * 32;                   // rows from this chunk on
+                    if (left < 32) valid &= left > 0 ? (1u << left) - 1u : 0u;
+                    if (p.allow) {                                  // the chunk's 32 rows are 4 bytes of the bitmap
+                        const int64_t byte0 = ((int64_t)row0 + c * 32) >> 3, n_bytes = (p.n_rows + 7) >> 3;
+                        uint32_t w = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (byte0 + i < n_bytes) w |= (uint32_t)p.allow[byte0 + i] << (8 * i);
+                        valid &= w;
+                    }
+                    m &= valid;
+                    if (__reduce_or_sync(0xffffffffu, m) != 0u) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = (m >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY;
+#pragma unroll
+                            for (int i = 0; i < kSampleM; ++i) {     // sorted insert: bubble x down the list
+                                const float hi = fmaxf(best[i], x);
+                                x = fminf(best[i], x);
+                                best[i] = hi;
+                            }
+                        }
+                    }
+                    continue;
+                }
                 uint32_t um = __reduce_or_sync(0xffffffffu, m);
                 while (um) {
                     const int j = __ffs(um) - 1;
