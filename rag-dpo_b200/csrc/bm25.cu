@@ -129,7 +129,8 @@ __device__ __forceinline__ void bm25_accumulate_range(const int64_t* __restrict_
     for (int t0 = 0; t0 < nt; t0 += kBmMaxTokens) {
         const int tn = nt - t0 < kBmMaxTokens ? nt - t0 : kBmMaxTokens;
         __syncthreads();                             // previous pass done with s_bound / acc zeroed
-        // one binary search per (token, boundary): postings of a term are sorted by row
+        // one search per (token, boundary): postings of a term are sorted by row.  8-ary search: 7 independent
+        // probes per round, so a 500k-posting list takes 7 dependent round trips to memory instead of 19
         for (int j = threadIdx.x; j < tn * (kBmWarps + 1); j += kBmThreads) {
             const int i = j / (kBmWarps + 1), bnd = j % (kBmWarps + 1);
             const int32_t t = terms[t0 + i];
@@ -140,41 +141,77 @@ __device__ __forceinline__ void bm25_accumulate_range(const int64_t* __restrict_
                 int64_t lo = term_ptr[t], hi = term_ptr[t + 1];
                 int64_t target = r0 + (int64_t)bnd * kBmSeg;
                 if (target > r1) target = r1;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if ((int64_t)post_row[mid] < target) lo = mid + 1; else hi = mid;
+                // invariant: the first posting with row >= target is in [lo, hi]
+                while (hi - lo > 8) {
+                    const int64_t step = (hi - lo) >> 3;
+                    int32_t v[7];
+#pragma unroll
+                    for (int u = 0; u < 7; ++u) v[u] = post_row[lo + step * (u + 1)];
+                    int c = 0;                            // probes below the target: a prefix (rows ascend)
+#pragma unroll
+                    for (int u = 0; u < 7; ++u) c += (int64_t)v[u] < target;
+                    const int64_t base = lo;
+                    if (c < 7) hi = base + step * (c + 1);
+                    if (c > 0) lo = base + step * c + 1;
                 }
-                pos = lo;
+                int c = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (lo + u < hi) c += (int64_t)post_row[lo + u] < target;
+                pos = lo + c;
             }
             s_bound[i][bnd] = pos;
             if (bnd == 0) s_w[i] = w;
         }
         __syncthreads();
         // every warp accumulates ITS 512 rows token by token (numpy's `score +=` order) with no block-wide
-        // barrier; the first chunk of the next token is prefetched while the current one is added
-        int64_t p_next = s_bound[0][warp] + lane;
-        int32_t row_n = 0;
-        double imp_n = 0.0;
-        if (p_next < s_bound[0][warp + 1]) { row_n = post_row[p_next]; imp_n = impact[p_next]; }
-        for (int i = 0; i < tn; ++i) {
-            const double w = s_w[i];
-            const int64_t hi = s_bound[i][warp + 1];
-            int64_t p = p_next;
-            int32_t row = row_n;
-            double imp = imp_n;
-            if (i + 1 < tn) {
-                p_next = s_bound[i + 1][warp] + lane;
-                if (p_next < s_bound[i + 1][warp + 1]) { row_n = post_row[p_next]; imp_n = impact[p_next]; }
-            }
-            if (w != 0.0) {
-                while (p < hi) {
-                    const int r = (int)(row - r0);
-                    acc[r] = __dadd_rn(acc[r], __dmul_rn(w, imp));
-                    p += 32;
-                    if (p < hi) { row = post_row[p]; imp = impact[p]; }
+        // barrier.  Tokens are taken in groups of kGroup: the first chunks of the whole group are requested
+        // before the first one is added, and a long posting run is read 4 chunks at a time, so several loads
+        // are in flight per lane instead of one
+        constexpr int kGroup = 4;
+        for (int i0 = 0; i0 < tn; i0 += kGroup) {
+            int64_t p_g[kGroup], hi_g[kGroup];
+            int32_t row_g[kGroup];
+            double imp_g[kGroup], w_g[kGroup];
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+                const int i = i0 + g;
+                p_g[g] = 0; hi_g[g] = 0; w_g[g] = 0.0; row_g[g] = 0; imp_g[g] = 0.0;
+                if (i < tn) {
+                    w_g[g] = s_w[i];
+                    p_g[g] = s_bound[i][warp] + lane;
+                    hi_g[g] = w_g[g] != 0.0 ? s_bound[i][warp + 1] : 0;
+                    if (p_g[g] < hi_g[g]) { row_g[g] = post_row[p_g[g]]; imp_g[g] = impact[p_g[g]]; }
                 }
             }
-            __syncwarp();                            // two tokens may hit the same row from different lanes
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+                if (i0 + g < tn) {
+                    const double w = w_g[g];
+                    const int64_t hi = hi_g[g];
+                    int64_t p = p_g[g];
+                    if (p < hi) {
+                        const int r = (int)(row_g[g] - r0);
+                        acc[r] = __dadd_rn(acc[r], __dmul_rn(w, imp_g[g]));
+                        p += 32;
+                    }
+                    while (p < hi) {                 // within a token every posting is a different row
+                        int32_t rr[4];
+                        double mm[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (p + 32 * u < hi) { rr[u] = post_row[p + 32 * u]; mm[u] = impact[p + 32 * u]; }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (p + 32 * u < hi) {
+                                const int r = (int)(rr[u] - r0);
+                                acc[r] = __dadd_rn(acc[r], __dmul_rn(w, mm[u]));
+                            }
+                        p += 128;
+                    }
+                    __syncwarp();                    // two tokens may hit the same row from different lanes
+                }
+            }
         }
     }
     __syncwarp();
