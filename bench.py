@@ -174,6 +174,19 @@ def time_cpu(x, q, k, batch, steps, warmup, budget_s):
     return batch * done / dt, 1e3 * dt / done, done
 
 
+UNIT = "queries/s (1M-row-corpus equivalents: corpus = n_gpus x 1M rows)"
+
+
+def workload_config(n_local, world, d, k, B, dtype):
+    esz = 4 if dtype == "f32" else 2
+    return {"workload": f"dense exact top-{k}: {n_local} x {d} {dtype} rows per GPU ({n_local * world} total), "
+                        f"batch {B} queries per step",
+            "corpus_rows": n_local * world, "rows_per_gpu": n_local, "dim": d, "k": k, "batch": B,
+            "parallelism": f"row-shard x{world} + all-gather merge" if world > 1 else "single GPU",
+            "l2": f"corpus shard ({n_local * d * esz / 1e9:.1f} GB) is larger than L2 (126 MB): every step "
+                  f"re-streams it from HBM"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -193,14 +206,17 @@ def run_reference(args):
     sample = (f"{done} steps of a {sample_b}-query numpy fp32 GEMM batch (X @ q, argpartition+sort) over the full "
               f"{n}x{d} fp32 corpus on {cores} BLAS threads (os.cpu_count={os.cpu_count()}); chromadb 1.4.1 (HNSW) is "
               f"not installable here, this is the exact search it approximates")
-    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s",
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = workload_config(n, world, d, k, args.batch, "f32")
+    cfg["cpu_sample"] = (f"each step = one {sample_b}-query batch over a {n}-row corpus (one GPU's share of the workload); "
+                         f"value is per-query throughput on that share, i.e. already in 1M-row-corpus equivalents")
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT,
             "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"dense exact top-{k}: {n} x {d} fp32 corpus, batch {sample_b} (CPU sample)",
-                       "corpus_rows": n, "dim": d, "k": k, "batch": sample_b},
+            "config": cfg,
             "latency_b1_ms_p50": float(np.median(lat)),
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -377,19 +393,14 @@ def run_b200(args):
         return
     line = {
         "metric": METRIC,
-        "value": qps * world * (n_local / 1e6), "unit": "queries/s (1M-row-corpus equivalents: corpus = n_gpus x 1M rows)",
+        "value": qps * world * (n_local / 1e6), "unit": UNIT,
         "queries_per_s": qps,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 (tcgen05 filter, fp32 accumulate) + f64 (exact refine of the candidates)",
         "storage_dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"dense exact top-{k}: {n_local} x {d} {args.dtype} rows per GPU ({n_total} total), "
-                               f"batch {B} queries per step",
-                   "corpus_rows": n_total, "rows_per_gpu": n_local, "dim": d, "k": k, "batch": B,
-                   "parallelism": f"row-shard x{world} + all-gather merge" if world > 1 else "single GPU",
-                   "l2": f"corpus shard ({n_local * d * esz / 1e9:.1f} GB) is larger than L2 (126 MB): every step "
-                         f"re-streams it from HBM"},
-        "e2e": {"value": qps_e2e * world * (n_local / 1e6), "unit": "queries/s (1M-row-corpus equivalents)",
+        "config": workload_config(n_local, world, d, k, B, args.dtype),
+        "e2e": {"value": qps_e2e * world * (n_local / 1e6), "unit": UNIT,
                 "queries_per_s": qps_e2e,
                 "h2d_bytes_per_step": int(B * d * 4),
                 # single GPU: int32 rows + f64 scores + counts; sharded: int64 global ids + f64 scores + counts
