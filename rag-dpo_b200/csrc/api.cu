@@ -623,7 +623,8 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
     if (c->n == 0) {
         CU_TRY(refine_launch(rp, g.stream));
     } else {
-        CU_TRY(merge_refine_launch(g.cand.as<uint64_t>(), m_counts, m_flat, m_lists, m_len, overflow, rp, g.stream));
+        CU_TRY(merge_refine_launch(g.cand.as<uint64_t>(), m_counts, m_flat, m_lists, m_len, use_tc ? 0 : 1, overflow, rp,
+                                   g.stream));
     }
     ++g.n_launch;
     rec(3);

@@ -196,10 +196,13 @@ __device__ __forceinline__ int first_round(int k) {
 template <int DT, int MIN_BLOCKS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
 select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restrict__ counts, int flat_counts, int n_lists,
-                     int list_len, int32_t* __restrict__ overflow, RefineParams p) {
+                     int list_len, int sorted_lists, int32_t* __restrict__ overflow, RefineParams p) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     __shared__ double s_red[8];
     __shared__ double s_ek;
+    __shared__ uint64_t s_thr;
+    __shared__ int s_n;
+    bool merged = false;            // block-uniform: the candidate keys are already merged in sm_keys[0..kp)
     const int kp = p.kp, b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* sm_keys = reinterpret_cast<uint64_t*>(sm_raw);                      // kMergeWarps * 2 * kp
@@ -215,8 +218,8 @@ select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restric
         const uint64_t* src = cand + (size_t)b * n_lists * list_len;
         const int capacity = n_lists * list_len;
         WarpTopK t;
-        t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
         if (flat_counts) {          // ONE contiguous list with a count: 32-key blocks dealt round-robin to the warps
+            t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
             const int raw = counts[b];
             const int total = raw < capacity ? raw : capacity;
             if (overflow && threadIdx.x == 0) overflow[b] = raw > capacity ? 1 : 0;
@@ -226,6 +229,46 @@ select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restric
             }
         } else {                    // n_lists lists of list_len keys (0 = empty): warp w takes lists w, w+8, ...
             const int32_t* cnt = counts ? counts + (size_t)b * n_lists : nullptr;
+            // Sorted lists (the scan kernel's per-CTA top-kp lists): the kp-th largest list HEAD is a lower bound
+            // of the kp-th best key overall (kp distinct rows reach it), so only the list prefixes >= that bound
+            // can matter: kp + a handful of keys instead of n_lists * kp.  They are collected and sorted directly.
+            if (sorted_lists && !cnt && n_lists >= kp && n_lists <= (int)blockDim.x) {
+                const int cap = kMergeWarps * 2 * kp;
+                const uint64_t head = (int)threadIdx.x < n_lists ? src[(size_t)threadIdx.x * list_len] : 0ull;
+                sm_keys[threadIdx.x] = head;
+                if (threadIdx.x == 0) { s_thr = 0ull; s_n = 0; }
+                __syncthreads();
+                if (head != 0ull) {
+                    int rank = 0;
+                    for (int j = 0; j < n_lists; ++j) rank += sm_keys[j] > head;
+                    if (rank == kp - 1) s_thr = head;          // keys are distinct: at most one head has this rank
+                }
+                __syncthreads();
+                const uint64_t thr = s_thr;
+                if (thr != 0ull) {                             // block-uniform
+                    if ((int)threadIdx.x < n_lists) {
+                        const uint64_t* lp = src + (size_t)threadIdx.x * list_len;
+                        for (int i = 0; i < list_len; ++i) {
+                            const uint64_t e = lp[i];
+                            if (e < thr) break;                // also stops at the empty tail (key 0)
+                            const int slot = atomicAdd(&s_n, 1);
+                            if (slot < cap) sm_keys[slot] = e;
+                        }
+                    }
+                    __syncthreads();
+                    const int n = s_n;
+                    if (n <= cap) {                            // block-uniform
+                        int P = kp;
+                        while (P < n) P <<= 1;
+                        for (int i = n + threadIdx.x; i < P; i += blockDim.x) sm_keys[i] = 0ull;
+                        block_bitonic_desc(sm_keys, P);
+                        merged = true;
+                    }
+                }
+                __syncthreads();
+            }
+            if (!merged) {
+            t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);      // (a block barrier separates this from the above)
             if (overflow && counts) {
                 int over = 0;
                 for (int l = threadIdx.x; l < n_lists; l += blockDim.x) over |= cnt[l] > list_len;
@@ -240,7 +283,9 @@ select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restric
                     t.offer(i < n ? lp[i] : 0ull, lane);
                 }
             }
+            }
         }
+        if (!merged) {
         t.finish(lane);             // buf[0..n) sorted descending, the rest empty
         if (warp & 1) {             // odd warps: ascending, so that (even, odd) pairs are bitonic
             for (int j = lane; j < kp / 2; j += 32) {
@@ -269,6 +314,7 @@ select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restric
                     if (swap) { A[lo] = y; A[hi] = x; }
                 }
             }
+        }
         }
     }
     __syncthreads();
@@ -373,7 +419,8 @@ static size_t select_refine_smem(int kp, int dim) {
 
 template <int DT>
 static cudaError_t select_refine_dt(const uint64_t* cand, const int32_t* counts, int flat_counts, int n_lists,
-                                    int list_len, int32_t* overflow, const RefineParams& p, cudaStream_t st) {
+                                    int list_len, int sorted_lists, int32_t* overflow, const RefineParams& p,
+                                    cudaStream_t st) {
     const size_t smem = select_refine_smem(p.kp, p.dim);
     // big batches: 6 (fp32 rows: 5, the registers of the wider loads) CTAs per SM; MIN_BLOCKS = 2 keeps the
     // registers that let the refine loads overlap, which is what matters for a handful of queries
@@ -383,20 +430,22 @@ static cudaError_t select_refine_dt(const uint64_t* cand, const int32_t* counts,
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<p.B, 256, smem, st>>>(cand, counts, flat_counts, n_lists, list_len, overflow, p);
+    kern<<<p.B, 256, smem, st>>>(cand, counts, flat_counts, n_lists, list_len, sorted_lists, overflow, p);
     return cudaGetLastError();
 }
 
 cudaError_t merge_refine_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int n_lists, int list_len,
-                                int32_t* overflow, const RefineParams& p, cudaStream_t st) {
-    if (p.dtype == RAG_F32) return select_refine_dt<RAG_F32>(cand, counts, flat_counts, n_lists, list_len, overflow, p, st);
-    if (p.dtype == RAG_BF16) return select_refine_dt<RAG_BF16>(cand, counts, flat_counts, n_lists, list_len, overflow, p, st);
-    return select_refine_dt<RAG_F16>(cand, counts, flat_counts, n_lists, list_len, overflow, p, st);
+                                int sorted_lists, int32_t* overflow, const RefineParams& p, cudaStream_t st) {
+    if (p.dtype == RAG_F32)
+        return select_refine_dt<RAG_F32>(cand, counts, flat_counts, n_lists, list_len, sorted_lists, overflow, p, st);
+    if (p.dtype == RAG_BF16)
+        return select_refine_dt<RAG_BF16>(cand, counts, flat_counts, n_lists, list_len, sorted_lists, overflow, p, st);
+    return select_refine_dt<RAG_F16>(cand, counts, flat_counts, n_lists, list_len, sorted_lists, overflow, p, st);
 }
 
 // p.top already holds the merged kp keys per query (used for an empty corpus: all keys 0)
 cudaError_t refine_launch(const RefineParams& p, cudaStream_t st) {
-    return merge_refine_launch(nullptr, nullptr, 0, 0, 0, nullptr, p, st);
+    return merge_refine_launch(nullptr, nullptr, 0, 0, 0, 0, nullptr, p, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -110,8 +110,9 @@ cudaError_t refine_launch(const RefineParams& p, cudaStream_t st);
 // valid), or per (query, list) valid entries, or — flat_counts != 0 — ONE count per query for the whole
 // contiguous n_lists*list_len block; overflow (nullable): set to 1 for queries whose count exceeds the
 // capacity.  The merged top-kp never leaves shared memory (p.top is not used).
+// sorted_lists != 0: every list is sorted descending with its empties last (the scan kernel's lists)
 cudaError_t merge_refine_launch(const uint64_t* cand, const int32_t* counts, int flat_counts, int n_lists, int list_len,
-                                int32_t* overflow, const RefineParams& p, cudaStream_t st);
+                                int sorted_lists, int32_t* overflow, const RefineParams& p, cudaStream_t st);
 // fallback tail: exact scores of the collected rows + top-k select, one CTA per query
 struct CollectSelectParams {
     const uint32_t* rows_list;   // nq x cap

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=50_000)
     ap.add_argument("--questions", type=int, default=48)
     ap.add_argument("--cpu-questions", type=int, default=3)
+    ap.add_argument("--profile", action="store_true", help="cProfile of the per-question device path (top 25 lines on stderr)")
     args = ap.parse_args()
     from b200rag import DeviceCollection, DeviceChunkBM25Index, HybridRetriever, synth, tokenize_french
     import helpers
@@ -81,6 +82,14 @@ def main():
         t0 = time.perf_counter()
         res_single.append(r.retrieve_candidates(q, n_candidates=40))
         lat.append(1e3 * (time.perf_counter() - t0))
+    if args.profile:
+        import cProfile, pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for q in questions:
+            r.retrieve_candidates(q, n_candidates=40)
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(25)
     r.retrieve_candidates_batch(questions[:4], n_candidates=40)
     t0 = time.perf_counter()
     res_batch = r.retrieve_candidates_batch(questions, n_candidates=40)
