@@ -118,8 +118,10 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) issues it: the TMEM reads
+// are ordered by tcgen05.fence::before_thread_sync, no cluster-scope release of this thread's global stores is needed
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of a pair: data lands in THIS CTA's shared memory, the bytes are counted on the LEADER's barrier
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1,
@@ -510,7 +512,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (NCTA == 2) mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+                if (NCTA == 2) mbar_arrive_remote(buf ? tempty_leader1 : tempty_leader0);
                 else mbar_arrive(&tempty_bar[buf]);
             }
             if (MODE == 1 && npend > 0) {              // counts past the capacity flag an overflow

@@ -128,11 +128,12 @@ __device__ __forceinline__ void unpack8_f64(const uint4* v, double* x) {
     }
 }
 
-template <int DT>
+// WIDE: all loads of a 1024-d row in flight at once (small batches, registers to spare)
+template <int DT, bool WIDE = false>
 __device__ __forceinline__ double canonical_dot(const double* __restrict__ q64s, const void* __restrict__ rows,
                                                 size_t row, int dim, int lane) {
     constexpr int VPG = DT == RAG_F32 ? 2 : 1;       // 16-byte vectors per 8-element group
-    constexpr int CH = DT == RAG_F32 ? 2 : 4;        // chunks (of 32 groups) whose loads are in flight together
+    constexpr int CH = (DT == RAG_F32 && !WIDE) ? 2 : 4;   // chunks (of 32 groups) whose loads are in flight together
     const int groups = dim >> 3;
     const uint4* base = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(rows) +
                                                        row * (size_t)dim * (DT == RAG_F32 ? 4 : 2));
@@ -333,7 +334,7 @@ select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restric
     const int m1 = min(nc, first_round(p.k));
     for (int j = warp; j < m1; j += kMergeWarps) {
         const uint32_t row = key_row(top[j]);
-        const double s = canonical_dot<DT>(q64s, p.rows, row, p.dim, lane);
+        const double s = canonical_dot<DT, MIN_BLOCKS <= 2>(q64s, p.rows, row, p.dim, lane);
         if (lane == 0) { ek[j].s = s; ek[j].row = row; ek[j].pad = 0; }
     }
     __syncthreads();
@@ -356,7 +357,7 @@ select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restric
         }
         for (int j = m1 + warp; j < m2; j += kMergeWarps) {
             const uint32_t row = key_row(top[j]);
-            const double s = canonical_dot<DT>(q64s, p.rows, row, p.dim, lane);
+            const double s = canonical_dot<DT, MIN_BLOCKS <= 2>(q64s, p.rows, row, p.dim, lane);
             if (lane == 0) { ek[j].s = s; ek[j].row = row; ek[j].pad = 0; }
         }
         __syncthreads();
