@@ -433,7 +433,8 @@ def test_dense_batched_tensor_core_path_vs_oracle(dtype, n, d, B):
     c.close()
 
 
-@pytest.mark.parametrize("dtype,n,d,B", [("bf16", 50003, 1024, 512), ("f32", 40000, 512, 256), ("f16", 38000, 1024, 300)])
+@pytest.mark.parametrize("dtype,n,d,B", [("bf16", 50003, 1024, 512), ("f32", 40000, 512, 256), ("f16", 38000, 1024, 300),
+                                         ("f16", 38100, 256, 256)])
 def test_pair_mode_cta_group2_vs_oracle_and_single_cta(dtype, n, d, B):
     """Main pass as CTA pairs (tcgen05 cta_group::2): needs >= 148 row tiles and an even number of 128-query
     blocks (B = 300 -> 3 blocks: stays single-CTA).  Same results as the oracle and as the single-CTA kernel."""
