@@ -175,6 +175,7 @@ def time_cpu(x, q, k, batch, steps, warmup, budget_s):
 
 
 UNIT = "queries/s (1M-row-corpus equivalents: corpus = n_gpus x 1M rows)"
+EXCHANGE_NOTE = {}      # how the ranks exchanged their candidates in this run (filled by run_b200)
 
 
 def workload_config(n_local, world, d, k, B, dtype):
@@ -182,7 +183,8 @@ def workload_config(n_local, world, d, k, B, dtype):
     return {"workload": f"dense exact top-{k}: {n_local} x {d} {dtype} rows per GPU ({n_local * world} total), "
                         f"batch {B} queries per step",
             "corpus_rows": n_local * world, "rows_per_gpu": n_local, "dim": d, "k": k, "batch": B,
-            "parallelism": f"row-shard x{world} + all-gather merge" if world > 1 else "single GPU",
+            "parallelism": (f"row-shard x{world} + " + EXCHANGE_NOTE.get("kind", "all-gather merge")) if world > 1
+            else "single GPU",
             "l2": f"corpus shard ({n_local * d * esz / 1e9:.1f} GB) is larger than L2 (126 MB): every step "
                   f"re-streams it from HBM"}
 
@@ -267,19 +269,29 @@ def run_b200(args):
         m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         m_counts = torch.empty((nq,), dtype=torch.int32, device=dev)
 
+        ex = index.exchange(nq, k)       # peer-memory exchange (None: single GPU, or the NCCL all-gather path)
+
         def step():
             corpus.topk_dev(q_dev.data_ptr(), nq, k, o_rows.data_ptr(), o_scores.data_ptr(), o_counts.data_ptr())
             if world > 1:
                 my_ids.copy_(o_rows)                       # int32 -> int64
                 my_ids.add_(index.row_lo)                  # local row -> global id (k <= rows per shard: no padding)
-                dist.all_gather_into_tensor(gathered, mine)
-                _lib.check(L.rag_merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + nq * k * 8, world, nq, k,
-                                                2 * nq * k, m_scores.data_ptr(), m_ids.data_ptr(), m_counts.data_ptr()))
+                if ex is not None:                         # P2P stores into every peer's buffer + flags + merge
+                    ex.merge_topk_dev(o_scores.data_ptr(), my_ids.data_ptr(), nq, k, m_scores.data_ptr(),
+                                      m_ids.data_ptr(), m_counts.data_ptr())
+                else:
+                    dist.all_gather_into_tensor(gathered, mine)
+                    _lib.check(L.rag_merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + nq * k * 8, world, nq,
+                                                    k, 2 * nq * k, m_scores.data_ptr(), m_ids.data_ptr(),
+                                                    m_counts.data_ptr()))
             return (m_ids, m_scores) if world > 1 else (o_rows, o_scores)
         return step
 
     step_device = make_device_step(B)
     step_device_b1 = make_device_step(1)
+    if world > 1:
+        EXCHANGE_NOTE["kind"] = ("peer-memory exchange (P2P stores over NVLink + epoch flags) + merge"
+                                 if index.exchange(B, k) is not None else "NCCL all-gather + merge")
 
     def step_host():
         """the call a user makes: host buffers in, host results out"""
@@ -387,6 +399,8 @@ def run_b200(args):
     scan_ms = float(np.median([v[0] for v in scan_stage_ms]))
     achieved_scan = bytes_per_launch / (scan_ms / 1e3) / 1e9
 
+    if world > 1:
+        index.close()           # collective (barrier): every rank, before the non-zero ranks leave
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

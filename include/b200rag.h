@@ -115,6 +115,25 @@ int rag_dense_topk_dev(rag_corpus_t* c, const float* q_dev, int B, int k, const 
 int rag_merge_topk_dev(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k, int64_t rank_stride,
                        double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev);
 
+/* The same exchange step WITHOUT a collective library: every rank stores its (score, global id) block straight
+ * into every peer's gather buffer over NVLink peer memory (cudaIpc-mapped), raises an epoch flag there, and the
+ * merge kernel of each rank waits for the G flags before it merges (csrc/exchange.cu).  Set-up, once:
+ *   rag_exchange_create   allocates this rank's buffer (slot_bytes >= B*k*16 of the largest call) and returns
+ *                         its RAG_IPC_HANDLE_BYTES-byte handle; exchange the handles between the processes by
+ *                         any means (e.g. torch.distributed.all_gather_object);
+ *   rag_exchange_connect  handles = world x RAG_IPC_HANDLE_BYTES bytes, rank-major (this rank's own entry is
+ *                         ignored).
+ * rag_exchange_merge_topk_dev is STREAM-ORDERED (two launches, no host synchronisation); all ranks must call it
+ * once per step with the same B and k; a rank that never arrives makes the others fail with a CUDA error after
+ * ~10 s instead of hanging. */
+#define RAG_IPC_HANDLE_BYTES 64
+typedef struct rag_exchange rag_exchange_t;
+int rag_exchange_create(rag_exchange_t** out, int world, int rank, size_t slot_bytes, void* handle_out);
+int rag_exchange_connect(rag_exchange_t* ex, const void* handles);
+int rag_exchange_destroy(rag_exchange_t* ex);
+int rag_exchange_merge_topk_dev(rag_exchange_t* ex, const double* my_scores_dev, const int64_t* my_ids_dev, int B,
+                                int k, double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev);
+
 /* ---- BM25 keyword scoring over CSR postings -------------------------------
  * replaces rank_bm25.BM25Okapi(corpus_tokens) / .get_scores(tokens)
  * (src/rag/bm25_index.py:126,153,236,265) and the select loop of

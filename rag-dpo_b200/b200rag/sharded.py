@@ -34,6 +34,40 @@ def merge_lists_torch(scores, ids, k):
     return torch.where(valid, s2, torch.zeros_like(s2)), torch.where(valid, i2, torch.full_like(i2, -1)), valid.sum(1).to(torch.int32)
 
 
+class PeerExchange:
+    """The exchange step over NVLink peer memory (csrc/exchange.cu): every rank stores its local top-k block into
+    every peer's buffer and the merge kernel waits for the epoch flags — no collective library call per step.
+    One instance per process; `slot_bytes` bounds B*k*16 of a call."""
+
+    def __init__(self, world, rank, slot_bytes, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        self._lib, self._L = _lib, _lib.lib()
+        self.world, self.rank, self.slot_bytes, self.group = world, rank, int(slot_bytes), group
+        self._h = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _lib.check(self._L.rag_exchange_create(C.byref(self._h), world, rank, self.slot_bytes, handle))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(handle), group=group)
+        blob = b"".join(gathered)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _lib.check(self._L.rag_exchange_connect(self._h, buf))
+        dist.barrier(group=group)                      # every rank has mapped every buffer
+
+    def merge_topk_dev(self, my_scores_ptr, my_ids_ptr, B, k, out_scores_ptr, out_ids_ptr, out_counts_ptr):
+        self._lib.check(self._L.rag_exchange_merge_topk_dev(self._h, my_scores_ptr, my_ids_ptr, int(B), int(k),
+                                                            out_scores_ptr, out_ids_ptr, out_counts_ptr))
+
+    def close(self):
+        if self._h:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.barrier(group=self.group)         # nobody is still pushing into a buffer that goes away
+            self._L.rag_exchange_destroy(self._h)
+            self._h = None
+
+
 class ShardedDenseIndex:
     """local_topk(q32 np (B,d), k) -> (rows int32 (B,k) [-1 pad], scores f64 (B,k), counts).
     On the GPU box leave local_topk/merge at None: the shard lives in a
@@ -59,6 +93,36 @@ class ShardedDenseIndex:
             self.corpus = DeviceCorpus(dim, dtype, capacity=self.row_hi - self.row_lo)
         else:
             self.device = torch.device("cpu")
+        self._exchange = None                    # PeerExchange, created on first use (GPU path, world > 1)
+        self._exchange_failed = False
+
+    def exchange(self, B, k):
+        """the peer-memory exchange for calls up to this size, or None (single rank, B200RAG_EXCHANGE=nccl, or the
+        buffers could not be shared between the processes: the NCCL all-gather + merge path is used instead)"""
+        import os
+        if self.world == 1 or self.corpus is None or self._exchange_failed:
+            return None
+        if os.environ.get("B200RAG_EXCHANGE", "peer") == "nccl":
+            return None
+        need = B * k * 16
+        if self._exchange is not None and self._exchange.slot_bytes >= need:
+            return self._exchange
+        try:
+            if self._exchange is not None:
+                self._exchange.close()
+                self._exchange = None
+            self._exchange = PeerExchange(self.world, self.rank, max(need, 1 << 20), group=self.group)
+        except Exception as exc:                      # every rank fails alike (same box, same driver)
+            import warnings
+            warnings.warn(f"peer-memory exchange unavailable ({exc}); using the NCCL all-gather")
+            self._exchange_failed = True
+            return None
+        return self._exchange
+
+    def close(self):
+        if self._exchange is not None:
+            self._exchange.close()
+            self._exchange = None
 
     def fill_synthetic(self, seed):
         """each rank generates exactly its own rows of the global synthetic corpus"""
@@ -110,16 +174,22 @@ class ShardedDenseIndex:
                 mine[0, :, :kl] = buf["o_scores"]
                 gid = buf["o_rows"].to(torch.int64)
                 my_ids[:, :kl] = torch.where(gid >= 0, gid + self.row_lo, gid)
-        if self.world > 1:
-            gathered = buf["gathered"]
-            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        ex = self.exchange(B, kk) if shared else None
+        if ex is not None:
+            # stores into the peers' buffers + epoch flags + merge: two launches, no collective call
+            ex.merge_topk_dev(mine[0].data_ptr(), my_ids.data_ptr(), B, kk, buf["m_scores"].data_ptr(),
+                              buf["m_ids"].data_ptr(), buf["m_counts"].data_ptr())
         else:
-            gathered = mine[None]
-        if not shared:
-            stream.synchronize()                      # the gather has landed before the library's stream merges
-        _lib.check(L.rag_merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + B * kk * 8, self.world, B, kk,
-                                        2 * B * kk, buf["m_scores"].data_ptr(), buf["m_ids"].data_ptr(),
-                                        buf["m_counts"].data_ptr()))
+            if self.world > 1:
+                gathered = buf["gathered"]
+                dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            else:
+                gathered = mine[None]
+            if not shared:
+                stream.synchronize()                  # the gather has landed before the library's stream merges
+            _lib.check(L.rag_merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + B * kk * 8, self.world, B, kk,
+                                            2 * B * kk, buf["m_scores"].data_ptr(), buf["m_ids"].data_ptr(),
+                                            buf["m_counts"].data_ptr()))
         h = buf["host_out"]
         if not shared:
             _lib.sync_stream_of(torch, dev)

@@ -820,6 +820,118 @@ int rag_dense_topk(rag_corpus_t* c, const float* q, int B, int k, const uint8_t*
     return RAG_OK;
 }
 
+// ---------------------------------------------------------------------------
+// peer-memory exchange (exchange.cu)
+// ---------------------------------------------------------------------------
+struct rag_exchange {
+    int world = 0, rank = 0;
+    size_t slot_bytes = 0, total_bytes = 0;
+    uint8_t* local = nullptr;                 // payload[2][world][slot] | flags[2][world] | counter
+    void* mapped[kMaxExchangeRanks] = {};     // peers' buffers as opened in this process (mine: == local)
+    bool connected = false;
+    uint64_t epoch = 0;
+    ExchangeDev dev{};
+};
+
+static size_t exchange_flags_offset(const rag_exchange* ex) { return 2 * (size_t)ex->world * ex->slot_bytes; }
+
+int rag_exchange_create(rag_exchange_t** out, int world, int rank, size_t slot_bytes, void* handle_out) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!out || !handle_out) return fail(RAG_EINVAL, "NULL argument");
+    if (world < 1 || world > kMaxExchangeRanks || rank < 0 || rank >= world || slot_bytes == 0)
+        return fail(RAG_ERANGE, "world=%d rank=%d slot_bytes=%zu outside the supported range", world, rank, slot_bytes);
+    static_assert(sizeof(cudaIpcMemHandle_t) == RAG_IPC_HANDLE_BYTES, "handle size");
+    rag_exchange* ex = new rag_exchange();
+    ex->world = world;
+    ex->rank = rank;
+    ex->slot_bytes = (slot_bytes + 255) / 256 * 256;
+    ex->total_bytes = exchange_flags_offset(ex) + 2 * (size_t)world * 8 + 256;
+    cudaError_t e = cudaMalloc((void**)&ex->local, ex->total_bytes);
+    if (e != cudaSuccess) {
+        delete ex;
+        return fail(RAG_ENOMEM, "cudaMalloc(%zu) for the exchange buffer: %s", ex->total_bytes, cudaGetErrorString(e));
+    }
+    e = cudaMemset(ex->local, 0, ex->total_bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();      // zeroed flags are in place before any peer can map them
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ex->local);
+    if (e != cudaSuccess) {
+        cudaFree(ex->local);
+        delete ex;
+        cudaGetLastError();
+        return fail(RAG_ECUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    *out = ex;
+    return RAG_OK;
+}
+
+int rag_exchange_connect(rag_exchange_t* ex, const void* handles) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!ex || !handles) return fail(RAG_EINVAL, "NULL argument");
+    if (ex->connected) return fail(RAG_EINVAL, "exchange already connected");
+    const size_t fo = exchange_flags_offset(ex);
+    for (int r = 0; r < ex->world; ++r) {
+        void* p = ex->local;
+        if (r != ex->rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, reinterpret_cast<const uint8_t*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                for (int q = 0; q < r; ++q)
+                    if (q != ex->rank && ex->mapped[q]) { cudaIpcCloseMemHandle(ex->mapped[q]); ex->mapped[q] = nullptr; }
+                return fail(RAG_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+            }
+        }
+        ex->mapped[r] = p;
+        ex->dev.peer_base[r] = reinterpret_cast<uint8_t*>(p);
+        ex->dev.peer_flags[r] = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(p) + fo);
+    }
+    ex->dev.my_base = ex->local;
+    ex->dev.my_flags = reinterpret_cast<uint64_t*>(ex->local + fo);
+    ex->dev.done_counter = reinterpret_cast<unsigned*>(ex->local + fo + 2 * (size_t)ex->world * 8);
+    ex->dev.world = ex->world;
+    ex->dev.rank = ex->rank;
+    ex->dev.slot_bytes = ex->slot_bytes;
+    ex->connected = true;
+    return RAG_OK;
+}
+
+int rag_exchange_destroy(rag_exchange_t* ex) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!ex) return RAG_OK;
+    if (g.inited) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < ex->world; ++r)
+            if (r != ex->rank && ex->mapped[r]) cudaIpcCloseMemHandle(ex->mapped[r]);
+        if (ex->local) cudaFree(ex->local);
+        cudaGetLastError();
+    }
+    delete ex;
+    return RAG_OK;
+}
+
+int rag_exchange_merge_topk_dev(rag_exchange_t* ex, const double* my_scores_dev, const int64_t* my_ids_dev, int B, int k,
+                                double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!ex || !my_scores_dev || !my_ids_dev || !out_scores_dev || !out_ids_dev || !out_counts_dev)
+        return fail(RAG_EINVAL, "NULL argument");
+    if (!ex->connected) return fail(RAG_EINVAL, "exchange not connected");
+    if (B <= 0 || k <= 0 || k > RAG_MAX_K || (int64_t)ex->world * k > 8192)
+        return fail(RAG_ERANGE, "world=%d B=%d k=%d outside the supported range", ex->world, B, k);
+    if ((size_t)B * k * 16 > ex->slot_bytes)
+        return fail(RAG_ERANGE, "B*k*16 = %zu bytes exceed the exchange slot (%zu)", (size_t)B * k * 16, ex->slot_bytes);
+    ++ex->epoch;
+    CU_TRY(exchange_launch(ex->dev, my_scores_dev, my_ids_dev, B, k, ex->epoch, out_scores_dev, out_ids_dev,
+                           out_counts_dev, g.stream));
+    g.n_launch += 2;
+    return RAG_OK;
+}
+
 int rag_merge_topk_dev(const double* scores_dev, const int64_t* ids_dev, int G, int B, int k, int64_t rank_stride,
                        double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev) {
     std::lock_guard<std::mutex> lk(g.mu);

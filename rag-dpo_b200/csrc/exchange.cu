@@ -1,0 +1,137 @@
+// exchange.cu — the multi-GPU exchange step over NVLink peer memory, without a collective library call.
+//
+// One process per GPU: every rank holds the exact local top-k of the same query batch and the
+// global top-k is the merge of the G lists.  Instead of an NCCL all-gather followed by a merge kernel, each rank
+// STORES its (score, global id) block straight into every peer's gather buffer (cudaIpc-mapped device memory,
+// NVLink 5 / NVSwitch P2P), raises an epoch flag there, and the merge kernel of every rank waits for the G
+// flags of the epoch before it merges.  Two launches on the caller's stream, no host synchronisation, no
+// rendezvous in a communication library.
+//
+// Buffer of a rank (allocated locally, mapped by every peer):
+//   payload[2][G][slot_bytes]   parity (epoch & 1) x source rank x (scores f64[B*k] | ids i64[B*k])
+//   flags  [2][G]               u64: last epoch whose payload from that source rank is complete
+// Reuse is safe with two parities: a rank can raise its flag for epoch e+1 only after its own merge of epoch e
+// (stream order), i.e. after every rank's flag for e — so nobody is still reading parity (e+2)&1 == e&1 when a
+// fast rank overwrites it for e+2, because that fast rank first had to see everyone's flag for e+1.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200rag {
+
+__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// grid = (blocks_per_peer, G): copy my payload into slot `rank` of peer blockIdx.y; the last block to finish
+// (device-wide counter) publishes the epoch flag in every peer
+__global__ void __launch_bounds__(256)
+exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const int64_t* __restrict__ my_ids,
+                     int64_t n_elems /* B*k */, uint64_t epoch) {
+    const int peer = blockIdx.y;
+    const int parity = (int)(epoch & 1);
+    uint8_t* dst = ex.peer_base[peer] + ((size_t)parity * ex.world + ex.rank) * ex.slot_bytes;
+    // n_elems doubles then n_elems int64: both 8-byte items; 16-byte vectors when the count is even
+    uint64_t* d64 = reinterpret_cast<uint64_t*>(dst);
+    const uint64_t* s0 = reinterpret_cast<const uint64_t*>(my_scores);
+    const uint64_t* s1 = reinterpret_cast<const uint64_t*>(my_ids);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_elems; i += (int64_t)gridDim.x * blockDim.x)
+        d64[i] = i < n_elems ? s0[i] : s1[i - n_elems];
+    __threadfence_system();                         // my stores are performed before the flag can be seen
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned prev = atomicAdd(ex.done_counter, 1u);
+        if (prev == total - 1) {
+            *ex.done_counter = 0u;                  // ready for the next launch (stream-ordered)
+            __threadfence_system();
+            for (int p = 0; p < ex.world; ++p)
+                st_release_sys_u64(ex.peer_flags[p] + (size_t)parity * ex.world + ex.rank, epoch);
+        }
+    }
+}
+
+// bounded wait for the G flags of this epoch in MY buffer (thread 0), then the caller merges
+__device__ __forceinline__ void exchange_wait(const uint64_t* flags, int world, uint64_t epoch) {
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < world; ++r) {
+            if (ld_acquire_sys_u64(flags + r) >= epoch) continue;
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u64(flags + r) < epoch) {
+                if (clock64() - t0 > 20000000000LL) __trap();     // ~10 s: a lost peer must not hang the GPU
+                __nanosleep(200);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+struct XKey {
+    double s;
+    int64_t id;
+    __device__ __forceinline__ bool operator<(const XKey& o) const { return s < o.s || (s == o.s && id > o.id); }
+};
+
+// one CTA per query: wait for the epoch, then G sorted (score, id) lists -> global top-k (ties -> lowest id)
+__global__ void __launch_bounds__(256)
+exchange_merge_kernel(ExchangeDev ex, int B, int k, uint64_t epoch, int nsort, double* __restrict__ out_scores,
+                      int64_t* __restrict__ out_ids, int32_t* __restrict__ out_counts) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    XKey* ek = reinterpret_cast<XKey*>(sm_raw);
+    __shared__ int s_count;
+    const int parity = (int)(epoch & 1);
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) s_count = 0;
+    exchange_wait(ex.my_flags + (size_t)parity * ex.world, ex.world, epoch);
+    const uint8_t* base = ex.my_base + (size_t)parity * ex.world * ex.slot_bytes;
+    const int64_t n_elems = (int64_t)B * k;
+    int local = 0;
+    for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
+        XKey e;
+        e.s = -INFINITY; e.id = INT64_MAX;
+        if (i < ex.world * k) {
+            const int g = i / k, j = i % k;
+            const double* sc = reinterpret_cast<const double*>(base + (size_t)g * ex.slot_bytes);
+            const int64_t* ids = reinterpret_cast<const int64_t*>(sc + n_elems);
+            const int64_t id = ids[(size_t)b * k + j];
+            if (id >= 0) { e.s = sc[(size_t)b * k + j]; e.id = id; ++local; }
+        }
+        ek[i] = e;
+    }
+    atomicAdd(&s_count, local);
+    block_bitonic_desc(ek, nsort);
+    const int nout = s_count < k ? s_count : k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        out_ids[(size_t)b * k + i] = i < nout ? ek[i].id : -1;
+        out_scores[(size_t)b * k + i] = i < nout ? ek[i].s : 0.0;
+    }
+    if (threadIdx.x == 0) out_counts[b] = nout;
+}
+
+cudaError_t exchange_launch(const ExchangeDev& ex, const double* my_scores, const int64_t* my_ids, int B, int k,
+                            uint64_t epoch, double* out_scores, int64_t* out_ids, int32_t* out_counts,
+                            cudaStream_t st) {
+    const int64_t n_elems = (int64_t)B * k;
+    int bx = (int)((2 * n_elems + 256 * 8 - 1) / (256 * 8));
+    if (bx < 1) bx = 1;
+    if (bx > 32) bx = 32;
+    dim3 grid(bx, ex.world);
+    exchange_push_kernel<<<grid, 256, 0, st>>>(ex, my_scores, my_ids, n_elems, epoch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    int nsort = 32;
+    while (nsort < ex.world * k) nsort <<= 1;
+    const size_t smem = (size_t)nsort * sizeof(XKey);
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    exchange_merge_kernel<<<B, 256, smem, st>>>(ex, B, k, epoch, nsort, out_scores, out_ids, out_counts);
+    return cudaGetLastError();
+}
+
+}  // namespace b200rag

@@ -132,6 +132,21 @@ cudaError_t collect_select_launch(const CollectSelectParams& p, cudaStream_t st)
 cudaError_t merge_exact_launch(const double* scores, const int64_t* ids, int G, int B, int k, int64_t rank_stride,
                                double* out_scores, int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
 
+// ---- exchange.cu -----------------------------------------------------------
+constexpr int kMaxExchangeRanks = 16;
+struct ExchangeDev {
+    uint8_t* peer_base[kMaxExchangeRanks];     // every rank's payload area (mine included), as mapped in this process
+    uint64_t* peer_flags[kMaxExchangeRanks];   // every rank's flag area
+    uint8_t* my_base;
+    uint64_t* my_flags;
+    unsigned* done_counter;                     // local: blocks of the push kernel that have finished
+    int world, rank;
+    size_t slot_bytes;                          // payload capacity per (parity, source rank)
+};
+// push my (scores | ids) block into every rank's buffer, flag the epoch, wait for all ranks, merge -> top-k
+cudaError_t exchange_launch(const ExchangeDev& ex, const double* my_scores, const int64_t* my_ids, int B, int k,
+                            uint64_t epoch, double* out_scores, int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
+
 // ---- corpus.cu -------------------------------------------------------------
 cudaError_t convert_rows_launch(const float* src, void* dst, int dtype, int64_t n_elems, cudaStream_t st);
 cudaError_t widen_rows_launch(const void* src, int dtype, float* dst, int64_t n_elems, cudaStream_t st);

@@ -385,6 +385,43 @@ def test_merge_topk_dev_vs_host_merge():
         assert torch.equal(o_i.cpu(), want_i) and torch.equal(o_s.cpu(), want_s) and torch.equal(o_c.cpu(), want_c)
 
 
+def test_peer_exchange_single_rank_roundtrip():
+    """rag_exchange_* with world = 1: the rank pushes its block into its own buffer, the merge kernel waits for the
+    epoch flag and merges.  Several epochs (both buffer parities, flag reuse); the multi-rank path runs under
+    torchrun (bench.py --gpus N, tests/test_dist.py covers the host logic on gloo)."""
+    import ctypes as C
+    import torch
+    from b200rag import _lib
+    from b200rag.sharded import merge_lists_torch
+    L = _lib.lib()
+    h = C.c_void_p()
+    handle = (C.c_uint8 * 64)()
+    _lib.check(L.rag_exchange_create(C.byref(h), 1, 0, 1 << 20, handle))
+    _lib.check(L.rag_exchange_connect(h, handle))
+    g = torch.Generator().manual_seed(1)
+    try:
+        for epoch, (B, k) in enumerate([(7, 10), (1, 1), (64, 100), (7, 10), (300, 50)]):
+            scores = torch.randn(1, B, k, generator=g, dtype=torch.float64).sort(dim=2, descending=True).values
+            ids = torch.randperm(10 ** 6, generator=g)[: B * k].reshape(1, B, k)
+            if k > 2:
+                ids[0, :, -1] = -1
+            want_s, want_i, want_c = merge_lists_torch(scores, ids, k)
+            ds, di = scores[0].contiguous().cuda(), ids[0].contiguous().cuda()
+            o_s = torch.empty(B, k, dtype=torch.float64, device="cuda")
+            o_i = torch.empty(B, k, dtype=torch.int64, device="cuda")
+            o_c = torch.empty(B, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            _lib.check(L.rag_exchange_merge_topk_dev(h, ds.data_ptr(), di.data_ptr(), B, k, o_s.data_ptr(),
+                                                     o_i.data_ptr(), o_c.data_ptr()))
+            torch.cuda.synchronize()
+            assert torch.equal(o_i.cpu(), want_i) and torch.equal(o_s.cpu(), want_s) and torch.equal(o_c.cpu(), want_c)
+        # a payload larger than the slot is refused, not truncated
+        assert L.rag_exchange_merge_topk_dev(h, ds.data_ptr(), di.data_ptr(), 4096, 224, o_s.data_ptr(),
+                                             o_i.data_ptr(), o_c.data_ptr()) != 0
+    finally:
+        _lib.check(L.rag_exchange_destroy(h))
+
+
 # --------------------------------------------------- BASELINE-size cases ----
 def test_dense_config2_full_size_properties():
     """BASELINE config 2 (1M x 1024 fp32, top-10): size-independent properties + two queries against the oracle."""
