@@ -18,8 +18,8 @@
 
 namespace b200rag {
 
-__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
     uint64_t v;
@@ -41,16 +41,18 @@ exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const
     const uint64_t* s1 = reinterpret_cast<const uint64_t*>(my_ids);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_elems; i += (int64_t)gridDim.x * blockDim.x)
         d64[i] = i < n_elems ? s0[i] : s1[i - n_elems];
-    __threadfence_system();                         // my stores are performed before the flag can be seen
-    __syncthreads();
+    __syncthreads();                                // the block's stores happen-before thread 0's fence
     if (threadIdx.x == 0) {
+        __threadfence_system();                     // ... which orders them before the counter / the flags (cumulative)
         const unsigned total = gridDim.x * gridDim.y;
         const unsigned prev = atomicAdd(ex.done_counter, 1u);
         if (prev == total - 1) {
             *ex.done_counter = 0u;                  // ready for the next launch (stream-ordered)
-            __threadfence_system();
+            __threadfence_system();                 // every block's payload is ordered before the flags below
+            // plain system-scope stores, issued back to back: one NVLink trip for all peers instead of one
+            // release (= wait for the previous store to land) per peer
             for (int p = 0; p < ex.world; ++p)
-                st_release_sys_u64(ex.peer_flags[p] + (size_t)parity * ex.world + ex.rank, epoch);
+                st_relaxed_sys_u64(ex.peer_flags[p] + (size_t)parity * ex.world + ex.rank, epoch);
         }
     }
 }
