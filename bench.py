@@ -399,7 +399,18 @@ def run_b200(args):
     scan_ms = float(np.median([v[0] for v in scan_stage_ms]))
     achieved_scan = bytes_per_launch / (scan_ms / 1e3) / 1e9
 
+    exchange_check = None
     if world > 1:
+        # the peer-memory exchange must return what the NCCL all-gather + merge path returns (ids and fp64 scores)
+        if index.exchange(B, k) is not None:
+            got = index.topk(q_host[:16], k)
+            os.environ["B200RAG_EXCHANGE"] = "nccl"
+            want = index.topk(q_host[:16], k)
+            os.environ["B200RAG_EXCHANGE"] = "peer"
+            same = all(np.array_equal(a, b) for a, b in zip(got, want))
+            exchange_check = "peer-memory exchange == NCCL all-gather path on 16 queries" if same else "MISMATCH"
+            if not same:
+                raise SystemExit("peer-memory exchange and NCCL path disagree")
         index.close()           # collective (barrier): every rank, before the non-zero ranks leave
     if rank != 0:
         if world > 1:
@@ -422,6 +433,7 @@ def run_b200(args):
                 "call_ms_p50": float(np.median(call_ms["step_host"])), "call_ms_max": float(max(call_ms["step_host"]))},
         "step_call_ms": {"p50": float(np.median(call_ms["step"])), "max": float(max(call_ms["step"]))},
         "gpu_launches": int(launches),
+        "exchange_check": exchange_check,
         "latency_b1": {"device_ms_p50": float(np.percentile(lat, 50)), "device_ms_p99": float(np.percentile(lat, 99)),
                        "host_call_ms_p50": float(np.percentile(lat_host, 50)),
                        "host_call_ms_p99": float(np.percentile(lat_host, 99)),
