@@ -549,7 +549,7 @@ static int dense_core_slice(rag_corpus* c, const float* q_dev, int B, int k, con
         CU_TRY(cudaMemsetAsync(g.cand_cnt.p, 0, (size_t)bpad * 4, g.stream));
         rec(0);
         if (p.use_sample) {
-            // sample pass -> per-query threshold (16th best sample score)
+            // sample pass -> per-query threshold (the 8th best sample score)
             CU_TRY(gemm_launch(p, 0, g.q16.p, x16, grid, smem, g.stream));
             CU_TRY(sample_tau_launch(g.sample_keys.as<uint64_t>(), B, p.n_lists * sm, sm, g.tau_keys.as<uint64_t>(),
                                      g.stream));

@@ -19,8 +19,10 @@
 //
 // Fused select, two launches of the same kernel:
 //   SAMPLE pass  over a fraction 8/E of the rows, E = max(1024, 4*kp) (column-granular): every thread keeps
-//                the 8 best scores of its query in registers; merged per query, the 8th best sample
-//                score tau_q is a VALID lower bound of the corpus-wide 8th best score.
+//                the 8 best scores of its query in registers (inserted branch-free from the LDTM.x32
+//                registers); merged per query (sample_tau_kernel), the 8th best sample score tau_q is a
+//                VALID lower bound of the corpus-wide 8th best score.  A sample of <= 64 rows per CTA stays
+//                RESIDENT in shared memory for all query blocks and is multiplied with a 64-wide MMA.
 //   MAIN pass    over all tiles (row tile outer, query block inner: a corpus tile is fetched from HBM
 //                once and re-read from L2 by the other query blocks): a branch-free compare mask per
 //                32-column chunk against tau_q; the ~E survivors per query are parked per thread and
