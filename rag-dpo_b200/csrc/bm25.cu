@@ -355,26 +355,21 @@ bm25_scores_heads_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __
     }
 }
 
-// tau[q] = k-th largest head (empty key when fewer than k heads exist: no bound).  Rank counting: every
-// thread counts the heads that beat its own (keys of distinct rows are distinct; empty heads never count).
+// tau[q] = k-th largest head (empty key when fewer than k heads exist: no bound).  A block bitonic sort of the
+// <= 4096 heads: 36 barrier steps for 256 heads, which beats rank counting here (245 dependent compares per thread)
 __global__ void __launch_bounds__(256)
 bm25_tau_kernel(const Bm25Key* __restrict__ heads, int n_heads, int k, Bm25Key* __restrict__ tau, int32_t* counts) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
-    Bm25Key* s_keys = reinterpret_cast<Bm25Key*>(sm_raw);          // n_heads
+    Bm25Key* s_keys = reinterpret_cast<Bm25Key*>(sm_raw);
     const int q = blockIdx.x;
-    for (int i = threadIdx.x; i < n_heads; i += blockDim.x) s_keys[i] = heads[(size_t)q * n_heads + i];
+    int nsort = 32;
+    while (nsort < n_heads) nsort <<= 1;
+    for (int i = threadIdx.x; i < nsort; i += blockDim.x)
+        s_keys[i] = i < n_heads ? heads[(size_t)q * n_heads + i] : Bm25Key{0ull, 0u, 0u};
+    block_bitonic_desc(s_keys, nsort);
     if (threadIdx.x == 0) {
-        tau[q] = Bm25Key{0ull, 0u, 0u};
+        tau[q] = k <= n_heads ? s_keys[k - 1] : Bm25Key{0ull, 0u, 0u};
         counts[q] = 0;
-    }
-    __syncthreads();
-    if (k > n_heads) return;
-    for (int i = threadIdx.x; i < n_heads; i += blockDim.x) {
-        const Bm25Key me = s_keys[i];
-        if (me.s == 0ull) continue;
-        int rank = 0;
-        for (int j = 0; j < n_heads; ++j) rank += me < s_keys[j];
-        if (rank == k - 1) tau[q] = me;                 // exactly one non-empty head has this rank, if any
     }
 }
 
@@ -480,7 +475,9 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int n_heads = n_ranges * H;
-    const size_t smem_b = (size_t)n_heads * sizeof(Bm25Key);
+    int nsort = 32;
+    while (nsort < n_heads) nsort <<= 1;
+    const size_t smem_b = (size_t)nsort * sizeof(Bm25Key);
     if (smem_b > 48 * 1024) {
         e = cudaFuncSetAttribute(bm25_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
         if (e != cudaSuccess) return e;
