@@ -849,8 +849,10 @@ int rag_exchange_create(rag_exchange_t** out, int world, int rank, size_t slot_b
     ex->total_bytes = exchange_flags_offset(ex) + 2 * (size_t)world * 8 + 256;
     cudaError_t e = cudaMalloc((void**)&ex->local, ex->total_bytes);
     if (e != cudaSuccess) {
+        const size_t want = ex->total_bytes;
         delete ex;
-        return fail(RAG_ENOMEM, "cudaMalloc(%zu) for the exchange buffer: %s", ex->total_bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return fail(RAG_ENOMEM, "cudaMalloc(%zu) for the exchange buffer: %s", want, cudaGetErrorString(e));
     }
     e = cudaMemset(ex->local, 0, ex->total_bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();      // zeroed flags are in place before any peer can map them
