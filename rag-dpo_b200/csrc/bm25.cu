@@ -117,6 +117,41 @@ constexpr int kBmThreads = 256;
 constexpr int kBmWarps = kBmThreads / 32;
 constexpr int kBmSeg = kBmRange / kBmWarps;      // rows owned by one warp: 512
 
+// first position in post_row[lo, hi) whose row is >= target (rows ascend); 8-ary: 7 independent probes per round
+__device__ __forceinline__ int64_t bm25_lower_bound(const int32_t* __restrict__ post_row, int64_t lo, int64_t hi,
+                                                    int64_t target) {
+    while (hi - lo > 8) {
+        const int64_t step = (hi - lo) >> 3;
+        int32_t v[7];
+#pragma unroll
+        for (int u = 0; u < 7; ++u) v[u] = post_row[lo + step * (u + 1)];
+        int c = 0;                            // probes below the target: a prefix (rows ascend)
+#pragma unroll
+        for (int u = 0; u < 7; ++u) c += (int64_t)v[u] < target;
+        const int64_t base = lo;
+        if (c < 7) hi = base + step * (c + 1);
+        if (c > 0) lo = base + step * c + 1;
+    }
+    int c = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (lo + u < hi) c += (int64_t)post_row[lo + u] < target;
+    return lo + c;
+}
+
+// 16-bit UPPER bound of a positive fp64 score (the top half of the fp32 rounded up, rounded up again): monotone,
+// so "coarse(score) >= coarse_floor(tau)" never misses a row with score >= tau.  0 = not selectable (score <= 0).
+__device__ __forceinline__ uint16_t bm25_coarse_up(double sc) {
+    if (!(sc > 0.0)) return 0;
+    const uint32_t b = __float_as_uint(__double2float_ru(sc));
+    const uint32_t c = (b + 0xFFFFu) >> 16;
+    return (uint16_t)(c > 0xFFFFu ? 0xFFFFu : c);
+}
+__device__ __forceinline__ uint16_t bm25_coarse_floor(double sc) {     // sc > 0
+    const uint32_t c = __float_as_uint(__double2float_rd(sc)) >> 16;
+    return (uint16_t)(c == 0 ? 1 : c);
+}
+
 // accumulate the scores of the CTA's row range [r0, r1) for query qi into acc (shared memory)
 __device__ __forceinline__ void bm25_accumulate_range(const int64_t* __restrict__ term_ptr,
                                                       const int32_t* __restrict__ post_row,
@@ -141,24 +176,7 @@ __device__ __forceinline__ void bm25_accumulate_range(const int64_t* __restrict_
                 int64_t lo = term_ptr[t], hi = term_ptr[t + 1];
                 int64_t target = r0 + (int64_t)bnd * kBmSeg;
                 if (target > r1) target = r1;
-                // invariant: the first posting with row >= target is in [lo, hi]
-                while (hi - lo > 8) {
-                    const int64_t step = (hi - lo) >> 3;
-                    int32_t v[7];
-#pragma unroll
-                    for (int u = 0; u < 7; ++u) v[u] = post_row[lo + step * (u + 1)];
-                    int c = 0;                            // probes below the target: a prefix (rows ascend)
-#pragma unroll
-                    for (int u = 0; u < 7; ++u) c += (int64_t)v[u] < target;
-                    const int64_t base = lo;
-                    if (c < 7) hi = base + step * (c + 1);
-                    if (c > 0) lo = base + step * c + 1;
-                }
-                int c = 0;
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (lo + u < hi) c += (int64_t)post_row[lo + u] < target;
-                pos = lo + c;
+                pos = bm25_lower_bound(post_row, lo, hi, target);
             }
             s_bound[i][bnd] = pos;
             if (bnd == 0) s_w[i] = w;
@@ -292,12 +310,13 @@ __device__ __forceinline__ Bm25Key warp_max_key(Bm25Key k) {
     return k;
 }
 
+template <bool COARSE>          // COARSE: the score vector holds 16-bit upper bounds (batched calls), else fp64
 __global__ void __launch_bounds__(kBmThreads)
 bm25_scores_heads_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_row,
                          const double* __restrict__ impact, const double* __restrict__ idf, int64_t n_docs,
                          int64_t n_terms, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
-                         int q0, const uint8_t* __restrict__ allow, int H, double* __restrict__ scores_out,
-                         Bm25Key* __restrict__ heads) {
+                         int q0, const uint8_t* __restrict__ allow, int H, void* __restrict__ scores_out,
+                         int64_t score_stride, Bm25Key* __restrict__ heads) {
     __shared__ __align__(16) double acc[kBmRange];
     __shared__ int64_t s_bound[kBmMaxTokens][kBmWarps + 1];
     __shared__ double s_w[kBmMaxTokens];
@@ -310,14 +329,15 @@ bm25_scores_heads_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __
                           r1, acc, s_bound, s_w);
     // my 16 rows of the warp's segment: write the scores out, keep the selectable ones as keys in registers
     Bm25Key mine[kBmSeg / 32];
-    double* out = scores_out + (size_t)blockIdx.y * n_docs;
+    double* out = reinterpret_cast<double*>(scores_out) + (size_t)blockIdx.y * score_stride;
+    uint16_t* out16 = reinterpret_cast<uint16_t*>(scores_out) + (size_t)blockIdx.y * score_stride;
 #pragma unroll
     for (int j = 0; j < kBmSeg / 32; ++j) {
         const int i = warp * kBmSeg + j * 32 + lane;
         Bm25Key key{0ull, 0u, 0u};
         if (r0 + i < r1) {
             const double sc = acc[i];
-            out[r0 + i] = sc;
+            if (COARSE) out16[r0 + i] = bm25_coarse_up(sc); else out[r0 + i] = sc;
             const uint32_t r = (uint32_t)(r0 + i);
             if (sc > 0.0 && bitmap_test(allow, r)) { key.s = (uint64_t)__double_as_longlong(sc); key.nrow = ~r; }
         }
@@ -373,13 +393,36 @@ bm25_tau_kernel(const Bm25Key* __restrict__ heads, int n_heads, int k, Bm25Key* 
     }
 }
 
+template <bool COARSE>
 __global__ void __launch_bounds__(256)
-bm25_filter_kernel(const double* __restrict__ scores, int64_t n_docs, const uint8_t* __restrict__ allow,
-                   const Bm25Key* __restrict__ tau, Bm25Key* __restrict__ surv, int32_t* __restrict__ counts) {
+bm25_filter_kernel(const void* __restrict__ scores, int64_t n_docs, int64_t score_stride,
+                   const uint8_t* __restrict__ allow, const Bm25Key* __restrict__ tau, Bm25Key* __restrict__ surv,
+                   int32_t* __restrict__ counts) {
     const int q = blockIdx.y;
     const Bm25Key thr = tau[q];
-    const double* sc = scores + (size_t)q * n_docs;
     const double thr_s = thr.s ? __longlong_as_double((long long)thr.s) : 0.0;
+    if (COARSE) {
+        // 16-bit upper bounds: everything that CAN reach tau survives (a few more than k); the exact fp64 score of
+        // a survivor is recomputed from the postings by bm25_final_kernel
+        const uint16_t* sc = reinterpret_cast<const uint16_t*>(scores) + (size_t)q * score_stride;
+        const uint16_t cthr = thr.s ? bm25_coarse_floor(thr_s) : (uint16_t)1;
+        const int64_t n_vec = (n_docs + 7) >> 3;            // the stride is a multiple of 8: 16-byte vectors
+        for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
+            const uint4 w = *reinterpret_cast<const uint4*>(sc + 8 * v);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint16_t c = (uint16_t)(ww[j >> 1] >> (16 * (j & 1)));
+                const int64_t r = 8 * v + j;
+                if (c >= cthr && r < n_docs && bitmap_test(allow, (uint32_t)r)) {
+                    const int slot = atomicAdd(&counts[q], 1);
+                    if (slot < kBmSurvivors) surv[(size_t)q * kBmSurvivors + slot] = Bm25Key{0ull, ~(uint32_t)r, 0u};
+                }
+            }
+        }
+        return;
+    }
+    const double* sc = reinterpret_cast<const double*>(scores) + (size_t)q * score_stride;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_docs; r += (int64_t)gridDim.x * blockDim.x) {
         const double v = sc[r];
         if (v > 0.0 && v >= thr_s) {
@@ -392,21 +435,64 @@ bm25_filter_kernel(const double* __restrict__ scores, int64_t n_docs, const uint
     }
 }
 
+// exact fp64 score of one row for one query: the same products in the same (token) order as the accumulation
+__device__ __forceinline__ double bm25_exact_score(const int64_t* __restrict__ term_ptr,
+                                                   const int32_t* __restrict__ post_row,
+                                                   const double* __restrict__ impact, const double* __restrict__ idf,
+                                                   int64_t n_terms, const int32_t* __restrict__ terms, int nt,
+                                                   uint32_t row) {
+    double sc = 0.0;
+    for (int i = 0; i < nt; ++i) {
+        const int32_t t = terms[i];
+        if (t < 0 || t >= n_terms) continue;
+        const double w = idf[t];
+        if (w == 0.0) continue;
+        const int64_t hi = term_ptr[t + 1];
+        const int64_t pos = bm25_lower_bound(post_row, term_ptr[t], hi, (int64_t)row);
+        if (pos < hi && (uint32_t)post_row[pos] == row) sc = __dadd_rn(sc, __dmul_rn(w, impact[pos]));
+    }
+    return sc;
+}
+
+template <bool COARSE>
 __global__ void __launch_bounds__(256)
-bm25_final_kernel(const Bm25Key* __restrict__ surv, const int32_t* __restrict__ counts, int k, int32_t* out_rows,
-                  double* out_scores, int32_t* out_counts) {
+bm25_final_kernel(const Bm25Key* __restrict__ surv, const int32_t* __restrict__ counts, int k,
+                  const Bm25Key* __restrict__ tau, const int64_t* __restrict__ term_ptr,
+                  const int32_t* __restrict__ post_row, const double* __restrict__ impact,
+                  const double* __restrict__ idf, int64_t n_terms, const int32_t* __restrict__ q_terms,
+                  const int32_t* __restrict__ q_ptr, int q0, int32_t* out_rows, double* out_scores,
+                  int32_t* out_counts) {
     __shared__ Bm25Key s_keys[kBmSurvivors];
+    __shared__ int s_n;
     const int q = blockIdx.x;
-    const int n = counts[q];
+    int n = counts[q];
     if (n > kBmSurvivors) {                         // mass ties at the bound: robust path must redo this query
         if (threadIdx.x == 0) out_counts[q] = -1;
         return;
+    }
+    if (COARSE) {
+        // survivors of the 16-bit filter: recompute their exact scores, keep those that really reach tau
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const Bm25Key thr = tau[q];
+        const int32_t* terms = q_terms + q_ptr[q0 + q];
+        const int nt = q_ptr[q0 + q + 1] - q_ptr[q0 + q];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t row = ~surv[(size_t)q * kBmSurvivors + i].nrow;
+            const double sc = bm25_exact_score(term_ptr, post_row, impact, idf, n_terms, terms, nt, row);
+            const Bm25Key key{(uint64_t)__double_as_longlong(sc), ~row, 0u};
+            if (sc > 0.0 && !(key < thr)) s_keys[atomicAdd(&s_n, 1)] = key;
+        }
+        __syncthreads();
+        n = s_n;
+        __syncthreads();
     }
     const int nout = n < k ? n : k;
     if (n <= 256) {
         // the usual case (k + a handful of survivors): order by rank counting, no sort
         Bm25Key me{0ull, 0u, 0u};
-        if ((int)threadIdx.x < n) me = surv[(size_t)q * kBmSurvivors + threadIdx.x];
+        if ((int)threadIdx.x < n) me = COARSE ? s_keys[threadIdx.x] : surv[(size_t)q * kBmSurvivors + threadIdx.x];
+        __syncthreads();
         s_keys[threadIdx.x] = me;
         __syncthreads();
         if ((int)threadIdx.x < n) {
@@ -426,8 +512,10 @@ bm25_final_kernel(const Bm25Key* __restrict__ surv, const int32_t* __restrict__ 
     }
     int nsort = 32;
     while (nsort < n) nsort <<= 1;
-    for (int i = threadIdx.x; i < nsort; i += blockDim.x)
-        s_keys[i] = i < n ? surv[(size_t)q * kBmSurvivors + i] : Bm25Key{0ull, 0u, 0u};
+    for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
+        if (COARSE) { if (i >= n) s_keys[i] = Bm25Key{0ull, 0u, 0u}; }
+        else s_keys[i] = i < n ? surv[(size_t)q * kBmSurvivors + i] : Bm25Key{0ull, 0u, 0u};
+    }
     block_bitonic_desc(s_keys, nsort);
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
         const bool ok = i < nout;
@@ -449,7 +537,7 @@ bool bm25_fast_supported(int64_t n_docs, int k) {
 size_t bm25_fast_scratch_bytes(int64_t n_docs, int k, int Q) {
     const int n_ranges = (int)((n_docs + kBmRange - 1) / kBmRange);
     const int H = bm25_fast_heads_per_range(n_docs, k);
-    return (size_t)Q * n_docs * 8 + (size_t)Q * n_ranges * H * sizeof(Bm25Key) + (size_t)Q * sizeof(Bm25Key) +
+    return (size_t)Q * (n_docs + 8) * 8 + (size_t)Q * n_ranges * H * sizeof(Bm25Key) + (size_t)Q * sizeof(Bm25Key) +
            (size_t)Q * kBmSurvivors * sizeof(Bm25Key) + (size_t)Q * 4 + 1024;
 }
 
@@ -459,9 +547,13 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
                              int32_t* out_counts, cudaStream_t st) {
     const int n_ranges = (int)((ix.n_docs + kBmRange - 1) / kBmRange);
     const int H = bm25_fast_heads_per_range(ix.n_docs, k);
+    // batched calls keep 16-bit upper bounds in the score vector (a quarter of the bytes) and recompute the exact
+    // score of the k + few survivors; a handful of queries keeps the fp64 vector (no recompute latency)
+    const bool coarse = Q >= 8;
+    const int64_t stride = (ix.n_docs + 7) & ~(int64_t)7;
     uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
-    double* scores = reinterpret_cast<double*>(base);
-    base += (size_t)Q * ix.n_docs * 8;
+    void* scores = base;
+    base += (size_t)Q * (ix.n_docs + 8) * 8;
     Bm25Key* heads = reinterpret_cast<Bm25Key*>(base);
     base += (size_t)Q * n_ranges * H * sizeof(Bm25Key);
     Bm25Key* tau = reinterpret_cast<Bm25Key*>(base);
@@ -470,8 +562,14 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     base += (size_t)Q * kBmSurvivors * sizeof(Bm25Key);
     int32_t* counts = reinterpret_cast<int32_t*>(base);
     dim3 grid_a(n_ranges, Q);
-    bm25_scores_heads_kernel<<<grid_a, kBmThreads, 0, st>>>(ix.term_ptr, ix.post_row, ix.post_impact, ix.idf, ix.n_docs,
-                                                           ix.n_terms, d_q_terms, d_q_ptr, q0, allow, H, scores, heads);
+    if (coarse)
+        bm25_scores_heads_kernel<true><<<grid_a, kBmThreads, 0, st>>>(ix.term_ptr, ix.post_row, ix.post_impact, ix.idf,
+                                                                     ix.n_docs, ix.n_terms, d_q_terms, d_q_ptr, q0, allow,
+                                                                     H, scores, stride, heads);
+    else
+        bm25_scores_heads_kernel<false><<<grid_a, kBmThreads, 0, st>>>(ix.term_ptr, ix.post_row, ix.post_impact, ix.idf,
+                                                                      ix.n_docs, ix.n_terms, d_q_terms, d_q_ptr, q0,
+                                                                      allow, H, scores, stride, heads);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int n_heads = n_ranges * H;
@@ -487,9 +585,18 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     if (gx > 148 * 4) gx = 148 * 4;
     if (gx < 1) gx = 1;
     dim3 grid_c(gx, Q);
-    bm25_filter_kernel<<<grid_c, 256, 0, st>>>(scores, ix.n_docs, allow, tau, surv, counts);
-    bm25_final_kernel<<<Q, 256, 0, st>>>(surv, counts, k, out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k,
-                                         out_counts + q0);
+    int32_t* o_r = out_rows + (size_t)q0 * k;
+    double* o_s = out_scores + (size_t)q0 * k;
+    int32_t* o_c = out_counts + q0;
+    if (coarse) {
+        bm25_filter_kernel<true><<<grid_c, 256, 0, st>>>(scores, ix.n_docs, stride, allow, tau, surv, counts);
+        bm25_final_kernel<true><<<Q, 256, 0, st>>>(surv, counts, k, tau, ix.term_ptr, ix.post_row, ix.post_impact, ix.idf,
+                                                   ix.n_terms, d_q_terms, d_q_ptr, q0, o_r, o_s, o_c);
+    } else {
+        bm25_filter_kernel<false><<<grid_c, 256, 0, st>>>(scores, ix.n_docs, stride, allow, tau, surv, counts);
+        bm25_final_kernel<false><<<Q, 256, 0, st>>>(surv, counts, k, tau, ix.term_ptr, ix.post_row, ix.post_impact,
+                                                    ix.idf, ix.n_terms, d_q_terms, d_q_ptr, q0, o_r, o_s, o_c);
+    }
     return cudaGetLastError();
 }
 
