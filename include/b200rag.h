@@ -133,6 +133,14 @@ int rag_exchange_connect(rag_exchange_t* ex, const void* handles);
 int rag_exchange_destroy(rag_exchange_t* ex);
 int rag_exchange_merge_topk_dev(rag_exchange_t* ex, const double* my_scores_dev, const int64_t* my_ids_dev, int B,
                                 int k, double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev);
+/* same, the rank hands over the LOCAL int32 rows rag_dense_topk_dev wrote: the push kernel turns them into
+ * global ids (row_lo + row, -1 stays padding) on the way out */
+int rag_exchange_merge_rows_dev(rag_exchange_t* ex, const double* my_scores_dev, const int32_t* my_rows_dev,
+                                int64_t row_lo, int B, int k, double* out_scores_dev, int64_t* out_ids_dev,
+                                int32_t* out_counts_dev);
+/* *timed_out != 0: a peer did not arrive within "exchange_timeout_ms" (rag_set_option, default 10000) in some
+ * earlier step; the queries of that step carry out_counts = -2 */
+int rag_exchange_status(rag_exchange_t* ex, int* timed_out);
 
 /* ---- BM25 keyword scoring over CSR postings -------------------------------
  * replaces rank_bm25.BM25Okapi(corpus_tokens) / .get_scores(tokens)
@@ -163,6 +171,15 @@ int rag_bm25_scores(rag_bm25_t* ix, const int32_t* q_terms, int n_q_terms, doubl
  * at most `top`; -1 padded. */
 int rag_rrf_fuse(const int32_t* ids, const double* weights, int Q, int R, int L, int rrf_k, int top,
                  int32_t* out_ids, double* out_scores, int32_t* out_counts);
+
+/* ---- host-side index construction (multi-threaded C++, no GPU needed) ----------------------------------
+ * replaces the per-document dict building of rank_bm25.BM25Okapi._initialize (rank-bm25 0.2.2; reached from
+ * ChunkBM25Index.build_from_collection, src/rag/bm25_index.py:236, and SummaryBM25Index.build, :126):
+ * documents as concatenated term ids (doc_ptr: n_docs+1 offsets) -> CSR postings (term_ptr n_terms+1,
+ * post_row ascending per term, post_tf).  post_row / post_tf hold `capacity` entries (doc_ptr[n_docs] always
+ * suffices); *nnz_out = entries written.  n_threads <= 0: all host cores. */
+int rag_csr_build(int64_t n_docs, const int64_t* doc_ptr, const int32_t* tokens, int64_t n_terms, int64_t* term_ptr,
+                  int32_t* post_row, int32_t* post_tf, int64_t capacity, int64_t* nnz_out, int n_threads);
 
 #ifdef __cplusplus
 }

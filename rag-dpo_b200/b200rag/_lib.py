@@ -46,6 +46,9 @@ SYMBOLS = {
     "rag_exchange_connect": (_i, [_vp, _vp]),
     "rag_exchange_destroy": (_i, [_vp]),
     "rag_exchange_merge_topk_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "rag_exchange_merge_rows_dev": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "rag_exchange_status": (_i, [_vp, _vp]),
+    "rag_csr_build": (_i, [_i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i]),
     "rag_bm25_create": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _d, _d, _d]),
     "rag_bm25_destroy": (_i, [_vp]),
     "rag_bm25_search": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),

@@ -73,39 +73,62 @@ class Postings:
         return np.array(idf, dtype=np.float64)
 
     @classmethod
+    def from_flat_tokens(cls, doc_ptr, tokens, n_terms=None, k1=1.5, b=0.75, epsilon=0.25, vocab=None, threads=0):
+        """documents as ONE int32 array of term ids (vocabulary = first-seen order) + n_docs+1 offsets.  The CSR
+        is built by the library's multi-threaded host code (rag_csr_build, csrc/host_csr.cu; no GPU involved)."""
+        doc_ptr = np.ascontiguousarray(doc_ptr, dtype=np.int64)
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        n_docs = len(doc_ptr) - 1
+        if n_docs <= 0:
+            raise ValueError("cannot build a BM25 index over zero documents")
+        if n_terms is None:
+            n_terms = int(tokens.max()) + 1 if len(tokens) else 0
+        total = int(doc_ptr[-1])
+        term_ptr = np.zeros(n_terms + 1, dtype=np.int64)
+        post_row = np.empty(max(total, 1), dtype=np.int32)
+        post_tf = np.empty(max(total, 1), dtype=np.int32)
+        nnz = C.c_int64()
+        rc = _lib.load().rag_csr_build(n_docs, _lib.ptr(doc_ptr), _lib.ptr(tokens) if total else None, n_terms,
+                                       _lib.ptr(term_ptr), _lib.ptr(post_row), _lib.ptr(post_tf), len(post_row),
+                                       C.byref(nnz), int(threads))
+        if rc != 0:
+            raise ValueError(f"rag_csr_build failed ({rc}): term ids must lie in [0, n_terms)")
+        lens = np.diff(doc_ptr)
+        df = np.diff(term_ptr)
+        avgdl = int(lens.sum()) / n_docs
+        idf = cls.idf_table(df, n_docs, epsilon)
+        return cls(term_ptr, post_row[:nnz.value].copy(), post_tf[:nnz.value].copy(), lens, idf, avgdl, k1, b, epsilon,
+                   vocab)
+
+    @classmethod
     def from_term_ids(cls, docs_term_ids, n_terms=None, k1=1.5, b=0.75, epsilon=0.25, vocab=None):
         """docs_term_ids: sequence of 1-D int arrays, ids in vocabulary (first-seen) order."""
         n_docs = len(docs_term_ids)
         if n_docs == 0:
             raise ValueError("cannot build a BM25 index over zero documents")
         lens = np.fromiter((len(d) for d in docs_term_ids), dtype=np.int64, count=n_docs)
-        flat = (np.concatenate([np.asarray(d, dtype=np.int64) for d in docs_term_ids])
-                if lens.sum() else np.zeros(0, np.int64))
-        rows = np.repeat(np.arange(n_docs, dtype=np.int64), lens)
-        if n_terms is None:
-            n_terms = int(flat.max()) + 1 if len(flat) else 0
-        key, tf = np.unique(flat * n_docs + rows, return_counts=True)     # sorted by (term, row)
-        terms = key // n_docs
-        df = np.bincount(terms, minlength=n_terms)
-        term_ptr = np.zeros(n_terms + 1, dtype=np.int64)
-        np.cumsum(df, out=term_ptr[1:])
-        avgdl = int(lens.sum()) / n_docs
-        idf = cls.idf_table(df, n_docs, epsilon)
-        return cls(term_ptr, key % n_docs, tf, lens, idf, avgdl, k1, b, epsilon, vocab)
+        doc_ptr = np.zeros(n_docs + 1, dtype=np.int64)
+        np.cumsum(lens, out=doc_ptr[1:])
+        flat = (np.concatenate([np.asarray(d, dtype=np.int32) for d in docs_term_ids])
+                if doc_ptr[-1] else np.zeros(0, np.int32))
+        return cls.from_flat_tokens(doc_ptr, flat, n_terms=n_terms, k1=k1, b=b, epsilon=epsilon, vocab=vocab)
 
     @classmethod
     def from_token_lists(cls, corpus_tokens, **kw):
+        """corpus_tokens: list of token lists (what ChunkBM25Index keeps, src/rag/bm25_index.py:186); the
+        vocabulary is numbered in first-seen order (the order rank-bm25 sums the idfs in)."""
         vocab = {}
-        docs = []
+        n_docs = len(corpus_tokens)
+        doc_ptr = np.zeros(n_docs + 1, dtype=np.int64)
+        np.cumsum([len(t) for t in corpus_tokens], out=doc_ptr[1:])
+        flat = np.empty(int(doc_ptr[-1]), dtype=np.int32)
+        setdefault = vocab.setdefault
+        pos = 0
         for toks in corpus_tokens:
-            ids = np.empty(len(toks), dtype=np.int64)
-            for j, w in enumerate(toks):
-                t = vocab.get(w)
-                if t is None:
-                    t = vocab[w] = len(vocab)
-                ids[j] = t
-            docs.append(ids)
-        return cls.from_term_ids(docs, n_terms=len(vocab), vocab=vocab, **kw)
+            for w in toks:
+                flat[pos] = setdefault(w, len(vocab))
+                pos += 1
+        return cls.from_flat_tokens(doc_ptr, flat, n_terms=len(vocab), vocab=vocab, **kw)
 
     def term_ids(self, tokens):
         return np.array([self.vocab.get(w, -1) for w in tokens], dtype=np.int32)
@@ -135,6 +158,8 @@ class DeviceBM25:
         """queries_term_ids: list of int32 arrays.  Returns rows (Q,k) int32 [-1 padded],
         scores (Q,k) fp64, counts (Q,) int32."""
         Q = len(queries_term_ids)
+        if k > _lib.RAG_MAX_K:
+            return self._search_multipass(queries_term_ids, int(k), allow_bitmap)
         q_ptr = np.zeros(Q + 1, dtype=np.int32)
         np.cumsum([len(t) for t in queries_term_ids], out=q_ptr[1:])
         flat = (np.concatenate([np.asarray(t, dtype=np.int32) for t in queries_term_ids])
@@ -148,6 +173,32 @@ class DeviceBM25:
                                            _lib.ptr(rows), _lib.ptr(scores), _lib.ptr(counts)))
         return rows, scores, counts
 
+    def _search_multipass(self, queries_term_ids, k, allow_bitmap):
+        """top_k above RAG_MAX_K: successive passes with the rows already returned masked out (still exact)"""
+        n, Q = self.p.n_docs, len(queries_term_ids)
+        rows = np.full((Q, k), -1, dtype=np.int32)
+        scores = np.zeros((Q, k), dtype=np.float64)
+        counts = np.zeros(Q, dtype=np.int32)
+        base = (np.unpackbits(np.asarray(allow_bitmap, dtype=np.uint8), bitorder="little")[:n].astype(bool)
+                if allow_bitmap is not None else np.ones(n, dtype=bool))
+        for qi, terms in enumerate(queries_term_ids):
+            mask, got = base.copy(), 0
+            while got < k:
+                kk = min(_lib.RAG_MAX_K, k - got)
+                r, s, c = self.search_ids([terms], kk, np.packbits(mask, bitorder="little"))
+                c0 = int(c[0])
+                rows[qi, got:got + c0], scores[qi, got:got + c0] = r[0, :c0], s[0, :c0]
+                mask[r[0, :c0]] = False
+                got += c0
+                if c0 < kk:
+                    break
+            counts[qi] = got
+        return rows, scores, counts
+
+    def bytes_per_posting(self):
+        """bytes the search kernels stream per posting (the algorithmic bytes of the roofline)"""
+        return 12
+
     def scores(self, term_ids):
         """full fp64 score vector (BM25Okapi.get_scores)"""
         t = np.ascontiguousarray(term_ids, dtype=np.int32)
@@ -157,10 +208,7 @@ class DeviceBM25:
 
 
 def _clamp_k(top_k, n):
-    k = min(int(top_k), n)
-    if k > _lib.RAG_MAX_K:
-        raise ValueError(f"top_k={top_k} exceeds the fused select limit {_lib.RAG_MAX_K}")
-    return k
+    return min(int(top_k), n)        # top_k above RAG_MAX_K is served in several passes (DeviceBM25.search_ids)
 
 
 class DeviceChunkBM25Index:

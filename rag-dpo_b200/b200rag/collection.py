@@ -102,6 +102,8 @@ class DeviceCorpus:
         B = q32.shape[0]
         if q32.shape[1] != self.dim:
             raise ValueError(f"query dim {q32.shape[1]} != collection dim {self.dim}")
+        if k > _lib.RAG_MAX_K and out is None:
+            return self._topk_multipass(q32, int(k), allow_bitmap)
         if out is not None:
             rows, scores, counts = out              # caller-provided (e.g. pinned) result buffers
         else:
@@ -111,6 +113,30 @@ class DeviceCorpus:
         ab = np.ascontiguousarray(allow_bitmap, dtype=np.uint8) if allow_bitmap is not None else None
         _lib.check(self._L.rag_dense_topk(self._h, _lib.ptr(q32), B, int(k), _lib.ptr(ab), _lib.ptr(rows),
                                           _lib.ptr(scores), _lib.ptr(counts)))
+        return rows, scores, counts
+
+    def _topk_multipass(self, q32, k, allow_bitmap):
+        """k above the fused select's limit (RAG_MAX_K): exact all the same — each pass takes the next RAG_MAX_K
+        rows with the rows already returned masked out (Chroma itself has no such limit: retrieve_candidates with
+        n_candidates > 224 must not degrade)."""
+        n, B = self.count(), q32.shape[0]
+        rows = np.full((B, k), -1, dtype=np.int32)
+        scores = np.zeros((B, k), dtype=np.float64)
+        counts = np.zeros(B, dtype=np.int32)
+        base = (np.unpackbits(np.asarray(allow_bitmap, dtype=np.uint8), bitorder="little")[:n].astype(bool)
+                if allow_bitmap is not None else np.ones(n, dtype=bool))
+        for b in range(B):
+            mask, got = base.copy(), 0
+            while got < k:
+                kk = min(_lib.RAG_MAX_K, k - got)
+                r, s, c = self.topk(q32[b:b + 1], kk, np.packbits(mask, bitorder="little"))
+                c0 = int(c[0])
+                rows[b, got:got + c0], scores[b, got:got + c0] = r[0, :c0], s[0, :c0]
+                mask[r[0, :c0]] = False
+                got += c0
+                if c0 < kk:
+                    break
+            counts[b] = got
         return rows, scores, counts
 
     def topk_dev(self, q_dev_ptr, B, k, out_rows_ptr, out_scores_ptr, out_counts_ptr, allow_dev_ptr=None):

@@ -9,11 +9,14 @@ DeviceChunkBM25Index instead.
 All arithmetic on the path (similarity, top-k, BM25, RRF) runs on the device
 through the injected objects; this file only orchestrates.
 """
+import logging
 from collections import defaultdict
 from dataclasses import dataclass
 from typing import Any, Callable, Dict, List, Optional
 
 from . import rrf as _rrf
+
+logger = logging.getLogger(__name__)
 
 
 @dataclass
@@ -103,7 +106,8 @@ class HybridRetriever:
             try:
                 res = self.collection.query(query_embeddings=[emb], n_results=n_fetch, where=where_filter,
                                             include=["documents", "metadatas", "distances"])
-            except Exception:
+            except Exception as e:      # the reference logs and skips this query variant (retriever.py:221-223)
+                logger.error("dense query failed (variant %d): %s", q_idx, e)
                 continue
             chunks = [_chunk_from_meta(i, t, m, d) for i, t, m, d in
                       zip(res["ids"][0], res["documents"][0], res["metadatas"][0], res["distances"][0])]
@@ -203,6 +207,7 @@ def _retrieve_candidates_batch(self, queries, n_candidates: int = 100, where_fil
     if not hasattr(col, "query_rows") or (use_bm25 and not hasattr(bm, "search_rows")):
         return [self.retrieve_candidates(q, n_candidates, where_filter) for q in queries]
     n_fetch = max(n_candidates, 50)
+    from .rrf import rrf_capacity
     # 1. query variants + summary pre-filter per question
     variants, filters = [], []
     for q in queries:
@@ -235,12 +240,23 @@ def _retrieve_candidates_batch(self, queries, n_candidates: int = 100, where_fil
                 continue
             r, s, c = bm.search_rows([tokens[vi] for vi in live], n_fetch, set(key) if key is not None else None)
             b_rows[live, :r.shape[1]], b_scores[live, :r.shape[1]], b_counts[live] = r, s, c
-        if not hasattr(bm, "_to_col") or len(bm._to_col) != len(bm.chunk_ids):
-            bm._to_col = np.array([col._pos[cid] for cid in bm.chunk_ids], dtype=np.int32)
+        # BM25 row -> collection row (-1: the chunk left the collection since the index was built).  Rebuilt
+        # whenever the collection mutates or the index is rebuilt: rows shift on delete/compaction.
+        stamp = (id(bm.index), getattr(col, "mutation_version", None))
+        if getattr(bm, "_to_col_stamp", None) != stamp or stamp[1] is None:
+            pos = col._pos
+            bm._to_col = np.array([pos.get(cid, -1) for cid in bm.chunk_ids], dtype=np.int32)
+            bm._to_col_stamp = stamp
+        if len(bm._to_col) and int(bm._to_col.min()) < 0:
+            # a stale keyword index (chunks deleted from the collection since it was built): the per-question path
+            # fuses by chunk id and still reports those hits from the index's own metadata — take it
+            return [self.retrieve_candidates(q, n_candidates, where_filter) for q in queries]
     # 4. rankings in the reference's order: dense v0, bm25 v0, dense v1, bm25 v1, ...
     Q = len(queries)
     vmax = max(len(vs) for vs in variants)
     R = vmax * (2 if use_bm25 else 1)
+    if R * n_fetch > rrf_capacity():        # more ranking entries than one device RRF call holds
+        return [self.retrieve_candidates(q, n_candidates, where_filter) for q in queries]
     ids = np.full((Q, R, n_fetch), -1, np.int32)
     weights = np.zeros((Q, R), np.float64)
     dense_lists = {}

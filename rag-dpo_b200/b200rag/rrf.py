@@ -10,6 +10,13 @@ import numpy as np
 from . import _lib
 
 
+RRF_MAX_ENTRIES = 8192      # R * L of one question (csrc/rrf.cu kRrfMaxEntries)
+
+
+def rrf_capacity():
+    return RRF_MAX_ENTRIES
+
+
 def rrf_fuse_rows(ids, weights, rrf_k=60, top=None):
     """ids: int32 array (Q, R, L), negative = padding; weights (Q, R) or (R,).
     Returns out_ids (Q, top) [-1 padded], out_scores (Q, top), counts (Q,)."""

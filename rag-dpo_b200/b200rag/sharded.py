@@ -59,6 +59,11 @@ class PeerExchange:
         self._lib.check(self._L.rag_exchange_merge_topk_dev(self._h, my_scores_ptr, my_ids_ptr, int(B), int(k),
                                                             out_scores_ptr, out_ids_ptr, out_counts_ptr))
 
+    def merge_rows_dev(self, my_scores_ptr, my_rows_ptr, row_lo, B, k, out_scores_ptr, out_ids_ptr, out_counts_ptr):
+        """same, the rank hands over its LOCAL int32 rows: the push kernel turns them into global ids on the way"""
+        self._lib.check(self._L.rag_exchange_merge_rows_dev(self._h, my_scores_ptr, my_rows_ptr, int(row_lo), int(B),
+                                                            int(k), out_scores_ptr, out_ids_ptr, out_counts_ptr))
+
     def close(self):
         if self._h:
             import torch.distributed as dist
@@ -198,6 +203,52 @@ class ShardedDenseIndex:
         h[2].copy_(buf["m_counts"], non_blocking=True)
         stream.synchronize()
         return h[0].numpy().copy(), h[1].numpy().copy(), h[2].numpy().copy()
+
+    def make_device_step(self, q_dev_ptr, nq, k):
+        """Stream-ordered device step for HBM-resident queries (bench / serving loops): local top-k, then — when
+        sharded — the exchange of the (score, global id) lists over NVLink peer memory and the merge.  Returns
+        (step, out): step() only queues work on torch's current stream (which must be the library's stream,
+        _lib.set_stream); out holds the device tensors it fills: "ids"/"scores"/"counts" (merged over the ranks;
+        the local rows on a single rank) and "local_rows"/"local_scores"."""
+        torch, dist = self.torch, self.dist
+        from . import _lib
+        L = _lib.lib()
+        dev, world = self.device, self.world
+        if k > self.row_hi - self.row_lo:
+            raise ValueError("make_device_step needs k <= rows per shard")
+        o_rows = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        o_counts = torch.empty((nq,), dtype=torch.int32, device=dev)
+        # one packed buffer per rank: [scores (nq x k f64) | global ids (nq x k i64)] -> ONE all-gather on the NCCL path
+        mine = torch.empty((2, nq, k), dtype=torch.float64, device=dev)
+        o_scores = mine[0]
+        my_ids = mine[1].view(torch.int64)
+        out = {"ids": o_rows, "scores": o_scores, "counts": o_counts, "local_rows": o_rows, "local_scores": o_scores}
+        if world == 1:
+            def step():
+                self.corpus.topk_dev(q_dev_ptr, nq, k, o_rows.data_ptr(), o_scores.data_ptr(), o_counts.data_ptr())
+            return step, out
+        m_scores = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        m_counts = torch.empty((nq,), dtype=torch.int32, device=dev)
+        out.update(ids=m_ids, scores=m_scores, counts=m_counts)
+        ex = self.exchange(nq, k)       # peer-memory exchange, or None: the NCCL all-gather path
+        if ex is not None:
+            def step():
+                self.corpus.topk_dev(q_dev_ptr, nq, k, o_rows.data_ptr(), o_scores.data_ptr(), o_counts.data_ptr())
+                # P2P stores of (scores | local rows -> global ids) into every peer's buffer + flags + merge
+                ex.merge_rows_dev(o_scores.data_ptr(), o_rows.data_ptr(), self.row_lo, nq, k, m_scores.data_ptr(),
+                                  m_ids.data_ptr(), m_counts.data_ptr())
+            return step, out
+        gathered = torch.empty((world, 2, nq, k), dtype=torch.float64, device=dev)
+
+        def step():
+            self.corpus.topk_dev(q_dev_ptr, nq, k, o_rows.data_ptr(), o_scores.data_ptr(), o_counts.data_ptr())
+            my_ids.copy_(o_rows)                       # int32 -> int64
+            my_ids.add_(self.row_lo)                   # local row -> global id (k <= rows per shard: no padding)
+            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            _lib.check(L.rag_merge_topk_dev(gathered.data_ptr(), gathered.data_ptr() + nq * k * 8, world, nq, k,
+                                            2 * nq * k, m_scores.data_ptr(), m_ids.data_ptr(), m_counts.data_ptr()))
+        return step, out
 
     def _buffers(self, B, kk, kl):
         """device / pinned buffers reused across calls of the same shape"""

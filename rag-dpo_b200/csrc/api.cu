@@ -86,6 +86,7 @@ struct Ctx {
 Ctx g;
 int g_tc_min_batch = 2;     // smallest batch served by the tcgen05 path (env B200RAG_TC_MIN_BATCH)
 int g_tc_b1_shadow = 1;     // batch-1 on fp32/fp16 corpora goes through the bf16 shadow (env B200RAG_TC_B1_SHADOW)
+int g_exchange_timeout_ms = 10000;   // bound of the exchange's flag wait (option "exchange_timeout_ms")
 
 int ensure_pinned(size_t need) {
     if (need <= g.pinned_bytes) return RAG_OK;
@@ -199,6 +200,7 @@ int rag_set_option(const char* key, int64_t value) {
     else if (!strcmp(key, "balance_tail")) gemm_set_balance_tail((int)value);
     else if (!strcmp(key, "pair_mode")) gemm_set_pair_mode((int)value);
     else if (!strcmp(key, "sample_resident")) gemm_set_sample_resident((int)value);
+    else if (!strcmp(key, "exchange_timeout_ms")) g_exchange_timeout_ms = (int)std::max<int64_t>(1, std::min<int64_t>(value, 600000));
     else return fail(RAG_EINVAL, "unknown option %s", key);
     return RAG_OK;
 }
@@ -830,6 +832,7 @@ struct rag_exchange {
     void* mapped[kMaxExchangeRanks] = {};     // peers' buffers as opened in this process (mine: == local)
     bool connected = false;
     uint64_t epoch = 0;
+    cudaStream_t stream = nullptr;            // every step runs on the stream of the first one
     ExchangeDev dev{};
 };
 
@@ -916,21 +919,52 @@ int rag_exchange_destroy(rag_exchange_t* ex) {
     return RAG_OK;
 }
 
-int rag_exchange_merge_topk_dev(rag_exchange_t* ex, const double* my_scores_dev, const int64_t* my_ids_dev, int B, int k,
-                                double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev) {
-    std::lock_guard<std::mutex> lk(g.mu);
+static int exchange_step(rag_exchange_t* ex, const double* my_scores_dev, const int64_t* my_ids_dev,
+                         const int32_t* my_rows_dev, int64_t row_lo, int B, int k, double* out_scores_dev,
+                         int64_t* out_ids_dev, int32_t* out_counts_dev) {
     RAG_TRY(require_init());
-    if (!ex || !my_scores_dev || !my_ids_dev || !out_scores_dev || !out_ids_dev || !out_counts_dev)
+    if (!ex || !my_scores_dev || (!my_ids_dev && !my_rows_dev) || !out_scores_dev || !out_ids_dev || !out_counts_dev)
         return fail(RAG_EINVAL, "NULL argument");
     if (!ex->connected) return fail(RAG_EINVAL, "exchange not connected");
     if (B <= 0 || k <= 0 || k > RAG_MAX_K || (int64_t)ex->world * k > 8192)
         return fail(RAG_ERANGE, "world=%d B=%d k=%d outside the supported range", ex->world, B, k);
     if ((size_t)B * k * 16 > ex->slot_bytes)
         return fail(RAG_ERANGE, "B*k*16 = %zu bytes exceed the exchange slot (%zu)", (size_t)B * k * 16, ex->slot_bytes);
+    // the two buffer parities are only safe when every step of this exchange is ordered on ONE stream
+    if (ex->epoch == 0) ex->stream = g.stream;
+    else if (ex->stream != g.stream)
+        return fail(RAG_EINVAL, "the exchange is pinned to the stream of its first step (rag_set_stream changed it)");
+    ex->dev.timeout_cycles = (long long)g_exchange_timeout_ms * 2000000LL;
+    // the epoch advances only once the push is queued: a failed launch must not desynchronise the ranks
+    CU_TRY(exchange_push_launch(ex->dev, my_scores_dev, my_ids_dev, my_rows_dev, row_lo, B, k, ex->epoch + 1, g.stream));
     ++ex->epoch;
-    CU_TRY(exchange_launch(ex->dev, my_scores_dev, my_ids_dev, B, k, ex->epoch, out_scores_dev, out_ids_dev,
-                           out_counts_dev, g.stream));
-    g.n_launch += 2;
+    ++g.n_launch;
+    CU_TRY(exchange_merge_launch(ex->dev, B, k, ex->epoch, out_scores_dev, out_ids_dev, out_counts_dev, g.stream));
+    ++g.n_launch;
+    return RAG_OK;
+}
+
+int rag_exchange_merge_topk_dev(rag_exchange_t* ex, const double* my_scores_dev, const int64_t* my_ids_dev, int B, int k,
+                                double* out_scores_dev, int64_t* out_ids_dev, int32_t* out_counts_dev) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    return exchange_step(ex, my_scores_dev, my_ids_dev, nullptr, 0, B, k, out_scores_dev, out_ids_dev, out_counts_dev);
+}
+
+int rag_exchange_merge_rows_dev(rag_exchange_t* ex, const double* my_scores_dev, const int32_t* my_rows_dev,
+                                int64_t row_lo, int B, int k, double* out_scores_dev, int64_t* out_ids_dev,
+                                int32_t* out_counts_dev) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    return exchange_step(ex, my_scores_dev, nullptr, my_rows_dev, row_lo, B, k, out_scores_dev, out_ids_dev,
+                         out_counts_dev);
+}
+
+int rag_exchange_status(rag_exchange_t* ex, int* timed_out) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    RAG_TRY(require_init());
+    if (!ex || !timed_out) return fail(RAG_EINVAL, "NULL argument");
+    unsigned w = 0;
+    CU_TRY(cudaMemcpy(&w, ex->dev.done_counter + 1, sizeof(w), cudaMemcpyDeviceToHost));
+    *timed_out = w != 0;
     return RAG_OK;
 }
 

@@ -31,7 +31,7 @@ __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
 // (device-wide counter) publishes the epoch flag in every peer
 __global__ void __launch_bounds__(256)
 exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const int64_t* __restrict__ my_ids,
-                     int64_t n_elems /* B*k */, uint64_t epoch) {
+                     const int32_t* __restrict__ my_rows, int64_t row_lo, int64_t n_elems /* B*k */, uint64_t epoch) {
     const int peer = blockIdx.y;
     const int parity = (int)(epoch & 1);
     uint8_t* dst = ex.peer_base[peer] + ((size_t)parity * ex.world + ex.rank) * ex.slot_bytes;
@@ -39,8 +39,18 @@ exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const
     uint64_t* d64 = reinterpret_cast<uint64_t*>(dst);
     const uint64_t* s0 = reinterpret_cast<const uint64_t*>(my_scores);
     const uint64_t* s1 = reinterpret_cast<const uint64_t*>(my_ids);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_elems; i += (int64_t)gridDim.x * blockDim.x)
-        d64[i] = i < n_elems ? s0[i] : s1[i - n_elems];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_elems; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t v;
+        if (i < n_elems) {
+            v = s0[i];
+        } else if (my_rows) {               // local int32 rows -> global ids on the way out (-1 stays padding)
+            const int32_t r = my_rows[i - n_elems];
+            v = (uint64_t)(r < 0 ? (int64_t)-1 : (int64_t)r + row_lo);
+        } else {
+            v = s1[i - n_elems];
+        }
+        d64[i] = v;
+    }
     __syncthreads();                                // the block's stores happen-before thread 0's fence
     if (threadIdx.x == 0) {
         __threadfence_system();                     // ... which orders them before the counter / the flags (cumulative)
@@ -57,19 +67,28 @@ exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const
     }
 }
 
-// bounded wait for the G flags of this epoch in MY buffer (thread 0), then the caller merges
-__device__ __forceinline__ void exchange_wait(const uint64_t* flags, int world, uint64_t epoch) {
+// bounded wait for the G flags of this epoch in MY buffer (thread 0), then the caller merges.  A peer that does
+// not arrive within the timeout does NOT take the CUDA context down: the block reports it (returns false, the
+// kernel marks its query with count = -2 and raises the exchange's error word), the host sees it at its next
+// synchronisation (rag_exchange_status).
+__device__ __forceinline__ bool exchange_wait(const uint64_t* flags, int world, uint64_t epoch, long long timeout_cycles,
+                                              unsigned* err_word) {
+    __shared__ int s_ok;
     if (threadIdx.x == 0) {
-        for (int r = 0; r < world; ++r) {
+        int ok = 1;
+        for (int r = 0; r < world && ok; ++r) {
             if (ld_acquire_sys_u64(flags + r) >= epoch) continue;
             const long long t0 = clock64();
             while (ld_acquire_sys_u64(flags + r) < epoch) {
-                if (clock64() - t0 > 20000000000LL) __trap();     // ~10 s: a lost peer must not hang the GPU
+                if (clock64() - t0 > timeout_cycles) { ok = 0; break; }
                 __nanosleep(200);
             }
         }
+        if (!ok) atomicExch(err_word, 1u);
+        s_ok = ok;
     }
     __syncthreads();
+    return s_ok != 0;
 }
 
 struct XKey {
@@ -88,7 +107,14 @@ exchange_merge_kernel(ExchangeDev ex, int B, int k, uint64_t epoch, int nsort, d
     const int parity = (int)(epoch & 1);
     const int b = blockIdx.x;
     if (threadIdx.x == 0) s_count = 0;
-    exchange_wait(ex.my_flags + (size_t)parity * ex.world, ex.world, epoch);
+    if (!exchange_wait(ex.my_flags + (size_t)parity * ex.world, ex.world, epoch, ex.timeout_cycles, ex.done_counter + 1)) {
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            out_ids[(size_t)b * k + i] = -1;
+            out_scores[(size_t)b * k + i] = 0.0;
+        }
+        if (threadIdx.x == 0) out_counts[b] = -2;
+        return;
+    }
     const uint8_t* base = ex.my_base + (size_t)parity * ex.world * ex.slot_bytes;
     const int64_t n_elems = (int64_t)B * k;
     int local = 0;
@@ -114,26 +140,29 @@ exchange_merge_kernel(ExchangeDev ex, int B, int k, uint64_t epoch, int nsort, d
     if (threadIdx.x == 0) out_counts[b] = nout;
 }
 
-cudaError_t exchange_launch(const ExchangeDev& ex, const double* my_scores, const int64_t* my_ids, int B, int k,
-                            uint64_t epoch, double* out_scores, int64_t* out_ids, int32_t* out_counts,
-                            cudaStream_t st) {
+cudaError_t exchange_push_launch(const ExchangeDev& ex, const double* my_scores, const int64_t* my_ids,
+                                 const int32_t* my_rows, int64_t row_lo, int B, int k, uint64_t epoch, cudaStream_t st) {
     const int64_t n_elems = (int64_t)B * k;
     int bx = (int)((2 * n_elems + 256 * 8 - 1) / (256 * 8));
     if (bx < 1) bx = 1;
     if (bx > 32) bx = 32;
     dim3 grid(bx, ex.world);
-    exchange_push_kernel<<<grid, 256, 0, st>>>(ex, my_scores, my_ids, n_elems, epoch);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    exchange_push_kernel<<<grid, 256, 0, st>>>(ex, my_scores, my_ids, my_rows, row_lo, n_elems, epoch);
+    return cudaGetLastError();
+}
+
+cudaError_t exchange_merge_launch(const ExchangeDev& ex, int B, int k, uint64_t epoch, double* out_scores,
+                                  int64_t* out_ids, int32_t* out_counts, cudaStream_t st) {
     int nsort = 32;
     while (nsort < ex.world * k) nsort <<= 1;
     const size_t smem = (size_t)nsort * sizeof(XKey);
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     exchange_merge_kernel<<<B, 256, smem, st>>>(ex, B, k, epoch, nsort, out_scores, out_ids, out_counts);
     return cudaGetLastError();
 }
+
 
 }  // namespace b200rag

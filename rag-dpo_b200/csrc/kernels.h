@@ -139,13 +139,17 @@ struct ExchangeDev {
     uint64_t* peer_flags[kMaxExchangeRanks];   // every rank's flag area
     uint8_t* my_base;
     uint64_t* my_flags;
-    unsigned* done_counter;                     // local: blocks of the push kernel that have finished
+    unsigned* done_counter;                     // local: blocks of the push kernel that have finished; [1] = error word
+    long long timeout_cycles;                   // bound of the flag wait (option "exchange_timeout_ms")
     int world, rank;
     size_t slot_bytes;                          // payload capacity per (parity, source rank)
 };
-// push my (scores | ids) block into every rank's buffer, flag the epoch, wait for all ranks, merge -> top-k
-cudaError_t exchange_launch(const ExchangeDev& ex, const double* my_scores, const int64_t* my_ids, int B, int k,
-                            uint64_t epoch, double* out_scores, int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
+// push my (scores | ids) block into every rank's buffer and flag the epoch (ids: int64 global ids, or — my_rows
+// != NULL — local int32 rows turned into global ids row_lo + row on the way); then wait for all ranks, merge -> top-k
+cudaError_t exchange_push_launch(const ExchangeDev& ex, const double* my_scores, const int64_t* my_ids,
+                                 const int32_t* my_rows, int64_t row_lo, int B, int k, uint64_t epoch, cudaStream_t st);
+cudaError_t exchange_merge_launch(const ExchangeDev& ex, int B, int k, uint64_t epoch, double* out_scores,
+                                  int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
 
 // ---- corpus.cu -------------------------------------------------------------
 cudaError_t convert_rows_launch(const float* src, void* dst, int dtype, int64_t n_elems, cudaStream_t st);

@@ -5,7 +5,7 @@
 // accumulated in ranking order (fp64, correctly rounded divide and add), then a
 // STABLE descending sort over first-seen order and a cut to `top`.
 //
-// One CTA per question; R*L <= 2048 entries live in shared memory.  The work
+// One CTA per question; R*L <= 8192 entries live in (dynamic) shared memory.  The work
 // per question is ~400 entries, so the kernel is latency-bound by design; it
 // exists so that fused lists never leave the device when many questions are
 // served per call.
@@ -14,18 +14,20 @@
 
 namespace b200rag {
 
-constexpr int kRrfMaxEntries = 2048;
+constexpr int kRrfMaxEntries = 8192;
 
 __global__ void __launch_bounds__(256)
 rrf_kernel(const int32_t* __restrict__ ids, const double* __restrict__ weights, int R, int L, int rrf_k, int top,
            int32_t* __restrict__ out_ids, double* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
-    __shared__ int32_t s_id[kRrfMaxEntries];
-    __shared__ int16_t s_rank[kRrfMaxEntries];      // enumerate() index inside its ranking
-    __shared__ uint8_t s_first[kRrfMaxEntries];     // 1 = first occurrence of its id
-    __shared__ double s_score[kRrfMaxEntries];
+    extern __shared__ __align__(16) uint8_t rrf_smem[];
     __shared__ int s_distinct;
     const int q = blockIdx.x;
     const int n = R * L;
+    const int np = (n + 7) & ~7;
+    double* s_score = reinterpret_cast<double*>(rrf_smem);              // np
+    int32_t* s_id = reinterpret_cast<int32_t*>(s_score + np);           // np
+    int16_t* s_rank = reinterpret_cast<int16_t*>(s_id + np);            // np: enumerate() index inside its ranking
+    uint8_t* s_first = reinterpret_cast<uint8_t*>(s_rank + np);         // np: 1 = first occurrence of its id
     const int32_t* my_ids = ids + (size_t)q * n;
     const double* w = weights + (size_t)q * R;
 
@@ -84,7 +86,13 @@ int rrf_max_entries() { return kRrfMaxEntries; }
 
 cudaError_t rrf_launch(const int32_t* ids, const double* weights, int Q, int R, int L, int rrf_k, int top,
                        int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st) {
-    rrf_kernel<<<Q, 256, 0, st>>>(ids, weights, R, L, rrf_k, top, out_ids, out_scores, out_counts);
+    const int np = (R * L + 7) & ~7;
+    const size_t smem = (size_t)np * (8 + 4 + 2 + 1);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    rrf_kernel<<<Q, 256, smem, st>>>(ids, weights, R, L, rrf_k, top, out_ids, out_scores, out_counts);
     return cudaGetLastError();
 }
 

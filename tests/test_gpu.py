@@ -133,8 +133,9 @@ def test_dense_edge_cases():
     c.append(x)
     rows, scores, counts = check_topk(c, q, 10, no.DT_BF16)   # fewer rows than k
     assert counts.tolist() == [3, 3]
-    with pytest.raises(B200RagError):
-        c.topk(q, 225)
+    # k above the fused select's limit is served in several passes (still exact), not refused
+    rows, scores, counts = c.topk(q, 225)
+    assert counts.tolist() == [3, 3] and rows.shape == (2, 225)
     with pytest.raises(B200RagError):
         DeviceCorpus(100, "bf16")
     with pytest.raises(ValueError):
