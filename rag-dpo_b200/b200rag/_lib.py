@@ -21,6 +21,8 @@ DTYPES = {"f32": RAG_F32, "fp32": RAG_F32, "float32": RAG_F32, "bf16": RAG_BF16,
 _vp, _i, _i64, _u64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
 SYMBOLS = {
     "rag_init": (_i, [_i]),
+    "rag_init_devices": (_i, [_i, _vp]),
+    "rag_slot_count": (_i, [_vp]),
     "rag_set_stream": (_i, [_vp]),
     "rag_last_error": (C.c_char_p, []),
     "rag_abi_version": (_i, []),
@@ -31,6 +33,11 @@ SYMBOLS = {
     "rag_last_timings": (_i, [_vp, _i]),
     "rag_counters": (_i, [_vp, _i]),
     "rag_corpus_create": (_i, [_vp, _i64, _i, _i]),
+    "rag_corpus_create_sharded": (_i, [_vp, _i64, _i, _i, _i]),
+    "rag_corpus_delete_rows": (_i, [_vp, _vp, _i64]),
+    "rag_corpus_live_count": (_i, [_vp, _vp]),
+    "rag_corpus_set_codes": (_i, [_vp, _i, _i64, _i64, _vp]),
+    "rag_dense_topk_where": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "rag_corpus_destroy": (_i, [_vp]),
     "rag_corpus_reserve": (_i, [_vp, _i64]),
     "rag_corpus_upload": (_i, [_vp, _i64, _i64, _vp]),
@@ -46,11 +53,13 @@ SYMBOLS = {
     "rag_exchange_connect": (_i, [_vp, _vp]),
     "rag_exchange_destroy": (_i, [_vp]),
     "rag_exchange_merge_topk_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
-    "rag_exchange_merge_rows_dev": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "rag_exchange_merge_rows_dev": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "rag_exchange_status": (_i, [_vp, _vp]),
     "rag_csr_build": (_i, [_i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i]),
     "rag_bm25_create": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _d, _d, _d]),
+    "rag_bm25_create_sharded": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _d, _d, _d]),
     "rag_bm25_destroy": (_i, [_vp]),
+    "rag_bm25_info": (_i, [_vp, _vp, _vp]),
     "rag_bm25_search": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "rag_bm25_scores": (_i, [_vp, _vp, _i, _vp]),
     "rag_rrf_fuse": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -88,7 +97,7 @@ def check(rc):
 
 
 def lib():
-    """The library bound to this process's GPU (LOCAL_RANK, default 0)."""
+    """The library bound to this process's primary GPU (B200RAG_DEVICE, else LOCAL_RANK, default 0)."""
     global _ready
     L = load()
     if not _ready:
@@ -98,6 +107,40 @@ def lib():
                 check(L.rag_init(dev))
                 _ready = True
     return L
+
+
+def init_devices(devices):
+    """One process, several GPUs: shard slot i of a sharded corpus / index runs on devices[i] (a device may repeat).
+    devices[0] must be the primary device lib() binds.  Idempotent; a longer list extends a shorter one."""
+    L = lib()
+    arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+    check(L.rag_init_devices(len(devices), arr))
+    return slot_count()
+
+
+def slot_count():
+    n = C.c_int()
+    check(lib().rag_slot_count(C.byref(n)))
+    return n.value
+
+
+def ensure_slots(n_shards, devices=None):
+    """make at least n_shards shard slots available: the given devices, else B200RAG_DEVICES ("0,1,2,3"), else the
+    primary device followed by the other visible GPUs in order (wrapping around when there are fewer GPUs)"""
+    if n_shards <= slot_count() and devices is None:
+        return
+    if devices is None:
+        env = os.environ.get("B200RAG_DEVICES")
+        if env:
+            devices = [int(x) for x in env.split(",") if x.strip() != ""]
+        else:
+            import torch
+            n_gpu = max(1, torch.cuda.device_count())
+            first = int(os.environ.get("B200RAG_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            devices = [(first + i) % n_gpu for i in range(n_shards)]
+    if len(devices) < n_shards:
+        raise B200RagError(f"{n_shards} shards need {n_shards} shard slots, got devices {devices}")
+    init_devices(devices)
 
 
 def ptr(a):
@@ -154,7 +197,7 @@ def last_timings():
 def counters():
     out = np.zeros(4, dtype=np.int64)
     check(lib().rag_counters(ptr(out), 4))
-    return {"launches": int(out[0]), "fallbacks": int(out[1])}
+    return {"launches": int(out[0]), "fallbacks": int(out[1]), "fallback_queries": int(out[2])}
 
 
 def sync_stream_of(torch, device):

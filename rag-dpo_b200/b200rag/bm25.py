@@ -135,16 +135,24 @@ class Postings:
 
 
 class DeviceBM25:
-    """Owner of a rag_bm25_t handle."""
+    """Owner of a rag_bm25_t handle.  n_shards > 1: the documents are spread over the GPUs of this process like a
+    sharded corpus (every GPU holds the postings of its rows; idf / avgdl are the global statistics)."""
 
-    def __init__(self, postings: Postings):
+    def __init__(self, postings: Postings, n_shards=1, devices=None):
         self.p = postings
+        self.n_shards = int(n_shards)
         self._L = _lib.lib()
         h = C.c_void_p()
         p = postings
-        _lib.check(self._L.rag_bm25_create(C.byref(h), p.n_docs, p.n_terms, len(p.post_row), _lib.ptr(p.term_ptr),
-                                           _lib.ptr(p.post_row), _lib.ptr(p.post_tf), _lib.ptr(p.doc_len),
-                                           _lib.ptr(p.idf), p.avgdl, p.k1, p.b))
+        if self.n_shards > 1:
+            _lib.ensure_slots(self.n_shards, devices)
+            _lib.check(self._L.rag_bm25_create_sharded(C.byref(h), self.n_shards, p.n_docs, p.n_terms, len(p.post_row),
+                                                       _lib.ptr(p.term_ptr), _lib.ptr(p.post_row), _lib.ptr(p.post_tf),
+                                                       _lib.ptr(p.doc_len), _lib.ptr(p.idf), p.avgdl, p.k1, p.b))
+        else:
+            _lib.check(self._L.rag_bm25_create(C.byref(h), p.n_docs, p.n_terms, len(p.post_row), _lib.ptr(p.term_ptr),
+                                               _lib.ptr(p.post_row), _lib.ptr(p.post_tf), _lib.ptr(p.doc_len),
+                                               _lib.ptr(p.idf), p.avgdl, p.k1, p.b))
         self._h = h
 
     def close(self):
@@ -196,8 +204,16 @@ class DeviceBM25:
         return rows, scores, counts
 
     def bytes_per_posting(self):
-        """bytes the search kernels stream per posting (the algorithmic bytes of the roofline)"""
-        return 12
+        """bytes the search kernels stream per posting (the algorithmic bytes of the roofline): 4 on the packed
+        filter path, 12 (row + fp64 impact) when only the exact range path serves this index"""
+        b = C.c_int()
+        _lib.check(self._L.rag_bm25_info(self._h, C.byref(b), None))
+        return b.value
+
+    def index_bytes(self):
+        n = C.c_int64()
+        _lib.check(self._L.rag_bm25_info(self._h, None, C.byref(n)))
+        return n.value
 
     def scores(self, term_ids):
         """full fp64 score vector (BM25Okapi.get_scores)"""
@@ -214,8 +230,9 @@ def _clamp_k(top_k, n):
 class DeviceChunkBM25Index:
     """Drop-in for ChunkBM25Index (src/rag/bm25_index.py:176-296)."""
 
-    def __init__(self, tokenizer=tokenize_french):
+    def __init__(self, tokenizer=tokenize_french, n_shards=1, devices=None):
         self.tokenizer = tokenizer
+        self.n_shards, self.devices = int(n_shards), devices
         self.index: Optional[DeviceBM25] = None
         self.chunk_ids: List[str] = []
         self.chunk_texts: List[str] = []
@@ -256,8 +273,9 @@ class DeviceChunkBM25Index:
         if self.index is not None:
             self.index.close()
         self.postings = postings
-        self.index = DeviceBM25(postings)
+        self.index = DeviceBM25(postings, n_shards=self.n_shards, devices=self.devices)
         self._filter_cache = {}
+        self._to_col_stamp = None          # the batched front-end's row map belongs to the previous index
         self._is_built = True
 
     @property

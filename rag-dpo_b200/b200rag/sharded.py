@@ -59,10 +59,13 @@ class PeerExchange:
         self._lib.check(self._L.rag_exchange_merge_topk_dev(self._h, my_scores_ptr, my_ids_ptr, int(B), int(k),
                                                             out_scores_ptr, out_ids_ptr, out_counts_ptr))
 
-    def merge_rows_dev(self, my_scores_ptr, my_rows_ptr, row_lo, B, k, out_scores_ptr, out_ids_ptr, out_counts_ptr):
-        """same, the rank hands over its LOCAL int32 rows: the push kernel turns them into global ids on the way"""
-        self._lib.check(self._L.rag_exchange_merge_rows_dev(self._h, my_scores_ptr, my_rows_ptr, int(row_lo), int(B),
-                                                            int(k), out_scores_ptr, out_ids_ptr, out_counts_ptr))
+    def merge_rows_dev(self, my_scores_ptr, my_rows_ptr, row_lo, B, k, out_scores_ptr, out_ids_ptr, out_counts_ptr,
+                       my_counts_ptr=None):
+        """same, the rank hands over its LOCAL int32 rows (the push kernel turns them into global ids on the way)
+        and its counts: a query some rank left unresolved (-1) comes out with count -1 on every rank"""
+        self._lib.check(self._L.rag_exchange_merge_rows_dev(self._h, my_scores_ptr, my_rows_ptr, int(row_lo),
+                                                            my_counts_ptr, int(B), int(k), out_scores_ptr, out_ids_ptr,
+                                                            out_counts_ptr))
 
     def close(self):
         if self._h:
@@ -140,9 +143,12 @@ class ShardedDenseIndex:
             return self._topk_device(q32, int(k))
         return self._topk_host(q32, int(k))
 
-    def _topk_device(self, q32, kk):
-        """GPU path: queries H2D once, local top-k with device-resident outputs, ONE packed all-gather
-        ([scores | global ids] per rank), stream-ordered merge, one D2H of the merged result."""
+    def _topk_device(self, q32, kk, exact_local=False):
+        """GPU path: queries H2D once, local top-k with device-resident outputs (stream-ordered call), the
+        exchange over NVLink peer memory (or ONE packed NCCL all-gather) + merge, one D2H of the merged result.
+        Queries some rank could not finish exactly inside the stream-ordered call (more deep ties than its
+        device-driven fallback serves; the exchange marks them -1 on every rank) are redone by all ranks together
+        with the host-checked local call (exact_local)."""
         torch, dist = self.torch, self.dist
         from . import _lib
         L = _lib.lib()
@@ -164,26 +170,47 @@ class ShardedDenseIndex:
         mine, my_ids = buf["mine"], buf["my_ids"]
         if not shared:
             stream.synchronize()                      # inputs are in place before the library's own stream reads them
-        if kl == kk:
+        if exact_local:
+            r, s_, c = self.corpus.topk(np.ascontiguousarray(q32, dtype=np.float32), kl) if kl > 0 else (None, None, None)
+            mine[0].zero_()
+            my_ids.fill_(-1)
+            if kl > 0:
+                mine[0, :, :kl] = torch.from_numpy(s_).to(dev)
+                gid = torch.from_numpy(r.astype(np.int64)).to(dev)
+                my_ids[:, :kl] = torch.where(gid >= 0, gid + self.row_lo, gid)
+        elif kl == kk:
             # the local scores land directly in the packed exchange buffer; k <= rows per shard: no padding
             self.corpus.topk_dev(buf["q_dev"].data_ptr(), B, kl, buf["o_rows"].data_ptr(), mine[0].data_ptr(),
                                  buf["o_counts"].data_ptr())
-            my_ids.copy_(buf["o_rows"])               # int32 -> int64
-            my_ids.add_(self.row_lo)                  # local row -> global id
+            if not shared:
+                _lib.sync_stream_of(torch, dev)       # the call is stream-ordered on the library's own stream
+            if not (shared and self.exchange(B, kk) is not None):     # the peer exchange converts rows on the way out
+                my_ids.copy_(buf["o_rows"])           # int32 -> int64
+                my_ids.add_(self.row_lo)              # local row -> global id
         else:
             mine[0].zero_()
             my_ids.fill_(-1)
             if kl > 0:
                 self.corpus.topk_dev(buf["q_dev"].data_ptr(), B, kl, buf["o_rows"].data_ptr(),
                                      buf["o_scores"].data_ptr(), buf["o_counts"].data_ptr())
+                if not shared:
+                    _lib.sync_stream_of(torch, dev)
                 mine[0, :, :kl] = buf["o_scores"]
                 gid = buf["o_rows"].to(torch.int64)
                 my_ids[:, :kl] = torch.where(gid >= 0, gid + self.row_lo, gid)
         ex = self.exchange(B, kk) if shared else None
+        unresolved_local = None
+        if not exact_local and kl > 0:
+            unresolved_local = (buf["o_counts"] < 0).any().to(torch.int32).reshape(1)
         if ex is not None:
             # stores into the peers' buffers + epoch flags + merge: two launches, no collective call
-            ex.merge_topk_dev(mine[0].data_ptr(), my_ids.data_ptr(), B, kk, buf["m_scores"].data_ptr(),
-                              buf["m_ids"].data_ptr(), buf["m_counts"].data_ptr())
+            if not exact_local and kl == kk:
+                ex.merge_rows_dev(mine[0].data_ptr(), buf["o_rows"].data_ptr(), self.row_lo, B, kk,
+                                  buf["m_scores"].data_ptr(), buf["m_ids"].data_ptr(), buf["m_counts"].data_ptr(),
+                                  buf["o_counts"].data_ptr())
+            else:
+                ex.merge_topk_dev(mine[0].data_ptr(), my_ids.data_ptr(), B, kk, buf["m_scores"].data_ptr(),
+                                  buf["m_ids"].data_ptr(), buf["m_counts"].data_ptr())
         else:
             if self.world > 1:
                 gathered = buf["gathered"]
@@ -201,8 +228,19 @@ class ShardedDenseIndex:
         h[0].copy_(buf["m_ids"], non_blocking=True)
         h[1].copy_(buf["m_scores"], non_blocking=True)
         h[2].copy_(buf["m_counts"], non_blocking=True)
+        redo_all = False
+        if unresolved_local is not None and not (ex is not None and kl == kk):
+            # paths without the in-band flag (NCCL all-gather, padded lists): agree with one tiny all-reduce
+            if self.world > 1:
+                dist.all_reduce(unresolved_local, op=dist.ReduceOp.MAX, group=self.group)
+            redo_all = bool(unresolved_local.item())
         stream.synchronize()
-        return h[0].numpy().copy(), h[1].numpy().copy(), h[2].numpy().copy()
+        ids, scores, counts = h[0].numpy().copy(), h[1].numpy().copy(), h[2].numpy().copy()
+        bad = np.arange(B) if redo_all else np.nonzero(counts < 0)[0]
+        if len(bad):
+            r_ids, r_scores, r_counts = self._topk_device(np.ascontiguousarray(q32[bad]), kk, exact_local=True)
+            ids[bad], scores[bad], counts[bad] = r_ids, r_scores, r_counts
+        return ids, scores, counts
 
     def make_device_step(self, q_dev_ptr, nq, k):
         """Stream-ordered device step for HBM-resident queries (bench / serving loops): local top-k, then — when
@@ -237,7 +275,7 @@ class ShardedDenseIndex:
                 self.corpus.topk_dev(q_dev_ptr, nq, k, o_rows.data_ptr(), o_scores.data_ptr(), o_counts.data_ptr())
                 # P2P stores of (scores | local rows -> global ids) into every peer's buffer + flags + merge
                 ex.merge_rows_dev(o_scores.data_ptr(), o_rows.data_ptr(), self.row_lo, nq, k, m_scores.data_ptr(),
-                                  m_ids.data_ptr(), m_counts.data_ptr())
+                                  m_ids.data_ptr(), m_counts.data_ptr(), o_counts.data_ptr())
             return step, out
         gathered = torch.empty((world, 2, nq, k), dtype=torch.float64, device=dev)
 

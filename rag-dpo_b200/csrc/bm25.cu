@@ -139,19 +139,6 @@ __device__ __forceinline__ int64_t bm25_lower_bound(const int32_t* __restrict__ 
     return lo + c;
 }
 
-// 16-bit UPPER bound of a positive fp64 score (the top half of the fp32 rounded up, rounded up again): monotone,
-// so "coarse(score) >= coarse_floor(tau)" never misses a row with score >= tau.  0 = not selectable (score <= 0).
-__device__ __forceinline__ uint16_t bm25_coarse_up(double sc) {
-    if (!(sc > 0.0)) return 0;
-    const uint32_t b = __float_as_uint(__double2float_ru(sc));
-    const uint32_t c = (b + 0xFFFFu) >> 16;
-    return (uint16_t)(c > 0xFFFFu ? 0xFFFFu : c);
-}
-__device__ __forceinline__ uint16_t bm25_coarse_floor(double sc) {     // sc > 0
-    const uint32_t c = __float_as_uint(__double2float_rd(sc)) >> 16;
-    return (uint16_t)(c == 0 ? 1 : c);
-}
-
 // accumulate the scores of the CTA's row range [r0, r1) for query qi into acc (shared memory)
 __device__ __forceinline__ void bm25_accumulate_range(const int64_t* __restrict__ term_ptr,
                                                       const int32_t* __restrict__ post_row,
@@ -286,317 +273,534 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
 }
 
 // ---------------------------------------------------------------------------
-// FAST path (4 launches for a batch of queries):
-//   A  bm25_scores_heads_kernel  accumulate as above, write the range's fp64 scores to global memory and
-//                                its H best (score > 0, allowed) keys as "heads", H = ceil(k / n_ranges)
-//   B  bm25_tau_kernel           tau = k-th largest head: k distinct rows reach it, so it is a valid lower
-//                                bound of the global k-th score
-//   C  bm25_filter_kernel        every row with key >= tau is appended to the query's survivor list
-//   D  bm25_final_kernel         sort the (k + few) survivors; more than kBmSurvivors of them (mass ties)
-//                                flags the query (count = -1) and the caller re-runs it on the robust path
+// FAST path (2 launches for a batch of queries).
+//
+// The product idf[t] * impact[p] of a posting does not depend on the query, so the index holds it a second time
+// as a 20-bit fixed-point UPPER bound q (unit = max product / 2^20, rounded up, +1) packed with the 12-bit local row
+// of its 4096-row range: 4 bytes per posting instead of 12.  The filter pass adds these integers:
+//     U[row] = sum over the query's tokens of q      (exact integer arithmetic, any order)
+// is an upper bound of the row's fp64 score in units, and U[row] - 2 * (number of tokens) a lower bound.
+//   A  bm25_filter_kernel   grid (ranges, queries): integer accumulators of the range in shared memory;
+//        HIGH terms (long runs): a segment table gives every warp the postings of ITS 512 rows: 128-bit loads,
+//        plain read-modify-write, no atomics, no search;  MID terms: a range table gives the run, added with
+//        shared-memory atomics (a handful of postings);  LOW terms: warp-cooperative 32-ary search, atomics.
+//        The range's H best allowed rows by U ("heads") and the (H+1)-th best U ("rho": nothing that was not
+//        emitted is above it) go to global memory: scores never leave the SM.
+//   B  bm25_finish_kernel   one CTA per query: tau = k-th largest head minus the slack (k distinct rows reach it:
+//        a valid lower bound of the k-th best exact score); every rho must be below it, else the query is flagged
+//        (count = -1) and redone on the robust path; heads with U >= tau are the survivors (k + a handful): their
+//        exact fp64 scores are recomputed from the postings — the same products, added in token order, so
+//        bit-identical to numpy — and ordered by (score desc, row asc).
+// Selective row filters (doc_filter keeping <= 4096 rows) skip the posting stream altogether: bm25_rows_kernel
+// computes the exact scores of the listed rows only.
 // ---------------------------------------------------------------------------
-constexpr int kBmSurvivors = 2048;
-constexpr int kBmMaxH = 32;       // heads per range the fast path supports (static shared memory budget)
+constexpr int kBmMaxH = 31;           // heads per range (static shared memory of the filter kernel)
+constexpr int kBmSurvivors = 1024;    // survivors per query the finish kernel re-scores
+constexpr int kBmContrib = 4096;      // (survivor, token) products staged at a time
+constexpr int kBmMaxQueryTokens = 1024;
+constexpr int kBmGroup = 4;           // HIGH tokens whose first loads are in flight together
 
-__device__ __forceinline__ Bm25Key warp_max_key(Bm25Key k) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        Bm25Key other;
-        other.s = __shfl_xor_sync(0xffffffffu, (unsigned long long)k.s, o);
-        other.nrow = __shfl_xor_sync(0xffffffffu, k.nrow, o);
-        other.pad = 0;
-        if (k < other) k = other;
+// first position in post_row[lo, hi) whose row is >= target, searched by a whole warp: 32 probes per round
+__device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ post_row, int64_t lo, int64_t hi,
+                                                    int64_t target, int lane) {
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo + 31) >> 5;
+        const int64_t base = lo;
+        int64_t idx = base + step * (lane + 1) - 1;
+        if (idx > hi - 1) idx = hi - 1;
+        const bool below = (int64_t)post_row[idx] < target;
+        const int c = __popc(__ballot_sync(0xffffffffu, below));     // probes below the target: a prefix (rows ascend)
+        if (c < 32) {                            // probe c is the first one >= target: the answer is at or before it
+            int64_t nh = base + step * (c + 1) - 1;
+            if (nh > hi - 1) nh = hi - 1;
+            hi = nh;
+        }
+        lo = base + step * c;
+        if (lo > hi) lo = hi;
     }
-    return k;
+    const int64_t idx = lo + lane;
+    const bool below = idx < hi && (int64_t)post_row[idx] < target;
+    return lo + __popc(__ballot_sync(0xffffffffu, below));
 }
 
-template <bool COARSE>          // COARSE: the score vector holds 16-bit upper bounds (batched calls), else fp64
+__device__ __forceinline__ void bm25_add4(uint32_t* acc, const uint4& v, int64_t idx0, int64_t a, int64_t b) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t idx = idx0 + j;
+        if (idx >= a && idx < b) acc[w[j] >> 20] += w[j] & 0xFFFFFu;   // every posting of a term is a different row
+    }
+}
+
 __global__ void __launch_bounds__(kBmThreads)
-bm25_scores_heads_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ post_row,
-                         const double* __restrict__ impact, const double* __restrict__ idf, int64_t n_docs,
-                         int64_t n_terms, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
-                         int q0, const uint8_t* __restrict__ allow, int H, void* __restrict__ scores_out,
-                         int64_t score_stride, Bm25Key* __restrict__ heads) {
-    __shared__ __align__(16) double acc[kBmRange];
-    __shared__ int64_t s_bound[kBmMaxTokens][kBmWarps + 1];
-    __shared__ double s_w[kBmMaxTokens];
-    __shared__ Bm25Key s_heads[kBmWarps][kBmMaxH];
+bm25_filter_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr, int q0,
+                   const uint8_t* __restrict__ allow, int H, unsigned long long* __restrict__ heads) {
+    __shared__ __align__(16) uint32_t acc[kBmRange];
+    __shared__ long long s_lo[kBmMaxTokens], s_hi[kBmMaxTokens];
+    __shared__ __align__(16) uint16_t s_seg[kBmMaxTokens][8];
+    __shared__ uint8_t s_kind[kBmMaxTokens];
+    __shared__ uint8_t s_high[kBmMaxTokens], s_other[kBmMaxTokens];
+    __shared__ int s_nhigh, s_nother;
+    __shared__ unsigned long long s_heads[kBmWarps][kBmMaxH + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rg = blockIdx.x;
     const int qi = q0 + blockIdx.y;
-    const int64_t r0 = (int64_t)blockIdx.x * kBmRange;
-    const int64_t r1 = r0 + kBmRange < n_docs ? r0 + kBmRange : n_docs;
-    bm25_accumulate_range(term_ptr, post_row, impact, idf, n_terms, q_terms + q_ptr[qi], q_ptr[qi + 1] - q_ptr[qi], r0,
-                          r1, acc, s_bound, s_w);
-    // my 16 rows of the warp's segment: write the scores out, keep the selectable ones as keys in registers
-    Bm25Key mine[kBmSeg / 32];
-    double* out = reinterpret_cast<double*>(scores_out) + (size_t)blockIdx.y * score_stride;
-    uint16_t* out16 = reinterpret_cast<uint16_t*>(scores_out) + (size_t)blockIdx.y * score_stride;
+    const int64_t r0 = (int64_t)rg * kBmRange;
+    const int64_t r1 = r0 + kBmRange < ix.n_docs ? r0 + kBmRange : ix.n_docs;
+    const int32_t* terms = q_terms + q_ptr[qi];
+    const int nt = q_ptr[qi + 1] - q_ptr[qi];
+    for (int i = threadIdx.x; i < kBmRange; i += kBmThreads) acc[i] = 0u;
+    for (int t0 = 0; t0 < nt; t0 += kBmMaxTokens) {
+        const int tn = nt - t0 < kBmMaxTokens ? nt - t0 : kBmMaxTokens;
+        if (threadIdx.x == 0) { s_nhigh = 0; s_nother = 0; }
+        __syncthreads();                  // accumulators zeroed / previous pass done with the token table
+        // ---- resolve the tokens: all lookups of all tokens are in flight together
+        if ((int)threadIdx.x < tn) {
+            const int i = threadIdx.x;
+            const int32_t t = terms[t0 + i];
+            int kind = kBmSkip;
+            long long lo = 0, hi = 0;
+            if (t >= 0 && t < ix.n_terms) {
+                const int2 info = ix.term_info[t];
+                const int cls = (int)((unsigned)info.x >> 30);
+                const long long base = ix.term_ptr[t];
+                if (cls == kBmLow) {
+                    kind = kBmLow; lo = base; hi = ix.term_ptr[t + 1];
+                } else if (cls != kBmSkip) {
+                    const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_ranges + 1) + rg;
+                    lo = base + ro[0]; hi = base + ro[1];
+                    kind = cls;
+                    if (cls == kBmHigh)
+                        *reinterpret_cast<uint4*>(&s_seg[i][0]) =
+                            *reinterpret_cast<const uint4*>(ix.seg_off + ((size_t)info.y * ix.n_ranges + rg) * 8);
+                }
+                if (hi <= lo) kind = kBmSkip;
+            }
+            s_lo[i] = lo; s_hi[i] = hi; s_kind[i] = (uint8_t)kind;
+            if (kind == kBmHigh) s_high[atomicAdd(&s_nhigh, 1)] = (uint8_t)i;
+            else if (kind != kBmSkip) s_other[atomicAdd(&s_nother, 1)] = (uint8_t)i;
+        }
+        __syncthreads();
+        // ---- phase 1: MID / LOW tokens, a handful of postings each: shared-memory atomics, one token per warp
+        const int n_other = s_nother, n_high = s_nhigh;
+        for (int o = warp; o < n_other; o += kBmWarps) {
+            const int i = s_other[o];
+            int64_t lo = s_lo[i], hi = s_hi[i];
+            if (s_kind[i] == kBmMid) {
+                for (int64_t p = lo + lane; p < hi; p += 32) {
+                    const uint32_t pk = ix.post_pack[p];
+                    atomicAdd(&acc[pk >> 20], pk & 0xFFFFFu);
+                }
+            } else {
+                int64_t a = warp_lower_bound(ix.post_row, lo, hi, r0, lane);
+                while (true) {
+                    const int64_t idx = a + lane;
+                    const int64_t row = idx < hi ? (int64_t)ix.post_row[idx] : (int64_t)0x7FFFFFFF;
+                    const bool in = row < r1;
+                    if (in) atomicAdd(&acc[(int)(row - r0)], ix.post_pack[idx] & 0xFFFFFu);
+                    if (!__all_sync(0xffffffffu, in)) break;
+                    a += 32;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: HIGH tokens.  Warp w adds the postings of ITS 512 rows (segment table), 4 postings per
+        // 128-bit load; the first loads of kBmGroup tokens are requested before the first one is added
+        for (int g0 = 0; g0 < n_high; g0 += kBmGroup) {
+            int64_t a_g[kBmGroup], b_g[kBmGroup];
+            uint4 v_g[kBmGroup];
+#pragma unroll
+            for (int g = 0; g < kBmGroup; ++g) {
+                a_g[g] = 0; b_g[g] = 0; v_g[g] = make_uint4(0u, 0u, 0u, 0u);
+                if (g0 + g < n_high) {
+                    const int i = s_high[g0 + g];
+                    const int64_t lo = s_lo[i];
+                    a_g[g] = lo + (warp ? (int64_t)s_seg[i][warp - 1] : 0);
+                    b_g[g] = warp < kBmWarps - 1 ? lo + (int64_t)s_seg[i][warp] : (int64_t)s_hi[i];
+                    const int64_t idx0 = (a_g[g] & ~(int64_t)3) + 4 * lane;
+                    if (idx0 < b_g[g]) v_g[g] = __ldg(reinterpret_cast<const uint4*>(ix.post_pack + idx0));
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < kBmGroup; ++g) {
+                if (g0 + g < n_high) {                      // block-uniform
+                    const int64_t a = a_g[g], b = b_g[g];
+                    int64_t base = a & ~(int64_t)3;
+                    bm25_add4(acc, v_g[g], base + 4 * lane, a, b);
+                    base += 128;
+                    while (base < b) {                      // warp-uniform: long runs, two loads in flight
+                        const int64_t i0 = base + 4 * lane, i1 = i0 + 128;
+                        uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+                        if (i0 < b) v0 = __ldg(reinterpret_cast<const uint4*>(ix.post_pack + i0));
+                        if (i1 < b) v1 = __ldg(reinterpret_cast<const uint4*>(ix.post_pack + i1));
+                        bm25_add4(acc, v0, i0, a, b);
+                        bm25_add4(acc, v1, i1, a, b);
+                        base += 256;
+                    }
+                    __syncwarp();                           // two tokens may hit the same row from different lanes
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- the range's H best allowed rows by U, and the (H+1)-th best U (rho).  Warp level first: every lane
+    // holds its 16 rows of the warp's segment, H+1 rounds of warp-wide maximum (ties: lowest row)
+    uint32_t v[kBmSeg / 32];
 #pragma unroll
     for (int j = 0; j < kBmSeg / 32; ++j) {
         const int i = warp * kBmSeg + j * 32 + lane;
-        Bm25Key key{0ull, 0u, 0u};
-        if (r0 + i < r1) {
-            const double sc = acc[i];
-            if (COARSE) out16[r0 + i] = bm25_coarse_up(sc); else out[r0 + i] = sc;
-            const uint32_t r = (uint32_t)(r0 + i);
-            if (sc > 0.0 && bitmap_test(allow, r)) { key.s = (uint64_t)__double_as_longlong(sc); key.nrow = ~r; }
-        }
-        mine[j] = key;
+        const int64_t row = r0 + i;
+        v[j] = (row < r1 && bitmap_test(allow, (uint32_t)row)) ? acc[i] : 0u;
     }
-    // H rounds of warp arg-max: the warp's H best keys, descending
-    for (int h = 0; h < H; ++h) {
-        Bm25Key best{0ull, 0u, 0u};
+    for (int h = 0; h <= H; ++h) {
+        uint32_t m = 0u;
 #pragma unroll
-        for (int j = 0; j < kBmSeg / 32; ++j)
-            if (best < mine[j]) best = mine[j];
-        const Bm25Key top = warp_max_key(best);
+        for (int j = 0; j < kBmSeg / 32; ++j) m = v[j] > m ? v[j] : m;
+        const uint32_t wm = __reduce_max_sync(0xffffffffu, m);
+        if (wm == 0u) {                                      // warp-uniform: nothing (more) to emit
+            if (lane == 0)
+                for (int hh = h; hh <= H; ++hh) s_heads[warp][hh] = 0ull;
+            break;
+        }
+        int myj = kBmSeg / 32;
 #pragma unroll
-        for (int j = 0; j < kBmSeg / 32; ++j)
-            if (mine[j].s == top.s && mine[j].nrow == top.nrow) mine[j] = Bm25Key{0ull, 0u, 0u};
-        if (lane == 0) s_heads[warp][h] = top;
+        for (int j = kBmSeg / 32 - 1; j >= 0; --j)
+            if (v[j] == wm) myj = j;
+        const uint32_t myrow = (m == wm) ? (uint32_t)(myj * 32 + lane) : 0xFFFFFFFFu;
+        const uint32_t wr = __reduce_min_sync(0xffffffffu, myrow);
+        if (myrow == wr) {
+#pragma unroll
+            for (int j = 0; j < kBmSeg / 32; ++j)
+                if (j == myj) v[j] = 0u;
+        }
+        if (lane == 0)
+            s_heads[warp][h] = ((unsigned long long)wm << 32) | (unsigned long long)(~(uint32_t)(r0 + warp * kBmSeg + wr));
     }
     __syncthreads();
-    // warp 0: the range's H best among the 8 * H warp heads
-    if (warp == 0) {
-        Bm25Key* dst = heads + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * H;
-        const int n = kBmWarps * H;                 // <= 512
-        for (int h = 0; h < H; ++h) {
-            Bm25Key best{0ull, 0u, 0u};
-            int where = -1;
-            for (int i = lane; i < n; i += 32) {
-                const Bm25Key c = s_heads[i / H][i % H];
-                if (best < c) { best = c; where = i; }
+    if (warp == 0) {                     // the range's H+1 best among the 8 * (H+1) warp heads
+        const int n_e = kBmWarps * (H + 1);                 // <= 256
+        unsigned long long mine[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = lane + 32 * u;
+            mine[u] = e < n_e ? s_heads[e / (H + 1)][e % (H + 1)] : 0ull;
+        }
+        unsigned long long* dst = heads + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (H + 1);
+        for (int h = 0; h <= H; ++h) {
+            unsigned long long m = 0ull;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) m = mine[u] > m ? mine[u] : m;
+            const uint32_t whi = __reduce_max_sync(0xffffffffu, (uint32_t)(m >> 32));
+            const uint32_t wlo = __reduce_max_sync(0xffffffffu, (uint32_t)(m >> 32) == whi ? (uint32_t)m : 0u);
+            const unsigned long long top = ((unsigned long long)whi << 32) | wlo;
+            if (whi == 0u) {
+                if (lane == 0)
+                    for (int hh = h; hh <= H; ++hh) dst[hh] = 0ull;
+                break;
             }
-            const Bm25Key top = warp_max_key(best);
-            if (where >= 0 && best.s == top.s && best.nrow == top.nrow) s_heads[where / H][where % H] = Bm25Key{0ull, 0u, 0u};
-            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (mine[u] == top) mine[u] = 0ull;         // rows are distinct: exactly one entry
             if (lane == 0) dst[h] = top;
         }
     }
 }
 
-// tau[q] = k-th largest head (empty key when fewer than k heads exist: no bound).  A block bitonic sort of the
-// <= 4096 heads: 36 barrier steps for 256 heads, which beats rank counting here (245 dependent compares per thread)
-__global__ void __launch_bounds__(256)
-bm25_tau_kernel(const Bm25Key* __restrict__ heads, int n_heads, int k, Bm25Key* __restrict__ tau, int32_t* counts) {
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    Bm25Key* s_keys = reinterpret_cast<Bm25Key*>(sm_raw);
-    const int q = blockIdx.x;
-    int nsort = 32;
-    while (nsort < n_heads) nsort <<= 1;
-    for (int i = threadIdx.x; i < nsort; i += blockDim.x)
-        s_keys[i] = i < n_heads ? heads[(size_t)q * n_heads + i] : Bm25Key{0ull, 0u, 0u};
-    block_bitonic_desc(s_keys, nsort);
-    if (threadIdx.x == 0) {
-        tau[q] = k <= n_heads ? s_keys[k - 1] : Bm25Key{0ull, 0u, 0u};
-        counts[q] = 0;
-    }
-}
-
-template <bool COARSE>
-__global__ void __launch_bounds__(256)
-bm25_filter_kernel(const void* __restrict__ scores, int64_t n_docs, int64_t score_stride,
-                   const uint8_t* __restrict__ allow, const Bm25Key* __restrict__ tau, Bm25Key* __restrict__ surv,
-                   int32_t* __restrict__ counts) {
-    const int q = blockIdx.y;
-    const Bm25Key thr = tau[q];
-    const double thr_s = thr.s ? __longlong_as_double((long long)thr.s) : 0.0;
-    if (COARSE) {
-        // 16-bit upper bounds: everything that CAN reach tau survives (a few more than k); the exact fp64 score of
-        // a survivor is recomputed from the postings by bm25_final_kernel
-        const uint16_t* sc = reinterpret_cast<const uint16_t*>(scores) + (size_t)q * score_stride;
-        const uint16_t cthr = thr.s ? bm25_coarse_floor(thr_s) : (uint16_t)1;
-        const int64_t n_vec = (n_docs + 7) >> 3;            // the stride is a multiple of 8: 16-byte vectors
-        for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
-            const uint4 w = *reinterpret_cast<const uint4*>(sc + 8 * v);
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint16_t c = (uint16_t)(ww[j >> 1] >> (16 * (j & 1)));
-                const int64_t r = 8 * v + j;
-                if (c >= cthr && r < n_docs && bitmap_test(allow, (uint32_t)r)) {
-                    const int slot = atomicAdd(&counts[q], 1);
-                    if (slot < kBmSurvivors) surv[(size_t)q * kBmSurvivors + slot] = Bm25Key{0ull, ~(uint32_t)r, 0u};
-                }
-            }
-        }
-        return;
-    }
-    const double* sc = reinterpret_cast<const double*>(scores) + (size_t)q * score_stride;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_docs; r += (int64_t)gridDim.x * blockDim.x) {
-        const double v = sc[r];
-        if (v > 0.0 && v >= thr_s) {
-            Bm25Key key{(uint64_t)__double_as_longlong(v), ~(uint32_t)r, 0u};
-            if (!(key < thr) && bitmap_test(allow, (uint32_t)r)) {
-                const int slot = atomicAdd(&counts[q], 1);
-                if (slot < kBmSurvivors) surv[(size_t)q * kBmSurvivors + slot] = key;
-            }
+// w * impact of (term t, row) if the posting exists, else 0: the product the accumulation adds
+__device__ __forceinline__ double bm25_term_contrib(const Bm25Device& ix, int32_t t, uint32_t row) {
+    if (t < 0 || t >= ix.n_terms) return 0.0;
+    const double w = ix.idf[t];
+    if (w == 0.0) return 0.0;
+    int64_t lo = ix.term_ptr[t], hi = ix.term_ptr[t + 1];
+    if (ix.term_info) {
+        const int2 info = ix.term_info[t];
+        const int cls = (int)((unsigned)info.x >> 30);
+        if (cls == kBmMid || cls == kBmHigh) {             // the range table narrows the search to the row's range
+            const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_ranges + 1) + (row >> 12);
+            hi = lo + ro[1];
+            lo = lo + ro[0];
         }
     }
+    const int64_t pos = bm25_lower_bound(ix.post_row, lo, hi, (int64_t)row);
+    if (pos < hi && (uint32_t)ix.post_row[pos] == row) return __dmul_rn(w, ix.post_impact[pos]);
+    return 0.0;
 }
 
-// exact fp64 score of one row for one query: the same products in the same (token) order as the accumulation
-__device__ __forceinline__ double bm25_exact_score(const int64_t* __restrict__ term_ptr,
-                                                   const int32_t* __restrict__ post_row,
-                                                   const double* __restrict__ impact, const double* __restrict__ idf,
-                                                   int64_t n_terms, const int32_t* __restrict__ terms, int nt,
-                                                   uint32_t row) {
-    double sc = 0.0;
-    for (int i = 0; i < nt; ++i) {
-        const int32_t t = terms[i];
-        if (t < 0 || t >= n_terms) continue;
-        const double w = idf[t];
-        if (w == 0.0) continue;
-        const int64_t hi = term_ptr[t + 1];
-        const int64_t pos = bm25_lower_bound(post_row, term_ptr[t], hi, (int64_t)row);
-        if (pos < hi && (uint32_t)post_row[pos] == row) sc = __dadd_rn(sc, __dmul_rn(w, impact[pos]));
-    }
-    return sc;
-}
-
-template <bool COARSE>
-__global__ void __launch_bounds__(256)
-bm25_final_kernel(const Bm25Key* __restrict__ surv, const int32_t* __restrict__ counts, int k,
-                  const Bm25Key* __restrict__ tau, const int64_t* __restrict__ term_ptr,
-                  const int32_t* __restrict__ post_row, const double* __restrict__ impact,
-                  const double* __restrict__ idf, int64_t n_terms, const int32_t* __restrict__ q_terms,
-                  const int32_t* __restrict__ q_ptr, int q0, int32_t* out_rows, double* out_scores,
-                  int32_t* out_counts) {
-    __shared__ Bm25Key s_keys[kBmSurvivors];
-    __shared__ int s_n;
-    const int q = blockIdx.x;
-    int n = counts[q];
-    if (n > kBmSurvivors) {                         // mass ties at the bound: robust path must redo this query
-        if (threadIdx.x == 0) out_counts[q] = -1;
-        return;
-    }
-    if (COARSE) {
-        // survivors of the 16-bit filter: recompute their exact scores, keep those that really reach tau
-        if (threadIdx.x == 0) s_n = 0;
+// Block-wide: exact fp64 scores of n rows (token order, numpy's `score +=`), then the k best with score > 0 by
+// (score desc, row asc).  rows: shared or global memory; contrib: kBmContrib doubles; keys: the next power of
+// two >= max(n, 32) entries.  All threads of the 256-thread CTA call it.
+__device__ __forceinline__ void bm25_exact_topk(const Bm25Device& ix, const int32_t* __restrict__ terms, int nt,
+                                                const uint32_t* rows, int n, int k, double* contrib, Bm25Key* keys,
+                                                int32_t* out_rows, double* out_scores, int32_t* out_count) {
+    const int cs = nt > 0 ? (kBmContrib / nt > 0 ? kBmContrib / nt : 1) : (n > 0 ? n : 1);
+    for (int s0 = 0; s0 < n; s0 += cs) {
+        const int csn = n - s0 < cs ? n - s0 : cs;
         __syncthreads();
-        const Bm25Key thr = tau[q];
-        const int32_t* terms = q_terms + q_ptr[q0 + q];
-        const int nt = q_ptr[q0 + q + 1] - q_ptr[q0 + q];
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t row = ~surv[(size_t)q * kBmSurvivors + i].nrow;
-            const double sc = bm25_exact_score(term_ptr, post_row, impact, idf, n_terms, terms, nt, row);
-            const Bm25Key key{(uint64_t)__double_as_longlong(sc), ~row, 0u};
-            if (sc > 0.0 && !(key < thr)) s_keys[atomicAdd(&s_n, 1)] = key;
+        for (int pair = threadIdx.x; pair < csn * nt; pair += blockDim.x) {
+            const int s = pair / nt, i = pair - s * nt;
+            contrib[pair] = bm25_term_contrib(ix, terms[i], rows[s0 + s]);
         }
         __syncthreads();
-        n = s_n;
-        __syncthreads();
+        for (int s = threadIdx.x; s < csn; s += blockDim.x) {
+            double sc = 0.0;
+            for (int i = 0; i < nt; ++i) sc = __dadd_rn(sc, contrib[s * nt + i]);     // + 0.0 where no posting
+            Bm25Key key{0ull, 0u, 0u};
+            if (sc > 0.0) { key.s = (uint64_t)__double_as_longlong(sc); key.nrow = ~rows[s0 + s]; }
+            keys[s0 + s] = key;
+        }
     }
-    const int nout = n < k ? n : k;
-    if (n <= 256) {
+    __syncthreads();
+    if (n <= (int)blockDim.x) {
         // the usual case (k + a handful of survivors): order by rank counting, no sort
         Bm25Key me{0ull, 0u, 0u};
-        if ((int)threadIdx.x < n) me = COARSE ? s_keys[threadIdx.x] : surv[(size_t)q * kBmSurvivors + threadIdx.x];
-        __syncthreads();
-        s_keys[threadIdx.x] = me;
-        __syncthreads();
-        if ((int)threadIdx.x < n) {
-            int rank = 0;
-            for (int j = 0; j < n; ++j) rank += me < s_keys[j];
-            if (rank < k) {
-                out_rows[(size_t)q * k + rank] = (int32_t)(~me.nrow);
-                out_scores[(size_t)q * k + rank] = __longlong_as_double((long long)me.s);
-            }
+        if ((int)threadIdx.x < n) me = keys[threadIdx.x];
+        int rank = 0, valid = 0;
+        for (int j = 0; j < n; ++j) {
+            const Bm25Key o = keys[j];
+            rank += me < o;
+            valid += o.s != 0ull;
         }
-        for (int i = nout + threadIdx.x; i < k; i += blockDim.x) {
-            out_rows[(size_t)q * k + i] = -1;
-            out_scores[(size_t)q * k + i] = 0.0;
+        if (me.s != 0ull && rank < k) {
+            out_rows[rank] = (int32_t)(~me.nrow);
+            out_scores[rank] = __longlong_as_double((long long)me.s);
         }
-        if (threadIdx.x == 0) out_counts[q] = nout;
+        const int nout = valid < k ? valid : k;
+        for (int i = nout + threadIdx.x; i < k; i += blockDim.x) { out_rows[i] = -1; out_scores[i] = 0.0; }
+        if (threadIdx.x == 0) *out_count = nout;
         return;
     }
     int nsort = 32;
     while (nsort < n) nsort <<= 1;
-    for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
-        if (COARSE) { if (i >= n) s_keys[i] = Bm25Key{0ull, 0u, 0u}; }
-        else s_keys[i] = i < n ? surv[(size_t)q * kBmSurvivors + i] : Bm25Key{0ull, 0u, 0u};
-    }
-    block_bitonic_desc(s_keys, nsort);
+    for (int i = n + threadIdx.x; i < nsort; i += blockDim.x) keys[i] = Bm25Key{0ull, 0u, 0u};
+    block_bitonic_desc(keys, nsort);
+    int local = 0;
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const bool ok = i < nout;
-        out_rows[(size_t)q * k + i] = ok ? (int32_t)(~s_keys[i].nrow) : -1;
-        out_scores[(size_t)q * k + i] = ok ? __longlong_as_double((long long)s_keys[i].s) : 0.0;
+        const bool ok = i < nsort && keys[i].s != 0ull;
+        local += ok;
+        out_rows[i] = ok ? (int32_t)(~keys[i].nrow) : -1;
+        out_scores[i] = ok ? __longlong_as_double((long long)keys[i].s) : 0.0;
     }
-    if (threadIdx.x == 0) out_counts[q] = nout;
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) *out_count = s_cnt;
 }
 
-int bm25_fast_heads_per_range(int64_t n_docs, int k) {
-    const int n_ranges = (int)((n_docs + kBmRange - 1) / kBmRange);
-    return (k + n_ranges - 1) / n_ranges;
+__global__ void __launch_bounds__(256)
+bm25_finish_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr, int q0,
+                   const unsigned long long* __restrict__ heads, int H, int h_tau, int nsort_tau, int k,
+                   int32_t* out_rows, double* out_scores, int32_t* out_counts) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    // [ 32 KB: tau sort buffer, later the staged products | survivors' keys | survivors' rows ]
+    unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(sm_raw);
+    double* contrib = reinterpret_cast<double*>(sm_raw);
+    Bm25Key* keys = reinterpret_cast<Bm25Key*>(sm_raw + (size_t)kBmContrib * sizeof(double));
+    uint32_t* surv = reinterpret_cast<uint32_t*>(keys + kBmSurvivors);
+    __shared__ int s_n, s_flag;
+    const int q = blockIdx.x;
+    const int n_ranges = ix.n_ranges;
+    const unsigned long long* hq = heads + (size_t)q * n_ranges * (H + 1);
+    const int32_t* terms = q_terms + q_ptr[q0 + q];
+    const int nt = q_ptr[q0 + q + 1] - q_ptr[q0 + q];
+    if (threadIdx.x == 0) { s_n = 0; s_flag = 0; }
+    // tau: the k-th largest of the first h_tau heads of every range (distinct rows), minus the slack
+    const int n_tau = n_ranges * h_tau;
+    for (int e = threadIdx.x; e < nsort_tau; e += blockDim.x)
+        sbuf[e] = e < n_tau ? hq[(size_t)(e / h_tau) * (H + 1) + (e % h_tau)] : 0ull;
+    block_bitonic_desc(sbuf, nsort_tau);
+    const uint32_t tau_u = k <= n_tau ? (uint32_t)(sbuf[k - 1] >> 32) : 0u;
+    const uint32_t slack = 2u * (uint32_t)nt + 2u;          // U - 2 per contributing token <= score / unit <= U
+    uint32_t thr = tau_u > slack ? tau_u - slack : 0u;
+    if (thr < 1u) thr = 1u;                                  // no bound: every row with a positive upper bound
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_ranges * (H + 1); e += blockDim.x) {
+        const unsigned long long key = hq[e];
+        const uint32_t u = (uint32_t)(key >> 32);
+        if (u < thr) continue;
+        if (e % (H + 1) == H) {
+            s_flag = 1;                                      // a row that was NOT emitted may reach tau
+        } else {
+            const int slot = atomicAdd(&s_n, 1);
+            if (slot < kBmSurvivors) surv[slot] = ~(uint32_t)key;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (s_flag || n > kBmSurvivors || nt > kBmMaxQueryTokens) {      // redo on the robust path
+        if (threadIdx.x == 0) out_counts[q] = -1;
+        return;
+    }
+    bm25_exact_topk(ix, terms, nt, surv, n, k, contrib, keys, out_rows + (size_t)q * k, out_scores + (size_t)q * k,
+                    out_counts + q);
 }
-bool bm25_fast_supported(int64_t n_docs, int k) {
-    const int n_ranges = (int)((n_docs + kBmRange - 1) / kBmRange);
-    const int H = bm25_fast_heads_per_range(n_docs, k);
-    return H <= kBmMaxH && (int64_t)n_ranges * H <= 4096;
+
+// selective row filter: the exact scores of the listed rows, nothing else is read
+__global__ void __launch_bounds__(256)
+bm25_rows_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
+                 const int32_t* __restrict__ rows, int n_rows, int k, int32_t* out_rows, double* out_scores,
+                 int32_t* out_counts) {
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    double* contrib = reinterpret_cast<double*>(sm_raw);
+    Bm25Key* keys = reinterpret_cast<Bm25Key*>(sm_raw + (size_t)kBmContrib * sizeof(double));
+    const int q = blockIdx.x;
+    const int32_t* terms = q_terms + q_ptr[q];
+    int nt = q_ptr[q + 1] - q_ptr[q];
+    // more tokens than the staging area holds per row: take them in the kernel's stride (cs = 1 handles any nt
+    // up to kBmContrib; beyond that the host splits the call)
+    bm25_exact_topk(ix, terms, nt, reinterpret_cast<const uint32_t*>(rows), n_rows, k, contrib, keys,
+                    out_rows + (size_t)q * k, out_scores + (size_t)q * k, out_counts + q);
 }
-size_t bm25_fast_scratch_bytes(int64_t n_docs, int k, int Q) {
-    const int n_ranges = (int)((n_docs + kBmRange - 1) / kBmRange);
-    const int H = bm25_fast_heads_per_range(n_docs, k);
-    return (size_t)Q * (n_docs + 8) * 8 + (size_t)Q * n_ranges * H * sizeof(Bm25Key) + (size_t)Q * sizeof(Bm25Key) +
-           (size_t)Q * kBmSurvivors * sizeof(Bm25Key) + (size_t)Q * 4 + 1024;
+
+// ---------------------------------------------------------------------------
+// index-time kernels of the fast path
+// ---------------------------------------------------------------------------
+__global__ void bm25_maximpact_kernel(const double* __restrict__ impact, int64_t nnz, unsigned long long* out) {
+    double m = 0.0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        const double v = impact[p];
+        m = v > m ? v : m;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, m, o);
+        m = other > m ? other : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+cudaError_t bm25_cmax_launch(const Bm25Device& ix, unsigned long long* cmax, cudaStream_t st) {
+    int64_t g = (ix.nnz + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    if (g < 1) g = 1;
+    bm25_maximpact_kernel<<<(int)g, 256, 0, st>>>(ix.post_impact, ix.nnz, cmax);
+    return cudaGetLastError();
+}
+
+__global__ void bm25_pack_kernel(Bm25Device ix, double inv_unit) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < ix.nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = ix.n_terms;                     // the term of posting p: last t with term_ptr[t] <= p
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (ix.term_ptr[mid] <= p) lo = mid; else hi = mid;
+        }
+        const double c = __dmul_rn(ix.idf[lo], ix.post_impact[p]);
+        uint32_t q = 0u;
+        if (c > 0.0) {
+            const double v = ceil(c * inv_unit) + 1.0;       // q * unit >= c and (q - 2) * unit <= c
+            q = v > 1048575.0 ? 1048575u : (uint32_t)v;
+        }
+        ix.post_pack[p] = (((uint32_t)ix.post_row[p] & 4095u) << 20) | q;
+    }
+}
+
+__global__ void bm25_rng_kernel(Bm25Device ix, const int32_t* __restrict__ tabled_terms, int n_tabled) {
+    const int64_t total = (int64_t)n_tabled * (ix.n_ranges + 1);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int slot = (int)(e / (ix.n_ranges + 1)), r = (int)(e % (ix.n_ranges + 1));
+        const int32_t t = tabled_terms[slot];
+        const int64_t lo = ix.term_ptr[t], hi = ix.term_ptr[t + 1];
+        ix.rng_off[e] = (int32_t)(bm25_lower_bound(ix.post_row, lo, hi, (int64_t)r * kBmRange) - lo);
+    }
+}
+
+__global__ void bm25_seg_kernel(Bm25Device ix, const int32_t* __restrict__ high_terms, int n_high) {
+    const int64_t total = (int64_t)n_high * ix.n_ranges * 8;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int s = (int)(e & 7);
+        const int r = (int)((e >> 3) % ix.n_ranges);
+        const int hs = (int)((e >> 3) / ix.n_ranges);
+        uint16_t v = 0;
+        if (s < 7) {
+            const int32_t t = high_terms[hs];
+            const int32_t* ro = ix.rng_off + (size_t)(ix.term_info[t].x & 0x3FFFFFFF) * (ix.n_ranges + 1) + r;
+            const int64_t lo = ix.term_ptr[t] + ro[0], hi = ix.term_ptr[t] + ro[1];
+            v = (uint16_t)(bm25_lower_bound(ix.post_row, lo, hi, (int64_t)r * kBmRange + (int64_t)kBmSeg * (s + 1)) - lo);
+        }
+        ix.seg_off[e] = v;
+    }
+}
+
+cudaError_t bm25_index_build_launch(const Bm25Device& ix, double unit, const int32_t* tabled_terms, int n_tabled,
+                                    const int32_t* high_terms, int n_high, cudaStream_t st) {
+    auto grid_for = [](int64_t n) {
+        int64_t g = (n + 255) / 256;
+        if (g > 148 * 16) g = 148 * 16;
+        return (int)(g < 1 ? 1 : g);
+    };
+    if (ix.nnz > 0) {
+        bm25_pack_kernel<<<grid_for(ix.nnz), 256, 0, st>>>(ix, 1.0 / unit);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (n_tabled > 0) {
+        bm25_rng_kernel<<<grid_for((int64_t)n_tabled * (ix.n_ranges + 1)), 256, 0, st>>>(ix, tabled_terms, n_tabled);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (n_high > 0) {
+        bm25_seg_kernel<<<grid_for((int64_t)n_high * ix.n_ranges * 8), 256, 0, st>>>(ix, high_terms, n_high);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// heads per range: enough that a range holding more than H of the query's top rows is a < 1e-3 event when the
+// top rows fall into ranges independently (lambda = expected top rows per range)
+static int bm25_heads_per_range(int n_ranges, int k) {
+    const double lambda = 1.15 * k / n_ranges;
+    int H = (int)ceil(lambda + 4.0 * sqrt(lambda) + 4.0);
+    return H < 4 ? 4 : H;
+}
+static int bm25_tau_heads(int n_ranges, int k) { return (k + n_ranges - 1) / n_ranges; }
+
+bool bm25_fast_supported(const Bm25Device& ix, int k, int max_query_tokens) {
+    if (!ix.fast_ok || !ix.post_pack || ix.n_ranges < 1) return false;
+    const int H = bm25_heads_per_range(ix.n_ranges, k);
+    return H <= kBmMaxH && (int64_t)ix.n_ranges * bm25_tau_heads(ix.n_ranges, k) <= 4096 &&
+           max_query_tokens <= kBmMaxQueryTokens;
+}
+size_t bm25_fast_scratch_bytes(const Bm25Device& ix, int k, int Q) {
+    const int H = bm25_heads_per_range(ix.n_ranges, k);
+    return (size_t)Q * ix.n_ranges * (H + 1) * sizeof(unsigned long long) + 256;
 }
 
 // queries [q0, q0+Q) of the uploaded batch; outputs written at out_* + q0 (counts = -1: redo on the robust path)
 cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int q0, int Q,
                              const uint8_t* allow, int k, void* scratch, int32_t* out_rows, double* out_scores,
                              int32_t* out_counts, cudaStream_t st) {
-    const int n_ranges = (int)((ix.n_docs + kBmRange - 1) / kBmRange);
-    const int H = bm25_fast_heads_per_range(ix.n_docs, k);
-    // batched calls keep 16-bit upper bounds in the score vector (a quarter of the bytes) and recompute the exact
-    // score of the k + few survivors; a handful of queries keeps the fp64 vector (no recompute latency)
-    const bool coarse = Q >= 8;
-    const int64_t stride = (ix.n_docs + 7) & ~(int64_t)7;
-    uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
-    void* scores = base;
-    base += (size_t)Q * (ix.n_docs + 8) * 8;
-    Bm25Key* heads = reinterpret_cast<Bm25Key*>(base);
-    base += (size_t)Q * n_ranges * H * sizeof(Bm25Key);
-    Bm25Key* tau = reinterpret_cast<Bm25Key*>(base);
-    base += (size_t)Q * sizeof(Bm25Key);
-    Bm25Key* surv = reinterpret_cast<Bm25Key*>(base);
-    base += (size_t)Q * kBmSurvivors * sizeof(Bm25Key);
-    int32_t* counts = reinterpret_cast<int32_t*>(base);
-    dim3 grid_a(n_ranges, Q);
-    if (coarse)
-        bm25_scores_heads_kernel<true><<<grid_a, kBmThreads, 0, st>>>(ix.term_ptr, ix.post_row, ix.post_impact, ix.idf,
-                                                                     ix.n_docs, ix.n_terms, d_q_terms, d_q_ptr, q0, allow,
-                                                                     H, scores, stride, heads);
-    else
-        bm25_scores_heads_kernel<false><<<grid_a, kBmThreads, 0, st>>>(ix.term_ptr, ix.post_row, ix.post_impact, ix.idf,
-                                                                      ix.n_docs, ix.n_terms, d_q_terms, d_q_ptr, q0,
-                                                                      allow, H, scores, stride, heads);
+    const int H = bm25_heads_per_range(ix.n_ranges, k);
+    const int h_tau = bm25_tau_heads(ix.n_ranges, k);
+    unsigned long long* heads = reinterpret_cast<unsigned long long*>(scratch);
+    dim3 grid_a(ix.n_ranges, Q);
+    bm25_filter_kernel<<<grid_a, kBmThreads, 0, st>>>(ix, d_q_terms, d_q_ptr, q0, allow, H, heads);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const int n_heads = n_ranges * H;
     int nsort = 32;
-    while (nsort < n_heads) nsort <<= 1;
-    const size_t smem_b = (size_t)nsort * sizeof(Bm25Key);
-    if (smem_b > 48 * 1024) {
-        e = cudaFuncSetAttribute(bm25_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    while (nsort < ix.n_ranges * h_tau) nsort <<= 1;
+    const size_t smem = (size_t)kBmContrib * sizeof(double) + (size_t)kBmSurvivors * (sizeof(Bm25Key) + 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(bm25_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        attr_set = true;
     }
-    bm25_tau_kernel<<<Q, 256, smem_b, st>>>(heads, n_heads, k, tau, counts);
-    int gx = (int)((ix.n_docs + 256 * 8 - 1) / (256 * 8));
-    if (gx > 148 * 4) gx = 148 * 4;
-    if (gx < 1) gx = 1;
-    dim3 grid_c(gx, Q);
-    int32_t* o_r = out_rows + (size_t)q0 * k;
-    double* o_s = out_scores + (size_t)q0 * k;
-    int32_t* o_c = out_counts + q0;
-    if (coarse) {
-        bm25_filter_kernel<true><<<grid_c, 256, 0, st>>>(scores, ix.n_docs, stride, allow, tau, surv, counts);
-        bm25_final_kernel<true><<<Q, 256, 0, st>>>(surv, counts, k, tau, ix.term_ptr, ix.post_row, ix.post_impact, ix.idf,
-                                                   ix.n_terms, d_q_terms, d_q_ptr, q0, o_r, o_s, o_c);
-    } else {
-        bm25_filter_kernel<false><<<grid_c, 256, 0, st>>>(scores, ix.n_docs, stride, allow, tau, surv, counts);
-        bm25_final_kernel<false><<<Q, 256, 0, st>>>(surv, counts, k, tau, ix.term_ptr, ix.post_row, ix.post_impact,
-                                                    ix.idf, ix.n_terms, d_q_terms, d_q_ptr, q0, o_r, o_s, o_c);
-    }
+    bm25_finish_kernel<<<Q, 256, smem, st>>>(ix, d_q_terms, d_q_ptr, q0, heads, H, h_tau, nsort, k,
+                                             out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_counts + q0);
+    return cudaGetLastError();
+}
+
+cudaError_t bm25_rows_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int Q,
+                             const int32_t* d_rows, int n_rows, int k, int32_t* out_rows, double* out_scores,
+                             int32_t* out_counts, cudaStream_t st) {
+    int cap = 32;
+    while (cap < n_rows) cap <<= 1;
+    const size_t smem = (size_t)kBmContrib * sizeof(double) + (size_t)cap * sizeof(Bm25Key);
+    cudaError_t e = cudaFuncSetAttribute(bm25_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bm25_rows_kernel<<<Q, 256, smem, st>>>(ix, d_q_terms, d_q_ptr, d_rows, n_rows, k, out_rows, out_scores, out_counts);
     return cudaGetLastError();
 }
 

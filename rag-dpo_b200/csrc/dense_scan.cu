@@ -66,6 +66,13 @@ dense_scan_kernel(ScanParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // device-driven fallback pass: the number of queries is only known on the device (block-uniform early exit)
+    int n_queries = p.n_queries;
+    if (p.n_active_dev != nullptr) {
+        n_queries = *p.n_active_dev - p.active_first;
+        if (n_queries > NQ) n_queries = NQ;
+        if (n_queries <= 0) return;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
@@ -108,7 +115,7 @@ dense_scan_kernel(ScanParams p) {
 #pragma unroll
             for (int e = 0; e < EPL; ++e) {
                 int col = c * (32 * EPL) + lane * EPL + e;
-                qreg[qi][c * EPL + e] = (qi < p.n_queries && col < p.dim) ? p.q[(size_t)qi * p.dim + col] : 0.f;
+                qreg[qi][c * EPL + e] = (qi < n_queries && col < p.dim) ? p.q[(size_t)qi * p.dim + col] : 0.f;
             }
         }
     }
@@ -122,7 +129,7 @@ dense_scan_kernel(ScanParams p) {
     float tau[NQ];
     if constexpr (MODE == 1) {
 #pragma unroll
-        for (int qi = 0; qi < NQ; ++qi) tau[qi] = qi < p.n_queries ? p.tau[qi] : 3.0e38f;
+        for (int qi = 0; qi < NQ; ++qi) tau[qi] = qi < n_queries ? p.tau[qi] : 3.0e38f;
     }
 
     int stage = 0;
@@ -161,7 +168,7 @@ dense_scan_kernel(ScanParams p) {
                 float s = (acc[qi][0] + acc[qi][1]) + (acc[qi][2] + acc[qi][3]);
 #pragma unroll
                 for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (qi < p.n_queries && allowed) {
+                if (qi < n_queries && allowed) {
                     if constexpr (MODE == 0) {
                         top[qi].push(make_key(s, grow), lane);
                     } else {
@@ -183,12 +190,12 @@ dense_scan_kernel(ScanParams p) {
         // warps' KP best keys into its own and publishes ONE list per (query, CTA)
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi)
-            if (qi < p.n_queries) top[qi].finish(lane);
+            if (qi < n_queries) top[qi].finish(lane);
         asm volatile("bar.sync 1, %0;" ::"r"(CW * 32) : "memory");       // consumer warps only
         if (cw == 0) {
 #pragma unroll
             for (int qi = 0; qi < NQ; ++qi) {
-                if (qi >= p.n_queries) break;
+                if (qi >= n_queries) break;
                 for (int w = 1; w < CW; ++w) {
                     const uint64_t* other = cand_base + ((size_t)w * NQ + qi) * 2 * p.kp;
                     for (int i0 = 0; i0 < p.kp; i0 += kWarp) {

@@ -370,13 +370,15 @@ select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restric
         int rank = 0;
         for (int i = 0; i < m2; ++i) rank += me < ek[i];
         if (rank < p.k) {
-            p.out_rows[(size_t)b * p.k + rank] = (int32_t)me.row;
+            if (p.out_gids) p.out_gids[(size_t)b * p.k + rank] = shard_global_row(me.row, p.shard, p.n_shards, p.shard_block);
+            else p.out_rows[(size_t)b * p.k + rank] = (int32_t)me.row;
             p.out_scores[(size_t)b * p.k + rank] = me.s;
             if (rank == p.k - 1) s_ek = me.s;
         }
     }
     for (int i = nout + threadIdx.x; i < p.k; i += blockDim.x) {
-        p.out_rows[(size_t)b * p.k + i] = -1;
+        if (p.out_gids) p.out_gids[(size_t)b * p.k + i] = -1;
+        else p.out_rows[(size_t)b * p.k + i] = -1;
         p.out_scores[(size_t)b * p.k + i] = 0.0;
     }
     __syncthreads();
@@ -410,6 +412,52 @@ select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restric
         }
         p.flags[b] = flag;
         p.tau[b] = tau;
+    }
+    // ---- 4. device-driven fallback: the last CTA of the grid compacts the flagged queries --------------------
+    if (p.fb_done != nullptr) {
+        __shared__ int s_last, s_base, s_wsum[8];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();                                   // this CTA's flag / tau are visible device-wide
+            s_last = atomicAdd(p.fb_done, 1u) == gridDim.x - 1 ? 1 : 0;
+            s_base = 0;
+        }
+        __syncthreads();
+        if (s_last) {                                          // block-uniform
+            __threadfence();
+            for (int b0 = 0; b0 < p.B; b0 += blockDim.x) {
+                const int bb = b0 + threadIdx.x;
+                const bool f = bb < p.B && reinterpret_cast<volatile int32_t*>(p.flags)[bb] != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                if (lane == 0) s_wsum[warp] = __popc(m);
+                __syncthreads();
+                int off = s_base;
+                for (int w = 0; w < warp; ++w) off += s_wsum[w];
+                const int slot = off + __popc(m & ((1u << lane) - 1u));
+                if (f) {
+                    if (slot < p.fb_max) {
+                        p.fb_index[slot] = bb;
+                        p.fb_tau[slot] = reinterpret_cast<volatile float*>(p.tau)[bb];
+                    } else {
+                        p.out_counts[bb] = -1;                 // more fallbacks than one stream-ordered call serves
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int tot = 0;
+                    for (int w = 0; w < 8; ++w) tot += s_wsum[w];
+                    s_base += tot;
+                }
+                __syncthreads();
+            }
+            const int nfb = s_base < p.fb_max ? s_base : p.fb_max;
+            for (int s = 0; s < nfb; ++s) {
+                const int qb = p.fb_index[s];
+                for (int c = threadIdx.x; c < p.dim; c += blockDim.x) p.fb_q[(size_t)s * p.dim + c] = p.q[(size_t)qb * p.dim + c];
+            }
+            if ((int)threadIdx.x < p.fb_max) p.fb_counts[threadIdx.x] = 0u;
+            if (threadIdx.x == 0) { *p.fb_n = nfb; *p.fb_done = 0u; }
+        }
     }
 }
 
@@ -463,6 +511,11 @@ __global__ void __launch_bounds__(256) collect_select_kernel(CollectSelectParams
     double* q64s = reinterpret_cast<double*>(sm_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x;
+    if (p.n_active_dev != nullptr && qi >= *p.n_active_dev) return;      // block-uniform
+    if (p.counts[qi] > (unsigned)p.cap) {           // more rows at the bound than the collect list holds: the
+        if (threadIdx.x == 0) p.out_counts[p.query_index[qi]] = -1;      // host-checked call redoes this query
+        return;
+    }
     const uint32_t* list = p.rows_list + (size_t)qi * p.cap;
     double* sc = p.scratch_scores + (size_t)qi * p.cap;
     const int cnt = (int)(p.counts[qi] < (unsigned)p.cap ? p.counts[qi] : (unsigned)p.cap);
@@ -491,7 +544,10 @@ __global__ void __launch_bounds__(256) collect_select_kernel(CollectSelectParams
     const int out = p.query_index[qi];
     int nout = cnt < p.k ? cnt : p.k;
     for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
-        p.out_rows[(size_t)out * p.k + i] = i < nout ? (int32_t)ek[i].row : -1;
+        if (p.out_gids)
+            p.out_gids[(size_t)out * p.k + i] = i < nout ? shard_global_row(ek[i].row, p.shard, p.n_shards, p.shard_block) : -1;
+        else
+            p.out_rows[(size_t)out * p.k + i] = i < nout ? (int32_t)ek[i].row : -1;
         p.out_scores[(size_t)out * p.k + i] = i < nout ? ek[i].s : 0.0;
     }
     if (threadIdx.x == 0) p.out_counts[out] = nout;

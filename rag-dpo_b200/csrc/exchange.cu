@@ -31,7 +31,8 @@ __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
 // (device-wide counter) publishes the epoch flag in every peer
 __global__ void __launch_bounds__(256)
 exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const int64_t* __restrict__ my_ids,
-                     const int32_t* __restrict__ my_rows, int64_t row_lo, int64_t n_elems /* B*k */, uint64_t epoch) {
+                     const int32_t* __restrict__ my_rows, int64_t row_lo, const int32_t* __restrict__ my_counts, int k,
+                     int64_t n_elems /* B*k */, uint64_t epoch) {
     const int peer = blockIdx.y;
     const int parity = (int)(epoch & 1);
     uint8_t* dst = ex.peer_base[peer] + ((size_t)parity * ex.world + ex.rank) * ex.slot_bytes;
@@ -44,8 +45,12 @@ exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const
         if (i < n_elems) {
             v = s0[i];
         } else if (my_rows) {               // local int32 rows -> global ids on the way out (-1 stays padding)
-            const int32_t r = my_rows[i - n_elems];
+            const int64_t e = i - n_elems;
+            const int32_t r = my_rows[e];
             v = (uint64_t)(r < 0 ? (int64_t)-1 : (int64_t)r + row_lo);
+            // a query this rank could not finish exactly (count < 0: more deep ties than the stream-ordered fallback
+            // serves) is announced to every rank with id -2 in its first slot: all ranks mark it and redo it together
+            if (my_counts != nullptr && e % k == 0 && my_counts[e / k] < 0) v = (uint64_t)(int64_t)-2;
         } else {
             v = s1[i - n_elems];
         }
@@ -127,27 +132,31 @@ exchange_merge_kernel(ExchangeDev ex, int B, int k, uint64_t epoch, int nsort, d
             const int64_t* ids = reinterpret_cast<const int64_t*>(sc + n_elems);
             const int64_t id = ids[(size_t)b * k + j];
             if (id >= 0) { e.s = sc[(size_t)b * k + j]; e.id = id; ++local; }
+            else if (id == -2) local += 1 << 20;          // some rank could not finish this query exactly
         }
         ek[i] = e;
     }
     atomicAdd(&s_count, local);
     block_bitonic_desc(ek, nsort);
-    const int nout = s_count < k ? s_count : k;
+    const bool unresolved = s_count >= (1 << 20);
+    const int n_valid = s_count & ((1 << 20) - 1);
+    const int nout = n_valid < k ? n_valid : k;
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
         out_ids[(size_t)b * k + i] = i < nout ? ek[i].id : -1;
         out_scores[(size_t)b * k + i] = i < nout ? ek[i].s : 0.0;
     }
-    if (threadIdx.x == 0) out_counts[b] = nout;
+    if (threadIdx.x == 0) out_counts[b] = unresolved ? -1 : nout;
 }
 
 cudaError_t exchange_push_launch(const ExchangeDev& ex, const double* my_scores, const int64_t* my_ids,
-                                 const int32_t* my_rows, int64_t row_lo, int B, int k, uint64_t epoch, cudaStream_t st) {
+                                 const int32_t* my_rows, int64_t row_lo, const int32_t* my_counts, int B, int k,
+                                 uint64_t epoch, cudaStream_t st) {
     const int64_t n_elems = (int64_t)B * k;
     int bx = (int)((2 * n_elems + 256 * 8 - 1) / (256 * 8));
     if (bx < 1) bx = 1;
     if (bx > 32) bx = 32;
     dim3 grid(bx, ex.world);
-    exchange_push_kernel<<<grid, 256, 0, st>>>(ex, my_scores, my_ids, my_rows, row_lo, n_elems, epoch);
+    exchange_push_kernel<<<grid, 256, 0, st>>>(ex, my_scores, my_ids, my_rows, row_lo, my_counts, k, n_elems, epoch);
     return cudaGetLastError();
 }
 

@@ -28,6 +28,10 @@ struct ScanParams {
     unsigned* collect_count; // per query
     uint32_t* collect_rows;  // n_queries x collect_cap
     int collect_cap;
+    // device-driven fallback (stream-ordered calls): the launch serves queries [active_first, *n_active_dev) of
+    // the compacted fallback list (at most the template width) and returns at once when there are none
+    const int* n_active_dev;
+    int active_first;
 };
 int scan_nq_template(int n_queries);
 size_t scan_plan(ScanParams& p, int dtype, int sm_count, int smem_limit, int* grid_out, int* nch_out);
@@ -104,7 +108,23 @@ struct RefineParams {
     int32_t* flags;          // B: 1 = margin check failed -> fallback pass needed
     float* tau;              // B: threshold for the fallback collect pass
     int32_t* n_flagged;      // scalar counter
+    // sharded corpora (one process, several GPUs): the results go straight into the primary device's gather
+    // buffer as GLOBAL ids of the block-cyclic layout ((l / block * n_shards + shard) * block + l % block)
+    int64_t* out_gids;       // nullable: B x k, written instead of out_rows
+    int shard, n_shards, shard_block;
+    // device-driven fallback (stream-ordered calls, nullable): the last CTA to finish compacts the flagged queries
+    // into fb_index / fb_tau / fb_q (at most fb_max; the surplus gets out_counts = -1) and zeroes the collect counters
+    unsigned* fb_done;       // CTA completion counter (zero between launches)
+    int32_t* fb_n;           // number of compacted queries
+    int32_t* fb_index;       // their query numbers
+    float* fb_tau;           // their collect thresholds
+    float* fb_q;             // their query vectors (fb_max x dim)
+    unsigned* fb_counts;     // collect counters (zeroed)
+    int fb_max;
 };
+__host__ __device__ inline int64_t shard_global_row(int64_t local, int shard, int n_shards, int block) {
+    return ((local / block) * n_shards + shard) * block + local % block;
+}
 cudaError_t refine_launch(const RefineParams& p, cudaStream_t st);
 // merge + refine fused: cand = B x n_lists x list_len keys (any order, 0 = empty); counts: NULL (all entries
 // valid), or per (query, list) valid entries, or — flat_counts != 0 — ONE count per query for the whole
@@ -126,6 +146,9 @@ struct CollectSelectParams {
     int32_t* out_rows;           // B x k (indexed through query_index)
     double* out_scores;
     int32_t* out_counts;
+    int64_t* out_gids;           // nullable: global ids instead of out_rows (sharded corpora)
+    int shard, n_shards, shard_block;
+    const int* n_active_dev;     // nullable: device-side number of queries (CTAs beyond it return at once)
 };
 cudaError_t collect_select_launch(const CollectSelectParams& p, cudaStream_t st);
 // G sorted (score,id) lists per query -> global top-k
@@ -147,7 +170,8 @@ struct ExchangeDev {
 // push my (scores | ids) block into every rank's buffer and flag the epoch (ids: int64 global ids, or — my_rows
 // != NULL — local int32 rows turned into global ids row_lo + row on the way); then wait for all ranks, merge -> top-k
 cudaError_t exchange_push_launch(const ExchangeDev& ex, const double* my_scores, const int64_t* my_ids,
-                                 const int32_t* my_rows, int64_t row_lo, int B, int k, uint64_t epoch, cudaStream_t st);
+                                 const int32_t* my_rows, int64_t row_lo, const int32_t* my_counts, int B, int k,
+                                 uint64_t epoch, cudaStream_t st);
 cudaError_t exchange_merge_launch(const ExchangeDev& ex, int B, int k, uint64_t epoch, double* out_scores,
                                   int64_t* out_ids, int32_t* out_counts, cudaStream_t st);
 
@@ -162,31 +186,55 @@ cudaError_t gather_rows_launch(const void* src, void* dst, const int64_t* keep, 
                                cudaStream_t st);
 
 // ---- bm25.cu ---------------------------------------------------------------
+constexpr int kBm25Range = 4096;          // rows per CTA of the search kernels (12-bit local row)
 struct Bm25Device {
     int64_t n_docs, n_terms, nnz;
     int64_t* term_ptr;      // n_terms + 1
-    int32_t* post_row;      // nnz
+    int32_t* post_row;      // nnz, ascending per term
     double* post_impact;    // nnz: tf*(k1+1) / (tf + k1*(1-b+b*dl/avgdl))
     double* idf;            // n_terms
-    double* score;          // n_docs accumulator, all-zero between queries
+    double* score;          // n_docs accumulator, all-zero between queries (rag_bm25_scores)
+    // ---- filter index of the fast path (built by bm25_index_build) ----
+    uint32_t* post_pack;    // nnz + 4: (row & 4095) << 20 | q, q = idf*impact in units of `unit`, rounded up (+1)
+    int2* term_info;        // n_terms: x = class << 30 | slot (rng_off row), y = hslot (seg_off row)
+    int32_t* rng_off;       // n_tabled x (n_ranges + 1): first posting with row >= r * 4096, relative to term_ptr[t]
+    uint16_t* seg_off;      // n_high x n_ranges x 8: start of the 512-row segments 1..7 inside the range run
+    int n_ranges;
+    int fast_ok;            // 1: all idf >= 0 and the packed stream exists -> the integer filter bound is valid
 };
+// term classes (term_info.x >> 30)
+constexpr int kBmLow = 0;    // short list: no table, the range run is found by a warp-cooperative search
+constexpr int kBmMid = 1;    // rng_off row: runs are short, accumulated with shared-memory atomics
+constexpr int kBmHigh = 2;   // rng_off + seg_off rows: long runs, every warp owns the postings of its 512 rows
+constexpr int kBmSkip = 3;   // idf == 0 or empty list: contributes nothing
 cudaError_t bm25_impact_launch(const int32_t* post_row, const int32_t* post_tf, const int32_t* doc_len, int64_t nnz,
                                double avgdl, double k1, double b, double* impact, cudaStream_t st);
+// max over the postings of idf[t] * impact[p] (atomicMax on the bits of a positive double; *cmax zeroed by the caller)
+cudaError_t bm25_cmax_launch(const Bm25Device& ix, unsigned long long* cmax, cudaStream_t st);
+// packed stream + range / segment tables (tabled_terms: MID and HIGH terms in slot order, high_terms: in hslot order)
+cudaError_t bm25_index_build_launch(const Bm25Device& ix, double unit, const int32_t* tabled_terms, int n_tabled,
+                                    const int32_t* high_terms, int n_high, cudaStream_t st);
 // one token of one query: score[row] += w * impact[p] over postings [lo, hi)
 cudaError_t bm25_accumulate_launch(const Bm25Device& ix, int64_t lo, int64_t hi, double w, cudaStream_t st);
 int bm25_harvest_grid(int64_t total_postings, int sm_count);     // grid for the reset pass
 cudaError_t bm25_reset_launch(const Bm25Device& ix, const int64_t* d_ranges, int n_ranges, int grid, cudaStream_t st);
 size_t bm25_key_bytes();
-// fused search: grid (row ranges of 4096, queries); fp64 accumulators in shared memory, tokens in order
+// robust path: grid (row ranges of 4096, queries); fp64 accumulators in shared memory, tokens in order
 int bm25_range_lists(int64_t n_docs);
 cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr,
                               const int32_t* d_q_index, int Q, const uint8_t* allow, int kp, int k, void* cand,
                               int32_t* out_rows, double* out_scores, int32_t* out_counts, cudaStream_t st);
-// fast path: scores + range heads -> tau -> filter -> final sort (counts = -1: redo on the robust path)
-bool bm25_fast_supported(int64_t n_docs, int k);
-size_t bm25_fast_scratch_bytes(int64_t n_docs, int k, int Q);
+// fast path: integer filter pass over the packed postings (range heads) -> threshold, survivors, exact fp64
+// recompute, final order (counts = -1: redo on the robust path)
+bool bm25_fast_supported(const Bm25Device& ix, int k, int max_query_tokens);
+size_t bm25_fast_scratch_bytes(const Bm25Device& ix, int k, int Q);
 cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int q0, int Q,
                              const uint8_t* allow, int k, void* scratch, int32_t* out_rows, double* out_scores,
+                             int32_t* out_counts, cudaStream_t st);
+// selective row filter: exact scores of the listed rows only (no posting stream at all), top-k
+constexpr int kBm25MaxListedRows = 4096;
+cudaError_t bm25_rows_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int Q,
+                             const int32_t* d_rows, int n_rows, int k, int32_t* out_rows, double* out_scores,
                              int32_t* out_counts, cudaStream_t st);
 
 // ---- rrf.cu ----------------------------------------------------------------

@@ -800,3 +800,310 @@ def test_concurrent_callers_share_one_collection(e2e_data):
     for t in threads:
         t.join()
     assert not errors, errors[:2]
+
+
+# ------------------------------------------------ round 2: tombstones, device predicates, shards, BM25 v2 ----
+def test_tombstones_and_device_where_predicate(e2e_data):
+    """delete = tombstones on the device (row numbers stay), `where` = a compiled program evaluated on the device
+    into a cached bitmap; both against the oracle collection, incl. re-adding after deletes and compaction"""
+    from b200rag import DeviceCollection
+    gold, emb, table = e2e_data
+    qs = [list(map(float, v)) for v in list(table.values())[:4]]
+    wheres = [None, {"source": "CNIL"}, {"source": {"$ne": "ENTREPRISE"}}, {"tag_rh": True},
+              {"$or": [{"source": "CNIL"}, {"$and": [{"source": "ENTREPRISE"}, {"tag_rh": True}]}]},
+              {"chunk_nature": {"$in": ["GUIDE", "SANCTION"]}}, {"source": "NOPE"}, {"nope": {"$ne": 1}},
+              {"chunk_index": {"$gte": 2}}]                       # the last one takes the host evaluator
+    for dtype in ("bf16", "f32"):
+        dev = DeviceCollection(dim=emb.shape[1], dtype=dtype)
+        ora = no.ExactCollection(dim=emb.shape[1], dtype=DT[dtype])
+        half = len(gold["chunks"]) // 2
+        helpers.fill(dev, gold["chunks"][:half], emb[:half])
+        helpers.fill(ora, gold["chunks"][:half], emb[:half])
+        victims = [c["id"] for c in gold["chunks"][3:half:4]]
+        dev.delete(ids=victims); ora.delete(ids=victims)
+        assert dev.count() == ora.count() and dev.corpus.count() == half        # rows did not move
+        assert dev.corpus.live_count() == ora.count()
+        helpers.fill(dev, gold["chunks"][half:], emb[half:])                      # append after deletes
+        helpers.fill(ora, gold["chunks"][half:], emb[half:])
+        dev.delete(where={"tag_rh": True}); ora.delete(where={"tag_rh": True})
+        some = dev.get(limit=3, offset=5)["ids"]
+        dev.update(ids=some, metadatas=[{"source": "CNIL", "document_path": "x"}] * 3)
+        ora.update(ids=some, metadatas=[{"source": "CNIL", "document_path": "x"}] * 3)
+        for w in wheres:
+            for n_res in (50, 7):
+                assert dev.query(query_embeddings=qs[:2], n_results=n_res, where=w) == \
+                    ora.query(query_embeddings=qs[:2], n_results=n_res, where=w), (dtype, w)
+        got = dev.query(query_embeddings=qs[:1], n_results=5)
+        got["metadatas"][0][0]["mutated"] = True                                  # results are fresh objects
+        assert "mutated" not in dev.query(query_embeddings=qs[:1], n_results=5)["metadatas"][0][0]
+        assert dev.get(limit=40, offset=7) ["ids"] == ora.get(limit=40, offset=7)["ids"]
+        assert np.array_equal(dev.get(include=["embeddings"])["embeddings"], ora.get(include=["embeddings"])["embeddings"])
+        dev.compact()                                                             # physical compaction keeps results
+        assert dev.corpus.count() == ora.count()
+        for w in wheres[:6]:
+            assert dev.query(query_embeddings=qs[2:4], n_results=30, where=w) == \
+                ora.query(query_embeddings=qs[2:4], n_results=30, where=w), (dtype, w)
+
+
+def test_delete_is_cheap_and_exact_on_a_large_corpus():
+    """100 tombstones on a 2M-row corpus: no row moves, the deleted rows never come back, results stay exact"""
+    import time
+    from b200rag import DeviceCorpus
+    n, d = 2_000_000, 256
+    c = DeviceCorpus(d, "bf16", capacity=n)
+    c.fill_synthetic(seed=3, nrows=n)
+    q = helpers.synth_unit(5, d, seed=4)
+    rows0, scores0, _ = c.topk(q, 10)
+    victims = np.unique(np.concatenate([rows0[:, :3].ravel(), np.arange(1000, 1000 + 80)]))
+    t0 = time.perf_counter()
+    c.delete_rows(victims)
+    dt = time.perf_counter() - t0
+    assert dt < 0.05, f"delete of {len(victims)} rows took {dt * 1e3:.1f} ms"
+    assert c.count() == n and c.live_count() == n - len(victims)
+    allow = np.ones(n, bool)
+    allow[victims] = False
+    for B in (1, 5):
+        rows, scores, counts = c.topk(q[:B], 10)
+        assert not np.isin(rows, victims).any()
+        er, es, ec = c_oracle.dense_topk(q[:B], raw_rows(c.download(), no.DT_BF16), no.DT_BF16, 10,
+                                         np.packbits(allow, bitorder="little"))
+        assert rows.tolist() == er.tolist() and np.array_equal(scores, es)
+    c.close()
+
+
+def _sharded_devices(n_shards):
+    import torch
+    n_gpu = torch.cuda.device_count()
+    return [i % n_gpu for i in range(n_shards)]
+
+
+@pytest.mark.parametrize("dtype,n_shards", [("bf16", 3), ("f32", 2)])
+def test_sharded_corpus_in_one_process_vs_oracle(dtype, n_shards):
+    """rag_corpus_create_sharded: rows block-cyclic over shard slots (all GPUs of the box; with one GPU the slots
+    share it), queries on every shard, (score, GLOBAL id) written into the primary shard's gather buffers, merged
+    there.  Same results as the oracle over the whole corpus, incl. filters, tombstones and exact ties."""
+    from b200rag import DeviceCorpus, _lib
+    n, d = 23_456, 256
+    x = helpers.synth_unit(n, d, seed=77)
+    q = helpers.synth_unit(140, d, seed=78)
+    x[20_000] = x[1500]                                    # a tie across shards: lowest global row wins
+    q[1] = x[1500]
+    dup = np.random.default_rng(5).choice(n, size=700, replace=False)
+    x[dup] = q[7]                                          # deep ties: the exact fallback pass, per shard
+    c = DeviceCorpus(d, dtype, capacity=n, n_shards=n_shards, devices=_sharded_devices(n_shards))
+    c.append(x[:10_000])
+    c.append(x[10_000:])                                   # appended in two uploads, not block-aligned
+    assert c.count() == n
+    assert np.array_equal(c.download(), no.quantize(x, DT[dtype]))
+    assert np.array_equal(c.download(1000, 3000), no.quantize(x[1000:4000], DT[dtype]))
+    for B, k in [(1, 10), (3, 50), (140, 10), (9, 100)]:
+        check_topk(c, q[:B], k, DT[dtype])
+    assert check_topk(c, q[7:8], 10, DT[dtype])[0][0].tolist() == sorted(dup.tolist())[:10]
+    allow = np.random.default_rng(6).random(n) < 0.3
+    check_topk(c, q[:5], 10, DT[dtype], allow)
+    victims = np.unique(np.concatenate([np.arange(1500, 1600), dup[:300]]))
+    c.delete_rows(victims)
+    alive = np.ones(n, bool)
+    alive[victims] = False
+    rows, scores, counts = c.topk(q[:9], 10)
+    er, es, ec = c_oracle.dense_topk(q[:9], raw_rows(c.download(), DT[dtype]), DT[dtype], 10, np.packbits(alive, bitorder="little"))
+    assert rows.tolist() == er.tolist() and np.array_equal(scores, es)
+    rows, scores, counts = c.topk(q[:4], 10, np.packbits(allow, bitorder="little"))
+    er, es, ec = c_oracle.dense_topk(q[:4], raw_rows(c.download(), DT[dtype]), DT[dtype], 10, np.packbits(allow & alive, bitorder="little"))
+    assert rows.tolist() == er.tolist() and np.array_equal(scores, es)
+    c.close()
+
+
+def test_sharded_collection_and_bm25_behind_the_drop_in(e2e_data, golden_dir):
+    """DeviceCollection(n_shards=2) + DeviceChunkBM25Index(n_shards=2) inside ONE process return what the
+    reference's retriever returned (the same golden as the single-GPU path)"""
+    from b200rag import DeviceCollection, DeviceChunkBM25Index, DeviceSummaryBM25Index, HybridRetriever
+    gold, emb, table = e2e_data
+    devs = _sharded_devices(2)
+    col = DeviceCollection(dim=emb.shape[1], dtype="f32", n_shards=2, devices=devs)
+    helpers.fill(col, gold["chunks"], emb)
+    bm = DeviceChunkBM25Index(n_shards=2, devices=devs)
+    bm.build_from_collection(col)
+    sm = DeviceSummaryBM25Index()
+    sm.build(os.path.join(golden_dir, "e2e_summaries.json"))
+    for run in gold["runs"][::3]:
+        cands, docs = helpers.run_e2e_case(HybridRetriever, col, bm, sm, gold, table, run)
+        assert cands == run["candidates"], (run["config"], run["query"])
+        assert docs == run["documents"], (run["config"], run["query"])
+
+
+def test_sharded_bm25_vs_oracle():
+    from b200rag.bm25 import DeviceBM25, Postings
+    n_docs, vocab = 40_000, 9000
+    docs, n_terms = helpers.zipf_docs(n_docs, vocab, seed=11)
+    p = Postings.from_term_ids(docs, n_terms=n_terms)
+    o = no.CsrBM25(docs)
+    g = np.random.default_rng(2)
+    queries = [g.integers(0, 500, size=g.integers(2, 12)).astype(np.int32) for _ in range(20)]
+    allow = g.random(n_docs) < 0.4
+    few = np.zeros(n_docs, bool)
+    few[g.choice(n_docs, size=300, replace=False)] = True        # selective filter: the listed-rows kernel
+    for n_shards in (1, 3):
+        ix = DeviceBM25(p, n_shards=n_shards, devices=_sharded_devices(n_shards))
+        for k in (50, 10):
+            for mask in (None, allow, few):
+                bm = np.packbits(mask, bitorder="little") if mask is not None else None
+                rows, scores, counts = ix.search_ids(queries, k, bm)
+                for i, qt in enumerate(queries):
+                    er, es = o.search(qt.tolist(), k, mask)
+                    assert rows[i, :counts[i]].tolist() == er.tolist(), (n_shards, k, i)
+                    assert np.array_equal(scores[i, :counts[i]], es)
+        assert np.array_equal(ix.scores(queries[0]), o.get_scores(queries[0].tolist()))
+        ix.close()
+
+
+def test_bm25_config4_full_size_vs_oracle():
+    """BASELINE config 4 size: 1M documents, Zipf(1.07) over 200k terms, 16 queries (8-12 Zipf terms + 2
+    mid-frequency terms) against oracle.c over the same CSR: top-50 ids and fp64 scores bit-equal, batched and
+    single-query paths, with and without a row filter; the packed filter path must be the one that served it"""
+    import bench
+    from b200rag import _lib
+    from b200rag.bm25 import DeviceBM25, Postings
+    doc_ptr, tokens, n_terms = bench.zipf_tokens(1_000_000, 200_000, 1004)
+    post = Postings.from_flat_tokens(doc_ptr, tokens, n_terms)
+    ix = DeviceBM25(post)
+    assert ix.bytes_per_posting() == 4
+    g = np.random.default_rng(2004)
+    p = np.arange(1, n_terms + 1, dtype=np.float64) ** (-1.07)
+    p /= p.sum()
+    queries = []
+    for _ in range(16):
+        qt = g.choice(n_terms, size=g.integers(8, 13), p=p)
+        queries.append(np.concatenate([qt, g.integers(n_terms // 100, n_terms // 10, size=2)]).astype(np.int32))
+    queries[3] = np.concatenate([queries[3], queries[3][:2], [-1]]).astype(np.int32)      # repeats + unknown token
+    allow = g.random(post.n_docs) < 0.2
+    f0 = _lib.counters()["fallbacks"]
+    for mask in (None, allow):
+        bm = np.packbits(mask, bitorder="little") if mask is not None else None
+        rows, scores, counts = ix.search_ids(queries, 50, bm)
+        for i, qt in enumerate(queries):
+            want = c_oracle.bm25_scores(post.term_ptr, post.post_row, post.post_tf, post.doc_len, post.idf, post.avgdl,
+                                        post.k1, post.b, qt)
+            er, es = c_oracle.bm25_select(want, 50, bm)
+            assert rows[i, :counts[i]].tolist() == er.tolist() and np.array_equal(scores[i, :counts[i]], es), i
+            if i < 4:
+                r1, s1, c1 = ix.search_ids([qt], 50, bm)
+                assert r1[0, :c1[0]].tolist() == er.tolist() and np.array_equal(s1[0, :c1[0]], es)
+    assert _lib.counters()["fallbacks"] - f0 <= 2          # i.i.d. rows: the range heads cover the top-50
+    ix.close()
+
+
+def test_stream_ordered_dense_call_with_device_driven_fallback():
+    """rag_dense_topk_dev only queues work; queries whose margin check fails (700 exact ties) are redone by the
+    device-driven fallback pass inside the same stream-ordered call; more such queries than it serves are marked -1"""
+    import torch
+    from b200rag import DeviceCorpus
+    n, d, B, k = 30_000, 256, 64, 10
+    x = helpers.synth_unit(n, d, seed=31)
+    q = helpers.synth_unit(B, d, seed=32)
+    g = np.random.default_rng(9)
+    tied = [5, 17, 40]
+    dups = {}
+    for b in tied:
+        dups[b] = g.choice(n, size=700, replace=False)
+        x[dups[b]] = q[b]
+    for dtype in ("bf16", "f32"):
+        c = DeviceCorpus(d, dtype)
+        c.append(x)
+        qd = torch.from_numpy(q).cuda()
+        o_r = torch.full((B, k), -7, dtype=torch.int32, device="cuda")
+        o_s = torch.zeros((B, k), dtype=torch.float64, device="cuda")
+        o_c = torch.zeros((B,), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        for _ in range(2):                                   # twice: the completion counter must reset itself
+            c.topk_dev(qd.data_ptr(), B, k, o_r.data_ptr(), o_s.data_ptr(), o_c.data_ptr())
+        torch.cuda.synchronize()
+        er, es, ec = c_oracle.dense_topk(q, raw_rows(c.download(), DT[dtype]), DT[dtype], k)
+        assert o_c.cpu().tolist() == ec.tolist()
+        assert o_r.cpu().numpy().tolist() == er.tolist() and np.array_equal(o_s.cpu().numpy(), es)
+        # batch-1 (scan kernel) through the same entry point
+        c.topk_dev(qd[5:6].data_ptr(), 1, k, o_r.data_ptr(), o_s.data_ptr(), o_c.data_ptr())
+        torch.cuda.synchronize()
+        assert o_r[0].cpu().tolist() == er[5].tolist()
+        c.close()
+    # more deep-tie queries in one call than the device-driven pass serves: the surplus is flagged, not wrong
+    x2 = helpers.synth_unit(n, d, seed=33)
+    tied2 = list(range(0, 12, 2))
+    for b in tied2:
+        x2[g.choice(n, size=700, replace=False)] = q[b]
+    c = DeviceCorpus(d, "bf16")
+    c.append(x2)
+    c.topk_dev(qd.data_ptr(), B, k, o_r.data_ptr(), o_s.data_ptr(), o_c.data_ptr())
+    torch.cuda.synchronize()
+    counts = o_c.cpu().numpy()
+    er, es, ec = c_oracle.dense_topk(q, raw_rows(c.download(), no.DT_BF16), no.DT_BF16, k)
+    from b200rag import _lib
+    f0 = _lib.counters()["fallback_queries"]
+    rows, scores, _ = c.topk(q, k)                           # the host-buffer call serves all of them ...
+    assert rows.tolist() == er.tolist() and np.array_equal(scores, es)
+    n_flagged = _lib.counters()["fallback_queries"] - f0     # ... and tells how many queries needed the exact pass
+    assert n_flagged >= len(tied2)
+    assert (counts == -1).sum() == n_flagged - 4 and (counts[[8, 10]] == -1).all()
+    good = counts >= 0
+    assert o_r.cpu().numpy()[good].tolist() == er[good].tolist()
+    assert np.array_equal(o_s.cpu().numpy()[good], es[good])
+    c.close()
+
+
+def test_large_k_and_large_fusion_do_not_degrade(e2e_data):
+    """n_candidates above RAG_MAX_K (Chroma has no such limit): dense and BM25 serve it in passes, the batched
+    front-end falls back to per-question calls when the rankings exceed one RRF call"""
+    from b200rag import DeviceCorpus, reciprocal_rank_fusion
+    from b200rag.bm25 import DeviceBM25, Postings
+    n, d = 3000, 128
+    x = helpers.synth_unit(n, d, seed=1)
+    q = helpers.synth_unit(2, d, seed=2)
+    c = DeviceCorpus(d, "f32")
+    c.append(x)
+    rows, scores, counts = c.topk(q, 500)
+    er, es, ec = c_oracle.dense_topk(q, x, no.DT_F32, 500)
+    assert rows.tolist() == er.tolist() and np.array_equal(scores, es)
+    c.close()
+    docs, n_terms = helpers.zipf_docs(3000, 800, seed=4)
+    ix = DeviceBM25(Postings.from_term_ids(docs, n_terms=n_terms))
+    o = no.CsrBM25(docs)
+    qt = np.array([1, 5, 9, 40], np.int32)
+    r, s, cnt = ix.search_ids([qt], 400)
+    er, es = o.search(qt.tolist(), 400)
+    assert r[0, :cnt[0]].tolist() == er.tolist() and np.array_equal(s[0, :cnt[0]], es)
+    ix.close()
+    rankings = [[f"id{(7 * i + r) % 900}" for i in range(700)] for r in range(6)]      # 4200 entries
+    got = reciprocal_rank_fusion(rankings, k=60, weights=[2, 3, 1, 0.75, 1, 0.75])
+    ids, sc = no.rrf_fuse(rankings, [2, 3, 1, 0.75, 1, 0.75], 60)
+    assert got == dict(zip(ids, sc)) or {k: got[k] for k in ids} == dict(zip(ids, sc))
+
+
+def test_batch_front_end_after_collection_mutation(e2e_data, golden_dir):
+    """the batched front-end's BM25-row -> collection-row map must follow deletes / adds"""
+    from b200rag import DeviceCollection, DeviceChunkBM25Index, HybridRetriever
+    gold, emb, table = e2e_data
+    col = DeviceCollection(dim=emb.shape[1], dtype="f32")
+    helpers.fill(col, gold["chunks"], emb)
+    bm = DeviceChunkBM25Index()
+    bm.build_from_collection(col)
+    runs = [r for r in gold["runs"] if r["where"] is None and r["config"]["hybrid"] and not r["config"]["prefilter"]][:4]
+    assert runs
+    cfg = runs[0]["config"]
+    r = HybridRetriever(collection=col, embedding_provider=helpers.FixedEmbeddingProvider(table), chunk_bm25_index=bm,
+                        query_expander=helpers.FixedQueryExpander(gold["expansions"]) if cfg["expander"] else None,
+                        enable_hybrid=True, enable_summary_prefilter=False,
+                        acronym_expander=helpers.acronym_expander_for_golden(gold))
+    qs = [x["query"] for x in runs]
+    r.retrieve_candidates_batch(qs, n_candidates=40)             # builds the row map
+    victims = [c["id"] for c in gold["chunks"][10:200:7]]
+    col.delete(ids=victims)
+    col.compact()                                                # rows shift
+    for stale in (True, False):
+        if not stale:
+            bm.build_from_collection(col)                        # rebuilt index: fast batch path again
+        got = r.retrieve_candidates_batch(qs, n_candidates=40)
+        want = [r.retrieve_candidates(x, n_candidates=40) for x in qs]
+        for a, b in zip(got, want):
+            assert [helpers.chunk_dump(c) for c in a] == [helpers.chunk_dump(c) for c in b]
+            if not stale:
+                assert not set(c.chunk_id for c in a) & set(victims)

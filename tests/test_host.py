@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/b200rag.h but not exported"
     assert sorted(_lib.SYMBOLS) == declared
-    assert L.rag_abi_version() == 1
+    assert L.rag_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -119,3 +119,65 @@ def test_shard_bounds_cover_all_rows():
             spans = [shard_bounds(n, w, r) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_where_program_equals_host_evaluator():
+    """the compiled predicate (what csrc/rowfilter.cu evaluates on the device) against match() on every `where`
+    shape the reference emits, via the host interpreter of the program"""
+    from b200rag.where import ColumnCodes, Unsupported, compile_where, match, run_program
+    metas = [{"source": "CNIL", "n": 1, "document_path": "a"}, {"source": "ENTREPRISE", "tag_rh": True, "document_path": "b"},
+             {"source": "ENTREPRISE", "document_path": "b"}, {}, None,
+             {"source": "CNIL", "tag_rh": False, "chunk_nature": "GUIDE", "n": 3, "document_path": "c"},
+             {"source": "CNIL", "tag_rh": 1, "chunk_nature": ["list"], "document_path": "a"}]
+    cols = ColumnCodes()
+    coded = cols.encode_batch(metas)
+    def codes_of(row):
+        return lambda col: int(coded[col][row]) if col in coded else -1
+    wheres = [None, {}, {"source": "CNIL"}, {"tag_rh": True}, {"source": {"$ne": "ENTREPRISE"}}, {"tag_rh": 1},
+              {"chunk_nature": {"$in": ["GUIDE", "X"]}}, {"$and": [{"source": "ENTREPRISE"}, {"tag_rh": True}]},
+              {"$or": [{"source": "CNIL"}, {"$and": [{"source": "ENTREPRISE"}, {"tag_rh": True}]}]},
+              {"source": {"$nin": ["CNIL"]}}, {"nope": "x"}, {"nope": {"$ne": "x"}}, {"source": "NOPE"},
+              {"source": {"$in": []}}, {"source": "CNIL", "tag_rh": False},
+              {"$or": [{"tag_rh": {"$ne": True}}, {"n": 3}]}, {"source": {"$eq": "CNIL", "$ne": "X"}}]
+    for w in wheres:
+        for docs in (None, {"a", "zzz"}, set()):
+            prog = compile_where(w, cols, docs)
+            for r, m in enumerate(metas):
+                want = match(m, w) and (docs is None or (m or {}).get("document_path", "") in docs)
+                got = True if prog is None else run_program(prog, codes_of(r))
+                assert got == want, (w, docs, r)
+    with pytest.raises(Unsupported):
+        compile_where({"n": {"$gte": 2}}, cols)
+
+
+def test_native_csr_builder_matches_oracle():
+    """rag_csr_build (multi-threaded host code in the library, no GPU) == the oracle's numpy CSR"""
+    from b200rag.bm25 import Postings
+    for n_docs, vocab, threads in [(3000, 900, 0), (257, 50, 3), (1, 5, 1)]:
+        docs, n_terms = helpers.zipf_docs(n_docs, vocab, seed=n_docs, lo=0 if n_docs > 1 else 3, hi=60)
+        lens = np.array([len(d) for d in docs])
+        doc_ptr = np.concatenate([[0], np.cumsum(lens)])
+        flat = np.concatenate(docs).astype(np.int32) if lens.sum() else np.zeros(0, np.int32)
+        p = Postings.from_flat_tokens(doc_ptr, flat, n_terms, threads=threads)
+        o = no.CsrBM25(docs)
+        v = len(o.term_ptr) - 1
+        assert np.array_equal(p.term_ptr[:v + 1], o.term_ptr) and (p.term_ptr[v:] == p.term_ptr[v]).all()
+        assert np.array_equal(p.post_row, o.post_row) and np.array_equal(p.post_tf, o.post_tf)
+        assert np.array_equal(p.doc_len, o.doc_len) and np.array_equal(p.idf[:v], o.idf)
+    with pytest.raises(ValueError):
+        Postings.from_flat_tokens(np.array([0, 2]), np.array([0, 7], np.int32), 3)
+
+
+def test_block_cyclic_shard_layout_roundtrip():
+    """the block-cyclic layout of sharded corpora (RAG_SHARD_BLOCK rows per block), python twin of api_common.h"""
+    BS = 1024
+    for G in (1, 2, 3, 8):
+        n = 5 * BS * G + 17
+        rows = np.arange(n)
+        shard = (rows // BS) % G if G > 1 else np.zeros(n, int)
+        local = (rows // BS // G) * BS + rows % BS if G > 1 else rows
+        back = ((local // BS) * G + shard) * BS + local % BS if G > 1 else local
+        assert np.array_equal(back, rows)
+        for s in range(G):
+            ls = local[shard == s]
+            assert np.array_equal(ls, np.arange(len(ls)))          # local rows are dense and in global order

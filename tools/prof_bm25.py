@@ -1,23 +1,32 @@
 #!/usr/bin/env python
-"""small BM25 driver for profiling: 1M docs, a few single-query and one 64-query search"""
-import os, sys
+"""small BM25 driver for profiling: the C4 corpus of bench.py (1M docs), a few single-query searches and batched ones"""
+import os
+import sys
+
 import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "rag-dpo_b200")):
     sys.path.insert(0, p)
-from b200rag import synth
-from b200rag.bm25 import DeviceBM25, Postings
+import bench  # noqa: E402
+from b200rag import _lib  # noqa: E402
+from b200rag.bm25 import DeviceBM25, Postings  # noqa: E402
 
 n_docs = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-docs, n_terms = synth.zipf_corpus(n_docs, 200_000, seed=1004, lo=40, hi=250)
-post = Postings.from_term_ids(docs, n_terms=n_terms)
+Q = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+doc_ptr, tokens, n_terms = bench.zipf_tokens(n_docs, 200_000, 1004)
+post = Postings.from_flat_tokens(doc_ptr, tokens, n_terms)
 ix = DeviceBM25(post)
 g = np.random.default_rng(2004)
 p = np.arange(1, n_terms + 1, dtype=np.float64) ** (-1.07)
 p /= p.sum()
-qs = [np.concatenate([g.choice(n_terms, size=10, p=p), g.integers(n_terms // 100, n_terms // 10, size=2)]).astype(np.int32)
-      for _ in range(64)]
+qs = [np.concatenate([g.choice(n_terms, size=g.integers(8, 13), p=p), g.integers(n_terms // 100, n_terms // 10, size=2)]).astype(np.int32)
+      for _ in range(Q)]
 for q in qs[:6]:
     ix.search_ids([q], 50)
-ix.search_ids(qs, 50)
+    print("single device ms", float(_lib.last_timings()[0]))
+for _ in range(3):
+    ix.search_ids(qs, 50)
+    print("batch device ms", float(_lib.last_timings()[0]), "per query us", 1e3 * float(_lib.last_timings()[0]) / Q)
+print("index MB", ix.index_bytes() / 1e6, "bytes/posting", ix.bytes_per_posting())
 print("done")
