@@ -85,6 +85,12 @@ int rag_last_timings(float* ms, int n);
 /* counters since rag_init: [0] kernels launched, [1] fallback passes taken (host-checked calls), [2] queries
  * those passes re-did */
 int rag_counters(int64_t* out, int n);
+/* Test hook (no reference counterpart): the candidate lists the tensor-core filter of the last dense call on a
+ * single-shard corpus left behind. Keys: (order-preserving image of the fp32 filter score) << 32 | ~row; out_counts[b]
+ * = entries written for query b (-1: overflowed list); *eps_rel = the accumulation error bound of the margin check
+ * relative to |q| * max|x|. tests/test_gpu.py measures |filter - exact| against that bound with it. */
+int rag_debug_last_candidates(const rag_corpus_t* c, int n_queries, uint64_t* out_keys, int64_t cap_per_query,
+                              int32_t* out_counts, double* eps_rel);
 
 /* ---- corpus: the chunk-embedding matrix -----------------------------------
  * replaces the vector segment behind chromadb's Collection: written through
@@ -196,6 +202,11 @@ int rag_bm25_create_sharded(rag_bm25_t** out, int n_shards, int64_t n_docs, int6
                             const int64_t* term_ptr, const int32_t* post_row, const int32_t* post_tf,
                             const int32_t* doc_len, const double* idf, double avgdl, double k1, double b);
 int rag_bm25_destroy(rag_bm25_t* ix);
+/* measurement helper: the bytes the filter pass streams for each query = sum over its scoring tokens of the term's
+ * list in the index format that serves it (4 per posting of the packed stream, 2 per row of a dense column; 12 per
+ * posting when only the exact path exists), and the postings themselves (sum of df). Either output may be NULL. */
+int rag_bm25_query_bytes(const rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr, int Q, int64_t* out_bytes,
+                         int64_t* out_postings);
 /* Q queries; q_terms are the concatenated term ids (in token order, repeats
  * kept, -1 = token outside the vocabulary), q_ptr has Q+1 offsets.
  * allow_bitmap: NULL or one bitmap shared by all queries (doc_filter).

@@ -32,6 +32,7 @@ SYMBOLS = {
     "rag_host_free": (_i, [_vp]),
     "rag_last_timings": (_i, [_vp, _i]),
     "rag_counters": (_i, [_vp, _i]),
+    "rag_debug_last_candidates": (_i, [_vp, _i, _vp, _i64, _vp, _vp]),
     "rag_corpus_create": (_i, [_vp, _i64, _i, _i]),
     "rag_corpus_create_sharded": (_i, [_vp, _i64, _i, _i, _i]),
     "rag_corpus_delete_rows": (_i, [_vp, _vp, _i64]),
@@ -60,6 +61,7 @@ SYMBOLS = {
     "rag_bm25_create_sharded": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _d, _d, _d]),
     "rag_bm25_destroy": (_i, [_vp]),
     "rag_bm25_info": (_i, [_vp, _vp, _vp]),
+    "rag_bm25_query_bytes": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "rag_bm25_search": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "rag_bm25_scores": (_i, [_vp, _vp, _i, _vp]),
     "rag_rrf_fuse": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

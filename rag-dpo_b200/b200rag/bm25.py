@@ -181,6 +181,19 @@ class DeviceBM25:
                                            _lib.ptr(rows), _lib.ptr(scores), _lib.ptr(counts)))
         return rows, scores, counts
 
+    def query_bytes(self, queries_term_ids):
+        """measurement helper: (bytes the filter pass streams, postings) per query, int64 arrays"""
+        Q = len(queries_term_ids)
+        q_ptr = np.zeros(Q + 1, dtype=np.int32)
+        np.cumsum([len(t) for t in queries_term_ids], out=q_ptr[1:])
+        flat = (np.concatenate([np.asarray(t, dtype=np.int32) for t in queries_term_ids])
+                if q_ptr[-1] else np.zeros(1, np.int32))
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        nbytes = np.zeros(Q, dtype=np.int64)
+        npost = np.zeros(Q, dtype=np.int64)
+        _lib.check(self._L.rag_bm25_query_bytes(self._h, _lib.ptr(flat), _lib.ptr(q_ptr), Q, _lib.ptr(nbytes), _lib.ptr(npost)))
+        return nbytes, npost
+
     def _search_multipass(self, queries_term_ids, k, allow_bitmap):
         """top_k above RAG_MAX_K: successive passes with the rows already returned masked out (still exact)"""
         n, Q = self.p.n_docs, len(queries_term_ids)

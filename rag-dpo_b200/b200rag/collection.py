@@ -190,6 +190,22 @@ class DeviceCorpus:
             counts[b] = got
         return rows, scores, counts
 
+    def debug_last_candidates(self, n_queries, cap):
+        """test hook: the tensor-core filter's candidate lists of the last call -> (rows (B,cap) int64 [-1 padded],
+        fp32 filter scores (B,cap), counts (B,), eps_rel)"""
+        keys = np.zeros((n_queries, cap), dtype=np.uint64)
+        counts = np.zeros(n_queries, dtype=np.int32)
+        eps = C.c_double(0.0)
+        _lib.check(self._L.rag_debug_last_candidates(self._h, int(n_queries), _lib.ptr(keys), int(cap), _lib.ptr(counts),
+                                                     C.byref(eps)))
+        o = (keys >> np.uint64(32)).astype(np.uint32)
+        u = np.where(o & np.uint32(0x80000000), o & np.uint32(0x7FFFFFFF), ~o)
+        scores = u.astype(np.uint32).view(np.float32)
+        rows = (~keys.astype(np.uint32)).astype(np.int64)          # low word = ~row
+        live = np.arange(cap)[None, :] < counts[:, None]
+        rows[~live] = -1
+        return rows, scores, counts, float(eps.value)
+
     def topk_dev(self, q_dev_ptr, B, k, out_rows_ptr, out_scores_ptr, out_counts_ptr, allow_dev_ptr=None):
         """device-pointer variant (inputs resident in HBM): STREAM-ORDERED, only queues work."""
         _lib.check(self._L.rag_dense_topk_dev(self._h, q_dev_ptr, int(B), int(k), allow_dev_ptr, out_rows_ptr,

@@ -235,6 +235,7 @@ struct CorpusShard {
     DevBuf q, allow, cand, cand_cnt, sample_keys, tau_keys, overflow, q16, q_resid, top, flags, tau, nflag;
     DevBuf o_rows, o_scores, o_counts, stage_f32, idx64;
     DevBuf fb_q, fb_tau, fb_counts, fb_rows, fb_scores, fb_index, fb_n, fb_done;
+    int last_tc_queries = 0, last_tc_list_cap = 0;     // the tensor-core filter's candidate lists of the last call (rag_debug_last_candidates)
 };
 
 struct rag_corpus {
@@ -521,6 +522,41 @@ int rag_counters(int64_t* out, int n) {
     if (n > 1) out[1] = R.n_fallback.load();
     if (n > 2) out[2] = R.n_flagged.load();
     for (int i = 3; i < n; ++i) out[i] = 0;
+    return RAG_OK;
+}
+
+namespace { double eps_tc(int dim); }
+
+// Test hook: the candidate lists the tensor-core filter of the LAST dense call on a single-shard corpus left behind
+// (every row whose filter score reached the query's sample threshold): u64 keys = (order-preserving image of the
+// fp32 filter score) << 32 | ~row.  out_keys: n_queries x cap_per_query, out_counts: entries written per query
+// (-1: the list overflowed).  *eps_rel: the accumulation bound the margin check uses for this corpus,
+// relative to |q| * max|x|.  Tests use it to measure |filter - exact| against that bound.
+int rag_debug_last_candidates(const rag_corpus_t* c, int n_queries, uint64_t* out_keys, int64_t cap_per_query,
+                              int32_t* out_counts, double* eps_rel) {
+    RAG_TRY(require_init());
+    if (!c || !out_keys || !out_counts || n_queries <= 0 || cap_per_query <= 0) return fail(RAG_EINVAL, "bad arguments");
+    CorpusLock lk(c);
+    if (c->n_shards != 1) return fail(RAG_EINVAL, "single-shard corpora only");
+    CorpusShard& sh = *c->sh[0];
+    if (sh.last_tc_queries <= 0 || n_queries > sh.last_tc_queries)
+        return fail(RAG_EINVAL, "the last call did not run the tensor-core filter over %d queries", n_queries);
+    RAG_TRY(sh.cx.use());
+    cudaStream_t st = sh.cx.stream();
+    std::vector<int32_t> cnt((size_t)n_queries);
+    CU_TRY(cudaMemcpyAsync(cnt.data(), sh.cand_cnt.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    for (int b = 0; b < n_queries; ++b) {
+        int64_t n = cnt[(size_t)b];
+        if (n > sh.last_tc_list_cap) { out_counts[b] = -1; continue; }
+        if (n > cap_per_query) n = cap_per_query;
+        out_counts[b] = (int32_t)n;
+        if (n > 0)
+            CU_TRY(cudaMemcpyAsync(out_keys + (size_t)b * cap_per_query, sh.cand.as<uint64_t>() + (size_t)b * sh.last_tc_list_cap,
+                                   (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    if (eps_rel) *eps_rel = eps_tc(c->dim);
     return RAG_OK;
 }
 
@@ -905,6 +941,8 @@ int dense_core_slice(rag_corpus* c, CorpusShard& sh, int shard, const float* q_d
         CU_TRY(gemm_launch(p, 1, sh.q16.p, x16, grid, smem, st));
         ++R.n_launch;
         cx.rec(1);
+        sh.last_tc_queries = B;
+        sh.last_tc_list_cap = p.list_cap;
         // the per-query list is one contiguous block: the 8 merge warps split it (flat count per query)
         m_counts = sh.cand_cnt.as<int32_t>();
         m_flat = 1;
@@ -931,6 +969,7 @@ int dense_core_slice(rag_corpus* c, CorpusShard& sh, int shard, const float* q_d
         if (smem == 0) return fail(RAG_ERANGE, "k=%d does not fit the scan kernel's shared memory", k);
         const int n_lists = p.n_lists;
         RAG_TRY(sh.cand.ensure((size_t)B * n_lists * kp * 8));
+        sh.last_tc_queries = 0;
         cx.rec(0);
         for (int gi = 0; gi < n_groups; ++gi) {
             ScanParams pg = p;

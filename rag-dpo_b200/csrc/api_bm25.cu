@@ -11,6 +11,7 @@ namespace {
 
 int g_bm25_fast = 1;          // option "bm25_fast": 0 = always the exact fp64 range path
 int g_bm25_rows_max = kBm25MaxListedRows;   // option "bm25_rows_max": largest row filter served by the listed-rows kernel
+int g_bm25_dense_div = 8;     // option "bm25_dense_div": terms with df >= n_docs / div get a dense column (0 = none)
 
 struct Bm25Shard {
     Ctx cx;
@@ -18,8 +19,10 @@ struct Bm25Shard {
     int64_t index_bytes = 0;
     std::vector<int64_t> h_term_ptr;
     std::vector<double> h_idf;
+    std::vector<uint8_t> h_cls;        // term class of the filter index (kBmLow / kBmMid / kBmDense / kBmSkip); empty: no filter index
     // tables of the fast path (device)
-    DevBuf tabled_terms, high_terms;
+    DevBuf tabled_terms, dense_terms;
+    int n_dense = 0, n_tabled = 0;
     // scratch
     DevBuf terms, qptr, cand, rows, scores, counts, allow, scratch, index, listed, ranges;
 };
@@ -31,8 +34,8 @@ void shard_free(Bm25Shard* s) {
         cudaStreamSynchronize(s->cx.stream());
     }
     cudaFree(s->d.term_ptr); cudaFree(s->d.post_row); cudaFree(s->d.post_impact); cudaFree(s->d.idf); cudaFree(s->d.score);
-    cudaFree(s->d.post_pack); cudaFree(s->d.term_info); cudaFree(s->d.rng_off); cudaFree(s->d.seg_off);
-    for (DevBuf* b : {&s->tabled_terms, &s->high_terms, &s->terms, &s->qptr, &s->cand, &s->rows, &s->scores, &s->counts,
+    cudaFree(s->d.post_pack); cudaFree(s->d.term_info); cudaFree(s->d.rng_off); cudaFree(s->d.dense_col);
+    for (DevBuf* b : {&s->tabled_terms, &s->dense_terms, &s->terms, &s->qptr, &s->cand, &s->rows, &s->scores, &s->counts,
                       &s->allow, &s->scratch, &s->index, &s->listed, &s->ranges})
         b->release();
     {
@@ -117,48 +120,88 @@ int shard_build(Bm25Shard** out, int slot, int64_t n_docs, int64_t n_terms, int6
     }
     const double cbound = idf_max * max_impact;          // >= idf[t] * impact[p] for every posting (rn is monotone)
     d.fast_ok = 0;
-    if (nnz > 0 && d.n_ranges >= 1 && cbound > 0.0 && std::isfinite(cbound)) {
-        const double unit = cbound / 1048568.0;          // 2^20 - 8: q = ceil(c / unit) + 1 stays inside 20 bits
-        // term classes by document frequency
-        const int64_t high_min = std::max<int64_t>(32LL * d.n_ranges, 64);
-        const int64_t mid_min = std::max<int64_t>(2LL * d.n_ranges, 64);
-        std::vector<int2> info((size_t)std::max<int64_t>(n_terms, 1));
-        std::vector<int32_t> tabled, high;
+    // (the filter kernel addresses the packed stream with 32-bit offsets)
+    if (nnz > 0 && nnz < 0xFFFF0000LL && d.n_ranges >= 1 && cbound > 0.0 && std::isfinite(cbound)) {
+        // 2^20 - 576: q = ceil(c / unit) + 1 stays inside 20 bits and ceil(q / 16) inside 16
+        const double unit = cbound / 1048000.0;
+        // term classes by document frequency.  DENSE: df >= n_docs / g_bm25_dense_div, the most frequent first, while
+        // the columns (2 bytes x rows each) fit the budget of one more copy of the packed stream.  Tabled (range
+        // table row of (n_ranges + 1) x 4 bytes): df >= mid_min, raised until the tables fit a quarter of the stream.
+        const int64_t col_rows = (int64_t)d.n_ranges * kBm25Range;
+        const int64_t ddiv = std::max(g_bm25_dense_div, 1);
+        const int64_t dense_min = std::max<int64_t>((n_docs + ddiv - 1) / ddiv, 64);
+        std::vector<std::pair<int64_t, int32_t>> dense_cand;
+        std::vector<int64_t> dfs;
+        dfs.reserve((size_t)n_terms);
         for (int64_t t = 0; t < n_terms; ++t) {
             const int64_t df = term_ptr[t + 1] - term_ptr[t];
-            int cls = kBmLow, slot_t = 0, hslot = 0;
+            if (df > 0 && idf[t] != 0.0) {
+                dfs.push_back(df);
+                if (g_bm25_dense_div > 0 && df >= dense_min) dense_cand.emplace_back(-df, (int32_t)t);
+            }
+        }
+        std::sort(dense_cand.begin(), dense_cand.end());
+        const int64_t col_budget = std::max<int64_t>(nnz * 4, 64LL << 20);
+        size_t n_dense = 0;
+        while (n_dense < dense_cand.size() && n_dense < 4096 && (int64_t)(n_dense + 1) * col_rows * 2 <= col_budget) ++n_dense;
+        dense_cand.resize(n_dense);
+        int64_t mid_min = std::min<int64_t>(std::max<int64_t>(d.n_ranges, 64), 256);
+        {
+            std::sort(dfs.begin(), dfs.end(), std::greater<int64_t>());
+            const int64_t tab_budget = std::max<int64_t>(nnz, 16LL << 20);       // bytes: a quarter of the packed stream
+            const int64_t max_tabled = tab_budget / (4 * ((int64_t)d.n_ranges + 1));
+            if ((int64_t)dfs.size() > max_tabled && max_tabled >= 0) {
+                const int64_t cut = max_tabled > 0 ? dfs[(size_t)max_tabled - 1] : dfs[0] + 1;
+                mid_min = std::max(mid_min, cut + 1);
+            }
+        }
+        std::vector<int2> info((size_t)std::max<int64_t>(n_terms, 1));
+        std::vector<int32_t> tabled, dense;
+        std::vector<int32_t> col_of((size_t)std::max<int64_t>(n_terms, 1), -1);
+        for (size_t i = 0; i < dense_cand.size(); ++i) {
+            col_of[(size_t)dense_cand[i].second] = (int32_t)i;
+            dense.push_back(dense_cand[i].second);
+        }
+        for (int64_t t = 0; t < n_terms; ++t) {
+            const int64_t df = term_ptr[t + 1] - term_ptr[t];
+            int cls = kBmLow, slot_t = 0, col = 0;
             if (df == 0 || idf[t] == 0.0) {
                 cls = kBmSkip;
-            } else if (df >= mid_min) {
-                cls = df >= high_min ? kBmHigh : kBmMid;
+            } else if (col_of[(size_t)t] >= 0 || df >= mid_min) {
+                cls = col_of[(size_t)t] >= 0 ? kBmDense : kBmMid;
+                col = std::max(col_of[(size_t)t], 0);
                 slot_t = (int)tabled.size();
                 tabled.push_back((int32_t)t);
-                if (cls == kBmHigh) { hslot = (int)high.size(); high.push_back((int32_t)t); }
             }
-            info[(size_t)t] = make_int2((int)(((unsigned)cls << 30) | (unsigned)slot_t), hslot);
+            info[(size_t)t] = make_int2((int)(((unsigned)cls << 30) | (unsigned)slot_t), col);
         }
         const size_t rng_n = (size_t)std::max<size_t>(tabled.size(), 1) * (d.n_ranges + 1);
-        const size_t seg_n = (size_t)std::max<size_t>(high.size(), 1) * d.n_ranges * 8;
+        const size_t col_n = (size_t)std::max<size_t>(dense.size(), 1) * (size_t)col_rows;
         A((void**)&d.post_pack, (nz + 4) * 4);
         A((void**)&d.term_info, info.size() * sizeof(int2));
         A((void**)&d.rng_off, rng_n * 4);
-        A((void**)&d.seg_off, seg_n * 2);
+        A((void**)&d.dense_col, col_n * 2);
         int rc2 = RAG_OK;
         if (e == cudaSuccess) rc2 = s->tabled_terms.ensure(std::max<size_t>(tabled.size(), 1) * 4);
-        if (e == cudaSuccess && rc2 == RAG_OK) rc2 = s->high_terms.ensure(std::max<size_t>(high.size(), 1) * 4);
+        if (e == cudaSuccess && rc2 == RAG_OK) rc2 = s->dense_terms.ensure(std::max<size_t>(dense.size(), 1) * 4);
         if (rc2 != RAG_OK) { shard_free(s); return rc2; }
-        bytes += (int64_t)(s->tabled_terms.bytes + s->high_terms.bytes);
+        bytes += (int64_t)(s->tabled_terms.bytes + s->dense_terms.bytes);
         if (e == cudaSuccess) e = cudaMemsetAsync(d.post_pack + nz, 0, 16, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d.dense_col, 0, col_n * 2, st);
         C(d.term_info, info.data(), info.size() * sizeof(int2));
         C(s->tabled_terms.p, tabled.data(), tabled.size() * 4);
-        C(s->high_terms.p, high.data(), high.size() * 4);
+        C(s->dense_terms.p, dense.data(), dense.size() * 4);
         if (e == cudaSuccess) {
-            e = bm25_index_build_launch(d, unit, s->tabled_terms.as<int32_t>(), (int)tabled.size(), s->high_terms.as<int32_t>(),
-                                        (int)high.size(), st);
+            e = bm25_index_build_launch(d, unit, s->tabled_terms.as<int32_t>(), (int)tabled.size(), s->dense_terms.as<int32_t>(),
+                                        (int)dense.size(), st);
             R.n_launch += 3;
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return bail("filter index");
+        s->n_dense = (int)dense.size();
+        s->n_tabled = (int)tabled.size();
+        s->h_cls.resize((size_t)n_terms);
+        for (int64_t t = 0; t < n_terms; ++t) s->h_cls[(size_t)t] = (uint8_t)((unsigned)info[(size_t)t].x >> 30);
         d.fast_ok = any_negative ? 0 : 1;
     }
     s->index_bytes = bytes;
@@ -363,6 +406,7 @@ int accumulate_query(Bm25Shard& s, const int32_t* terms, int nt, std::vector<int
 
 int bm25_set_option(const char* key, int64_t value) {
     if (!strcmp(key, "bm25_fast")) g_bm25_fast = value != 0;
+    else if (!strcmp(key, "bm25_dense_div")) g_bm25_dense_div = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     else if (!strcmp(key, "bm25_rows_max")) g_bm25_rows_max = (int)std::max<int64_t>(0, std::min<int64_t>(value, kBm25MaxListedRows));
     else return RAG_EINVAL;
     return RAG_OK;
@@ -456,6 +500,31 @@ int rag_bm25_info(const rag_bm25_t* ix, int* bytes_per_posting, int64_t* index_b
     }
     if (bytes_per_posting) *bytes_per_posting = fast ? 4 : 12;
     if (index_bytes) *index_bytes = bytes;
+    return RAG_OK;
+}
+
+int rag_bm25_query_bytes(const rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr, int Q, int64_t* out_bytes,
+                         int64_t* out_postings) {
+    if (!ix || !q_ptr || Q <= 0 || (q_ptr[Q] > 0 && !q_terms)) return fail(RAG_EINVAL, "bad arguments");
+    IndexLock lk(ix);
+    for (int q = 0; q < Q; ++q) {
+        int64_t bytes = 0, postings = 0;
+        for (int i = q_ptr[q]; i < q_ptr[q + 1]; ++i) {
+            const int32_t t = q_terms[i];
+            if (t < 0 || t >= ix->n_terms) continue;
+            for (auto* s : ix->sh) {
+                const int64_t df = s->h_term_ptr[(size_t)t + 1] - s->h_term_ptr[(size_t)t];
+                if (df == 0 || s->h_idf[(size_t)t] == 0.0) continue;
+                postings += df;
+                const bool fast = g_bm25_fast && s->d.fast_ok && !s->h_cls.empty();
+                if (!fast) bytes += df * 12;                                  // exact path: row id + fp64 impact
+                else if (s->h_cls[(size_t)t] == kBmDense) bytes += s->d.n_docs * 2;   // one 16-bit column entry per row
+                else bytes += df * 4;                                          // packed stream
+            }
+        }
+        if (out_bytes) out_bytes[q] = bytes;
+        if (out_postings) out_postings[q] = postings;
+    }
     return RAG_OK;
 }
 

@@ -276,16 +276,23 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
 // FAST path (2 launches for a batch of queries).
 //
 // The product idf[t] * impact[p] of a posting does not depend on the query, so the index holds it a second time
-// as a 20-bit fixed-point UPPER bound q (unit = max product / 2^20, rounded up, +1) packed with the 12-bit local row
-// of its 4096-row range: 4 bytes per posting instead of 12.  The filter pass adds these integers:
-//     U[row] = sum over the query's tokens of q      (exact integer arithmetic, any order)
-// is an upper bound of the row's fp64 score in units, and U[row] - 2 * (number of tokens) a lower bound.
-//   A  bm25_filter_kernel   grid (ranges, queries): integer accumulators of the range in shared memory;
-//        HIGH terms (long runs): a segment table gives every warp the postings of ITS 512 rows: 128-bit loads,
-//        plain read-modify-write, no atomics, no search;  MID terms: a range table gives the run, added with
-//        shared-memory atomics (a handful of postings);  LOW terms: warp-cooperative 32-ary search, atomics.
-//        The range's H best allowed rows by U ("heads") and the (H+1)-th best U ("rho": nothing that was not
-//        emitted is above it) go to global memory: scores never leave the SM.
+// as a 20-bit fixed-point UPPER bound q (unit = max product / ~2^20, rounded up, +1):
+//   * packed with the 12-bit local row of its 4096-row range, 4 bytes per posting (every term), and
+//   * for DENSE terms (df >= n_docs / 8) as a 16-bit COLUMN over all rows: ceil(q / 16), 0 where the term does not
+//     occur — 2 bytes per row, read with fully coalesced loads and added into REGISTERS (a thread owns 16 fixed rows
+//     of the range), no row ids, no shared-memory traffic, no search.
+// The filter pass adds these integers:
+//     U[row] = sum over the query's tokens of q   (resp. 16 * column entry)      (exact integer arithmetic, any order)
+// is an upper bound of the row's fp64 score in units, and U[row] - slack a lower bound, slack = 2 per packed token
+// + 17 per column token.
+//   A  bm25_filter_kernel   grid (ranges, queries).  Column tokens: registers.  Other tokens: integer accumulators of
+//        the range in shared memory; the range table gives a tabled term's run inside the packed stream (no search),
+//        an untabled (short) list is scanned whole; the CTA adds one token at a time, thread i the i-th posting of
+//        the run (plain read-modify-write: the postings of one term are distinct rows), the loads of 4 tokens in
+//        flight.  Then the range's H best allowed rows by U ("heads") and the (H+1)-th best U ("rho": nothing that
+//        was not emitted is above it) go to global memory: scores never leave the SM.  Selection by threshold: the
+//        (H+1)-th largest of a warp's 32 per-lane maxima is reached by H+1 distinct rows, so only rows at or above
+//        it (H+1 and a few) can be among the warp's H+1 best.
 //   B  bm25_finish_kernel   one CTA per query: tau = k-th largest head minus the slack (k distinct rows reach it:
 //        a valid lower bound of the k-th best exact score); every rho must be below it, else the query is flagged
 //        (count = -1) and redone on the robust path; heads with U >= tau are the survivors (k + a handful): their
@@ -294,214 +301,253 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
 // Selective row filters (doc_filter keeping <= 4096 rows) skip the posting stream altogether: bm25_rows_kernel
 // computes the exact scores of the listed rows only.
 // ---------------------------------------------------------------------------
-constexpr int kBmMaxH = 31;           // heads per range (static shared memory of the filter kernel)
+constexpr int kBmMaxH = 31;           // heads per range
+constexpr int kBmList = 256;          // rows a CTA's warps hand to the final selection (8 warps x (H+1) and ties)
 constexpr int kBmSurvivors = 1024;    // survivors per query the finish kernel re-scores
 constexpr int kBmContrib = 4096;      // (survivor, token) products staged at a time
 constexpr int kBmMaxQueryTokens = 1024;
-constexpr int kBmGroup = 4;           // HIGH tokens whose first loads are in flight together
+constexpr int kBmSpGroup = 4;         // run tokens whose first loads are in flight together
+constexpr int kBmDnGroup = 2;         // column tokens whose loads are in flight together
+constexpr int kBmThetaHeads = 12;     // up to this many heads (+ rho) per range the warps select by threshold
 
-// first position in post_row[lo, hi) whose row is >= target, searched by a whole warp: 32 probes per round
-__device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ post_row, int64_t lo, int64_t hi,
-                                                    int64_t target, int lane) {
-    while (hi - lo > 32) {
-        const int64_t step = (hi - lo + 31) >> 5;
-        const int64_t base = lo;
-        int64_t idx = base + step * (lane + 1) - 1;
-        if (idx > hi - 1) idx = hi - 1;
-        const bool below = (int64_t)post_row[idx] < target;
-        const int c = __popc(__ballot_sync(0xffffffffu, below));     // probes below the target: a prefix (rows ascend)
-        if (c < 32) {                            // probe c is the first one >= target: the answer is at or before it
-            int64_t nh = base + step * (c + 1) - 1;
-            if (nh > hi - 1) nh = hi - 1;
-            hi = nh;
-        }
-        lo = base + step * c;
-        if (lo > hi) lo = hi;
-    }
-    const int64_t idx = lo + lane;
-    const bool below = idx < hi && (int64_t)post_row[idx] < target;
-    return lo + __popc(__ballot_sync(0xffffffffu, below));
-}
-
-__device__ __forceinline__ void bm25_add4(uint32_t* acc, const uint4& v, int64_t idx0, int64_t a, int64_t b) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+// the range's H+1 best of n_e (<= 32 * NU) list entries -> dst[0..H] (descending; 0 = none)
+template <int NU>
+__device__ __forceinline__ void bm25_emit_heads(const unsigned long long* s_list, int n_e, int H, int lane,
+                                                unsigned long long* __restrict__ dst) {
+    unsigned long long mine[NU];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int64_t idx = idx0 + j;
-        if (idx >= a && idx < b) acc[w[j] >> 20] += w[j] & 0xFFFFFu;   // every posting of a term is a different row
+    for (int u = 0; u < NU; ++u) {
+        const int e = lane + 32 * u;
+        mine[u] = e < n_e ? s_list[e] : 0ull;
+    }
+    for (int h = 0; h <= H; ++h) {
+        unsigned long long m = 0ull;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) m = mine[u] > m ? mine[u] : m;
+        const uint32_t whi = __reduce_max_sync(0xffffffffu, (uint32_t)(m >> 32));
+        const uint32_t wlo = __reduce_max_sync(0xffffffffu, (uint32_t)(m >> 32) == whi ? (uint32_t)m : 0u);
+        const unsigned long long top = ((unsigned long long)whi << 32) | wlo;
+        if (whi == 0u) {
+            if (lane == 0)
+                for (int hh = h; hh <= H; ++hh) dst[hh] = 0ull;
+            break;
+        }
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+            if (mine[u] == top) mine[u] = 0ull;             // rows are distinct: exactly one entry
+        if (lane == 0) dst[h] = top;
     }
 }
 
-__global__ void __launch_bounds__(kBmThreads)
+__global__ void __launch_bounds__(kBmThreads, 4)
 bm25_filter_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr, int q0,
                    const uint8_t* __restrict__ allow, int H, unsigned long long* __restrict__ heads) {
     __shared__ __align__(16) uint32_t acc[kBmRange];
-    __shared__ long long s_lo[kBmMaxTokens], s_hi[kBmMaxTokens];
-    __shared__ __align__(16) uint16_t s_seg[kBmMaxTokens][8];
-    __shared__ uint8_t s_kind[kBmMaxTokens];
-    __shared__ uint8_t s_high[kBmMaxTokens], s_other[kBmMaxTokens];
-    __shared__ int s_nhigh, s_nother;
-    __shared__ unsigned long long s_heads[kBmWarps][kBmMaxH + 1];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ uint2 s_runs[kBmMaxTokens];            // [lo, hi) inside the packed stream: tabled runs from the front,
+    __shared__ const uint16_t* s_colp[kBmMaxTokens];  // scanned lists from the back; column of the range per DENSE token
+    __shared__ int s_ntab, s_nscan, s_ncol, s_nlist;
+    __shared__ unsigned long long s_list[kBmList];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rg = blockIdx.x;
     const int qi = q0 + blockIdx.y;
     const int64_t r0 = (int64_t)rg * kBmRange;
     const int64_t r1 = r0 + kBmRange < ix.n_docs ? r0 + kBmRange : ix.n_docs;
     const int32_t* terms = q_terms + q_ptr[qi];
     const int nt = q_ptr[qi + 1] - q_ptr[qi];
-    for (int i = threadIdx.x; i < kBmRange; i += kBmThreads) acc[i] = 0u;
+    // a thread owns the local rows g * 1024 + 4 * tid + i (g, i = 0..3): 8-byte column loads and 16-byte shared
+    // accesses that are contiguous over the warp.  A column word holds two rows: s_all adds the words whole
+    // (sum of the low halves + 65536 * sum of the high halves, modulo 2^32), s_hi the high halves.
+    uint32_t s_all[8], s_hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(&acc[g * 1024 + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) s_nlist = 0;
     for (int t0 = 0; t0 < nt; t0 += kBmMaxTokens) {
         const int tn = nt - t0 < kBmMaxTokens ? nt - t0 : kBmMaxTokens;
-        if (threadIdx.x == 0) { s_nhigh = 0; s_nother = 0; }
         __syncthreads();                  // accumulators zeroed / previous pass done with the token table
+        if (tid == 0) { s_ntab = 0; s_nscan = 0; s_ncol = 0; }
+        __syncthreads();
         // ---- resolve the tokens: all lookups of all tokens are in flight together
-        if ((int)threadIdx.x < tn) {
-            const int i = threadIdx.x;
-            const int32_t t = terms[t0 + i];
-            int kind = kBmSkip;
-            long long lo = 0, hi = 0;
+        if (tid < tn) {
+            const int32_t t = terms[t0 + tid];
             if (t >= 0 && t < ix.n_terms) {
                 const int2 info = ix.term_info[t];
                 const int cls = (int)((unsigned)info.x >> 30);
-                const long long base = ix.term_ptr[t];
-                if (cls == kBmLow) {
-                    kind = kBmLow; lo = base; hi = ix.term_ptr[t + 1];
-                } else if (cls != kBmSkip) {
+                if (cls == kBmDense) {
+                    s_colp[atomicAdd(&s_ncol, 1)] =
+                        ix.dense_col + ((size_t)info.y * ix.n_ranges + rg) * kBmRange;
+                } else if (cls == kBmMid) {
+                    const uint32_t base = (uint32_t)ix.term_ptr[t];
                     const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_ranges + 1) + rg;
-                    lo = base + ro[0]; hi = base + ro[1];
-                    kind = cls;
-                    if (cls == kBmHigh)
-                        *reinterpret_cast<uint4*>(&s_seg[i][0]) =
-                            *reinterpret_cast<const uint4*>(ix.seg_off + ((size_t)info.y * ix.n_ranges + rg) * 8);
-                }
-                if (hi <= lo) kind = kBmSkip;
-            }
-            s_lo[i] = lo; s_hi[i] = hi; s_kind[i] = (uint8_t)kind;
-            if (kind == kBmHigh) s_high[atomicAdd(&s_nhigh, 1)] = (uint8_t)i;
-            else if (kind != kBmSkip) s_other[atomicAdd(&s_nother, 1)] = (uint8_t)i;
-        }
-        __syncthreads();
-        // ---- phase 1: MID / LOW tokens, a handful of postings each: shared-memory atomics, one token per warp
-        const int n_other = s_nother, n_high = s_nhigh;
-        for (int o = warp; o < n_other; o += kBmWarps) {
-            const int i = s_other[o];
-            int64_t lo = s_lo[i], hi = s_hi[i];
-            if (s_kind[i] == kBmMid) {
-                for (int64_t p = lo + lane; p < hi; p += 32) {
-                    const uint32_t pk = ix.post_pack[p];
-                    atomicAdd(&acc[pk >> 20], pk & 0xFFFFFu);
-                }
-            } else {
-                int64_t a = warp_lower_bound(ix.post_row, lo, hi, r0, lane);
-                while (true) {
-                    const int64_t idx = a + lane;
-                    const int64_t row = idx < hi ? (int64_t)ix.post_row[idx] : (int64_t)0x7FFFFFFF;
-                    const bool in = row < r1;
-                    if (in) atomicAdd(&acc[(int)(row - r0)], ix.post_pack[idx] & 0xFFFFFu);
-                    if (!__all_sync(0xffffffffu, in)) break;
-                    a += 32;
+                    const uint32_t lo = base + (uint32_t)ro[0], hi = base + (uint32_t)ro[1];
+                    if (hi > lo) s_runs[atomicAdd(&s_ntab, 1)] = make_uint2(lo, hi);
+                } else if (cls == kBmLow) {
+                    const uint32_t lo = (uint32_t)ix.term_ptr[t], hi = (uint32_t)ix.term_ptr[t + 1];
+                    if (hi > lo) s_runs[kBmMaxTokens - 1 - atomicAdd(&s_nscan, 1)] = make_uint2(lo, hi);
                 }
             }
         }
         __syncthreads();
-        // ---- phase 2: HIGH tokens.  Warp w adds the postings of ITS 512 rows (segment table), 4 postings per
-        // 128-bit load; the first loads of kBmGroup tokens are requested before the first one is added
-        for (int g0 = 0; g0 < n_high; g0 += kBmGroup) {
-            int64_t a_g[kBmGroup], b_g[kBmGroup];
-            uint4 v_g[kBmGroup];
+        const int n_tab = s_ntab, n_run = n_tab + s_nscan, n_col = s_ncol;
+        // ---- column tokens: 4 x 8 bytes per thread and token, straight into registers
+        for (int e0 = 0; e0 < n_col; e0 += kBmDnGroup) {
+            uint2 x[kBmDnGroup][4];
 #pragma unroll
-            for (int g = 0; g < kBmGroup; ++g) {
-                a_g[g] = 0; b_g[g] = 0; v_g[g] = make_uint4(0u, 0u, 0u, 0u);
-                if (g0 + g < n_high) {
-                    const int i = s_high[g0 + g];
-                    const int64_t lo = s_lo[i];
-                    a_g[g] = lo + (warp ? (int64_t)s_seg[i][warp - 1] : 0);
-                    b_g[g] = warp < kBmWarps - 1 ? lo + (int64_t)s_seg[i][warp] : (int64_t)s_hi[i];
-                    const int64_t idx0 = (a_g[g] & ~(int64_t)3) + 4 * lane;
-                    if (idx0 < b_g[g]) v_g[g] = __ldg(reinterpret_cast<const uint4*>(ix.post_pack + idx0));
+            for (int u = 0; u < kBmDnGroup; ++u) {
+                if (e0 + u < n_col) {
+                    const uint2* c = reinterpret_cast<const uint2*>(s_colp[e0 + u]) + tid;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) x[u][g] = __ldg(c + g * 256);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) x[u][g] = make_uint2(0u, 0u);
                 }
             }
 #pragma unroll
-            for (int g = 0; g < kBmGroup; ++g) {
-                if (g0 + g < n_high) {                      // block-uniform
-                    const int64_t a = a_g[g], b = b_g[g];
-                    int64_t base = a & ~(int64_t)3;
-                    bm25_add4(acc, v_g[g], base + 4 * lane, a, b);
-                    base += 128;
-                    while (base < b) {                      // warp-uniform: long runs, two loads in flight
-                        const int64_t i0 = base + 4 * lane, i1 = i0 + 128;
-                        uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-                        if (i0 < b) v0 = __ldg(reinterpret_cast<const uint4*>(ix.post_pack + i0));
-                        if (i1 < b) v1 = __ldg(reinterpret_cast<const uint4*>(ix.post_pack + i1));
-                        bm25_add4(acc, v0, i0, a, b);
-                        bm25_add4(acc, v1, i1, a, b);
-                        base += 256;
+            for (int u = 0; u < kBmDnGroup; ++u)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    s_all[2 * g + 0] += x[u][g].x;
+                    s_hi[2 * g + 0] += x[u][g].x >> 16;
+                    s_all[2 * g + 1] += x[u][g].y;
+                    s_hi[2 * g + 1] += x[u][g].y >> 16;
+                }
+        }
+        // ---- run tokens, one at a time for the whole CTA: thread i adds the i-th posting of the run (the postings of
+        // one term are distinct rows: plain read-modify-write), the barrier separates the terms.  An untabled list
+        // is scanned whole: only the rows of this range count.
+        for (int e0 = 0; e0 < n_run; e0 += kBmSpGroup) {
+            uint32_t pk[kBmSpGroup];
+#pragma unroll
+            for (int u = 0; u < kBmSpGroup; ++u) {
+                pk[u] = 0u;                                  // 0: adds nothing (a posting's q is >= 2)
+                const int e = e0 + u;
+                if (e < n_run) {
+                    const bool scan = e >= n_tab;            // block-uniform
+                    const uint2 r = s_runs[scan ? kBmMaxTokens - 1 - (e - n_tab) : e];
+                    const uint32_t p = r.x + (uint32_t)tid;
+                    if (p < r.y) {
+                        pk[u] = __ldg(ix.post_pack + p);
+                        if (scan) {
+                            const int64_t row = ix.post_row[p];
+                            if (row < r0 || row >= r1) pk[u] = 0u;
+                        }
                     }
-                    __syncwarp();                           // two tokens may hit the same row from different lanes
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBmSpGroup; ++u) {
+                const int e = e0 + u;
+                if (e < n_run) {                             // block-uniform
+                    if (pk[u]) acc[pk[u] >> 20] += pk[u] & 0xFFFFFu;
+                    const bool scan = e >= n_tab;
+                    const uint2 r = s_runs[scan ? kBmMaxTokens - 1 - (e - n_tab) : e];
+                    if (r.y - r.x > (uint32_t)kBmThreads) {  // block-uniform: a long run
+                        for (uint32_t p = r.x + kBmThreads + tid; p < r.y; p += kBmThreads) {
+                            uint32_t w = ix.post_pack[p];
+                            if (scan) {
+                                const int64_t row = ix.post_row[p];
+                                if (row < r0 || row >= r1) w = 0u;
+                            }
+                            if (w) acc[w >> 20] += w & 0xFFFFFu;
+                        }
+                    }
+                    __syncthreads();
                 }
             }
         }
     }
     __syncthreads();
-    // ---- the range's H best allowed rows by U, and the (H+1)-th best U (rho).  Warp level first: every lane
-    // holds its 16 rows of the warp's segment, H+1 rounds of warp-wide maximum (ties: lowest row)
-    uint32_t v[kBmSeg / 32];
+    // ---- the thread's 16 upper bounds (disallowed rows masked), kept in shared memory for the emission
+    uint32_t v[16];
 #pragma unroll
-    for (int j = 0; j < kBmSeg / 32; ++j) {
-        const int i = warp * kBmSeg + j * 32 + lane;
-        const int64_t row = r0 + i;
-        v[j] = (row < r1 && bitmap_test(allow, (uint32_t)row)) ? acc[i] : 0u;
+    for (int g = 0; g < 4; ++g) {
+        uint4 a = *reinterpret_cast<const uint4*>(&acc[g * 1024 + 4 * tid]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t hi = s_hi[2 * g + h];
+            const uint32_t lo = s_all[2 * g + h] - (hi << 16);
+            (h ? a.z : a.x) += lo << kBmDenseShift;
+            (h ? a.w : a.y) += hi << kBmDenseShift;
+        }
+        if (allow != nullptr) {
+            const int64_t row = r0 + g * 1024 + 4 * tid;     // 4 rows inside one byte of the bitmap
+            const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
+            if (!(bits & 1u)) a.x = 0u;
+            if (!(bits & 2u)) a.y = 0u;
+            if (!(bits & 4u)) a.z = 0u;
+            if (!(bits & 8u)) a.w = 0u;
+        }
+        *reinterpret_cast<uint4*>(&acc[g * 1024 + 4 * tid]) = a;
+        v[4 * g + 0] = a.x; v[4 * g + 1] = a.y; v[4 * g + 2] = a.z; v[4 * g + 3] = a.w;
     }
-    for (int h = 0; h <= H; ++h) {
-        uint32_t m = 0u;
+    uint32_t m = 0u;
 #pragma unroll
-        for (int j = 0; j < kBmSeg / 32; ++j) m = v[j] > m ? v[j] : m;
-        const uint32_t wm = __reduce_max_sync(0xffffffffu, m);
-        if (wm == 0u) {                                      // warp-uniform: nothing (more) to emit
-            if (lane == 0)
-                for (int hh = h; hh <= H; ++hh) s_heads[warp][hh] = 0ull;
-            break;
+    for (int j = 0; j < 16; ++j) m = v[j] > m ? v[j] : m;
+    const uint32_t row_base = (uint32_t)r0 + 4u * (uint32_t)tid;
+    if (H + 1 <= kBmThetaHeads) {
+        // ---- many ranges, few heads per range.  theta = the (H+1)-th largest of the warp's 32 per-lane maxima: H+1
+        // distinct rows reach it, so the warp's H+1 best rows are among the rows >= theta (H+1 and a few)
+        uint32_t theta = 0u;
+        {
+            uint32_t mc = m;
+            for (int h = 0; h <= H; ++h) {
+                theta = __reduce_max_sync(0xffffffffu, mc);
+                if (theta == 0u) break;
+                const unsigned who = __ballot_sync(0xffffffffu, mc == theta);
+                if (lane == __ffs(who) - 1) mc = 0u;
+            }
         }
-        int myj = kBmSeg / 32;
+        if (theta < 1u) theta = 1u;
+        uint32_t mask = 0u;
 #pragma unroll
-        for (int j = kBmSeg / 32 - 1; j >= 0; --j)
-            if (v[j] == wm) myj = j;
-        const uint32_t myrow = (m == wm) ? (uint32_t)(myj * 32 + lane) : 0xFFFFFFFFu;
-        const uint32_t wr = __reduce_min_sync(0xffffffffu, myrow);
-        if (myrow == wr) {
-#pragma unroll
-            for (int j = 0; j < kBmSeg / 32; ++j)
-                if (j == myj) v[j] = 0u;
+        for (int j = 0; j < 16; ++j) mask |= v[j] >= theta ? (1u << j) : 0u;
+        if (mask) {
+            int slot = atomicAdd(&s_nlist, __popc(mask));
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const uint32_t loc = (uint32_t)((j >> 2) << 10) + (uint32_t)(j & 3);
+                const uint32_t u = acc[loc + 4 * tid];
+                if (slot < kBmList) s_list[slot] = ((unsigned long long)u << 32) | (unsigned long long)(~(row_base + loc));
+                ++slot;
+            }
         }
-        if (lane == 0)
-            s_heads[warp][h] = ((unsigned long long)wm << 32) | (unsigned long long)(~(uint32_t)(r0 + warp * kBmSeg + wr));
+    } else {
+        // ---- few ranges, many heads per range: the warp's exact H+1 best, one per round (ties: lowest row)
+        for (int h = 0; h <= H; ++h) {
+            uint32_t mm = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mm = v[j] > mm ? v[j] : mm;
+            const uint32_t wm = __reduce_max_sync(0xffffffffu, mm);
+            if (wm == 0u) break;
+            int myj = 16;
+#pragma unroll
+            for (int j = 15; j >= 0; --j)
+                if (v[j] == wm) myj = j;
+            const uint32_t myloc = (uint32_t)((myj >> 2) << 10) + (uint32_t)(myj & 3);
+            const uint32_t myrow = mm == wm ? row_base + myloc : 0xFFFFFFFFu;
+            const uint32_t wr = __reduce_min_sync(0xffffffffu, myrow);
+            if (myrow == wr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j == myj) v[j] = 0u;
+                const int slot = atomicAdd(&s_nlist, 1);
+                if (slot < kBmList) s_list[slot] = ((unsigned long long)wm << 32) | (unsigned long long)(~wr);
+            }
+        }
     }
     __syncthreads();
-    if (warp == 0) {                     // the range's H+1 best among the 8 * (H+1) warp heads
-        const int n_e = kBmWarps * (H + 1);                 // <= 256
-        unsigned long long mine[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int e = lane + 32 * u;
-            mine[u] = e < n_e ? s_heads[e / (H + 1)][e % (H + 1)] : 0ull;
-        }
+    if (warp == 0) {
+        const int n_e = s_nlist;
         unsigned long long* dst = heads + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (H + 1);
-        for (int h = 0; h <= H; ++h) {
-            unsigned long long m = 0ull;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) m = mine[u] > m ? mine[u] : m;
-            const uint32_t whi = __reduce_max_sync(0xffffffffu, (uint32_t)(m >> 32));
-            const uint32_t wlo = __reduce_max_sync(0xffffffffu, (uint32_t)(m >> 32) == whi ? (uint32_t)m : 0u);
-            const unsigned long long top = ((unsigned long long)whi << 32) | wlo;
-            if (whi == 0u) {
-                if (lane == 0)
-                    for (int hh = h; hh <= H; ++hh) dst[hh] = 0ull;
-                break;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (mine[u] == top) mine[u] = 0ull;         // rows are distinct: exactly one entry
-            if (lane == 0) dst[h] = top;
+        if (n_e > kBmList) {                                 // mass ties inside the range: rho = "anything": redo
+            for (int hh = lane; hh <= H; hh += 32) dst[hh] = ~0ull;
+        } else if (n_e <= 64) {
+            bm25_emit_heads<2>(s_list, n_e, H, lane, dst);
+        } else {
+            bm25_emit_heads<8>(s_list, n_e, H, lane, dst);
         }
     }
 }
@@ -515,7 +561,7 @@ __device__ __forceinline__ double bm25_term_contrib(const Bm25Device& ix, int32_
     if (ix.term_info) {
         const int2 info = ix.term_info[t];
         const int cls = (int)((unsigned)info.x >> 30);
-        if (cls == kBmMid || cls == kBmHigh) {             // the range table narrows the search to the row's range
+        if (cls == kBmMid || cls == kBmDense) {            // the range table narrows the search to the row's range
             const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_ranges + 1) + (row >> 12);
             hi = lo + ro[1];
             lo = lo + ro[0];
@@ -598,20 +644,27 @@ bm25_finish_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int
     double* contrib = reinterpret_cast<double*>(sm_raw);
     Bm25Key* keys = reinterpret_cast<Bm25Key*>(sm_raw + (size_t)kBmContrib * sizeof(double));
     uint32_t* surv = reinterpret_cast<uint32_t*>(keys + kBmSurvivors);
-    __shared__ int s_n, s_flag;
+    __shared__ int s_n, s_flag, s_extra;
     const int q = blockIdx.x;
     const int n_ranges = ix.n_ranges;
     const unsigned long long* hq = heads + (size_t)q * n_ranges * (H + 1);
     const int32_t* terms = q_terms + q_ptr[q0 + q];
     const int nt = q_ptr[q0 + q + 1] - q_ptr[q0 + q];
-    if (threadIdx.x == 0) { s_n = 0; s_flag = 0; }
+    if (threadIdx.x == 0) { s_n = 0; s_flag = 0; s_extra = 0; }
     // tau: the k-th largest of the first h_tau heads of every range (distinct rows), minus the slack
     const int n_tau = n_ranges * h_tau;
     for (int e = threadIdx.x; e < nsort_tau; e += blockDim.x)
         sbuf[e] = e < n_tau ? hq[(size_t)(e / h_tau) * (H + 1) + (e % h_tau)] : 0ull;
     block_bitonic_desc(sbuf, nsort_tau);
     const uint32_t tau_u = k <= n_tau ? (uint32_t)(sbuf[k - 1] >> 32) : 0u;
-    const uint32_t slack = 2u * (uint32_t)nt + 2u;          // U - 2 per contributing token <= score / unit <= U
+    // U - slack <= score / unit <= U: a packed posting is at most 2 units above its product, a column entry at
+    // most 2 + 15 (tokens beyond kBmMaxQueryTokens: the query is redone on the robust path anyway)
+    for (int i = threadIdx.x; i < nt && i < kBmMaxQueryTokens; i += blockDim.x) {
+        const int32_t t = terms[i];
+        if (t >= 0 && t < ix.n_terms && (int)((unsigned)ix.term_info[t].x >> 30) == kBmDense) atomicAdd(&s_extra, 1);
+    }
+    __syncthreads();
+    const uint32_t slack = 2u * (uint32_t)nt + (uint32_t)((1 << kBmDenseShift) - 1) * (uint32_t)s_extra + 2u;
     uint32_t thr = tau_u > slack ? tau_u - slack : 0u;
     if (thr < 1u) thr = 1u;                                  // no bound: every row with a positive upper bound
     __syncthreads();
@@ -705,25 +758,19 @@ __global__ void bm25_rng_kernel(Bm25Device ix, const int32_t* __restrict__ table
     }
 }
 
-__global__ void bm25_seg_kernel(Bm25Device ix, const int32_t* __restrict__ high_terms, int n_high) {
-    const int64_t total = (int64_t)n_high * ix.n_ranges * 8;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int s = (int)(e & 7);
-        const int r = (int)((e >> 3) % ix.n_ranges);
-        const int hs = (int)((e >> 3) / ix.n_ranges);
-        uint16_t v = 0;
-        if (s < 7) {
-            const int32_t t = high_terms[hs];
-            const int32_t* ro = ix.rng_off + (size_t)(ix.term_info[t].x & 0x3FFFFFFF) * (ix.n_ranges + 1) + r;
-            const int64_t lo = ix.term_ptr[t] + ro[0], hi = ix.term_ptr[t] + ro[1];
-            v = (uint16_t)(bm25_lower_bound(ix.post_row, lo, hi, (int64_t)r * kBmRange + (int64_t)kBmSeg * (s + 1)) - lo);
-        }
-        ix.seg_off[e] = v;
+// column of a DENSE term: entry (row) = ceil(q / 16) of the term's posting on that row (columns zeroed by the caller)
+__global__ void bm25_column_kernel(Bm25Device ix, const int32_t* __restrict__ dense_terms) {
+    const int32_t t = dense_terms[blockIdx.y];
+    const int64_t lo = ix.term_ptr[t], hi = ix.term_ptr[t + 1];
+    uint16_t* col = ix.dense_col + (size_t)blockIdx.y * ((size_t)ix.n_ranges * kBmRange);
+    for (int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t q = ix.post_pack[p] & 0xFFFFFu;
+        col[ix.post_row[p]] = (uint16_t)((q + ((1u << kBmDenseShift) - 1u)) >> kBmDenseShift);
     }
 }
 
 cudaError_t bm25_index_build_launch(const Bm25Device& ix, double unit, const int32_t* tabled_terms, int n_tabled,
-                                    const int32_t* high_terms, int n_high, cudaStream_t st) {
+                                    const int32_t* dense_terms, int n_dense, cudaStream_t st) {
     auto grid_for = [](int64_t n) {
         int64_t g = (n + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
@@ -739,8 +786,9 @@ cudaError_t bm25_index_build_launch(const Bm25Device& ix, double unit, const int
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    if (n_high > 0) {
-        bm25_seg_kernel<<<grid_for((int64_t)n_high * ix.n_ranges * 8), 256, 0, st>>>(ix, high_terms, n_high);
+    if (n_dense > 0) {
+        dim3 grid(148, n_dense);
+        bm25_column_kernel<<<grid, 256, 0, st>>>(ix, dense_terms);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -196,24 +196,26 @@ struct Bm25Device {
     double* score;          // n_docs accumulator, all-zero between queries (rag_bm25_scores)
     // ---- filter index of the fast path (built by bm25_index_build) ----
     uint32_t* post_pack;    // nnz + 4: (row & 4095) << 20 | q, q = idf*impact in units of `unit`, rounded up (+1)
-    int2* term_info;        // n_terms: x = class << 30 | slot (rng_off row), y = hslot (seg_off row)
+    int2* term_info;        // n_terms: x = class << 30 | slot (rng_off row), y = column (dense_col) of a DENSE term
     int32_t* rng_off;       // n_tabled x (n_ranges + 1): first posting with row >= r * 4096, relative to term_ptr[t]
-    uint16_t* seg_off;      // n_high x n_ranges x 8: start of the 512-row segments 1..7 inside the range run
+    uint16_t* dense_col;    // n_dense x (n_ranges * 4096): ceil(q / 16) of the term's posting on that row, 0 = no posting
     int n_ranges;
     int fast_ok;            // 1: all idf >= 0 and the packed stream exists -> the integer filter bound is valid
 };
 // term classes (term_info.x >> 30)
-constexpr int kBmLow = 0;    // short list: no table, the range run is found by a warp-cooperative search
-constexpr int kBmMid = 1;    // rng_off row: runs are short, accumulated with shared-memory atomics
-constexpr int kBmHigh = 2;   // rng_off + seg_off rows: long runs, every warp owns the postings of its 512 rows
+constexpr int kBmLow = 0;    // short list, no table: every CTA scans the whole list and keeps the rows of its range
+constexpr int kBmMid = 1;    // rng_off row gives the run of the CTA's range inside the packed stream
+constexpr int kBmDense = 2;  // rng_off row (exact recompute) + a dense 16-bit column: coalesced, accumulated in registers
 constexpr int kBmSkip = 3;   // idf == 0 or empty list: contributes nothing
+constexpr int kBmDenseShift = 4;     // a column entry is ceil(q / 2^4): 16 bits, at most 15 + 2 units above the product
 cudaError_t bm25_impact_launch(const int32_t* post_row, const int32_t* post_tf, const int32_t* doc_len, int64_t nnz,
                                double avgdl, double k1, double b, double* impact, cudaStream_t st);
 // max over the postings of idf[t] * impact[p] (atomicMax on the bits of a positive double; *cmax zeroed by the caller)
 cudaError_t bm25_cmax_launch(const Bm25Device& ix, unsigned long long* cmax, cudaStream_t st);
-// packed stream + range / segment tables (tabled_terms: MID and HIGH terms in slot order, high_terms: in hslot order)
+// packed stream + range tables + dense columns (tabled_terms: MID and DENSE terms in slot order, dense_terms: in
+// column order; the columns must be zeroed by the caller)
 cudaError_t bm25_index_build_launch(const Bm25Device& ix, double unit, const int32_t* tabled_terms, int n_tabled,
-                                    const int32_t* high_terms, int n_high, cudaStream_t st);
+                                    const int32_t* dense_terms, int n_dense, cudaStream_t st);
 // one token of one query: score[row] += w * impact[p] over postings [lo, hi)
 cudaError_t bm25_accumulate_launch(const Bm25Device& ix, int64_t lo, int64_t hi, double w, cudaStream_t st);
 int bm25_harvest_grid(int64_t total_postings, int sm_count);     // grid for the reset pass

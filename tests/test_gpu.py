@@ -122,6 +122,69 @@ def test_dense_near_ties_within_filter_error():
         c.close()
 
 
+@pytest.mark.parametrize("dtype,dim", [("bf16", 1024), ("f16", 1024), ("bf16", 2048), ("f32", 1024), ("bf16", 256)])
+def test_tensor_core_filter_error_stays_inside_the_bound(dtype, dim, record_property):
+    """The margin check is only as sound as eps, the bound on |tensor-core filter score - exact score|
+    (accumulation part: eps_rel * |q| * max|x|).  Adversarial operands, all exactly representable in the 16-bit
+    operand format so that accumulation is the ONLY error: (a) aligned all-positive products (the accumulator is
+    as large as it gets, every truncation goes the same way), (b) alternating-sign pairs inside every K=16 block
+    (the sum cancels to ~0 while sum|products| stays |q||x|), (c) 2^-10..1 dynamic range inside every block with
+    random signs, (d) ordinary unit vectors.  > 1e5 (query, row) pairs per case; the observed max error / bound is
+    recorded and must stay below 1/2."""
+    from b200rag import DeviceCorpus
+    n, B = 4096, 256
+    g = np.random.default_rng(dim + len(dtype))
+    dt = DT[dtype]
+    sig = 8 if dtype != "f16" else 11                 # significand bits of the operand format
+
+    def representable(a):                              # round to `sig` bits, exponents inside fp16's normal range
+        a = np.asarray(a, np.float64)
+        e = np.floor(np.log2(np.maximum(np.abs(a), 2.0 ** -13)))
+        return (np.round(a / 2.0 ** (e - sig + 1)) * 2.0 ** (e - sig + 1)).astype(np.float32)
+
+    mag = representable(2.0 ** g.uniform(-3, 0, size=(n, dim)))
+    cases = {}
+    cases["aligned_positive"] = (mag, representable(mag[g.integers(0, n, B)] * 2.0 ** g.integers(-1, 2, size=(B, 1))))
+    alt = np.where(np.arange(dim) % 2 == 0, 1.0, -1.0).astype(np.float32)
+    xa = mag.copy()
+    xa[:, 1::2] = xa[:, 0::2]                          # pairs of equal magnitude ...
+    cases["alternating_cancel"] = (xa * alt, representable(np.abs(xa[g.integers(0, n, B)]) *
+                                                           (1 + 2.0 ** -6 * g.integers(0, 3, size=(B, dim)))))
+    wide = representable(2.0 ** g.uniform(-10, 0, size=(n, dim)) * g.choice([-1.0, 1.0], size=(n, dim)))
+    cases["wide_range"] = (wide, representable(2.0 ** g.uniform(-10, 0, size=(B, dim)) * g.choice([-1.0, 1.0], size=(B, dim))))
+    cases["unit"] = (representable(helpers.synth_unit(n, dim, seed=5)), representable(helpers.synth_unit(B, dim, seed=6)))
+    worst = 0.0
+    for name, (x, q) in cases.items():
+        c = DeviceCorpus(dim, dtype)
+        c.append(x)
+        stored = c.download()
+        if dtype != "f32":
+            assert np.array_equal(stored, x), name   # representable: stored as given
+        rows, scores, counts = c.topk(q, 10)
+        er, es, ec = c_oracle.dense_topk(q, raw_rows(stored, dt), dt, 10)
+        assert rows.tolist() == er.tolist() and np.array_equal(scores, es), name
+        cr, cs, cc, eps_rel = c.debug_last_candidates(B, 8192)
+        assert (cc >= 0).all(), name
+        # operands of the contraction: the stored rows (their bf16 shadow for an fp32 corpus) and the rounded queries
+        xo = stored if dtype != "f32" else no.quantize(stored, no.DT_BF16)
+        qo = no.quantize(q, no.DT_F16 if dtype == "f16" else no.DT_BF16)
+        assert np.array_equal(qo, q), name
+        exact = qo.astype(np.float64) @ xo.astype(np.float64).T            # fp64: products exact, sum to ~1e-16
+        bound = eps_rel * np.linalg.norm(qo.astype(np.float64), axis=1) * np.linalg.norm(xo.astype(np.float64), axis=1).max()
+        n_pairs, ratio = 0, 0.0
+        for b in range(B):
+            r = cr[b, :cc[b]]
+            err = np.abs(cs[b, :cc[b]].astype(np.float64) - exact[b, r])
+            ratio = max(ratio, float(err.max() / bound[b]) if len(r) else 0.0)
+            n_pairs += len(r)
+        assert n_pairs >= 100_000, (name, n_pairs)
+        record_property(f"{name}_max_error_over_bound", ratio)
+        print(f"[eps] {dtype} dim={dim} {name}: {n_pairs} pairs, max |filter - exact| / bound = {ratio:.4f}")
+        worst = max(worst, ratio)
+        c.close()
+    assert worst <= 0.5, worst
+
+
 def test_dense_edge_cases():
     from b200rag import DeviceCorpus, DeviceCollection, B200RagError
     d = 128
@@ -676,6 +739,61 @@ def test_bm25_mass_ties_and_many_ranges():
             er, es = o.search(qt.tolist(), k)
             assert rows[i, :counts[i]].tolist() == er.tolist() and np.array_equal(scores[i, :counts[i]], es)
     assert rows[0, :10].tolist() == dup[:10].tolist()
+    ix.close()
+
+
+@pytest.mark.parametrize("dense_div", [0, 2, 8, 64, 1 << 20])
+def test_bm25_filter_index_classes_vs_oracle(dense_div):
+    """The integer filter index holds a term three ways (untabled short list scanned whole, range-tabled run of the
+    packed stream, dense 16-bit column): every mix must select exactly the oracle's rows, on the fast path."""
+    from b200rag import _lib
+    from b200rag.bm25 import DeviceBM25, Postings
+    n_docs = 21000                                      # 6 ranges, the last one ragged
+    docs, n_terms = helpers.zipf_docs(n_docs, 3000, seed=77)
+    g = np.random.default_rng(5)
+    # a term present in every row, one clustered in a few rows of one range (a long run of a non-dense term),
+    # and documents that are exact duplicates (ties)
+    docs = [np.concatenate([d, [n_terms]]) for d in docs]
+    for r in range(9000, 9700):
+        docs[r] = np.concatenate([docs[r], [n_terms + 1] * int(g.integers(1, 4))])
+    for r in (100, 4095, 4096, 20999):
+        docs[r] = docs[7].copy()
+    n_terms += 2
+    p = Postings.from_term_ids(docs, n_terms=n_terms)
+    o = no.CsrBM25(docs)
+    _lib.set_option("bm25_dense_div", dense_div)
+    try:
+        ix = DeviceBM25(p)
+    finally:
+        _lib.set_option("bm25_dense_div", 8)
+    df = np.diff(p.term_ptr)
+    by_df = np.argsort(-df)
+    allow = g.random(n_docs) < 0.3
+    bitmap = np.packbits(allow, bitorder="little")
+    queries = []
+    for i in range(24):
+        qt = np.concatenate([by_df[g.integers(0, 12, size=3)], by_df[g.integers(12, 300, size=4)],
+                             g.integers(0, n_terms, size=g.integers(1, 6))]).astype(np.int32)
+        if i % 3 == 0:
+            qt = np.concatenate([qt, [n_terms - 1, n_terms - 2, -1, qt[0]]]).astype(np.int32)
+        queries.append(qt)
+    queries.append(np.array(list(docs[7][:6]) * 2, np.int32))               # the duplicated documents tie at the top
+    queries.append(by_df[:150].astype(np.int32))                            # more tokens than one pass of the kernel holds
+    before = _lib.counters()["fallbacks"]
+    rows, scores, counts = ix.search_ids(queries, 50)
+    assert _lib.counters()["fallbacks"] == before       # nothing of this was redone on the robust path
+    # only the clustered term: hundreds of rows of one range tie exactly -> flagged and redone, still exact
+    queries.append(np.array([n_terms - 1], np.int32))
+    for k in (10, 50):
+        rows, scores, counts = ix.search_ids(queries, k)
+        rows1, scores1, counts1 = ix.search_ids(queries[:1], k)             # single-query call
+        rows_f, scores_f, counts_f = ix.search_ids(queries, k, bitmap)
+        for i, qt in enumerate(queries):
+            er, es = o.search(qt.tolist(), k)
+            assert rows[i, :counts[i]].tolist() == er.tolist() and np.array_equal(scores[i, :counts[i]], es), (k, i)
+            er, es = o.search(qt.tolist(), k, allow)
+            assert rows_f[i, :counts_f[i]].tolist() == er.tolist() and np.array_equal(scores_f[i, :counts_f[i]], es), (k, i)
+        assert rows1[0].tolist() == rows[0].tolist() and np.array_equal(scores1[0], scores[0])
     ix.close()
 
 

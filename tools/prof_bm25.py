@@ -28,5 +28,8 @@ for q in qs[:6]:
 for _ in range(3):
     ix.search_ids(qs, 50)
     print("batch device ms", float(_lib.last_timings()[0]), "per query us", 1e3 * float(_lib.last_timings()[0]) / Q)
+nb, npost = ix.query_bytes(qs)
+print("avg filter bytes per query", float(nb.mean()), "avg postings per query", float(npost.mean()),
+      "GB/s at last batch", float(nb.sum()) / (float(_lib.last_timings()[0]) * 1e-3) / 1e9)
 print("index MB", ix.index_bytes() / 1e6, "bytes/posting", ix.bytes_per_posting())
 print("done")
