@@ -228,6 +228,17 @@ int rag_bm25_info(const rag_bm25_t* ix, int* bytes_per_posting, int64_t* index_b
 int rag_rrf_fuse(const int32_t* ids, const double* weights, int Q, int R, int L, int rrf_k, int top,
                  int32_t* out_ids, double* out_scores, int32_t* out_counts);
 
+/* ---- rerank select: the output step of the cross-encoder reranker -----------
+ * replaces the tail of CrossEncoderReranker.rerank (src/rag/reranker.py:172-211; called at
+ * src/rag/pipeline.py:250-256 right after retrieve_candidates) for Q questions at once. The cross-encoder itself is
+ * model inference and stays outside. scores: Q x L fp32 model scores in candidate order (what CrossEncoder.predict
+ * returns), boosts: Q x L fp64 topic boosts (NULL: none), lens: candidates per question (NULL: L each).
+ * final = (double)score + boost; stable descending order; first top_k; entries below min_score dropped, but at
+ * least 3 are returned when 3 candidates exist (so top_k >= 3 is required). out_idx: Q x top_k positions in the
+ * candidate list (-1 padded), out_scores: their final scores, out_counts: entries per question. L <= 1024. */
+int rag_rerank_select(const float* scores, const double* boosts, const int32_t* lens, int Q, int L, int top_k,
+                      double min_score, int32_t* out_idx, double* out_scores, int32_t* out_counts);
+
 /* ---- host-side index construction (multi-threaded C++, no GPU needed) ----------------------------------
  * replaces the per-document dict building of rank_bm25.BM25Okapi._initialize (rank-bm25 0.2.2; reached from
  * ChunkBM25Index.build_from_collection, src/rag/bm25_index.py:236, and SummaryBM25Index.build, :126):

@@ -9,6 +9,7 @@ Floats are stored as float.hex() strings so comparisons are bit-exact.
 """
 import json
 import os
+import sys
 import random
 
 import numpy as np
@@ -302,6 +303,70 @@ def gen_e2e(ref):
     return {"chunks": chunks, "queries": queries, "expanded": expanded_of, "expansions": expansions, "runs": runs}
 
 
+def rerank_cases():
+    """inputs of the rerank golden (regenerated identically by the tests): (query, chunks as dicts, model score per
+    chunk, top_k, min_score, topics)"""
+    rng = random.Random(23)
+    topics_pool = ["consentement", "cookies", "dpo", "transfert", "sanction", "registre"]
+    cases = []
+    for ci, (n, top_k, min_score, with_topics, mode) in enumerate([
+            (40, 10, 0.08, True, "spread"), (40, 8, 0.08, False, "spread"), (40, 10, 0.08, True, "ties"),
+            (40, 10, 0.5, False, "low"), (2, 8, 0.08, False, "low"), (3, 8, 0.9, True, "low"), (5, 2, 0.08, False, "spread"),
+            (40, 1, 0.99, False, "low"), (1, 8, 0.08, True, "spread"), (25, 40, 0.08, True, "spread"), (0, 8, 0.08, False, "spread")]):
+        chunks = []
+        for j in range(n):
+            tags = ", ".join(rng.sample(topics_pool, rng.randint(0, 3)))
+            meta = {"document_path": f"doc{j % 7}.html", "chunk_nature": "GUIDE", "chunk_index": j, "rgpd_topics": tags}
+            if j % 3 == 0:
+                meta["heading"] = f"Titre {j}"
+            text = (f"c{ci}-{j} " + make_text(rng, rng.randint(5, 60))) if j % 11 else (f"mot{j} " * 900)   # some texts beyond the truncation
+            chunks.append({"chunk_id": f"c{ci}_{j}", "text": text, "document_path": meta["document_path"],
+                           "distance": round(rng.uniform(0.2, 1.2), 4), "metadata": meta})
+        if mode == "spread":
+            sc = [rng.uniform(0.0, 1.0) for _ in range(n)]
+        elif mode == "ties":
+            sc = [rng.choice([0.25, 0.5, 0.75, 0.125]) for _ in range(n)]
+        else:
+            sc = [rng.uniform(0.0, 0.07) for _ in range(n)]
+        cases.append({"query": f"question {ci} sur le consentement", "chunks": chunks, "model_scores": sc, "top_k": top_k,
+                      "min_score": min_score, "topics": rng.sample(topics_pool, 2) if with_topics else None})
+    return cases
+
+
+def gen_rerank(ref):
+    """CrossEncoderReranker.rerank (src/rag/reranker.py:109-227), unmodified, around a table scorer"""
+    import numpy as np
+    mod = ref["reranker"]
+    RC = ref["retriever"].RetrievedChunk
+    out = []
+    for c in rerank_cases():
+        chunks = [RC(chunk_id=d["chunk_id"], text=d["text"], document_path=d["document_path"], chunk_nature="GUIDE",
+                     chunk_index=d["metadata"]["chunk_index"], confidence="high", distance=d["distance"], metadata=d["metadata"])
+                  for d in c["chunks"]]
+        rr = mod.CrossEncoderReranker(min_score=c["min_score"])
+        table = {}
+        for d, s in zip(c["chunks"], c["model_scores"]):
+            text = d["text"]
+            if d["metadata"].get("heading", ""):
+                text = f"{d['metadata']['heading']}\n{text}"
+            table[(c["query"], text[:rr.max_length * 4])] = np.float32(s)
+        scorer = ref_harness.TableScorer(table)
+        rr._model, rr._is_loaded = scorer, True
+        try:
+            got = rr.rerank(c["query"], chunks, top_k=c["top_k"], topic_matcher=ref_harness.TagTopicMatcher(),
+                            question_topics=c["topics"])
+        except IndexError:
+            # fewer than 3 candidates, all below min_score: the reference's closing log line indexes an empty result
+            # (src/rag/reranker.py:221-225) and the call raises
+            out.append({"top_k": c["top_k"], "min_score": c["min_score"], "pairs": scorer.calls[0], "raises": "IndexError"})
+            continue
+        out.append({"top_k": c["top_k"], "min_score": c["min_score"],
+                    "pairs": scorer.calls[0] if scorer.calls else [],
+                    "result": [{"chunk_id": r.chunk_id, "rerank_score": _hex(r.rerank_score), "original_rank": r.original_rank}
+                               for r in got]})
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_harness.load()
@@ -311,6 +376,10 @@ def main():
             json.dump(obj, f, ensure_ascii=False, indent=0)
         print("wrote", name)
 
+    if len(sys.argv) > 1 and sys.argv[1] == "rerank":       # only the rerank golden (added later than the others)
+        dump("rerank.json", gen_rerank(ref))
+        return
+    dump("rerank.json", gen_rerank(ref))
     dump("rrf.json", gen_rrf(ref))
     dump("tokenizer.json", gen_tokenizer(ref))
     dump("bm25_small.json", gen_bm25(ref))

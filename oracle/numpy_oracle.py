@@ -353,6 +353,26 @@ def rrf_fuse(rankings, weights=None, k=60, top=None):
     return ids, [scores[i] for i in ids]
 
 
+# --------------------------------------------------------------------------
+# rerank select: the tail of CrossEncoderReranker.rerank (src/rag/reranker.py:172-211)
+# --------------------------------------------------------------------------
+def rerank_select(scores, boosts, top_k, min_score):
+    """scores: model scores (fp32) in candidate order, boosts: per-candidate topic boost (0.0 = none).
+    Returns (positions in the candidate list, final scores) of what the reference returns."""
+    final = []
+    for s, b in zip(scores, boosts):
+        f = float(np.float32(s))
+        if b > 0:
+            f += float(b)
+        final.append(f)
+    order = list(range(len(final)))
+    order.sort(key=lambda i: final[i], reverse=True)            # stable
+    result = [i for i in order[:top_k] if final[i] >= min_score]
+    if len(result) < 3 and len(order) >= 3:
+        result = order[:3]
+    return result, [final[i] for i in result]
+
+
 def load_json(path):
     with open(path, "r", encoding="utf-8") as f:
         return json.load(f)

@@ -9,6 +9,7 @@ the device classes raise if the library or an sm_100 GPU is missing.
 from ._lib import B200RagError, RAG_BF16, RAG_F16, RAG_F32, RAG_MAX_K, pinned_empty
 from .bm25 import BM25Result, DeviceBM25, DeviceChunkBM25Index, DeviceSummaryBM25Index, Postings
 from .collection import DeviceCollection, DeviceCorpus, distance_from_score, l2_normalize_rows
+from .reranker import DeviceRerankStep, RankedChunk, rerank_select
 from .retriever import HybridRetriever, RetrievedChunk, RetrievedDocument
 from .rrf import fuse_ranked, reciprocal_rank_fusion, rrf_fuse_rows
 from .tokenizer import tokenize_french
@@ -19,4 +20,5 @@ __all__ = [
     "DeviceChunkBM25Index", "DeviceSummaryBM25Index", "DeviceBM25", "Postings", "BM25Result",
     "HybridRetriever", "RetrievedChunk", "RetrievedDocument",
     "reciprocal_rank_fusion", "fuse_ranked", "rrf_fuse_rows", "tokenize_french",
+    "DeviceRerankStep", "RankedChunk", "rerank_select",
 ]

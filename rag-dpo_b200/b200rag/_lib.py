@@ -65,6 +65,7 @@ SYMBOLS = {
     "rag_bm25_search": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "rag_bm25_scores": (_i, [_vp, _vp, _i, _vp]),
     "rag_rrf_fuse": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rag_rerank_select": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp]),
 }
 
 _lib = None

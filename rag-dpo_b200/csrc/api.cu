@@ -1691,4 +1691,44 @@ int rag_rrf_fuse(const int32_t* ids, const double* weights, int Q, int R_, int L
     return RAG_OK;
 }
 
+int rag_rerank_select(const float* scores, const double* boosts, const int32_t* lens, int Q, int L, int top_k,
+                      double min_score, int32_t* out_idx, double* out_scores, int32_t* out_counts) {
+    RAG_TRY(require_init());
+    if (!scores || !out_idx || !out_scores || !out_counts) return fail(RAG_EINVAL, "NULL argument");
+    if (Q <= 0 || L <= 0) return fail(RAG_EINVAL, "sizes must be positive");
+    if (top_k < 3) return fail(RAG_ERANGE, "top_k=%d: the step always returns at least 3 candidates", top_k);
+    if (L > rerank_max_candidates()) return fail(RAG_ERANGE, "L=%d exceeds %d", L, rerank_max_candidates());
+    Ctx* cx = nullptr;
+    RAG_TRY(misc_ctx(&cx));
+    std::lock_guard<std::recursive_mutex> lk(cx->mu);
+    RAG_TRY(cx->use());
+    cudaStream_t st = cx->stream();
+    const size_t sb = (size_t)Q * L * 4, bb = boosts ? (size_t)Q * L * 8 : 0, lb = lens ? (size_t)Q * 4 : 0;
+    const size_t oi = (size_t)Q * top_k * 4, os = (size_t)Q * top_k * 8, oc = (size_t)Q * 4;
+    RAG_TRY(g_rrf_w.ensure(bb + 8));                   // boosts (8-byte aligned first)
+    RAG_TRY(g_rrf_ids.ensure(sb + lb));                // scores | lens
+    RAG_TRY(g_rrf_oi.ensure(oi));
+    RAG_TRY(g_rrf_os.ensure(os));
+    RAG_TRY(g_rrf_oc.ensure(oc));
+    RAG_TRY(cx->ensure_pinned(std::max(bb + sb + lb, oi + os + oc)));
+    uint8_t* pin = reinterpret_cast<uint8_t*>(cx->pinned);
+    if (bb) memcpy(pin, boosts, bb);
+    memcpy(pin + bb, scores, sb);
+    if (lb) memcpy(pin + bb + sb, lens, lb);
+    if (bb) CU_TRY(cudaMemcpyAsync(g_rrf_w.p, pin, bb, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(g_rrf_ids.p, pin + bb, sb + lb, cudaMemcpyHostToDevice, st));
+    CU_TRY(rerank_select_launch(g_rrf_ids.as<float>(), bb ? g_rrf_w.as<double>() : nullptr,
+                                lb ? reinterpret_cast<const int32_t*>(reinterpret_cast<uint8_t*>(g_rrf_ids.p) + sb) : nullptr, Q, L,
+                                top_k, min_score, g_rrf_oi.as<int32_t>(), g_rrf_os.as<double>(), g_rrf_oc.as<int32_t>(), st));
+    ++R.n_launch;
+    CU_TRY(cudaMemcpyAsync(pin, g_rrf_os.p, os, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(pin + os, g_rrf_oi.p, oi, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(pin + os + oi, g_rrf_oc.p, oc, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    memcpy(out_scores, pin, os);
+    memcpy(out_idx, pin + os, oi);
+    memcpy(out_counts, pin + os + oi, oc);
+    return RAG_OK;
+}
+
 }  // extern "C"

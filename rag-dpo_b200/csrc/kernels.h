@@ -244,4 +244,9 @@ int rrf_max_entries();
 cudaError_t rrf_launch(const int32_t* ids, const double* weights, int Q, int R, int L, int rrf_k, int top,
                        int32_t* out_ids, double* out_scores, int32_t* out_counts, cudaStream_t st);
 
+int rerank_max_candidates();
+cudaError_t rerank_select_launch(const float* scores, const double* boosts, const int32_t* lens, int Q, int L, int top_k,
+                                 double min_score, int32_t* out_idx, double* out_scores, int32_t* out_counts,
+                                 cudaStream_t st);
+
 }  // namespace b200rag

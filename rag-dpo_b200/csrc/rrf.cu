@@ -82,6 +82,67 @@ rrf_kernel(const int32_t* __restrict__ ids, const double* __restrict__ weights, 
     if (threadIdx.x == 0) out_counts[q] = nout;
 }
 
+// ---------------------------------------------------------------------------
+// Rerank select: the output step of CrossEncoderReranker.rerank (src/rag/reranker.py:172-211) for a batch of
+// questions.  final = float(score) + topic boost (fp64 add), STABLE descending order (list.sort(reverse=True) keeps
+// the original order of equal scores), cut to top_k, drop entries below min_score, but never return fewer than 3
+// when at least 3 candidates exist.  One CTA per question, L <= 1024 candidates in shared memory.
+// ---------------------------------------------------------------------------
+constexpr int kRerankMax = 1024;
+
+__global__ void __launch_bounds__(256)
+rerank_select_kernel(const float* __restrict__ scores, const double* __restrict__ boosts, const int32_t* __restrict__ lens,
+                     int L, int top_k, double min_score, int32_t* __restrict__ out_idx, double* __restrict__ out_scores,
+                     int32_t* __restrict__ out_counts) {
+    __shared__ double s_final[kRerankMax];
+    __shared__ int s_kept;
+    const int q = blockIdx.x;
+    const int n = lens ? (lens[q] < L ? lens[q] : L) : L;
+    if (threadIdx.x == 0) s_kept = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double sc = (double)scores[(size_t)q * L + i];
+        s_final[i] = boosts ? __dadd_rn(sc, boosts[(size_t)q * L + i]) : sc;
+    }
+    __syncthreads();
+    const int cut = top_k < n ? top_k : n;
+    int local = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double sc = s_final[i];
+        int pos = 0;
+        for (int j = 0; j < n; ++j) {
+            const double o = s_final[j];
+            pos += (o > sc) || (o == sc && j < i);
+        }
+        if (pos < cut) {
+            out_idx[(size_t)q * top_k + pos] = i;
+            out_scores[(size_t)q * top_k + pos] = sc;
+            local += sc >= min_score;
+        }
+    }
+    if (local) atomicAdd(&s_kept, local);
+    __syncthreads();
+    // the entries >= min_score of a descending list are a prefix; fewer than 3 of them: the first 3 ranked instead
+    int kept = s_kept;
+    if (kept < 3 && n >= 3) kept = 3 < cut ? 3 : cut;
+    // (top_k < 3: the reference's ranked[:3] would return 3; the output holds top_k slots, so such calls are refused
+    // by the entry point)
+    __syncthreads();
+    for (int i = kept + threadIdx.x; i < top_k; i += blockDim.x) {
+        out_idx[(size_t)q * top_k + i] = -1;
+        out_scores[(size_t)q * top_k + i] = 0.0;
+    }
+    if (threadIdx.x == 0) out_counts[q] = kept;
+}
+
+int rerank_max_candidates() { return kRerankMax; }
+
+cudaError_t rerank_select_launch(const float* scores, const double* boosts, const int32_t* lens, int Q, int L, int top_k,
+                                 double min_score, int32_t* out_idx, double* out_scores, int32_t* out_counts,
+                                 cudaStream_t st) {
+    rerank_select_kernel<<<Q, 256, 0, st>>>(scores, boosts, lens, L, top_k, min_score, out_idx, out_scores, out_counts);
+    return cudaGetLastError();
+}
+
 int rrf_max_entries() { return kRrfMaxEntries; }
 
 cudaError_t rrf_launch(const int32_t* ids, const double* weights, int Q, int R, int L, int rrf_k, int top,

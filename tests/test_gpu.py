@@ -1225,3 +1225,68 @@ def test_batch_front_end_after_collection_mutation(e2e_data, golden_dir):
             assert [helpers.chunk_dump(c) for c in a] == [helpers.chunk_dump(c) for c in b]
             if not stale:
                 assert not set(c.chunk_id for c in a) & set(victims)
+
+
+# ------------------------------------------------------------- rerank ----
+def test_rerank_step_golden_from_reference_and_batched_vs_oracle():
+    """DeviceRerankStep.rerank == the reference's CrossEncoderReranker.rerank (golden: its own code around a table
+    scorer): same pairs handed to the scorer, same chunks, final scores bit-equal, same error on the empty result;
+    rerank_batch == question by question; random batches of the select kernel == the oracle restatement."""
+    from b200rag import DeviceRerankStep, RetrievedChunk, rerank_select
+    from oracle import gen_golden, ref_harness
+    cases = gen_golden.rerank_cases()
+    gold = load_golden("rerank.json")
+    tm = ref_harness.TagTopicMatcher()
+
+    def build(c):
+        chunks = [RetrievedChunk(chunk_id=d["chunk_id"], text=d["text"], document_path=d["document_path"], chunk_nature="GUIDE",
+                                 chunk_index=d["metadata"]["chunk_index"], confidence="high", distance=d["distance"],
+                                 metadata=d["metadata"]) for d in c["chunks"]]
+        table = {}
+        for d, s in zip(c["chunks"], c["model_scores"]):
+            text = d["text"]
+            if d["metadata"].get("heading", ""):
+                text = f"{d['metadata']['heading']}\n{text}"
+            table[(c["query"], text[:512 * 4])] = np.float32(s)
+        return chunks, table
+
+    for c, g in zip(cases, gold):
+        chunks, table = build(c)
+        scorer = ref_harness.TableScorer(table)
+        step = DeviceRerankStep(scorer, min_score=c["min_score"])
+        if "raises" in g:
+            with pytest.raises(IndexError):
+                step.rerank(c["query"], chunks, top_k=c["top_k"], topic_matcher=tm, question_topics=c["topics"])
+            continue
+        got = step.rerank(c["query"], chunks, top_k=c["top_k"], topic_matcher=tm, question_topics=c["topics"])
+        assert (scorer.calls[0] if scorer.calls else []) == g["pairs"]
+        assert [(r.chunk_id, float(r.rerank_score).hex(), r.original_rank) for r in got] == \
+            [(r["chunk_id"], r["rerank_score"], r["original_rank"]) for r in g["result"]]
+    # all questions with the same top_k / min_score in one call
+    same = [(c, g) for c, g in zip(cases, gold) if c["top_k"] == 10 and c["min_score"] == 0.08 and "raises" not in g]
+    assert len(same) >= 2
+    table = {}
+    lists = []
+    for c, _ in same:
+        chunks, t = build(c)
+        table.update(t)
+        lists.append(chunks)
+    scorer = ref_harness.TableScorer(table)
+    step = DeviceRerankStep(scorer, min_score=0.08)
+    out = step.rerank_batch([c["query"] for c, _ in same], lists, top_k=10, topic_matcher=tm,
+                            question_topics_list=[c["topics"] for c, _ in same])
+    assert len(scorer.calls) == 1                       # ONE scorer call for the whole batch
+    for res, (_, g) in zip(out, same):
+        assert [(r.chunk_id, float(r.rerank_score).hex()) for r in res] == [(r["chunk_id"], r["rerank_score"]) for r in g["result"]]
+    # the kernel against the oracle: ragged lengths, ties, boosts, thresholds
+    rng = np.random.default_rng(9)
+    Q, L = 200, 64
+    sc = rng.choice(np.linspace(0, 1, 23), size=(Q, L)).astype(np.float32)
+    bo = np.where(rng.random((Q, L)) < 0.2, rng.choice([0.15, 0.05, 0.1], size=(Q, L)), 0.0)
+    lens = rng.integers(0, L + 1, size=Q).astype(np.int32)
+    for top_k, ms in ((8, 0.08), (10, 0.6), (40, 0.3), (3, 2.0)):
+        idx, final, counts = rerank_select(sc, bo, lens, top_k, ms)
+        for q in range(Q):
+            ei, ef = no.rerank_select(sc[q, :lens[q]], bo[q, :lens[q]], top_k, ms)
+            assert idx[q, :counts[q]].tolist() == ei and np.array_equal(final[q, :counts[q]], np.array(ef)), (top_k, q)
+            assert (idx[q, counts[q]:] == -1).all()

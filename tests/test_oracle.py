@@ -202,3 +202,22 @@ def test_restated_hnsw_index_recall_against_exact_search():
         assert (np.diff(dist[i]) >= 0).all()
         np.testing.assert_allclose(dist[i], 1.0 - (x[ids[i]] @ q[i]), atol=2e-6)
     ix.close()
+
+
+def test_rerank_select_golden_from_reference():
+    """oracle restatement of the rerank tail == the reference's CrossEncoderReranker.rerank around a table scorer"""
+    from oracle import gen_golden, ref_harness
+    cases = gen_golden.rerank_cases()
+    gold = load_golden("rerank.json")
+    assert len(cases) == len(gold)
+    tm = ref_harness.TagTopicMatcher()
+    for c, g in zip(cases, gold):
+        boosts = [tm.topic_boost(c["topics"], d["metadata"].get("rgpd_topics", "")) if c["topics"] else 0.0
+                  for d in c["chunks"]]
+        idx, final = no.rerank_select(c["model_scores"], boosts, c["top_k"], c["min_score"])
+        if "raises" in g:
+            assert idx == []
+            continue
+        assert [c["chunks"][i]["chunk_id"] for i in idx] == [r["chunk_id"] for r in g["result"]]
+        assert [float(f).hex() for f in final] == [r["rerank_score"] for r in g["result"]]
+        assert idx == [r["original_rank"] for r in g["result"]]
