@@ -2,6 +2,8 @@
 // fp64 impacts + the packed filter index of the fast path), search (single GPU and sharded over the GPUs of one
 // process) and the full score vector.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "api_common.h"
 
@@ -305,12 +307,13 @@ int shard_search_launch(Bm25Shard& s, const int32_t* q_terms, const int32_t* q_p
                                 s.rows.as<int32_t>(), s.scores.as<double>(), s.counts.as<int32_t>(), st));
         ++R.n_launch;
     } else if (plan.fast) {
-        for (int q0 = 0; q0 < Q; q0 += 32768) {            // gridDim.y limit
-            const int nq = std::min(32768, Q - q0);
-            RAG_TRY(s.scratch.ensure(bm25_fast_scratch_bytes(d, k, nq)));
-            CU_TRY(bm25_fast_launch(d, s.terms.as<int32_t>(), s.qptr.as<int32_t>(), q0, nq, plan.allow_dev, k, s.scratch.p,
+        const int chunk = bm25_fast_chunk(d, max_tokens);  // scratch budget / gridDim.y limit
+        for (int q0 = 0; q0 < Q; q0 += chunk) {
+            const int nq = std::min(chunk, Q - q0);
+            RAG_TRY(s.scratch.ensure(bm25_fast_scratch_bytes(d, k, nq, max_tokens)));
+            CU_TRY(bm25_fast_launch(d, s.terms.as<int32_t>(), s.qptr.as<int32_t>(), q0, nq, max_tokens, plan.allow_dev, k, s.scratch.p,
                                     s.rows.as<int32_t>(), s.scores.as<double>(), s.counts.as<int32_t>(), st));
-            R.n_launch += 2;
+            R.n_launch += 3;
         }
     } else {
         RAG_TRY(s.cand.ensure((size_t)Q * plan.n_lists * plan.kp * bm25_key_bytes()));
@@ -331,6 +334,11 @@ int shard_search_redo(Bm25Shard& s, int Q, int k, const SearchPlan& plan, int32_
     for (int q = 0; q < Q; ++q)
         if (h_counts[q] < 0) redo.push_back(q);
     if (redo.empty()) return RAG_OK;
+    if (getenv("B200RAG_DEBUG")) {
+        fprintf(stderr, "[b200rag] bm25: %zu of %d queries redone on the exact range path:", redo.size(), Q);
+        for (size_t i = 0; i < redo.size() && i < 16; ++i) fprintf(stderr, " %d", redo[i]);
+        fprintf(stderr, "\n");
+    }
     RAG_TRY(s.cx.use());
     cudaStream_t st = s.cx.stream();
     ++R.n_fallback;

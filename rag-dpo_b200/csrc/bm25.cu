@@ -306,7 +306,7 @@ constexpr int kBmList = 256;          // rows a CTA's warps hand to the final se
 constexpr int kBmSurvivors = 1024;    // survivors per query the finish kernel re-scores
 constexpr int kBmContrib = 4096;      // (survivor, token) products staged at a time
 constexpr int kBmMaxQueryTokens = 1024;
-constexpr int kBmSpGroup = 4;         // run tokens whose first loads are in flight together
+constexpr int kBmSpGroup = 8;         // run tokens whose first loads are in flight together
 constexpr int kBmDnGroup = 2;         // column tokens whose loads are in flight together
 constexpr int kBmThetaHeads = 12;     // up to this many heads (+ rho) per range the warps select by threshold
 
@@ -339,9 +339,44 @@ __device__ __forceinline__ void bm25_emit_heads(const unsigned long long* s_list
     }
 }
 
+// One record per (query, range, token slot), written by bm25_resolve_kernel so that a range CTA starts with everything
+// it needs in ONE load per thread instead of walking q_ptr -> terms -> term_info -> term_ptr -> rng_off itself (five
+// dependent round trips per CTA; here they are paid by a flat, fully parallel kernel): x = class, and
+//   DENSE: y = column;   MID: [y, z) = the term's run inside this range;   LOW: [y, z) = the term's whole list.
+// Slots past the query's last token are kBmSkip.
+__global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
+                                    int q0, int Q, int stride, uint4* __restrict__ rec) {
+    const int64_t per_q = (int64_t)ix.n_ranges * stride;
+    const int64_t total = (int64_t)Q * per_q;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(e / per_q);
+        const int rem = (int)(e - (int64_t)q * per_q);
+        const int rg = rem / stride, i = rem - rg * stride;
+        const int lo = q_ptr[q0 + q], nt = q_ptr[q0 + q + 1] - lo;
+        uint4 d = make_uint4((uint32_t)kBmSkip, 0u, 0u, 0u);
+        if (i < nt) {
+            const int32_t t = q_terms[lo + i];
+            if (t >= 0 && t < ix.n_terms) {
+                const int2 info = ix.term_info[t];
+                const int cls = (int)((unsigned)info.x >> 30);
+                if (cls == kBmDense) {
+                    d = make_uint4((uint32_t)cls, (uint32_t)info.y, 0u, 0u);
+                } else if (cls == kBmMid) {
+                    const uint32_t base = (uint32_t)ix.term_ptr[t];
+                    const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_ranges + 1) + rg;
+                    d = make_uint4((uint32_t)cls, base + (uint32_t)ro[0], base + (uint32_t)ro[1], 0u);
+                } else if (cls == kBmLow) {
+                    d = make_uint4((uint32_t)cls, (uint32_t)ix.term_ptr[t], (uint32_t)ix.term_ptr[t + 1], 0u);
+                }
+            }
+        }
+        rec[e] = d;
+    }
+}
+
 __global__ void __launch_bounds__(kBmThreads, 4)
-bm25_filter_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr, int q0,
-                   const uint8_t* __restrict__ allow, int H, unsigned long long* __restrict__ heads) {
+bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, const uint8_t* __restrict__ allow, int H,
+                   unsigned long long* __restrict__ heads) {
     __shared__ __align__(16) uint32_t acc[kBmRange];
     __shared__ uint2 s_runs[kBmMaxTokens];            // [lo, hi) inside the packed stream: tabled runs from the front,
     __shared__ const uint16_t* s_colp[kBmMaxTokens];  // scanned lists from the back; column of the range per DENSE token
@@ -349,47 +384,60 @@ bm25_filter_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int
     __shared__ unsigned long long s_list[kBmList];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rg = blockIdx.x;
-    const int qi = q0 + blockIdx.y;
     const int64_t r0 = (int64_t)rg * kBmRange;
     const int64_t r1 = r0 + kBmRange < ix.n_docs ? r0 + kBmRange : ix.n_docs;
-    const int32_t* terms = q_terms + q_ptr[qi];
-    const int nt = q_ptr[qi + 1] - q_ptr[qi];
+    const uint4* my_rec = rec + ((size_t)blockIdx.y * gridDim.x + rg) * stride;
     // a thread owns the local rows g * 1024 + 4 * tid + i (g, i = 0..3): 8-byte column loads and 16-byte shared
     // accesses that are contiguous over the warp.  A column word holds two rows: s_all adds the words whole
     // (sum of the low halves + 65536 * sum of the high halves, modulo 2^32), s_hi the high halves.
     uint32_t s_all[8], s_hi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+    for (int t0 = 0; t0 < stride; t0 += kBmMaxTokens) {
+        const int tn = stride - t0 < kBmMaxTokens ? stride - t0 : kBmMaxTokens;
+        uint4 d = make_uint4((uint32_t)kBmSkip, 0u, 0u, 0u);
+        if (tid < tn) d = __ldg(my_rec + t0 + tid);
+        if (t0 == 0) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(&acc[g * 1024 + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0) s_nlist = 0;
-    for (int t0 = 0; t0 < nt; t0 += kBmMaxTokens) {
-        const int tn = nt - t0 < kBmMaxTokens ? nt - t0 : kBmMaxTokens;
-        __syncthreads();                  // accumulators zeroed / previous pass done with the token table
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(&acc[g * 1024 + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
+            if (tid == 0) s_nlist = 0;
+        } else {
+            __syncthreads();              // previous pass done with the token table
+        }
         if (tid == 0) { s_ntab = 0; s_nscan = 0; s_ncol = 0; }
         __syncthreads();
-        // ---- resolve the tokens: all lookups of all tokens are in flight together
-        if (tid < tn) {
-            const int32_t t = terms[t0 + tid];
-            if (t >= 0 && t < ix.n_terms) {
-                const int2 info = ix.term_info[t];
-                const int cls = (int)((unsigned)info.x >> 30);
-                if (cls == kBmDense) {
-                    s_colp[atomicAdd(&s_ncol, 1)] =
-                        ix.dense_col + ((size_t)info.y * ix.n_ranges + rg) * kBmRange;
-                } else if (cls == kBmMid) {
-                    const uint32_t base = (uint32_t)ix.term_ptr[t];
-                    const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_ranges + 1) + rg;
-                    const uint32_t lo = base + (uint32_t)ro[0], hi = base + (uint32_t)ro[1];
-                    if (hi > lo) s_runs[atomicAdd(&s_ntab, 1)] = make_uint2(lo, hi);
-                } else if (cls == kBmLow) {
-                    const uint32_t lo = (uint32_t)ix.term_ptr[t], hi = (uint32_t)ix.term_ptr[t + 1];
-                    if (hi > lo) s_runs[kBmMaxTokens - 1 - atomicAdd(&s_nscan, 1)] = make_uint2(lo, hi);
-                }
-            }
+        if (d.x == (uint32_t)kBmDense) {
+            s_colp[atomicAdd(&s_ncol, 1)] = ix.dense_col + ((size_t)d.y * ix.n_ranges + rg) * kBmRange;
+        } else if (d.x == (uint32_t)kBmMid) {
+            if (d.z > d.y) s_runs[atomicAdd(&s_ntab, 1)] = make_uint2(d.y, d.z);
+        } else if (d.x == (uint32_t)kBmLow) {
+            if (d.z > d.y) s_runs[kBmMaxTokens - 1 - atomicAdd(&s_nscan, 1)] = make_uint2(d.y, d.z);
         }
         __syncthreads();
-        const int n_tab = s_ntab, n_run = n_tab + s_nscan, n_col = s_ncol;
+        const int n_col = s_ncol, n_tab = s_ntab, n_run = n_tab + s_nscan;
+        // thread i's posting of each run of a group (0: nothing — a posting's q is >= 2).  An untabled list is
+        // scanned whole: only the rows of this range count.
+        uint32_t pk[kBmSpGroup];
+        auto load_group = [&](int e0) {
+#pragma unroll
+            for (int u = 0; u < kBmSpGroup; ++u) {
+                pk[u] = 0u;
+                const int e = e0 + u;
+                if (e < n_run) {
+                    const bool scan = e >= n_tab;            // block-uniform
+                    const uint2 r = s_runs[scan ? kBmMaxTokens - 1 - (e - n_tab) : e];
+                    const uint32_t p = r.x + (uint32_t)tid;
+                    if (p < r.y) {
+                        pk[u] = __ldg(ix.post_pack + p);
+                        if (scan) {
+                            const int64_t row = ix.post_row[p];
+                            if (row < r0 || row >= r1) pk[u] = 0u;
+                        }
+                    }
+                }
+            }
+        };
+        load_group(0);                    // in flight while the column tokens are added
         // ---- column tokens: 4 x 8 bytes per thread and token, straight into registers
         for (int e0 = 0; e0 < n_col; e0 += kBmDnGroup) {
             uint2 x[kBmDnGroup][4];
@@ -415,27 +463,9 @@ bm25_filter_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int
                 }
         }
         // ---- run tokens, one at a time for the whole CTA: thread i adds the i-th posting of the run (the postings of
-        // one term are distinct rows: plain read-modify-write), the barrier separates the terms.  An untabled list
-        // is scanned whole: only the rows of this range count.
+        // one term are distinct rows: plain read-modify-write), the barrier separates the terms
         for (int e0 = 0; e0 < n_run; e0 += kBmSpGroup) {
-            uint32_t pk[kBmSpGroup];
-#pragma unroll
-            for (int u = 0; u < kBmSpGroup; ++u) {
-                pk[u] = 0u;                                  // 0: adds nothing (a posting's q is >= 2)
-                const int e = e0 + u;
-                if (e < n_run) {
-                    const bool scan = e >= n_tab;            // block-uniform
-                    const uint2 r = s_runs[scan ? kBmMaxTokens - 1 - (e - n_tab) : e];
-                    const uint32_t p = r.x + (uint32_t)tid;
-                    if (p < r.y) {
-                        pk[u] = __ldg(ix.post_pack + p);
-                        if (scan) {
-                            const int64_t row = ix.post_row[p];
-                            if (row < r0 || row >= r1) pk[u] = 0u;
-                        }
-                    }
-                }
-            }
+            if (e0 > 0) load_group(e0);
 #pragma unroll
             for (int u = 0; u < kBmSpGroup; ++u) {
                 const int e = e0 + u;
@@ -802,7 +832,17 @@ static int bm25_heads_per_range(int n_ranges, int k) {
     int H = (int)ceil(lambda + 4.0 * sqrt(lambda) + 4.0);
     return H < 4 ? 4 : H;
 }
-static int bm25_tau_heads(int n_ranges, int k) { return (k + n_ranges - 1) / n_ranges; }
+// heads per range that enter the threshold: the k-th largest of n_ranges x h_tau heads (distinct rows) is a lower bound
+// of the k-th best score for any h_tau >= k / n_ranges.  Many ranges: the k-th largest range maximum is tight enough.
+// Few ranges: with k / n_ranges heads the k-th largest sits at the weakest range's last head (a ragged last range
+// drags it far down and every range then holds more than H rows above it), so take about 2k heads in total.
+static int bm25_tau_heads(int n_ranges, int k) {
+    const int need = (k + n_ranges - 1) / n_ranges;
+    if (n_ranges >= 4 * k) return need;
+    const int want = (2 * k + n_ranges - 1) / n_ranges + 2;
+    const int H = bm25_heads_per_range(n_ranges, k);
+    return want < H ? (want > need ? want : need) : (H > need ? H : need);
+}
 
 bool bm25_fast_supported(const Bm25Device& ix, int k, int max_query_tokens) {
     if (!ix.fast_ok || !ix.post_pack || ix.n_ranges < 1) return false;
@@ -810,20 +850,41 @@ bool bm25_fast_supported(const Bm25Device& ix, int k, int max_query_tokens) {
     return H <= kBmMaxH && (int64_t)ix.n_ranges * bm25_tau_heads(ix.n_ranges, k) <= 4096 &&
            max_query_tokens <= kBmMaxQueryTokens;
 }
-size_t bm25_fast_scratch_bytes(const Bm25Device& ix, int k, int Q) {
+static size_t bm25_heads_bytes(const Bm25Device& ix, int k, int Q) {
     const int H = bm25_heads_per_range(ix.n_ranges, k);
-    return (size_t)Q * ix.n_ranges * (H + 1) * sizeof(unsigned long long) + 256;
+    return (((size_t)Q * ix.n_ranges * (H + 1) * sizeof(unsigned long long)) + 255) & ~(size_t)255;
+}
+static int bm25_desc_stride(int max_query_tokens) { return max_query_tokens < 1 ? 1 : max_query_tokens; }
+size_t bm25_fast_scratch_bytes(const Bm25Device& ix, int k, int Q, int max_query_tokens) {
+    return bm25_heads_bytes(ix, k, Q) + (size_t)Q * ix.n_ranges * bm25_desc_stride(max_query_tokens) * sizeof(uint4) + 256;
+}
+// queries per launch: the records of a launch stay within ~256 MB of scratch (and gridDim.y within its limit)
+int bm25_fast_chunk(const Bm25Device& ix, int max_query_tokens) {
+    const size_t per_q = (size_t)ix.n_ranges * bm25_desc_stride(max_query_tokens) * sizeof(uint4);
+    size_t n = ((size_t)256 << 20) / (per_q ? per_q : 1);
+    if (n > 32768) n = 32768;
+    return n < 1 ? 1 : (int)n;
 }
 
 // queries [q0, q0+Q) of the uploaded batch; outputs written at out_* + q0 (counts = -1: redo on the robust path)
 cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int q0, int Q,
-                             const uint8_t* allow, int k, void* scratch, int32_t* out_rows, double* out_scores,
-                             int32_t* out_counts, cudaStream_t st) {
+                             int max_query_tokens, const uint8_t* allow, int k, void* scratch, int32_t* out_rows,
+                             double* out_scores, int32_t* out_counts, cudaStream_t st) {
     const int H = bm25_heads_per_range(ix.n_ranges, k);
     const int h_tau = bm25_tau_heads(ix.n_ranges, k);
+    const int stride = bm25_desc_stride(max_query_tokens);
     unsigned long long* heads = reinterpret_cast<unsigned long long*>(scratch);
+    uint4* desc = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(scratch) + bm25_heads_bytes(ix, k, Q));
+    {
+        const int64_t total = (int64_t)Q * ix.n_ranges * stride;
+        int64_t g = (total + 255) / 256;
+        if (g > 148 * 16) g = 148 * 16;
+        bm25_resolve_kernel<<<(int)g, 256, 0, st>>>(ix, d_q_terms, d_q_ptr, q0, Q, stride, desc);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     dim3 grid_a(ix.n_ranges, Q);
-    bm25_filter_kernel<<<grid_a, kBmThreads, 0, st>>>(ix, d_q_terms, d_q_ptr, q0, allow, H, heads);
+    bm25_filter_kernel<<<grid_a, kBmThreads, 0, st>>>(ix, desc, stride, allow, H, heads);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     int nsort = 32;

@@ -229,10 +229,11 @@ cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, co
 // fast path: integer filter pass over the packed postings (range heads) -> threshold, survivors, exact fp64
 // recompute, final order (counts = -1: redo on the robust path)
 bool bm25_fast_supported(const Bm25Device& ix, int k, int max_query_tokens);
-size_t bm25_fast_scratch_bytes(const Bm25Device& ix, int k, int Q);
+size_t bm25_fast_scratch_bytes(const Bm25Device& ix, int k, int Q, int max_query_tokens);
+int bm25_fast_chunk(const Bm25Device& ix, int max_query_tokens);     // queries per bm25_fast_launch
 cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int q0, int Q,
-                             const uint8_t* allow, int k, void* scratch, int32_t* out_rows, double* out_scores,
-                             int32_t* out_counts, cudaStream_t st);
+                             int max_query_tokens, const uint8_t* allow, int k, void* scratch, int32_t* out_rows,
+                             double* out_scores, int32_t* out_counts, cudaStream_t st);
 // selective row filter: exact scores of the listed rows only (no posting stream at all), top-k
 constexpr int kBm25MaxListedRows = 4096;
 cudaError_t bm25_rows_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int Q,
