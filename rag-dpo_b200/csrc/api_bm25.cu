@@ -61,7 +61,7 @@ int shard_build(Bm25Shard** out, int slot, int64_t n_docs, int64_t n_terms, int6
     d.n_docs = n_docs;
     d.n_terms = n_terms;
     d.nnz = nnz;
-    d.n_ranges = (int)((n_docs + kBm25Range - 1) / kBm25Range);
+    d.n_blocks = (int)((n_docs + kBm25Block - 1) / kBm25Block);
     if (n_docs == 0) nnz = 0;
     s->h_term_ptr.assign(term_ptr, term_ptr + n_terms + 1);
     s->h_idf.assign(idf, idf + n_terms);
@@ -123,13 +123,13 @@ int shard_build(Bm25Shard** out, int slot, int64_t n_docs, int64_t n_terms, int6
     const double cbound = idf_max * max_impact;          // >= idf[t] * impact[p] for every posting (rn is monotone)
     d.fast_ok = 0;
     // (the filter kernel addresses the packed stream with 32-bit offsets)
-    if (nnz > 0 && nnz < 0xFFFF0000LL && d.n_ranges >= 1 && cbound > 0.0 && std::isfinite(cbound)) {
-        // 2^20 - 576: q = ceil(c / unit) + 1 stays inside 20 bits and ceil(q / 16) inside 16
-        const double unit = cbound / 1048000.0;
+    if (nnz > 0 && nnz < 0xFFFF0000LL && d.n_blocks >= 1 && cbound > 0.0 && std::isfinite(cbound)) {
+        // 2^18 - 144: q = ceil(c / unit) + 1 stays inside 18 bits and ceil(q / 4) inside 16
+        const double unit = cbound / 262000.0;
         // term classes by document frequency.  DENSE: df >= n_docs / g_bm25_dense_div, the most frequent first, while
         // the columns (2 bytes x rows each) fit the budget of one more copy of the packed stream.  Tabled (range
-        // table row of (n_ranges + 1) x 4 bytes): df >= mid_min, raised until the tables fit a quarter of the stream.
-        const int64_t col_rows = (int64_t)d.n_ranges * kBm25Range;
+        // table row of (n_blocks + 1) x 4 bytes): df >= mid_min, raised until the tables fit a quarter of the stream.
+        const int64_t col_rows = (int64_t)d.n_blocks * kBm25Block;
         const int64_t ddiv = std::max(g_bm25_dense_div, 1);
         const int64_t dense_min = std::max<int64_t>((n_docs + ddiv - 1) / ddiv, 64);
         std::vector<std::pair<int64_t, int32_t>> dense_cand;
@@ -147,11 +147,11 @@ int shard_build(Bm25Shard** out, int slot, int64_t n_docs, int64_t n_terms, int6
         size_t n_dense = 0;
         while (n_dense < dense_cand.size() && n_dense < 4096 && (int64_t)(n_dense + 1) * col_rows * 2 <= col_budget) ++n_dense;
         dense_cand.resize(n_dense);
-        int64_t mid_min = std::min<int64_t>(std::max<int64_t>(d.n_ranges, 64), 256);
+        int64_t mid_min = std::min<int64_t>(std::max<int64_t>(d.n_blocks, 64), 256);
         {
             std::sort(dfs.begin(), dfs.end(), std::greater<int64_t>());
             const int64_t tab_budget = std::max<int64_t>(nnz, 16LL << 20);       // bytes: a quarter of the packed stream
-            const int64_t max_tabled = tab_budget / (4 * ((int64_t)d.n_ranges + 1));
+            const int64_t max_tabled = tab_budget / (4 * ((int64_t)d.n_blocks + 1));
             if ((int64_t)dfs.size() > max_tabled && max_tabled >= 0) {
                 const int64_t cut = max_tabled > 0 ? dfs[(size_t)max_tabled - 1] : dfs[0] + 1;
                 mid_min = std::max(mid_min, cut + 1);
@@ -177,7 +177,7 @@ int shard_build(Bm25Shard** out, int slot, int64_t n_docs, int64_t n_terms, int6
             }
             info[(size_t)t] = make_int2((int)(((unsigned)cls << 30) | (unsigned)slot_t), col);
         }
-        const size_t rng_n = (size_t)std::max<size_t>(tabled.size(), 1) * (d.n_ranges + 1);
+        const size_t rng_n = (size_t)std::max<size_t>(tabled.size(), 1) * (d.n_blocks + 1);
         const size_t col_n = (size_t)std::max<size_t>(dense.size(), 1) * (size_t)col_rows;
         A((void**)&d.post_pack, (nz + 4) * 4);
         A((void**)&d.term_info, info.size() * sizeof(int2));

@@ -273,26 +273,30 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
 }
 
 // ---------------------------------------------------------------------------
-// FAST path (2 launches for a batch of queries).
+// FAST path (3 launches for a batch of queries).
 //
 // The product idf[t] * impact[p] of a posting does not depend on the query, so the index holds it a second time
-// as a 20-bit fixed-point UPPER bound q (unit = max product / ~2^20, rounded up, +1):
-//   * packed with the 12-bit local row of its 4096-row range, 4 bytes per posting (every term), and
-//   * for DENSE terms (df >= n_docs / 8) as a 16-bit COLUMN over all rows: ceil(q / 16), 0 where the term does not
-//     occur — 2 bytes per row, read with fully coalesced loads and added into REGISTERS (a thread owns 16 fixed rows
-//     of the range), no row ids, no shared-memory traffic, no search.
+// as an 18-bit fixed-point UPPER bound q (unit = max product / ~2^18, rounded up, +1):
+//   * packed with the 14-bit local row of its 16384-row BLOCK, 4 bytes per posting (every term), and
+//   * for DENSE terms (df >= n_docs / 8) as a 16-bit COLUMN over all rows: ceil(q / 4), 0 where the term does not
+//     occur — 2 bytes per row, read with fully coalesced loads and added into REGISTERS (a thread owns fixed rows
+//     of the tile), no row ids, no shared-memory traffic, no search.
 // The filter pass adds these integers:
-//     U[row] = sum over the query's tokens of q   (resp. 16 * column entry)      (exact integer arithmetic, any order)
+//     U[row] = sum over the query's tokens of q   (resp. 4 * column entry)       (exact integer arithmetic, any order)
 // is an upper bound of the row's fp64 score in units, and U[row] - slack a lower bound, slack = 2 per packed token
-// + 17 per column token.
-//   A  bm25_filter_kernel   grid (ranges, queries).  Column tokens: registers.  Other tokens: integer accumulators of
-//        the range in shared memory; the range table gives a tabled term's run inside the packed stream (no search),
-//        an untabled (short) list is scanned whole; the CTA adds one token at a time, thread i the i-th posting of
-//        the run (plain read-modify-write: the postings of one term are distinct rows), the loads of 4 tokens in
-//        flight.  Then the range's H best allowed rows by U ("heads") and the (H+1)-th best U ("rho": nothing that
-//        was not emitted is above it) go to global memory: scores never leave the SM.  Selection by threshold: the
-//        (H+1)-th largest of a warp's 32 per-lane maxima is reached by H+1 distinct rows, so only rows at or above
-//        it (H+1 and a few) can be among the warp's H+1 best.
+// + 5 per column token.
+//   R  bm25_resolve_kernel  one record per (query, block, token): class and the term's run inside the block (range
+//        table: no search) — a flat, fully parallel kernel pays the dependent look-ups once instead of every CTA.
+//   A  bm25_filter_kernel<CH>  grid (tiles, queries), a tile = CH x 4096 rows (CH = 4: one block, used when the
+//        launch has enough tiles to fill the GPU; CH = 1: a quarter block, for small corpora / single queries).
+//        Run tokens: integer accumulators of the tile in shared memory; the CTA adds one token at a time, thread i
+//        the i-th posting of the run (plain read-modify-write: the postings of one term are distinct rows), 8 loads
+//        per thread in flight across rounds and tokens; an untabled (short) list is scanned whole.  Column tokens:
+//        registers, 4096 rows at a time, merged with the shared accumulators.  Then the tile's H best allowed rows
+//        by U ("heads") and the (H+1)-th best U ("rho": nothing that was not emitted is above it) go to global
+//        memory: scores never leave the SM.  Selection by threshold: the (H+1)-th largest of a warp's 32 per-lane
+//        maxima is reached by H+1 distinct rows, so only rows at or above it (H+1 and a few) can be among the
+//        warp's H+1 best.
 //   B  bm25_finish_kernel   one CTA per query: tau = k-th largest head minus the slack (k distinct rows reach it:
 //        a valid lower bound of the k-th best exact score); every rho must be below it, else the query is flagged
 //        (count = -1) and redone on the robust path; heads with U >= tau are the survivors (k + a handful): their
@@ -301,16 +305,19 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
 // Selective row filters (doc_filter keeping <= 4096 rows) skip the posting stream altogether: bm25_rows_kernel
 // computes the exact scores of the listed rows only.
 // ---------------------------------------------------------------------------
-constexpr int kBmMaxH = 31;           // heads per range
-constexpr int kBmList = 256;          // rows a CTA's warps hand to the final selection (8 warps x (H+1) and ties)
+constexpr int kBmBlock = kBm25Block;  // rows per block: the granularity of the range tables and of the local row
+constexpr int kBmQBits = 18;          // bits of q inside a packed posting
+constexpr uint32_t kBmQMask = (1u << kBmQBits) - 1u;
+constexpr int kBmMaxH = 31;           // heads per tile
+constexpr int kBmList = 512;          // rows a CTA's warps hand to the final selection (8 warps x (H+1) and ties)
+constexpr int kBmThetaHeads = 20;     // up to this many heads (+ rho) per tile the warps select by threshold
 constexpr int kBmSurvivors = 1024;    // survivors per query the finish kernel re-scores
 constexpr int kBmContrib = 4096;      // (survivor, token) products staged at a time
 constexpr int kBmMaxQueryTokens = 1024;
-constexpr int kBmSpGroup = 8;         // run tokens whose first loads are in flight together
+constexpr int kBmDepth = 8;           // run postings per thread in flight (across rounds and tokens)
 constexpr int kBmDnGroup = 2;         // column tokens whose loads are in flight together
-constexpr int kBmThetaHeads = 12;     // up to this many heads (+ rho) per range the warps select by threshold
 
-// the range's H+1 best of n_e (<= 32 * NU) list entries -> dst[0..H] (descending; 0 = none)
+// the tile's H+1 best of n_e (<= 32 * NU) list entries -> dst[0..H] (descending; 0 = none)
 template <int NU>
 __device__ __forceinline__ void bm25_emit_heads(const unsigned long long* s_list, int n_e, int H, int lane,
                                                 unsigned long long* __restrict__ dst) {
@@ -339,19 +346,18 @@ __device__ __forceinline__ void bm25_emit_heads(const unsigned long long* s_list
     }
 }
 
-// One record per (query, range, token slot), written by bm25_resolve_kernel so that a range CTA starts with everything
-// it needs in ONE load per thread instead of walking q_ptr -> terms -> term_info -> term_ptr -> rng_off itself (five
-// dependent round trips per CTA; here they are paid by a flat, fully parallel kernel): x = class, and
-//   DENSE: y = column;   MID: [y, z) = the term's run inside this range;   LOW: [y, z) = the term's whole list.
+// One record per (query, block, token slot), so that a tile's CTA starts with everything it needs in ONE load per
+// thread instead of walking q_ptr -> terms -> term_info -> term_ptr -> rng_off itself: x = class, and
+//   DENSE: y = column;   MID: [y, z) = the term's run inside this block;   LOW: [y, z) = the term's whole list.
 // Slots past the query's last token are kBmSkip.
 __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
                                     int q0, int Q, int stride, uint4* __restrict__ rec) {
-    const int64_t per_q = (int64_t)ix.n_ranges * stride;
+    const int64_t per_q = (int64_t)ix.n_blocks * stride;
     const int64_t total = (int64_t)Q * per_q;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int q = (int)(e / per_q);
         const int rem = (int)(e - (int64_t)q * per_q);
-        const int rg = rem / stride, i = rem - rg * stride;
+        const int blk = rem / stride, i = rem - blk * stride;
         const int lo = q_ptr[q0 + q], nt = q_ptr[q0 + q + 1] - lo;
         uint4 d = make_uint4((uint32_t)kBmSkip, 0u, 0u, 0u);
         if (i < nt) {
@@ -363,7 +369,7 @@ __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q
                     d = make_uint4((uint32_t)cls, (uint32_t)info.y, 0u, 0u);
                 } else if (cls == kBmMid) {
                     const uint32_t base = (uint32_t)ix.term_ptr[t];
-                    const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_ranges + 1) + rg;
+                    const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_blocks + 1) + blk;
                     d = make_uint4((uint32_t)cls, base + (uint32_t)ro[0], base + (uint32_t)ro[1], 0u);
                 } else if (cls == kBmLow) {
                     d = make_uint4((uint32_t)cls, (uint32_t)ix.term_ptr[t], (uint32_t)ix.term_ptr[t + 1], 0u);
@@ -374,151 +380,190 @@ __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q
     }
 }
 
-__global__ void __launch_bounds__(kBmThreads, 4)
+template <int CH>
+__global__ void __launch_bounds__(kBmThreads, 3)
 bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, const uint8_t* __restrict__ allow, int H,
                    unsigned long long* __restrict__ heads) {
-    __shared__ __align__(16) uint32_t acc[kBmRange];
+    extern __shared__ __align__(16) uint32_t acc[];   // CH x 4096 accumulators
     __shared__ uint2 s_runs[kBmMaxTokens];            // [lo, hi) inside the packed stream: tabled runs from the front,
-    __shared__ const uint16_t* s_colp[kBmMaxTokens];  // scanned lists from the back; column of the range per DENSE token
+    __shared__ const uint16_t* s_colp[kBmMaxTokens];  // scanned lists from the back; column of the tile per DENSE token
     __shared__ int s_ntab, s_nscan, s_ncol, s_nlist;
     __shared__ unsigned long long s_list[kBmList];
+    constexpr int kTile = CH * 4096;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rg = blockIdx.x;
-    const int64_t r0 = (int64_t)rg * kBmRange;
-    const int64_t r1 = r0 + kBmRange < ix.n_docs ? r0 + kBmRange : ix.n_docs;
-    const uint4* my_rec = rec + ((size_t)blockIdx.y * gridDim.x + rg) * stride;
-    // a thread owns the local rows g * 1024 + 4 * tid + i (g, i = 0..3): 8-byte column loads and 16-byte shared
-    // accesses that are contiguous over the warp.  A column word holds two rows: s_all adds the words whole
-    // (sum of the low halves + 65536 * sum of the high halves, modulo 2^32), s_hi the high halves.
-    uint32_t s_all[8], s_hi[8];
+    const int tile = blockIdx.x;
+    const int blk = CH == 4 ? tile : tile >> 2;
+    const uint32_t quarter = (uint32_t)(tile & 3);                 // CH == 1: which 4096 rows of the block
+    const int64_t r0 = (int64_t)tile * kTile;
+    const int64_t r1 = r0 + kTile < ix.n_docs ? r0 + kTile : ix.n_docs;
+    const uint4* my_rec = rec + ((size_t)blockIdx.y * ix.n_blocks + blk) * stride;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+    for (int j = 0; j < CH * 4; ++j) *reinterpret_cast<uint4*>(&acc[j * 1024 + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) s_nlist = 0;
+    uint32_t m = 0u;                      // the thread's largest upper bound (set in the last pass)
     for (int t0 = 0; t0 < stride; t0 += kBmMaxTokens) {
         const int tn = stride - t0 < kBmMaxTokens ? stride - t0 : kBmMaxTokens;
+        const bool last = t0 + kBmMaxTokens >= stride;
         uint4 d = make_uint4((uint32_t)kBmSkip, 0u, 0u, 0u);
         if (tid < tn) d = __ldg(my_rec + t0 + tid);
-        if (t0 == 0) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(&acc[g * 1024 + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
-            if (tid == 0) s_nlist = 0;
-        } else {
-            __syncthreads();              // previous pass done with the token table
-        }
+        __syncthreads();                  // accumulators zeroed / previous pass done with the token table
         if (tid == 0) { s_ntab = 0; s_nscan = 0; s_ncol = 0; }
         __syncthreads();
         if (d.x == (uint32_t)kBmDense) {
-            s_colp[atomicAdd(&s_ncol, 1)] = ix.dense_col + ((size_t)d.y * ix.n_ranges + rg) * kBmRange;
+            s_colp[atomicAdd(&s_ncol, 1)] =
+                ix.dense_col + ((size_t)d.y * ix.n_blocks + blk) * kBmBlock + (CH == 4 ? 0u : quarter * 4096u);
         } else if (d.x == (uint32_t)kBmMid) {
             if (d.z > d.y) s_runs[atomicAdd(&s_ntab, 1)] = make_uint2(d.y, d.z);
         } else if (d.x == (uint32_t)kBmLow) {
             if (d.z > d.y) s_runs[kBmMaxTokens - 1 - atomicAdd(&s_nscan, 1)] = make_uint2(d.y, d.z);
         }
         __syncthreads();
-        const int n_col = s_ncol, n_tab = s_ntab, n_run = n_tab + s_nscan;
-        // thread i's posting of each run of a group (0: nothing — a posting's q is >= 2).  An untabled list is
-        // scanned whole: only the rows of this range count.
-        uint32_t pk[kBmSpGroup];
-        auto load_group = [&](int e0) {
+        const int n_tab = s_ntab, n_run = n_tab + s_nscan, n_col = s_ncol;
+        // ---- run tokens, one at a time for the whole CTA: thread i adds the i-th, 256+i-th, ... posting of the run
+        // (the postings of one term are distinct rows: plain read-modify-write), a barrier separates the terms.
+        // The (token, round) sequence is the same for every thread; kBmDepth of its loads are in flight.
+        // An untabled list is scanned whole: only the rows of this tile count.
+        {
+            int it_e = -1;                // iterator state (block-uniform)
+            uint32_t it_p = 0u, it_hi = 0u;
+            bool it_scan = false;
+            auto next_item = [&](uint32_t& val, bool& first) -> bool {
+                first = false;
+                if (it_e >= 0) it_p += kBmThreads;
+                while (it_e < 0 || it_p >= it_hi) {
+                    if (++it_e >= n_run) { it_e = n_run; it_p = 1u; it_hi = 0u; return false; }
+                    it_scan = it_e >= n_tab;
+                    const uint2 r = s_runs[it_scan ? kBmMaxTokens - 1 - (it_e - n_tab) : it_e];
+                    it_p = r.x; it_hi = r.y;
+                    first = true;
+                }
+                val = 0u;                 // 0: adds nothing (a posting's q is >= 2)
+                const uint32_t p = it_p + (uint32_t)tid;
+                if (p < it_hi) {
+                    val = __ldg(ix.post_pack + p);
+                    if (it_scan) {
+                        const int64_t row = ix.post_row[p];
+                        if (row < r0 || row >= r1) val = 0u;
+                    }
+                }
+                return true;
+            };
+            uint32_t val[kBmDepth];
+            bool first[kBmDepth], ok[kBmDepth];
 #pragma unroll
-            for (int u = 0; u < kBmSpGroup; ++u) {
-                pk[u] = 0u;
-                const int e = e0 + u;
-                if (e < n_run) {
-                    const bool scan = e >= n_tab;            // block-uniform
-                    const uint2 r = s_runs[scan ? kBmMaxTokens - 1 - (e - n_tab) : e];
-                    const uint32_t p = r.x + (uint32_t)tid;
-                    if (p < r.y) {
-                        pk[u] = __ldg(ix.post_pack + p);
-                        if (scan) {
-                            const int64_t row = ix.post_row[p];
-                            if (row < r0 || row >= r1) pk[u] = 0u;
+            for (int dd = 0; dd < kBmDepth; ++dd) { val[dd] = 0u; first[dd] = false; ok[dd] = next_item(val[dd], first[dd]); }
+            bool more = ok[0], any = false;
+            while (more) {                // block-uniform
+#pragma unroll
+                for (int dd = 0; dd < kBmDepth; ++dd) {
+                    if (more && ok[dd]) {
+                        if (first[dd] && any) __syncthreads();       // the previous term is done
+                        any = true;
+                        if (val[dd]) {
+                            const uint32_t loc = val[dd] >> kBmQBits;                  // row inside the block
+                            if (CH == 4) acc[loc] += val[dd] & kBmQMask;
+                            else if ((loc >> 12) == quarter) acc[loc & 4095u] += val[dd] & kBmQMask;
                         }
+                        ok[dd] = next_item(val[dd], first[dd]);
+                    } else {
+                        more = false;     // slots are consumed in the order they were filled
                     }
                 }
             }
-        };
-        load_group(0);                    // in flight while the column tokens are added
-        // ---- column tokens: 4 x 8 bytes per thread and token, straight into registers
-        for (int e0 = 0; e0 < n_col; e0 += kBmDnGroup) {
+        }
+        __syncthreads();
+        // ---- column tokens, 4096 rows at a time: 4 x 8 bytes per thread and token straight into registers.  A thread
+        // owns the local rows c * 4096 + g * 1024 + 4 * tid + i (g, i = 0..3): 8-byte column loads and 16-byte
+        // shared accesses that are contiguous over the warp.  A column word holds two rows: s_all adds the words
+        // whole (sum of the low halves + 65536 * sum of the high halves, modulo 2^32), s_hi the high halves.  The
+        // sums are merged into the shared accumulators (the thread's own rows); the last pass also masks the
+        // disallowed rows and takes the thread's maximum.  The loads of the next step are requested before the
+        // current one is added.
+        if (n_col > 0 || last) {
+            const int ngroups = n_col > 0 ? (n_col + kBmDnGroup - 1) / kBmDnGroup : 1;
+            const int nsteps = CH * ngroups;
+            auto load_step = [&](int s, uint2 (&xx)[kBmDnGroup][4]) {
+                const int c = s / ngroups, e0 = (s - c * ngroups) * kBmDnGroup;
+#pragma unroll
+                for (int u = 0; u < kBmDnGroup; ++u) {
+                    if (e0 + u < n_col) {
+                        const uint2* cp = reinterpret_cast<const uint2*>(s_colp[e0 + u] + c * 4096) + tid;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(cp + g * 256);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u);
+                    }
+                }
+            };
             uint2 x[kBmDnGroup][4];
+            load_step(0, x);
+            uint32_t s_all[8], s_hi[8];
 #pragma unroll
-            for (int u = 0; u < kBmDnGroup; ++u) {
-                if (e0 + u < n_col) {
-                    const uint2* c = reinterpret_cast<const uint2*>(s_colp[e0 + u]) + tid;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) x[u][g] = __ldg(c + g * 256);
+            for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+            int c = 0, gi = 0;
+            for (int s = 0; s < nsteps; ++s) {
+                uint2 nx[kBmDnGroup][4];
+                if (s + 1 < nsteps) {
+                    load_step(s + 1, nx);
                 } else {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) x[u][g] = make_uint2(0u, 0u);
+                    for (int u = 0; u < kBmDnGroup; ++u)
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) nx[u][g] = make_uint2(0u, 0u);
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < kBmDnGroup; ++u)
+                for (int u = 0; u < kBmDnGroup; ++u)
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    s_all[2 * g + 0] += x[u][g].x;
-                    s_hi[2 * g + 0] += x[u][g].x >> 16;
-                    s_all[2 * g + 1] += x[u][g].y;
-                    s_hi[2 * g + 1] += x[u][g].y >> 16;
-                }
-        }
-        // ---- run tokens, one at a time for the whole CTA: thread i adds the i-th posting of the run (the postings of
-        // one term are distinct rows: plain read-modify-write), the barrier separates the terms
-        for (int e0 = 0; e0 < n_run; e0 += kBmSpGroup) {
-            if (e0 > 0) load_group(e0);
-#pragma unroll
-            for (int u = 0; u < kBmSpGroup; ++u) {
-                const int e = e0 + u;
-                if (e < n_run) {                             // block-uniform
-                    if (pk[u]) acc[pk[u] >> 20] += pk[u] & 0xFFFFFu;
-                    const bool scan = e >= n_tab;
-                    const uint2 r = s_runs[scan ? kBmMaxTokens - 1 - (e - n_tab) : e];
-                    if (r.y - r.x > (uint32_t)kBmThreads) {  // block-uniform: a long run
-                        for (uint32_t p = r.x + kBmThreads + tid; p < r.y; p += kBmThreads) {
-                            uint32_t w = ix.post_pack[p];
-                            if (scan) {
-                                const int64_t row = ix.post_row[p];
-                                if (row < r0 || row >= r1) w = 0u;
-                            }
-                            if (w) acc[w >> 20] += w & 0xFFFFFu;
-                        }
+                    for (int g = 0; g < 4; ++g) {
+                        s_all[2 * g + 0] += x[u][g].x;
+                        s_hi[2 * g + 0] += x[u][g].x >> 16;
+                        s_all[2 * g + 1] += x[u][g].y;
+                        s_hi[2 * g + 1] += x[u][g].y >> 16;
                     }
-                    __syncthreads();
+                if (++gi == ngroups) {    // the chunk's last group: merge
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 a = *reinterpret_cast<const uint4*>(&acc[c * 4096 + g * 1024 + 4 * tid]);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t hi = s_hi[2 * g + h];
+                            const uint32_t lo = s_all[2 * g + h] - (hi << 16);
+                            (h ? a.z : a.x) += lo << kBmDenseShift;
+                            (h ? a.w : a.y) += hi << kBmDenseShift;
+                        }
+                        if (last) {
+                            if (allow != nullptr) {
+                                const int64_t row = r0 + c * 4096 + g * 1024 + 4 * tid;   // 4 rows inside one bitmap byte
+                                const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
+                                if (!(bits & 1u)) a.x = 0u;
+                                if (!(bits & 2u)) a.y = 0u;
+                                if (!(bits & 4u)) a.z = 0u;
+                                if (!(bits & 8u)) a.w = 0u;
+                            }
+                            const uint32_t m01 = a.x > a.y ? a.x : a.y, m23 = a.z > a.w ? a.z : a.w;
+                            const uint32_t mg = m01 > m23 ? m01 : m23;
+                            m = mg > m ? mg : m;
+                        }
+                        *reinterpret_cast<uint4*>(&acc[c * 4096 + g * 1024 + 4 * tid]) = a;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+                    gi = 0;
+                    ++c;
                 }
+#pragma unroll
+                for (int u = 0; u < kBmDnGroup; ++u)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) x[u][g] = nx[u][g];
             }
         }
     }
-    __syncthreads();
-    // ---- the thread's 16 upper bounds (disallowed rows masked), kept in shared memory for the emission
-    uint32_t v[16];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        uint4 a = *reinterpret_cast<const uint4*>(&acc[g * 1024 + 4 * tid]);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint32_t hi = s_hi[2 * g + h];
-            const uint32_t lo = s_all[2 * g + h] - (hi << 16);
-            (h ? a.z : a.x) += lo << kBmDenseShift;
-            (h ? a.w : a.y) += hi << kBmDenseShift;
-        }
-        if (allow != nullptr) {
-            const int64_t row = r0 + g * 1024 + 4 * tid;     // 4 rows inside one byte of the bitmap
-            const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
-            if (!(bits & 1u)) a.x = 0u;
-            if (!(bits & 2u)) a.y = 0u;
-            if (!(bits & 4u)) a.z = 0u;
-            if (!(bits & 8u)) a.w = 0u;
-        }
-        *reinterpret_cast<uint4*>(&acc[g * 1024 + 4 * tid]) = a;
-        v[4 * g + 0] = a.x; v[4 * g + 1] = a.y; v[4 * g + 2] = a.z; v[4 * g + 3] = a.w;
-    }
-    uint32_t m = 0u;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) m = v[j] > m ? v[j] : m;
+    // (from here on every thread reads only the accumulators it wrote last: no barrier needed)
     const uint32_t row_base = (uint32_t)r0 + 4u * (uint32_t)tid;
     if (H + 1 <= kBmThetaHeads) {
-        // ---- many ranges, few heads per range.  theta = the (H+1)-th largest of the warp's 32 per-lane maxima: H+1
-        // distinct rows reach it, so the warp's H+1 best rows are among the rows >= theta (H+1 and a few)
+        // ---- theta = the (H+1)-th largest of the warp's 32 per-lane maxima: H+1 distinct rows reach it, so the
+        // warp's H+1 best rows are among the rows >= theta (H+1 and a few)
         uint32_t theta = 0u;
         {
             uint32_t mc = m;
@@ -530,39 +575,53 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
             }
         }
         if (theta < 1u) theta = 1u;
-        uint32_t mask = 0u;
+        if (m >= theta) {
+#pragma unroll 1
+            for (int c = 0; c < CH; ++c) {
+                uint32_t mask = 0u;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) mask |= v[j] >= theta ? (1u << j) : 0u;
-        if (mask) {
-            int slot = atomicAdd(&s_nlist, __popc(mask));
-            while (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1u;
-                const uint32_t loc = (uint32_t)((j >> 2) << 10) + (uint32_t)(j & 3);
-                const uint32_t u = acc[loc + 4 * tid];
-                if (slot < kBmList) s_list[slot] = ((unsigned long long)u << 32) | (unsigned long long)(~(row_base + loc));
-                ++slot;
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(&acc[c * 4096 + g * 1024 + 4 * tid]);
+                    mask |= (a.x >= theta ? 1u : 0u) << (4 * g);
+                    mask |= (a.y >= theta ? 2u : 0u) << (4 * g);
+                    mask |= (a.z >= theta ? 4u : 0u) << (4 * g);
+                    mask |= (a.w >= theta ? 8u : 0u) << (4 * g);
+                }
+                if (mask) {
+                    int slot = atomicAdd(&s_nlist, __popc(mask));
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1u;
+                        const uint32_t loc = (uint32_t)(c * 4096) + (uint32_t)((j >> 2) << 10) + (uint32_t)(j & 3);
+                        const uint32_t u = acc[loc + 4 * tid];
+                        if (slot < kBmList) s_list[slot] = ((unsigned long long)u << 32) | (unsigned long long)(~(row_base + loc));
+                        ++slot;
+                    }
+                }
             }
         }
     } else {
-        // ---- few ranges, many heads per range: the warp's exact H+1 best, one per round (ties: lowest row)
+        // ---- many heads per tile (few tiles, or a large k): the warp's exact H+1 best, one per round (ties: lowest
+        // row), straight from the shared accumulators
         for (int h = 0; h <= H; ++h) {
-            uint32_t mm = 0u;
+            uint32_t best = 0u, bloc = 0xFFFFFFFFu;
+#pragma unroll 1
+            for (int c = 0; c < CH; ++c)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) mm = v[j] > mm ? v[j] : mm;
-            const uint32_t wm = __reduce_max_sync(0xffffffffu, mm);
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t base = (uint32_t)(c * 4096 + g * 1024);
+                    const uint4 a = *reinterpret_cast<const uint4*>(&acc[base + 4 * tid]);
+                    if (a.x > best) { best = a.x; bloc = base + 0u; }     // ascending rows, strict >: lowest row wins
+                    if (a.y > best) { best = a.y; bloc = base + 1u; }
+                    if (a.z > best) { best = a.z; bloc = base + 2u; }
+                    if (a.w > best) { best = a.w; bloc = base + 3u; }
+                }
+            const uint32_t wm = __reduce_max_sync(0xffffffffu, best);
             if (wm == 0u) break;
-            int myj = 16;
-#pragma unroll
-            for (int j = 15; j >= 0; --j)
-                if (v[j] == wm) myj = j;
-            const uint32_t myloc = (uint32_t)((myj >> 2) << 10) + (uint32_t)(myj & 3);
-            const uint32_t myrow = mm == wm ? row_base + myloc : 0xFFFFFFFFu;
+            const uint32_t myrow = best == wm ? row_base + bloc : 0xFFFFFFFFu;
             const uint32_t wr = __reduce_min_sync(0xffffffffu, myrow);
             if (myrow == wr) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j == myj) v[j] = 0u;
+                acc[bloc + 4 * tid] = 0u;
                 const int slot = atomicAdd(&s_nlist, 1);
                 if (slot < kBmList) s_list[slot] = ((unsigned long long)wm << 32) | (unsigned long long)(~wr);
             }
@@ -572,12 +631,14 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
     if (warp == 0) {
         const int n_e = s_nlist;
         unsigned long long* dst = heads + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (H + 1);
-        if (n_e > kBmList) {                                 // mass ties inside the range: rho = "anything": redo
+        if (n_e > kBmList) {                                 // mass ties inside the tile: rho = "anything": redo
             for (int hh = lane; hh <= H; hh += 32) dst[hh] = ~0ull;
         } else if (n_e <= 64) {
             bm25_emit_heads<2>(s_list, n_e, H, lane, dst);
-        } else {
+        } else if (n_e <= 256) {
             bm25_emit_heads<8>(s_list, n_e, H, lane, dst);
+        } else {
+            bm25_emit_heads<16>(s_list, n_e, H, lane, dst);
         }
     }
 }
@@ -592,7 +653,7 @@ __device__ __forceinline__ double bm25_term_contrib(const Bm25Device& ix, int32_
         const int2 info = ix.term_info[t];
         const int cls = (int)((unsigned)info.x >> 30);
         if (cls == kBmMid || cls == kBmDense) {            // the range table narrows the search to the row's range
-            const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_ranges + 1) + (row >> 12);
+            const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_blocks + 1) + (row / (uint32_t)kBmBlock);
             hi = lo + ro[1];
             lo = lo + ro[0];
         }
@@ -666,7 +727,7 @@ __device__ __forceinline__ void bm25_exact_topk(const Bm25Device& ix, const int3
 
 __global__ void __launch_bounds__(256)
 bm25_finish_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr, int q0,
-                   const unsigned long long* __restrict__ heads, int H, int h_tau, int nsort_tau, int k,
+                   const unsigned long long* __restrict__ heads, int n_tiles, int H, int h_tau, int nsort_tau, int k,
                    int32_t* out_rows, double* out_scores, int32_t* out_counts) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     // [ 32 KB: tau sort buffer, later the staged products | survivors' keys | survivors' rows ]
@@ -676,7 +737,7 @@ bm25_finish_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int
     uint32_t* surv = reinterpret_cast<uint32_t*>(keys + kBmSurvivors);
     __shared__ int s_n, s_flag, s_extra;
     const int q = blockIdx.x;
-    const int n_ranges = ix.n_ranges;
+    const int n_ranges = n_tiles;
     const unsigned long long* hq = heads + (size_t)q * n_ranges * (H + 1);
     const int32_t* terms = q_terms + q_ptr[q0 + q];
     const int nt = q_ptr[q0 + q + 1] - q_ptr[q0 + q];
@@ -772,19 +833,19 @@ __global__ void bm25_pack_kernel(Bm25Device ix, double inv_unit) {
         uint32_t q = 0u;
         if (c > 0.0) {
             const double v = ceil(c * inv_unit) + 1.0;       // q * unit >= c and (q - 2) * unit <= c
-            q = v > 1048575.0 ? 1048575u : (uint32_t)v;
+            q = v > (double)kBmQMask ? kBmQMask : (uint32_t)v;
         }
-        ix.post_pack[p] = (((uint32_t)ix.post_row[p] & 4095u) << 20) | q;
+        ix.post_pack[p] = (((uint32_t)ix.post_row[p] & (uint32_t)(kBmBlock - 1)) << kBmQBits) | q;
     }
 }
 
 __global__ void bm25_rng_kernel(Bm25Device ix, const int32_t* __restrict__ tabled_terms, int n_tabled) {
-    const int64_t total = (int64_t)n_tabled * (ix.n_ranges + 1);
+    const int64_t total = (int64_t)n_tabled * (ix.n_blocks + 1);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int slot = (int)(e / (ix.n_ranges + 1)), r = (int)(e % (ix.n_ranges + 1));
+        const int slot = (int)(e / (ix.n_blocks + 1)), r = (int)(e % (ix.n_blocks + 1));
         const int32_t t = tabled_terms[slot];
         const int64_t lo = ix.term_ptr[t], hi = ix.term_ptr[t + 1];
-        ix.rng_off[e] = (int32_t)(bm25_lower_bound(ix.post_row, lo, hi, (int64_t)r * kBmRange) - lo);
+        ix.rng_off[e] = (int32_t)(bm25_lower_bound(ix.post_row, lo, hi, (int64_t)r * kBmBlock) - lo);
     }
 }
 
@@ -792,9 +853,9 @@ __global__ void bm25_rng_kernel(Bm25Device ix, const int32_t* __restrict__ table
 __global__ void bm25_column_kernel(Bm25Device ix, const int32_t* __restrict__ dense_terms) {
     const int32_t t = dense_terms[blockIdx.y];
     const int64_t lo = ix.term_ptr[t], hi = ix.term_ptr[t + 1];
-    uint16_t* col = ix.dense_col + (size_t)blockIdx.y * ((size_t)ix.n_ranges * kBmRange);
+    uint16_t* col = ix.dense_col + (size_t)blockIdx.y * ((size_t)ix.n_blocks * kBmBlock);
     for (int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t q = ix.post_pack[p] & 0xFFFFFu;
+        const uint32_t q = ix.post_pack[p] & kBmQMask;
         col[ix.post_row[p]] = (uint16_t)((q + ((1u << kBmDenseShift) - 1u)) >> kBmDenseShift);
     }
 }
@@ -812,7 +873,7 @@ cudaError_t bm25_index_build_launch(const Bm25Device& ix, double unit, const int
         if (e != cudaSuccess) return e;
     }
     if (n_tabled > 0) {
-        bm25_rng_kernel<<<grid_for((int64_t)n_tabled * (ix.n_ranges + 1)), 256, 0, st>>>(ix, tabled_terms, n_tabled);
+        bm25_rng_kernel<<<grid_for((int64_t)n_tabled * (ix.n_blocks + 1)), 256, 0, st>>>(ix, tabled_terms, n_tabled);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -825,42 +886,65 @@ cudaError_t bm25_index_build_launch(const Bm25Device& ix, double unit, const int
     return cudaSuccess;
 }
 
-// heads per range: enough that a range holding more than H of the query's top rows is a < 1e-3 event when the
-// top rows fall into ranges independently (lambda = expected top rows per range)
-static int bm25_heads_per_range(int n_ranges, int k) {
-    const double lambda = 1.15 * k / n_ranges;
+// heads per tile: enough that a tile holding more than H of the query's top rows is a < 1e-3 event when the top rows
+// fall into tiles independently (lambda = expected top rows per tile)
+static int bm25_heads_per_tile(int n_tiles, int k) {
+    const double lambda = 1.15 * k / n_tiles;
     int H = (int)ceil(lambda + 4.0 * sqrt(lambda) + 4.0);
     return H < 4 ? 4 : H;
 }
-// heads per range that enter the threshold: the k-th largest of n_ranges x h_tau heads (distinct rows) is a lower bound
-// of the k-th best score for any h_tau >= k / n_ranges.  Many ranges: the k-th largest range maximum is tight enough.
-// Few ranges: with k / n_ranges heads the k-th largest sits at the weakest range's last head (a ragged last range
-// drags it far down and every range then holds more than H rows above it), so take about 2k heads in total.
-static int bm25_tau_heads(int n_ranges, int k) {
-    const int need = (k + n_ranges - 1) / n_ranges;
-    if (n_ranges >= 4 * k) return need;
-    const int want = (2 * k + n_ranges - 1) / n_ranges + 2;
-    const int H = bm25_heads_per_range(n_ranges, k);
+// heads per tile that enter the threshold: the k-th largest of n_tiles x h_tau heads (distinct rows) is a lower bound
+// of the k-th best score for any h_tau >= k / n_tiles.  Many tiles: the k-th largest tile maximum is tight enough.
+// Few tiles: with k / n_tiles heads the k-th largest sits at the weakest tile's last head (a ragged last tile
+// drags it far down and every tile then holds more than H rows above it), so take about 2k heads in total.
+static int bm25_tau_heads(int n_tiles, int k) {
+    const int need = (k + n_tiles - 1) / n_tiles;
+    if (n_tiles >= 4 * k) return need;
+    const int want = (2 * k + n_tiles - 1) / n_tiles + 2;
+    const int H = bm25_heads_per_tile(n_tiles, k);
     return want < H ? (want > need ? want : need) : (H > need ? H : need);
 }
 
+struct Bm25Plan {
+    int ch;          // 4096-row chunks per tile: 4 (a whole block) or 1
+    int n_tiles, H, h_tau;
+};
+static bool bm25_plan_for(const Bm25Device& ix, int k, int ch, Bm25Plan* p) {
+    p->ch = ch;
+    p->n_tiles = ch == 4 ? ix.n_blocks : (int)((ix.n_docs + 4095) / 4096);
+    if (p->n_tiles < 1) return false;
+    p->H = bm25_heads_per_tile(p->n_tiles, k);
+    p->h_tau = bm25_tau_heads(p->n_tiles, k);
+    return p->H <= kBmMaxH && (int64_t)p->n_tiles * p->h_tau <= 4096;
+}
+// block tiles when the launch has enough of them to fill the GPU (148 SMs x 3 CTAs, twice over); quarter-block tiles
+// for small corpora and single queries (more, shorter CTAs: latency)
+static bool bm25_plan(const Bm25Device& ix, int k, int Q, Bm25Plan* p) {
+    if ((int64_t)Q * ix.n_blocks >= 2 * 148 * 3 && bm25_plan_for(ix, k, 4, p)) return true;
+    if (bm25_plan_for(ix, k, 1, p)) return true;
+    return bm25_plan_for(ix, k, 4, p);
+}
+
 bool bm25_fast_supported(const Bm25Device& ix, int k, int max_query_tokens) {
-    if (!ix.fast_ok || !ix.post_pack || ix.n_ranges < 1) return false;
-    const int H = bm25_heads_per_range(ix.n_ranges, k);
-    return H <= kBmMaxH && (int64_t)ix.n_ranges * bm25_tau_heads(ix.n_ranges, k) <= 4096 &&
-           max_query_tokens <= kBmMaxQueryTokens;
+    if (!ix.fast_ok || !ix.post_pack || ix.n_blocks < 1 || max_query_tokens > kBmMaxQueryTokens) return false;
+    Bm25Plan a, b;
+    return bm25_plan_for(ix, k, 1, &a) || bm25_plan_for(ix, k, 4, &b);
 }
 static size_t bm25_heads_bytes(const Bm25Device& ix, int k, int Q) {
-    const int H = bm25_heads_per_range(ix.n_ranges, k);
-    return (((size_t)Q * ix.n_ranges * (H + 1) * sizeof(unsigned long long)) + 255) & ~(size_t)255;
+    // the larger of the two tilings (the plan of a launch depends on its query count)
+    size_t per_q = 0;
+    Bm25Plan p;
+    for (int ch : {1, 4})
+        if (bm25_plan_for(ix, k, ch, &p)) per_q = std::max(per_q, (size_t)p.n_tiles * (p.H + 1) * sizeof(unsigned long long));
+    return (((size_t)Q * per_q) + 255) & ~(size_t)255;
 }
 static int bm25_desc_stride(int max_query_tokens) { return max_query_tokens < 1 ? 1 : max_query_tokens; }
 size_t bm25_fast_scratch_bytes(const Bm25Device& ix, int k, int Q, int max_query_tokens) {
-    return bm25_heads_bytes(ix, k, Q) + (size_t)Q * ix.n_ranges * bm25_desc_stride(max_query_tokens) * sizeof(uint4) + 256;
+    return bm25_heads_bytes(ix, k, Q) + (size_t)Q * ix.n_blocks * bm25_desc_stride(max_query_tokens) * sizeof(uint4) + 256;
 }
 // queries per launch: the records of a launch stay within ~256 MB of scratch (and gridDim.y within its limit)
 int bm25_fast_chunk(const Bm25Device& ix, int max_query_tokens) {
-    const size_t per_q = (size_t)ix.n_ranges * bm25_desc_stride(max_query_tokens) * sizeof(uint4);
+    const size_t per_q = (size_t)ix.n_blocks * bm25_desc_stride(max_query_tokens) * sizeof(uint4);
     size_t n = ((size_t)256 << 20) / (per_q ? per_q : 1);
     if (n > 32768) n = 32768;
     return n < 1 ? 1 : (int)n;
@@ -870,25 +954,36 @@ int bm25_fast_chunk(const Bm25Device& ix, int max_query_tokens) {
 cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, const int32_t* d_q_ptr, int q0, int Q,
                              int max_query_tokens, const uint8_t* allow, int k, void* scratch, int32_t* out_rows,
                              double* out_scores, int32_t* out_counts, cudaStream_t st) {
-    const int H = bm25_heads_per_range(ix.n_ranges, k);
-    const int h_tau = bm25_tau_heads(ix.n_ranges, k);
+    Bm25Plan pl;
+    if (!bm25_plan(ix, k, Q, &pl)) return cudaErrorInvalidValue;
     const int stride = bm25_desc_stride(max_query_tokens);
     unsigned long long* heads = reinterpret_cast<unsigned long long*>(scratch);
-    uint4* desc = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(scratch) + bm25_heads_bytes(ix, k, Q));
+    uint4* rec = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(scratch) + bm25_heads_bytes(ix, k, Q));
     {
-        const int64_t total = (int64_t)Q * ix.n_ranges * stride;
+        const int64_t total = (int64_t)Q * ix.n_blocks * stride;
         int64_t g = (total + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
-        bm25_resolve_kernel<<<(int)g, 256, 0, st>>>(ix, d_q_terms, d_q_ptr, q0, Q, stride, desc);
+        bm25_resolve_kernel<<<(int)g, 256, 0, st>>>(ix, d_q_terms, d_q_ptr, q0, Q, stride, rec);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    dim3 grid_a(ix.n_ranges, Q);
-    bm25_filter_kernel<<<grid_a, kBmThreads, 0, st>>>(ix, desc, stride, allow, H, heads);
-    cudaError_t e = cudaGetLastError();
+    dim3 grid_a(pl.n_tiles, Q);
+    cudaError_t e = cudaSuccess;
+    if (pl.ch == 4) {
+        static bool attr4 = false;
+        if (!attr4) {
+            e = cudaFuncSetAttribute(bm25_filter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4);
+            if (e != cudaSuccess) return e;
+            attr4 = true;
+        }
+        bm25_filter_kernel<4><<<grid_a, kBmThreads, 4 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
+    } else {
+        bm25_filter_kernel<1><<<grid_a, kBmThreads, 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
+    }
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     int nsort = 32;
-    while (nsort < ix.n_ranges * h_tau) nsort <<= 1;
+    while (nsort < pl.n_tiles * pl.h_tau) nsort <<= 1;
     const size_t smem = (size_t)kBmContrib * sizeof(double) + (size_t)kBmSurvivors * (sizeof(Bm25Key) + 4);
     static bool attr_set = false;
     if (!attr_set) {
@@ -896,7 +991,7 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    bm25_finish_kernel<<<Q, 256, smem, st>>>(ix, d_q_terms, d_q_ptr, q0, heads, H, h_tau, nsort, k,
+    bm25_finish_kernel<<<Q, 256, smem, st>>>(ix, d_q_terms, d_q_ptr, q0, heads, pl.n_tiles, pl.H, pl.h_tau, nsort, k,
                                              out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_counts + q0);
     return cudaGetLastError();
 }

@@ -186,7 +186,8 @@ cudaError_t gather_rows_launch(const void* src, void* dst, const int64_t* keep, 
                                cudaStream_t st);
 
 // ---- bm25.cu ---------------------------------------------------------------
-constexpr int kBm25Range = 4096;          // rows per CTA of the search kernels (12-bit local row)
+constexpr int kBm25Range = 4096;          // rows per CTA of the exact range kernel
+constexpr int kBm25Block = 16384;         // rows per block of the filter index (14-bit local row, range tables, columns)
 struct Bm25Device {
     int64_t n_docs, n_terms, nnz;
     int64_t* term_ptr;      // n_terms + 1
@@ -195,11 +196,11 @@ struct Bm25Device {
     double* idf;            // n_terms
     double* score;          // n_docs accumulator, all-zero between queries (rag_bm25_scores)
     // ---- filter index of the fast path (built by bm25_index_build) ----
-    uint32_t* post_pack;    // nnz + 4: (row & 4095) << 20 | q, q = idf*impact in units of `unit`, rounded up (+1)
+    uint32_t* post_pack;    // nnz + 4: (row & 16383) << 18 | q, q = idf*impact in units of `unit`, rounded up (+1)
     int2* term_info;        // n_terms: x = class << 30 | slot (rng_off row), y = column (dense_col) of a DENSE term
-    int32_t* rng_off;       // n_tabled x (n_ranges + 1): first posting with row >= r * 4096, relative to term_ptr[t]
-    uint16_t* dense_col;    // n_dense x (n_ranges * 4096): ceil(q / 16) of the term's posting on that row, 0 = no posting
-    int n_ranges;
+    int32_t* rng_off;       // n_tabled x (n_blocks + 1): first posting with row >= b * 16384, relative to term_ptr[t]
+    uint16_t* dense_col;    // n_dense x (n_blocks * 16384): ceil(q / 4) of the term's posting on that row, 0 = no posting
+    int n_blocks;
     int fast_ok;            // 1: all idf >= 0 and the packed stream exists -> the integer filter bound is valid
 };
 // term classes (term_info.x >> 30)
@@ -207,7 +208,7 @@ constexpr int kBmLow = 0;    // short list, no table: every CTA scans the whole 
 constexpr int kBmMid = 1;    // rng_off row gives the run of the CTA's range inside the packed stream
 constexpr int kBmDense = 2;  // rng_off row (exact recompute) + a dense 16-bit column: coalesced, accumulated in registers
 constexpr int kBmSkip = 3;   // idf == 0 or empty list: contributes nothing
-constexpr int kBmDenseShift = 4;     // a column entry is ceil(q / 2^4): 16 bits, at most 15 + 2 units above the product
+constexpr int kBmDenseShift = 2;     // a column entry is ceil(q / 2^2): 16 bits, at most 3 + 2 units above the product
 cudaError_t bm25_impact_launch(const int32_t* post_row, const int32_t* post_tf, const int32_t* doc_len, int64_t nnz,
                                double avgdl, double k1, double b, double* impact, cudaStream_t st);
 // max over the postings of idf[t] * impact[p] (atomicMax on the bits of a positive double; *cmax zeroed by the caller)

@@ -775,15 +775,17 @@ def test_bm25_filter_index_classes_vs_oracle(dense_div):
         qt = np.concatenate([by_df[g.integers(0, 12, size=3)], by_df[g.integers(12, 300, size=4)],
                              g.integers(0, n_terms, size=g.integers(1, 6))]).astype(np.int32)
         if i % 3 == 0:
-            qt = np.concatenate([qt, [n_terms - 1, n_terms - 2, -1, qt[0]]]).astype(np.int32)
+            qt = np.concatenate([qt, [n_terms - 2, -1, qt[0]]]).astype(np.int32)
         queries.append(qt)
     queries.append(np.array(list(docs[7][:6]) * 2, np.int32))               # the duplicated documents tie at the top
     queries.append(by_df[:150].astype(np.int32))                            # more tokens than one pass of the kernel holds
     before = _lib.counters()["fallbacks"]
     rows, scores, counts = ix.search_ids(queries, 50)
     assert _lib.counters()["fallbacks"] == before       # nothing of this was redone on the robust path
-    # only the clustered term: hundreds of rows of one range tie exactly -> flagged and redone, still exact
+    # the clustered term: hundreds of rows of one tile tie exactly / hold the whole top-k -> flagged and redone on the
+    # exact range path, still exact
     queries.append(np.array([n_terms - 1], np.int32))
+    queries.append(np.concatenate([queries[0], [n_terms - 1]]).astype(np.int32))
     for k in (10, 50):
         rows, scores, counts = ix.search_ids(queries, k)
         rows1, scores1, counts1 = ix.search_ids(queries[:1], k)             # single-query call
