@@ -392,8 +392,9 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
     constexpr int kTile = CH * 4096;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
-    const int blk = CH == 4 ? tile : tile >> 2;
-    const uint32_t quarter = (uint32_t)(tile & 3);                 // CH == 1: which 4096 rows of the block
+    constexpr int kSubBits = CH == 4 ? 0 : (CH == 2 ? 1 : 2);      // tiles per block = 1 << kSubBits
+    const int blk = tile >> kSubBits;
+    const uint32_t quarter = (uint32_t)(tile & ((1 << kSubBits) - 1));   // CH < 4: which part of the block
     const int64_t r0 = (int64_t)tile * kTile;
     const int64_t r1 = r0 + kTile < ix.n_docs ? r0 + kTile : ix.n_docs;
     const uint4* my_rec = rec + ((size_t)blockIdx.y * ix.n_blocks + blk) * stride;
@@ -411,7 +412,7 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
         __syncthreads();
         if (d.x == (uint32_t)kBmDense) {
             s_colp[atomicAdd(&s_ncol, 1)] =
-                ix.dense_col + ((size_t)d.y * ix.n_blocks + blk) * kBmBlock + (CH == 4 ? 0u : quarter * 4096u);
+                ix.dense_col + ((size_t)d.y * ix.n_blocks + blk) * kBmBlock + quarter * (uint32_t)kTile;
         } else if (d.x == (uint32_t)kBmMid) {
             if (d.z > d.y) s_runs[atomicAdd(&s_ntab, 1)] = make_uint2(d.y, d.z);
         } else if (d.x == (uint32_t)kBmLow) {
@@ -424,52 +425,61 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
         // The (token, round) sequence is the same for every thread; kBmDepth of its loads are in flight.
         // An untabled list is scanned whole: only the rows of this tile count.
         {
-            int it_e = -1;                // iterator state (block-uniform)
-            uint32_t it_p = 0u, it_hi = 0u;
-            bool it_scan = false;
-            auto next_item = [&](uint32_t& val, bool& first) -> bool {
-                first = false;
-                if (it_e >= 0) it_p += kBmThreads;
-                while (it_e < 0 || it_p >= it_hi) {
-                    if (++it_e >= n_run) { it_e = n_run; it_p = 1u; it_hi = 0u; return false; }
-                    it_scan = it_e >= n_tab;
-                    const uint2 r = s_runs[it_scan ? kBmMaxTokens - 1 - (it_e - n_tab) : it_e];
-                    it_p = r.x; it_hi = r.y;
-                    first = true;
-                }
-                val = 0u;                 // 0: adds nothing (a posting's q is >= 2)
-                const uint32_t p = it_p + (uint32_t)tid;
-                if (p < it_hi) {
-                    val = __ldg(ix.post_pack + p);
-                    if (it_scan) {
-                        const int64_t row = ix.post_row[p];
-                        if (row < r0 || row >= r1) val = 0u;
-                    }
-                }
-                return true;
-            };
+            // iterator over (token, round), block-uniform: the runs in s_runs are non-empty
+            int it_e = 0;
+            bool it_scan = n_tab == 0;
+            uint2 it_r = n_run > 0 ? s_runs[it_scan ? kBmMaxTokens - 1 : 0] : make_uint2(0u, 0u);
+            uint32_t it_p = it_r.x;
+            bool it_first = true;
             uint32_t val[kBmDepth];
             bool first[kBmDepth], ok[kBmDepth];
+            // fills slot dd with the thread's posting of the current item and moves on
+#define BM25_FETCH(dd)                                                                              \
+            do {                                                                                    \
+                ok[dd] = it_e < n_run;                                                              \
+                first[dd] = it_first;                                                               \
+                val[dd] = 0u;                     /* 0: adds nothing (a posting's q is >= 2) */     \
+                if (ok[dd]) {                                                                       \
+                    const uint32_t p = it_p + (uint32_t)tid;                                        \
+                    if (p < it_r.y) {                                                               \
+                        val[dd] = __ldg(ix.post_pack + p);                                          \
+                        if (it_scan) {                                                              \
+                            const int64_t row = ix.post_row[p];                                     \
+                            if (row < r0 || row >= r1) val[dd] = 0u;                                \
+                        }                                                                           \
+                    }                                                                               \
+                    it_p += kBmThreads;                                                             \
+                    it_first = false;                                                               \
+                    if (it_p >= it_r.y) {         /* next token */                                  \
+                        ++it_e;                                                                     \
+                        it_first = true;                                                            \
+                        if (it_e < n_run) {                                                         \
+                            it_scan = it_e >= n_tab;                                                \
+                            it_r = s_runs[it_scan ? kBmMaxTokens - 1 - (it_e - n_tab) : it_e];      \
+                            it_p = it_r.x;                                                          \
+                        }                                                                           \
+                    }                                                                               \
+                }                                                                                   \
+            } while (0)
 #pragma unroll
-            for (int dd = 0; dd < kBmDepth; ++dd) { val[dd] = 0u; first[dd] = false; ok[dd] = next_item(val[dd], first[dd]); }
-            bool more = ok[0], any = false;
-            while (more) {                // block-uniform
+            for (int dd = 0; dd < kBmDepth; ++dd) BM25_FETCH(dd);
+            bool any = false;
+            while (ok[0]) {               // block-uniform; slots are consumed in the order they were filled
 #pragma unroll
                 for (int dd = 0; dd < kBmDepth; ++dd) {
-                    if (more && ok[dd]) {
+                    if (ok[dd]) {
                         if (first[dd] && any) __syncthreads();       // the previous term is done
                         any = true;
                         if (val[dd]) {
                             const uint32_t loc = val[dd] >> kBmQBits;                  // row inside the block
                             if (CH == 4) acc[loc] += val[dd] & kBmQMask;
-                            else if ((loc >> 12) == quarter) acc[loc & 4095u] += val[dd] & kBmQMask;
+                            else if ((loc / (uint32_t)kTile) == quarter) acc[loc % (uint32_t)kTile] += val[dd] & kBmQMask;
                         }
-                        ok[dd] = next_item(val[dd], first[dd]);
-                    } else {
-                        more = false;     // slots are consumed in the order they were filled
+                        BM25_FETCH(dd);
                     }
                 }
             }
+#undef BM25_FETCH
         }
         __syncthreads();
         // ---- column tokens, 4096 rows at a time: 4 x 8 bytes per thread and token straight into registers.  A thread
@@ -477,17 +487,21 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
         // shared accesses that are contiguous over the warp.  A column word holds two rows: s_all adds the words
         // whole (sum of the low halves + 65536 * sum of the high halves, modulo 2^32), s_hi the high halves.  The
         // sums are merged into the shared accumulators (the thread's own rows); the last pass also masks the
-        // disallowed rows and takes the thread's maximum.  The loads of the next step are requested before the
-        // current one is added.
+        // disallowed rows and takes the thread's maximum.  Steps = (chunk, group of kBmDnGroup tokens); the loads
+        // of the next step are requested before the current one is added (two register buffers, ping-pong).
         if (n_col > 0 || last) {
             const int ngroups = n_col > 0 ? (n_col + kBmDnGroup - 1) / kBmDnGroup : 1;
-            const int nsteps = CH * ngroups;
-            auto load_step = [&](int s, uint2 (&xx)[kBmDnGroup][4]) {
-                const int c = s / ngroups, e0 = (s - c * ngroups) * kBmDnGroup;
+            uint32_t s_all[8], s_hi[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+            int lc = 0, lg = 0;           // (chunk, group) of the next step to load
+            int cc = 0, cg = 0;           // ... of the next step to add
+            auto load_step = [&](uint2 (&xx)[kBmDnGroup][4]) {
+                const bool live = lc < CH;
 #pragma unroll
                 for (int u = 0; u < kBmDnGroup; ++u) {
-                    if (e0 + u < n_col) {
-                        const uint2* cp = reinterpret_cast<const uint2*>(s_colp[e0 + u] + c * 4096) + tid;
+                    if (live && lg * kBmDnGroup + u < n_col) {
+                        const uint2* cp = reinterpret_cast<const uint2*>(s_colp[lg * kBmDnGroup + u] + lc * 4096) + tid;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(cp + g * 256);
                     } else {
@@ -495,36 +509,23 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                         for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u);
                     }
                 }
+                if (++lg == ngroups) { lg = 0; ++lc; }
             };
-            uint2 x[kBmDnGroup][4];
-            load_step(0, x);
-            uint32_t s_all[8], s_hi[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
-            int c = 0, gi = 0;
-            for (int s = 0; s < nsteps; ++s) {
-                uint2 nx[kBmDnGroup][4];
-                if (s + 1 < nsteps) {
-                    load_step(s + 1, nx);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < kBmDnGroup; ++u)
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) nx[u][g] = make_uint2(0u, 0u);
-                }
+            auto add_step = [&](const uint2 (&xx)[kBmDnGroup][4]) {
 #pragma unroll
                 for (int u = 0; u < kBmDnGroup; ++u)
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        s_all[2 * g + 0] += x[u][g].x;
-                        s_hi[2 * g + 0] += x[u][g].x >> 16;
-                        s_all[2 * g + 1] += x[u][g].y;
-                        s_hi[2 * g + 1] += x[u][g].y >> 16;
+                        s_all[2 * g + 0] += xx[u][g].x;
+                        s_hi[2 * g + 0] += xx[u][g].x >> 16;
+                        s_all[2 * g + 1] += xx[u][g].y;
+                        s_hi[2 * g + 1] += xx[u][g].y >> 16;
                     }
-                if (++gi == ngroups) {    // the chunk's last group: merge
+                if (++cg == ngroups) {    // the chunk's last group: merge
+                    uint32_t* arow = acc + cc * 4096 + 4 * tid;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        uint4 a = *reinterpret_cast<const uint4*>(&acc[c * 4096 + g * 1024 + 4 * tid]);
+                        uint4 a = *reinterpret_cast<const uint4*>(arow + g * 1024);
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const uint32_t hi = s_hi[2 * g + h];
@@ -534,7 +535,7 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                         }
                         if (last) {
                             if (allow != nullptr) {
-                                const int64_t row = r0 + c * 4096 + g * 1024 + 4 * tid;   // 4 rows inside one bitmap byte
+                                const int64_t row = r0 + cc * 4096 + g * 1024 + 4 * tid;  // 4 rows inside one bitmap byte
                                 const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
                                 if (!(bits & 1u)) a.x = 0u;
                                 if (!(bits & 2u)) a.y = 0u;
@@ -545,17 +546,22 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                             const uint32_t mg = m01 > m23 ? m01 : m23;
                             m = mg > m ? mg : m;
                         }
-                        *reinterpret_cast<uint4*>(&acc[c * 4096 + g * 1024 + 4 * tid]) = a;
+                        *reinterpret_cast<uint4*>(arow + g * 1024) = a;
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
-                    gi = 0;
-                    ++c;
+                    cg = 0;
+                    ++cc;
                 }
-#pragma unroll
-                for (int u = 0; u < kBmDnGroup; ++u)
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) x[u][g] = nx[u][g];
+            };
+            uint2 xa[kBmDnGroup][4], xb[kBmDnGroup][4];
+            load_step(xa);
+            while (cc < CH) {
+                load_step(xb);
+                add_step(xa);
+                if (cc >= CH) break;
+                load_step(xa);
+                add_step(xb);
             }
         }
     }
@@ -576,28 +582,29 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
         }
         if (theta < 1u) theta = 1u;
         if (m >= theta) {
-#pragma unroll 1
-            for (int c = 0; c < CH; ++c) {
-                uint32_t mask = 0u;
+            // which of the thread's 4-row groups hold a row >= theta (a handful of rows per warp) ...
+            uint32_t gmask = 0u;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(&acc[c * 4096 + g * 1024 + 4 * tid]);
-                    mask |= (a.x >= theta ? 1u : 0u) << (4 * g);
-                    mask |= (a.y >= theta ? 2u : 0u) << (4 * g);
-                    mask |= (a.z >= theta ? 4u : 0u) << (4 * g);
-                    mask |= (a.w >= theta ? 8u : 0u) << (4 * g);
-                }
-                if (mask) {
-                    int slot = atomicAdd(&s_nlist, __popc(mask));
-                    while (mask) {
-                        const int j = __ffs(mask) - 1;
-                        mask &= mask - 1u;
-                        const uint32_t loc = (uint32_t)(c * 4096) + (uint32_t)((j >> 2) << 10) + (uint32_t)(j & 3);
-                        const uint32_t u = acc[loc + 4 * tid];
-                        if (slot < kBmList) s_list[slot] = ((unsigned long long)u << 32) | (unsigned long long)(~(row_base + loc));
+            for (int j = 0; j < CH * 4; ++j) {
+                const uint4 a = *reinterpret_cast<const uint4*>(&acc[j * 1024 + 4 * tid]);
+                const uint32_t m01 = a.x > a.y ? a.x : a.y, m23 = a.z > a.w ? a.z : a.w;
+                gmask |= ((m01 > m23 ? m01 : m23) >= theta ? 1u : 0u) << j;
+            }
+            // ... and those rows
+            while (gmask) {
+                const int j = __ffs(gmask) - 1;
+                gmask &= gmask - 1u;
+                const uint32_t loc0 = (uint32_t)j * 1024u;
+                const uint4 a = *reinterpret_cast<const uint4*>(&acc[loc0 + 4 * tid]);
+                const uint32_t vv[4] = {a.x, a.y, a.z, a.w};
+                int slot = atomicAdd(&s_nlist, (int)(a.x >= theta) + (int)(a.y >= theta) + (int)(a.z >= theta) + (int)(a.w >= theta));
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (vv[i] >= theta) {
+                        if (slot < kBmList)
+                            s_list[slot] = ((unsigned long long)vv[i] << 32) | (unsigned long long)(~(row_base + loc0 + i));
                         ++slot;
                     }
-                }
             }
         }
     } else {
@@ -911,7 +918,7 @@ struct Bm25Plan {
 };
 static bool bm25_plan_for(const Bm25Device& ix, int k, int ch, Bm25Plan* p) {
     p->ch = ch;
-    p->n_tiles = ch == 4 ? ix.n_blocks : (int)((ix.n_docs + 4095) / 4096);
+    p->n_tiles = (int)((ix.n_docs + (int64_t)ch * 4096 - 1) / ((int64_t)ch * 4096));
     if (p->n_tiles < 1) return false;
     p->H = bm25_heads_per_tile(p->n_tiles, k);
     p->h_tau = bm25_tau_heads(p->n_tiles, k);
@@ -919,22 +926,26 @@ static bool bm25_plan_for(const Bm25Device& ix, int k, int ch, Bm25Plan* p) {
 }
 // block tiles when the launch has enough of them to fill the GPU (148 SMs x 3 CTAs, twice over); quarter-block tiles
 // for small corpora and single queries (more, shorter CTAs: latency)
+int g_bm25_tile_chunks = 0;             // option "bm25_tile": force 1 / 2 / 4 chunks per tile (0 = automatic)
 static bool bm25_plan(const Bm25Device& ix, int k, int Q, Bm25Plan* p) {
+    if (g_bm25_tile_chunks == 1 || g_bm25_tile_chunks == 2 || g_bm25_tile_chunks == 4)
+        if (bm25_plan_for(ix, k, g_bm25_tile_chunks, p)) return true;
     if ((int64_t)Q * ix.n_blocks >= 2 * 148 * 3 && bm25_plan_for(ix, k, 4, p)) return true;
     if (bm25_plan_for(ix, k, 1, p)) return true;
+    if (bm25_plan_for(ix, k, 2, p)) return true;
     return bm25_plan_for(ix, k, 4, p);
 }
 
 bool bm25_fast_supported(const Bm25Device& ix, int k, int max_query_tokens) {
     if (!ix.fast_ok || !ix.post_pack || ix.n_blocks < 1 || max_query_tokens > kBmMaxQueryTokens) return false;
-    Bm25Plan a, b;
-    return bm25_plan_for(ix, k, 1, &a) || bm25_plan_for(ix, k, 4, &b);
+    Bm25Plan a;
+    return bm25_plan_for(ix, k, 1, &a) || bm25_plan_for(ix, k, 2, &a) || bm25_plan_for(ix, k, 4, &a);
 }
 static size_t bm25_heads_bytes(const Bm25Device& ix, int k, int Q) {
     // the larger of the two tilings (the plan of a launch depends on its query count)
     size_t per_q = 0;
     Bm25Plan p;
-    for (int ch : {1, 4})
+    for (int ch : {1, 2, 4})
         if (bm25_plan_for(ix, k, ch, &p)) per_q = std::max(per_q, (size_t)p.n_tiles * (p.H + 1) * sizeof(unsigned long long));
     return (((size_t)Q * per_q) + 255) & ~(size_t)255;
 }
@@ -977,6 +988,8 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
             attr4 = true;
         }
         bm25_filter_kernel<4><<<grid_a, kBmThreads, 4 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
+    } else if (pl.ch == 2) {
+        bm25_filter_kernel<2><<<grid_a, kBmThreads, 2 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
     } else {
         bm25_filter_kernel<1><<<grid_a, kBmThreads, 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
     }

@@ -25,6 +25,9 @@ qs = [np.concatenate([g.choice(n_terms, size=g.integers(8, 13), p=p), g.integers
 for q in qs[:6]:
     ix.search_ids([q], 50)
     print("single device ms", float(_lib.last_timings()[0]))
+import os
+if os.environ.get("BM25_TILE"):
+    _lib.set_option("bm25_tile", int(os.environ["BM25_TILE"]))
 for _ in range(3):
     ix.search_ids(qs, 50)
     print("batch device ms", float(_lib.last_timings()[0]), "per query us", 1e3 * float(_lib.last_timings()[0]) / Q)
