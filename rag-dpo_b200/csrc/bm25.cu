@@ -424,6 +424,19 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
         // (the postings of one term are distinct rows: plain read-modify-write), a barrier separates the terms.
         // The (token, round) sequence is the same for every thread; kBmDepth of its loads are in flight.
         // An untabled list is scanned whole: only the rows of this tile count.
+        // the first column step (chunk 0, first group) is requested now: in flight while the run tokens are added
+        uint2 xa[kBmDnGroup][4];
+#pragma unroll
+        for (int u = 0; u < kBmDnGroup; ++u) {
+            if (u < n_col) {
+                const uint2* cp = reinterpret_cast<const uint2*>(s_colp[u]) + tid;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xa[u][g] = __ldg(cp + g * 256);
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xa[u][g] = make_uint2(0u, 0u);
+            }
+        }
         {
             // iterator over (token, round), block-uniform: the runs in s_runs are non-empty
             int it_e = 0;
@@ -554,8 +567,8 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                     ++cc;
                 }
             };
-            uint2 xa[kBmDnGroup][4], xb[kBmDnGroup][4];
-            load_step(xa);
+            uint2 xb[kBmDnGroup][4];
+            if (++lg == ngroups) { lg = 0; ++lc; }       // step 0 was requested before the run tokens
             while (cc < CH) {
                 load_step(xb);
                 add_step(xa);
@@ -732,7 +745,8 @@ __device__ __forceinline__ void bm25_exact_topk(const Bm25Device& ix, const int3
     if (threadIdx.x == 0) *out_count = s_cnt;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kBmFinishThreads = 1024;   // (survivor, token) look-ups are chains of dependent loads: all of them at once
+__global__ void __launch_bounds__(kBmFinishThreads)
 bm25_finish_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr, int q0,
                    const unsigned long long* __restrict__ heads, int n_tiles, int H, int h_tau, int nsort_tau, int k,
                    int32_t* out_rows, double* out_scores, int32_t* out_counts) {
@@ -1004,7 +1018,7 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    bm25_finish_kernel<<<Q, 256, smem, st>>>(ix, d_q_terms, d_q_ptr, q0, heads, pl.n_tiles, pl.H, pl.h_tau, nsort, k,
+    bm25_finish_kernel<<<Q, kBmFinishThreads, smem, st>>>(ix, d_q_terms, d_q_ptr, q0, heads, pl.n_tiles, pl.H, pl.h_tau, nsort, k,
                                              out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_counts + q0);
     return cudaGetLastError();
 }
