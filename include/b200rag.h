@@ -70,7 +70,9 @@ int rag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_by
  * "sample_resident", "balance_tail", "sample_div" (experiments; defaults 1),
  * "exchange_timeout_ms" (bound of the exchange's flag wait, default 10000),
  * "bm25_fast" (1 = packed-postings filter path, default 1), "bm25_rows_max" (largest row filter served by the
- * listed-rows kernel, default 4096) */
+ * listed-rows kernel, default 4096), "bm25_dense_div" (terms with df >= n_docs / div get a dense 16-bit column when
+ * an index is built, default 8; 0 = none), "bm25_tile" (force 1 / 2 / 4 chunks of 4096 rows per filter CTA,
+ * default 0 = by launch size) */
 int rag_set_option(const char* key, int64_t value);
 /* page-locked host memory: buffers allocated here are DMA'd directly by the host-pointer entry points
  * (no staging copy); any other host pointer is staged through an internal pinned block. */
