@@ -568,13 +568,61 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                 }
             };
             uint2 xb[kBmDnGroup][4];
-            if (++lg == ngroups) { lg = 0; ++lc; }       // step 0 was requested before the run tokens
-            while (cc < CH) {
-                load_step(xb);
-                add_step(xa);
-                if (cc >= CH) break;
-                load_step(xa);
-                add_step(xb);
+            if (n_col <= 3 * kBmDnGroup) {
+                // the usual case, up to 6 column tokens: their pointers stay in registers and the group loop is
+                // unrolled, so a step costs its loads and adds and little else
+                const uint2* cp[3 * kBmDnGroup];
+#pragma unroll
+                for (int u = 0; u < 3 * kBmDnGroup; ++u)
+                    cp[u] = u < n_col ? reinterpret_cast<const uint2*>(s_colp[u]) + tid : nullptr;
+                // requests step (chunk c, group G) into xx; G is a compile-time constant
+#define BM25_LOAD_STEP(xx, G, c)                                                                        \
+                do {                                                                                    \
+                    _Pragma("unroll") for (int u = 0; u < kBmDnGroup; ++u) {                            \
+                        if ((G) * kBmDnGroup + u < n_col) {                                             \
+                            const uint2* q_ = cp[(G) * kBmDnGroup + u] + (c) * 1024;                    \
+                            _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(q_ + g * 256); \
+                        } else {                                                                        \
+                            _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u); \
+                        }                                                                               \
+                    }                                                                                   \
+                } while (0)
+#pragma unroll 1
+                for (int c = 0; c < CH; ++c) {
+                    // xa holds (c, 0)
+                    if (ngroups == 1) {
+                        if (c + 1 < CH) BM25_LOAD_STEP(xb, 0, c + 1);
+                        add_step(xa);
+                    } else {
+                        BM25_LOAD_STEP(xb, 1, c);
+                        add_step(xa);
+                        if (ngroups == 2) {
+                            if (c + 1 < CH) BM25_LOAD_STEP(xa, 0, c + 1);
+                            add_step(xb);
+                            continue;
+                        }
+                        BM25_LOAD_STEP(xa, 2, c);
+                        add_step(xb);
+                        if (c + 1 < CH) BM25_LOAD_STEP(xb, 0, c + 1);
+                        add_step(xa);
+                    }
+                    if (c + 1 < CH) {
+#pragma unroll
+                        for (int u = 0; u < kBmDnGroup; ++u)
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) xa[u][g] = xb[u][g];
+                    }
+                }
+#undef BM25_LOAD_STEP
+            } else {
+                if (++lg == ngroups) { lg = 0; ++lc; }   // step 0 was requested before the run tokens
+                while (cc < CH) {
+                    load_step(xb);
+                    add_step(xa);
+                    if (cc >= CH) break;
+                    load_step(xa);
+                    add_step(xb);
+                }
             }
         }
     }
@@ -995,12 +1043,9 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     dim3 grid_a(pl.n_tiles, Q);
     cudaError_t e = cudaSuccess;
     if (pl.ch == 4) {
-        static bool attr4 = false;
-        if (!attr4) {
-            e = cudaFuncSetAttribute(bm25_filter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4);
-            if (e != cudaSuccess) return e;
-            attr4 = true;
-        }
+        // (a function attribute belongs to the current device: set on every launch, a sharded index runs on several)
+        e = cudaFuncSetAttribute(bm25_filter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4);
+        if (e != cudaSuccess) return e;
         bm25_filter_kernel<4><<<grid_a, kBmThreads, 4 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
     } else if (pl.ch == 2) {
         bm25_filter_kernel<2><<<grid_a, kBmThreads, 2 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
@@ -1012,12 +1057,8 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     int nsort = 32;
     while (nsort < pl.n_tiles * pl.h_tau) nsort <<= 1;
     const size_t smem = (size_t)kBmContrib * sizeof(double) + (size_t)kBmSurvivors * (sizeof(Bm25Key) + 4);
-    static bool attr_set = false;
-    if (!attr_set) {
-        e = cudaFuncSetAttribute(bm25_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    e = cudaFuncSetAttribute(bm25_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     bm25_finish_kernel<<<Q, kBmFinishThreads, smem, st>>>(ix, d_q_terms, d_q_ptr, q0, heads, pl.n_tiles, pl.H, pl.h_tau, nsort, k,
                                              out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_counts + q0);
     return cudaGetLastError();
