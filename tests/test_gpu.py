@@ -1292,3 +1292,31 @@ def test_rerank_step_golden_from_reference_and_batched_vs_oracle():
             ei, ef = no.rerank_select(sc[q, :lens[q]], bo[q, :lens[q]], top_k, ms)
             assert idx[q, :counts[q]].tolist() == ei and np.array_equal(final[q, :counts[q]], np.array(ef)), (top_k, q)
             assert (idx[q, counts[q]:] == -1).all()
+
+
+def test_collection_loaded_from_a_chroma_persist_directory(tmp_path):
+    """DeviceCollection built by b200rag.chroma_store.load_collection from a Chroma persist directory answers like
+    the collection the same rows were add()ed to (cosine space: the stored unit vectors and the raw log vectors
+    normalise to the same rows up to the last bit of the normalisation, so ids are compared, distances to 1e-6)"""
+    from b200rag import DeviceCollection
+    from b200rag.chroma_store import load_collection
+    from oracle import chroma_fixture as cf
+    g = np.random.default_rng(12)
+    n, dim = 3000, 128
+    emb = helpers.synth_unit(n, dim, seed=21) * g.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)
+    ids = [f"c{i}" for i in range(n)]
+    docs = [f"document {i}" for i in range(n)]
+    metas = [{"document_path": f"doc{i % 37}", "chunk_nature": ["GUIDE", "FAQ", "LOI"][i % 3], "chunk_index": i} for i in range(n)]
+    cf.write_store(str(tmp_path), ids, docs, metas, emb, n_flushed=2000, deleted_labels=(777777,))
+    col = load_collection(str(tmp_path), dtype="f32")
+    ref = DeviceCollection(dim=dim, dtype="f32")
+    ref.add(ids=ids, documents=docs, embeddings=emb, metadatas=metas)
+    assert col.count() == n
+    q = helpers.synth_unit(6, dim, seed=22)
+    for where in (None, {"chunk_nature": "FAQ"}, {"document_path": {"$in": ["doc3", "doc5"]}}):
+        a = col.query(query_embeddings=q.tolist(), n_results=10, where=where)
+        b = ref.query(query_embeddings=q.tolist(), n_results=10, where=where)
+        assert a["ids"] == b["ids"] and a["documents"] == b["documents"] and a["metadatas"] == b["metadatas"]
+        assert np.allclose(np.array(a["distances"]), np.array(b["distances"]), atol=1e-6)
+    got = col.get(ids=["c5", "c2500"])
+    assert got["documents"] == ["document 5", "document 2500"]

@@ -181,3 +181,29 @@ def test_block_cyclic_shard_layout_roundtrip():
         for s in range(G):
             ls = local[shard == s]
             assert np.array_equal(ls, np.arange(len(ls)))          # local rows are dense and in global order
+
+
+def test_chroma_store_reader_roundtrip(tmp_path):
+    """the loader of the reference's on-disk vector store (chroma.sqlite3 + HNSW segment; scripts/package_cnil_db.py
+    ships exactly these files) against a fixture written in the same layout: ids / documents / typed metadata in
+    insertion order, flushed vectors from data_level0.bin (deleted elements skipped), the unflushed tail from the
+    write-ahead log (stale records ignored).  FORMAT PARITY UNPINNED (no chromadb wheel here): both sides restate it."""
+    from oracle import chroma_fixture as cf
+    from b200rag import chroma_store as cs
+    g = np.random.default_rng(4)
+    n, dim = 70, 64
+    emb = g.standard_normal((n, dim)).astype(np.float32)
+    ids = [f"chunk_{i}" for i in range(n)]
+    docs = [f"texte {i} é" if i % 7 else None for i in range(n)]
+    metas = [{"document_path": f"p{i % 5}.html", "chunk_index": i, "score": 0.5 * i, "is_enterprise": bool(i % 2)}
+             if i % 9 else None for i in range(n)]
+    for as_object in (False, True):
+        d = tmp_path / f"store_{int(as_object)}"
+        info = cf.write_store(str(d), ids, docs, metas, emb, n_flushed=40, deleted_labels=(999, 1000), pickle_as_object=as_object)
+        st = cs.read_chroma_store(str(d))
+        assert st["ids"] == ids and st["documents"] == docs and st["metadatas"] == metas
+        assert st["dim"] == dim and st["metadata"] == {"hnsw:space": "cosine"}
+        assert np.array_equal(st["embeddings"][:40], info["normalized_flushed"].astype(np.float32))
+        assert np.array_equal(st["embeddings"][40:], emb[40:])
+    with pytest.raises(KeyError):
+        cs.read_chroma_store(str(d), "no_such_collection")
