@@ -27,7 +27,12 @@ struct Bm25Shard {
     DevBuf tabled_terms, dense_terms;
     int n_dense = 0, n_tabled = 0;
     // scratch
-    DevBuf terms, qptr, cand, rows, scores, counts, allow, scratch, index, listed, ranges;
+    DevBuf inbuf, outbuf, cand, scratch, index, ranges;
+    // views into inbuf (terms | q_ptr | allow bitmap | listed rows: ONE upload) and outbuf (scores | rows | counts:
+    // ONE download), set by shard_search_launch
+    int32_t *d_terms = nullptr, *d_qptr = nullptr, *d_listed = nullptr, *d_rows = nullptr, *d_counts = nullptr;
+    uint8_t* d_allow = nullptr;
+    double* d_scores = nullptr;
 };
 
 void shard_free(Bm25Shard* s) {
@@ -38,8 +43,7 @@ void shard_free(Bm25Shard* s) {
     }
     cudaFree(s->d.term_ptr); cudaFree(s->d.post_row); cudaFree(s->d.post_impact); cudaFree(s->d.idf); cudaFree(s->d.score);
     cudaFree(s->d.post_pack); cudaFree(s->d.term_info); cudaFree(s->d.rng_off); cudaFree(s->d.dense_col);
-    for (DevBuf* b : {&s->tabled_terms, &s->dense_terms, &s->terms, &s->qptr, &s->cand, &s->rows, &s->scores, &s->counts,
-                      &s->allow, &s->scratch, &s->index, &s->listed, &s->ranges})
+    for (DevBuf* b : {&s->tabled_terms, &s->dense_terms, &s->inbuf, &s->outbuf, &s->cand, &s->scratch, &s->index, &s->ranges})
         b->release();
     {
         std::lock_guard<std::mutex> tl(R.tmu);
@@ -271,31 +275,33 @@ int shard_search_launch(Bm25Shard& s, const int32_t* q_terms, const int32_t* q_p
     const size_t rb = (size_t)Q * k * 4, sb = (size_t)Q * k * 8, cb = (size_t)Q * 4;
     plan.kp = std::max(16, next_pow2(k));
     plan.n_lists = bm25_range_lists(d.n_docs);
-    RAG_TRY(s.terms.ensure(tb));
-    RAG_TRY(s.qptr.ensure(pb));
-    if (ab) RAG_TRY(s.allow.ensure(ab + 16));
-    if (lb) RAG_TRY(s.listed.ensure(lb));
-    RAG_TRY(s.rows.ensure(rb));
-    RAG_TRY(s.scores.ensure(sb));
-    RAG_TRY(s.counts.ensure(cb));
-    RAG_TRY(s.cx.ensure_pinned(std::max(tb + pb + ab + lb, sb + rb + cb)));
+    auto up16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
+    const size_t o_qptr = up16(tb), o_allow = o_qptr + up16(pb), o_listed = o_allow + up16(ab ? ab + 16 : 0);
+    const size_t in_bytes = o_listed + up16(lb);
+    RAG_TRY(s.inbuf.ensure(in_bytes));
+    RAG_TRY(s.outbuf.ensure(sb + rb + cb));
+    s.d_terms = s.inbuf.as<int32_t>();
+    s.d_qptr = reinterpret_cast<int32_t*>(s.inbuf.as<uint8_t>() + o_qptr);
+    s.d_allow = s.inbuf.as<uint8_t>() + o_allow;
+    s.d_listed = reinterpret_cast<int32_t*>(s.inbuf.as<uint8_t>() + o_listed);
+    s.d_scores = s.outbuf.as<double>();
+    s.d_rows = reinterpret_cast<int32_t*>(s.outbuf.as<uint8_t>() + sb);
+    s.d_counts = reinterpret_cast<int32_t*>(s.outbuf.as<uint8_t>() + sb + rb);
+    RAG_TRY(s.cx.ensure_pinned(std::max(in_bytes, sb + rb + cb)));
     uint8_t* pin = reinterpret_cast<uint8_t*>(s.cx.pinned);
     if (n_tok > 0) memcpy(pin, q_terms, (size_t)n_tok * 4);
-    memcpy(pin + tb, q_ptr, pb);
-    if (ab) memcpy(pin + tb + pb, allow_local, ab);
-    if (lb && n_listed > 0) memcpy(pin + tb + pb + ab, listed_rows, (size_t)n_listed * 4);
-    CU_TRY(cudaMemcpyAsync(s.terms.p, pin, tb, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(s.qptr.p, pin + tb, pb, cudaMemcpyHostToDevice, st));
-    if (ab) CU_TRY(cudaMemcpyAsync(s.allow.p, pin + tb + pb, ab, cudaMemcpyHostToDevice, st));
-    if (lb && n_listed > 0) CU_TRY(cudaMemcpyAsync(s.listed.p, pin + tb + pb + ab, (size_t)n_listed * 4, cudaMemcpyHostToDevice, st));
-    plan.allow_dev = ab ? s.allow.as<uint8_t>() : nullptr;
+    memcpy(pin + o_qptr, q_ptr, pb);
+    if (ab) memcpy(pin + o_allow, allow_local, ab);
+    if (lb && n_listed > 0) memcpy(pin + o_listed, listed_rows, (size_t)n_listed * 4);
+    CU_TRY(cudaMemcpyAsync(s.inbuf.p, pin, in_bytes, cudaMemcpyHostToDevice, st));
+    plan.allow_dev = ab ? s.d_allow : nullptr;
     s.cx.clear_timing();
     set_last_ctx(&s.cx);
     s.cx.rec(0);
     if (d.n_docs == 0) {                       // an empty shard of a small sharded index
-        CU_TRY(cudaMemsetAsync(s.rows.p, 0xFF, rb, st));
-        CU_TRY(cudaMemsetAsync(s.scores.p, 0, sb, st));
-        CU_TRY(cudaMemsetAsync(s.counts.p, 0, cb, st));
+        CU_TRY(cudaMemsetAsync(s.d_rows, 0xFF, rb, st));
+        CU_TRY(cudaMemsetAsync(s.d_scores, 0, sb, st));
+        CU_TRY(cudaMemsetAsync(s.d_counts, 0, cb, st));
         plan.fast = plan.listed = false;
         s.cx.rec(1);
         return RAG_OK;
@@ -304,22 +310,22 @@ int shard_search_launch(Bm25Shard& s, const int32_t* q_terms, const int32_t* q_p
     plan.fast = !plan.listed && g_bm25_fast && bm25_fast_supported(d, k, max_tokens);
     if (plan.listed) {
         // selective row filter: exact scores of the listed rows only — no posting stream at all
-        CU_TRY(bm25_rows_launch(d, s.terms.as<int32_t>(), s.qptr.as<int32_t>(), Q, s.listed.as<int32_t>(), n_listed, k,
-                                s.rows.as<int32_t>(), s.scores.as<double>(), s.counts.as<int32_t>(), st));
+        CU_TRY(bm25_rows_launch(d, s.d_terms, s.d_qptr, Q, s.d_listed, n_listed, k,
+                                s.d_rows, s.d_scores, s.d_counts, st));
         ++R.n_launch;
     } else if (plan.fast) {
         const int chunk = bm25_fast_chunk(d, max_tokens);  // scratch budget / gridDim.y limit
         for (int q0 = 0; q0 < Q; q0 += chunk) {
             const int nq = std::min(chunk, Q - q0);
             RAG_TRY(s.scratch.ensure(bm25_fast_scratch_bytes(d, k, nq, max_tokens)));
-            CU_TRY(bm25_fast_launch(d, s.terms.as<int32_t>(), s.qptr.as<int32_t>(), q0, nq, max_tokens, plan.allow_dev, k, s.scratch.p,
-                                    s.rows.as<int32_t>(), s.scores.as<double>(), s.counts.as<int32_t>(), st));
+            CU_TRY(bm25_fast_launch(d, s.d_terms, s.d_qptr, q0, nq, max_tokens, plan.allow_dev, k, s.scratch.p,
+                                    s.d_rows, s.d_scores, s.d_counts, st));
             R.n_launch += 3;
         }
     } else {
         RAG_TRY(s.cand.ensure((size_t)Q * plan.n_lists * plan.kp * bm25_key_bytes()));
-        CU_TRY(bm25_range_launch(d, s.terms.as<int32_t>(), s.qptr.as<int32_t>(), nullptr, Q, plan.allow_dev, plan.kp, k,
-                                 s.cand.p, s.rows.as<int32_t>(), s.scores.as<double>(), s.counts.as<int32_t>(), st));
+        CU_TRY(bm25_range_launch(d, s.d_terms, s.d_qptr, nullptr, Q, plan.allow_dev, plan.kp, k,
+                                 s.cand.p, s.d_rows, s.d_scores, s.d_counts, st));
         R.n_launch += 2;
     }
     s.cx.rec(1);
@@ -357,19 +363,19 @@ int shard_search_redo(Bm25Shard& s, int Q, int k, const SearchPlan& plan, int32_
     if (rc != RAG_OK) return done(rc);
     cudaError_t e = cudaMemcpyAsync(s.index.p, redo.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess)
-        e = bm25_range_launch(s.d, s.terms.as<int32_t>(), s.qptr.as<int32_t>(), s.index.as<int32_t>(), nr, plan.allow_dev, plan.kp, k,
+        e = bm25_range_launch(s.d, s.d_terms, s.d_qptr, s.index.as<int32_t>(), nr, plan.allow_dev, plan.kp, k,
                               s.cand.p, r_rows.as<int32_t>(), r_scores.as<double>(), r_counts.as<int32_t>(), st);
     R.n_launch += 2;
     // scatter the redone results into the shard's result buffers
     for (int i = 0; i < nr && e == cudaSuccess; ++i) {
         const int q = redo[i];
-        e = cudaMemcpyAsync(s.rows.as<int32_t>() + (size_t)q * k, r_rows.as<int32_t>() + (size_t)i * k, (size_t)k * 4,
+        e = cudaMemcpyAsync(s.d_rows + (size_t)q * k, r_rows.as<int32_t>() + (size_t)i * k, (size_t)k * 4,
                             cudaMemcpyDeviceToDevice, st);
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(s.scores.as<double>() + (size_t)q * k, r_scores.as<double>() + (size_t)i * k, (size_t)k * 8,
+            e = cudaMemcpyAsync(s.d_scores + (size_t)q * k, r_scores.as<double>() + (size_t)i * k, (size_t)k * 8,
                                 cudaMemcpyDeviceToDevice, st);
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(s.counts.as<int32_t>() + q, r_counts.as<int32_t>() + i, 4, cudaMemcpyDeviceToDevice, st);
+            e = cudaMemcpyAsync(s.d_counts + q, r_counts.as<int32_t>() + i, 4, cudaMemcpyDeviceToDevice, st);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return done(fail(RAG_ECUDA, "bm25 redo: %s", cudaGetErrorString(e)));
@@ -590,9 +596,7 @@ int rag_bm25_search(rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr
         cudaStream_t st = sh.cx.stream();
         uint8_t* pin = reinterpret_cast<uint8_t*>(sh.cx.pinned);
         for (int attempt = 0; attempt < 2; ++attempt) {
-            CU_TRY(cudaMemcpyAsync(pin, sh.scores.p, sb, cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaMemcpyAsync(pin + sb, sh.rows.p, rb, cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaMemcpyAsync(pin + sb + rb, sh.counts.p, cb, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(pin, sh.outbuf.p, sb + rb + cb, cudaMemcpyDeviceToHost, st));   // scores | rows | counts
             CU_TRY(cudaStreamSynchronize(st));
             int n_redone = 0;
             if (attempt == 0)
@@ -619,14 +623,14 @@ int rag_bm25_search(rag_bm25_t* ix, const int32_t* q_terms, const int32_t* q_ptr
         cudaStream_t st = sh.cx.stream();
         if (plans[s].fast) {
             int32_t* hc = reinterpret_cast<int32_t*>(sh.cx.pinned);
-            CU_TRY(cudaMemcpyAsync(hc, sh.counts.p, cb, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(hc, sh.d_counts, cb, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
             int n_redone = 0;
             RAG_TRY(shard_search_redo(sh, Q, k, plans[s], hc, &n_redone));
         }
         const int64_t n = (int64_t)Q * k;
         int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 4);
-        bm25_publish_kernel<<<grid < 1 ? 1 : grid, 256, 0, st>>>(sh.rows.as<int32_t>(), sh.scores.as<double>(), n, s, G,
+        bm25_publish_kernel<<<grid < 1 ? 1 : grid, 256, 0, st>>>(sh.d_rows, sh.d_scores, n, s, G,
                                                                    ix->g_ids.as<int64_t>() + (size_t)s * n,
                                                                    ix->g_scores.as<double>() + (size_t)s * n);
         CU_TRY(cudaGetLastError());

@@ -504,10 +504,17 @@ def test_dense_config2_full_size_properties():
         assert rows[4 + j, 0] == r and abs(scores[4 + j, 0] - 1.0) < 1e-6
     r1, s1, _ = c.topk(qq[:1], 10)                                     # batch-1 == batch-7 row
     assert r1[0].tolist() == rows[0].tolist() and np.array_equal(s1[0], scores[0])
-    # against the oracle on the regenerated rows (numpy twin of the generator), 2 queries
+    # against the oracle on the regenerated rows (numpy twin of the generator), 2 queries over all rows ...
     x = synth.synth_rows(1002, 0, n, d)
     er, es, ec = c_oracle.dense_topk(qq[:2], x, no.DT_F32, 10)
     assert rows[:2].tolist() == er.tolist() and np.array_equal(scores[:2], es)
+    # ... and 64 queries through the batched (tensor-core) path against the pooled oracle: an fp32 GEMM proposes 256
+    # rows per query, oracle.c re-scores them in the canonical fp64 order (the pool's depth is asserted inside)
+    import bench
+    q64 = synth.unit_queries(64, d, 2012)
+    rows64, scores64, counts64 = c.topk(q64, 10)
+    ei, es64 = bench.oracle_topk_full(x, q64, 10, "f32")
+    assert (counts64 == 10).all() and rows64.tolist() == ei.tolist() and np.array_equal(scores64, es64)
     c.close()
 
 
@@ -691,10 +698,15 @@ def test_config3_shard_shape_batch4096_top100():
     rows, scores, counts = c.topk(q, k)
     assert (counts == k).all() and (np.diff(scores, axis=1) <= 0).all()
     assert _lib.counters()["fallbacks"] - f0 <= 1
+    stored = c.download()
     pick = [0, 1, 2047, 4095]
-    raw = raw_rows(c.download(), no.DT_BF16)
-    er, es, ec = c_oracle.dense_topk(q[pick], raw, no.DT_BF16, k)
+    er, es, ec = c_oracle.dense_topk(q[pick], raw_rows(stored, no.DT_BF16), no.DT_BF16, k)
     assert rows[pick].tolist() == er.tolist() and np.array_equal(scores[pick], es)
+    # 64 more queries against the pooled oracle (fp32 GEMM pool of 512 rows, canonical fp64 re-score by oracle.c)
+    import bench
+    pick64 = list(range(5, 4096, 64))
+    ei, es64 = bench.oracle_topk_full(stored, q[pick64], k, "bf16", pool=512)
+    assert rows[pick64].tolist() == ei.tolist() and np.array_equal(scores[pick64], es64)
     c.close()
 
 
