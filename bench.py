@@ -770,6 +770,17 @@ def run_c1(env, args):
     t0 = time.perf_counter()
     res_batch = r.retrieve_candidates_batch(questions, n_candidates=40)
     t_batch = time.perf_counter() - t0
+    if os.environ.get("B200RAG_PROFILE_C1"):       # where the host time of the two front-ends goes (stderr)
+        import cProfile
+        import pstats
+        for name, fn in (("per question", lambda: [r.retrieve_candidates(q, n_candidates=40) for q in questions]),
+                         ("batch", lambda: r.retrieve_candidates_batch(questions, n_candidates=40))):
+            pr = cProfile.Profile()
+            pr.enable()
+            fn()
+            pr.disable()
+            log(f"--- cProfile: {name}")
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(22)
     same = all([c.chunk_id for c in a] == [c.chunk_id for c in b] and
                [c.hybrid_score for c in a] == [c.hybrid_score for c in b] and
                [c.distance for c in a] == [c.distance for c in b] and

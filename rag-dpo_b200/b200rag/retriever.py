@@ -286,14 +286,20 @@ def _retrieve_candidates_batch(self, queries, n_candidates: int = 100, where_fil
     f_ids, f_scores, f_counts = rrf_fuse_rows(ids, weights, 60, n_candidates)
     # 6. materialise only the final candidates
     out = []
+    dist_all = (1.0 - d_scores).astype(np.float32)                # distance_from_score, vectorised
     for qi in range(Q):
         nv = len(variants[qi])
         best_dist, best_bm25 = {}, {}
         for v in range(nv):
             rows, vi = dense_lists[(qi, v)]
-            pos = {r: j for j, r in enumerate(d_rows[vi, :d_counts[vi]].tolist())}
-            for r in rows:
-                dist = distance_from_score(d_scores[vi, pos[r]])
+            all_rows = d_rows[vi, :d_counts[vi]].tolist()
+            dists = dist_all[vi, :d_counts[vi]].tolist()          # float32(1 - score) as python floats
+            if len(rows) == len(all_rows):                        # no doc_filter: the list as returned
+                pairs = zip(all_rows, dists)
+            else:
+                pos = dict(zip(all_rows, dists))
+                pairs = ((r, pos[r]) for r in rows)
+            for r, dist in pairs:
                 if r not in best_dist or dist < best_dist[r]:
                     best_dist[r] = dist
             if use_bm25:

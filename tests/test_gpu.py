@@ -811,6 +811,36 @@ def test_bm25_filter_index_classes_vs_oracle(dense_div):
     ix.close()
 
 
+@pytest.mark.parametrize("tile", [1, 2, 4])
+def test_bm25_filter_tile_sizes_vs_oracle(tile):
+    """the filter kernel's three tile sizes (4096 / 8192 / 16384 rows per CTA; picked by launch size in production,
+    forced here) over column, run and scanned tokens, with and without a row filter, all equal to the oracle"""
+    from b200rag import _lib
+    from b200rag.bm25 import DeviceBM25, Postings
+    n_docs = 40000
+    docs, n_terms = helpers.zipf_docs(n_docs, 2000, seed=3, lo=10, hi=40)
+    p = Postings.from_term_ids(docs, n_terms=n_terms)
+    o = no.CsrBM25(docs)
+    ix = DeviceBM25(p)
+    g = np.random.default_rng(1)
+    by_df = np.argsort(-np.diff(p.term_ptr))
+    qs = [np.concatenate([by_df[g.integers(0, 10, size=3)], by_df[g.integers(10, 200, size=4)],
+                          g.integers(0, n_terms, size=3)]).astype(np.int32) for _ in range(12)]
+    allow = g.random(n_docs) < 0.4
+    bm = np.packbits(allow, bitorder="little")
+    _lib.set_option("bm25_tile", tile)
+    try:
+        for k in (10, 50):
+            for mask, bits in ((None, None), (allow, bm)):
+                rows, scores, counts = ix.search_ids(qs, k, bits)
+                for i, qt in enumerate(qs):
+                    er, es = o.search(qt.tolist(), k, mask)
+                    assert rows[i, :counts[i]].tolist() == er.tolist() and np.array_equal(scores[i, :counts[i]], es), (k, i)
+    finally:
+        _lib.set_option("bm25_tile", 0)
+    ix.close()
+
+
 def test_clustered_corpus_through_the_tensor_core_path():
     """Rows sorted by cluster (adjacent rows are near-duplicates, as chunks of one document are): every query's
     neighbours sit in one or two row tiles, and the sample may miss the query's cluster entirely."""
