@@ -271,7 +271,74 @@ class DeviceChunkBM25Index:
                 self.chunk_metadatas.append(metadata)
                 self.corpus_tokens.append(tokens)
             offset += batch_size
-        self._finish(Postings.from_token_lists(self.corpus_tokens))
+        self._vocab, self._flat, self._doc_ptr = {}, np.zeros(0, np.int32), np.zeros(1, np.int64)
+        self._append_tokens(self.corpus_tokens)
+        self._finish(Postings.from_flat_tokens(self._doc_ptr, self._flat, n_terms=len(self._vocab), vocab=self._vocab))
+
+    # ---- incremental maintenance (the reference rebuilds from the whole collection, src/rag/pipeline.py:1031-1036;
+    # these keep the tokens of the chunks already indexed and only tokenise what is new) ------------------------
+    def _append_tokens(self, token_lists):
+        """term ids of new documents appended to the cached flat array; the vocabulary keeps its first-seen order"""
+        n_new = sum(len(t) for t in token_lists)
+        flat = np.empty(n_new, dtype=np.int32)
+        setdefault, vocab = self._vocab.setdefault, self._vocab
+        pos = 0
+        for toks in token_lists:
+            for w in toks:
+                flat[pos] = setdefault(w, len(vocab))
+                pos += 1
+        ptr = np.zeros(len(token_lists), dtype=np.int64)
+        if len(token_lists):
+            np.cumsum([len(t) for t in token_lists], out=ptr)
+        self._doc_ptr = np.concatenate([self._doc_ptr, self._doc_ptr[-1] + ptr])
+        self._flat = np.concatenate([self._flat, flat])
+
+    def add_chunks(self, ids, documents, metadatas=None) -> int:
+        """collection.add for the keyword index (enterprise ingestion, src/processing/ingest_enterprise.py:241-246):
+        the new chunks are tokenised, the CSR is rebuilt natively from the cached term ids (rag_csr_build) and the
+        device index replaced.  Identical to build_from_collection over the grown collection.  Returns the number
+        of chunks indexed (empty texts are skipped, as in the build)."""
+        if not self._is_built or not hasattr(self, "_vocab"):
+            raise RuntimeError("Index non construit. Appelez build_from_collection() d'abord.")
+        metadatas = metadatas if metadatas is not None else [{} for _ in ids]
+        new_tokens = []
+        for chunk_id, text, metadata in zip(ids, documents, metadatas):
+            if not text or not text.strip():
+                continue
+            tokens = self.tokenizer(text)
+            if not tokens:
+                continue
+            self.chunk_ids.append(chunk_id)
+            self.chunk_texts.append(text)
+            self.chunk_metadatas.append(metadata)
+            self.corpus_tokens.append(tokens)
+            new_tokens.append(tokens)
+        if new_tokens:
+            self._append_tokens(new_tokens)
+            self._finish(Postings.from_flat_tokens(self._doc_ptr, self._flat, n_terms=len(self._vocab), vocab=self._vocab))
+        return len(new_tokens)
+
+    def remove_chunks(self, ids) -> int:
+        """collection.delete for the keyword index (src/processing/ingest_enterprise.py:272,304): the chunks leave
+        the index; the vocabulary is renumbered in first-seen order of what remains (what a fresh build yields),
+        nothing is re-tokenised."""
+        if not self._is_built or not hasattr(self, "_vocab"):
+            raise RuntimeError("Index non construit. Appelez build_from_collection() d'abord.")
+        gone = set(ids)
+        keep = [i for i, cid in enumerate(self.chunk_ids) if cid not in gone]
+        removed = len(self.chunk_ids) - len(keep)
+        if removed == 0:
+            return 0
+        if not keep:
+            raise ValueError("cannot remove every chunk of a BM25 index")
+        self.chunk_ids = [self.chunk_ids[i] for i in keep]
+        self.chunk_texts = [self.chunk_texts[i] for i in keep]
+        self.chunk_metadatas = [self.chunk_metadatas[i] for i in keep]
+        self.corpus_tokens = [self.corpus_tokens[i] for i in keep]
+        self._vocab, self._flat, self._doc_ptr = {}, np.zeros(0, np.int32), np.zeros(1, np.int64)
+        self._append_tokens(self.corpus_tokens)
+        self._finish(Postings.from_flat_tokens(self._doc_ptr, self._flat, n_terms=len(self._vocab), vocab=self._vocab))
+        return removed
 
     def build_from_postings(self, postings, chunk_ids=None, chunk_texts=None, chunk_metadatas=None):
         """Index pre-tokenised / synthetic corpora (integer term ids)."""
