@@ -380,8 +380,10 @@ __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q
     }
 }
 
-template <int CH>
-__global__ void __launch_bounds__(kBmThreads, 3)
+// CH: 4096-row units per tile; T: threads.  A thread owns 16 rows of every CHUNK of 16 * T rows (4 groups of 4 rows,
+// 4 * T rows apart), so a tile is NCK = CH * 4096 / (16 * T) chunks.
+template <int CH, int T>
+__global__ void __launch_bounds__(T, T >= 512 ? 2 : 3)
 bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, const uint8_t* __restrict__ allow, int H,
                    unsigned long long* __restrict__ heads) {
     extern __shared__ __align__(16) uint32_t acc[];   // CH x 4096 accumulators
@@ -390,6 +392,8 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
     __shared__ int s_ntab, s_nscan, s_ncol, s_nlist;
     __shared__ unsigned long long s_list[kBmList];
     constexpr int kTile = CH * 4096;
+    constexpr int kChunk = 16 * T, kGrp = 4 * T, NCK = kTile / kChunk;
+    static_assert(NCK >= 1 && NCK * kChunk == kTile, "tile must be whole chunks");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x;
     constexpr int kSubBits = CH == 4 ? 0 : (CH == 2 ? 1 : 2);      // tiles per block = 1 << kSubBits
@@ -399,7 +403,7 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
     const int64_t r1 = r0 + kTile < ix.n_docs ? r0 + kTile : ix.n_docs;
     const uint4* my_rec = rec + ((size_t)blockIdx.y * ix.n_blocks + blk) * stride;
 #pragma unroll
-    for (int j = 0; j < CH * 4; ++j) *reinterpret_cast<uint4*>(&acc[j * 1024 + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
+    for (int j = 0; j < NCK * 4; ++j) *reinterpret_cast<uint4*>(&acc[j * kGrp + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s_nlist = 0;
     uint32_t m = 0u;                      // the thread's largest upper bound (set in the last pass)
     for (int t0 = 0; t0 < stride; t0 += kBmMaxTokens) {
@@ -431,7 +435,7 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
             if (u < n_col) {
                 const uint2* cp = reinterpret_cast<const uint2*>(s_colp[u]) + tid;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) xa[u][g] = __ldg(cp + g * 256);
+                for (int g = 0; g < 4; ++g) xa[u][g] = __ldg(cp + g * T);
             } else {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) xa[u][g] = make_uint2(0u, 0u);
@@ -461,7 +465,7 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                             if (row < r0 || row >= r1) val[dd] = 0u;                                \
                         }                                                                           \
                     }                                                                               \
-                    it_p += kBmThreads;                                                             \
+                    it_p += T;                                                                      \
                     it_first = false;                                                               \
                     if (it_p >= it_r.y) {         /* next token */                                  \
                         ++it_e;                                                                     \
@@ -510,13 +514,13 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
             int lc = 0, lg = 0;           // (chunk, group) of the next step to load
             int cc = 0, cg = 0;           // ... of the next step to add
             auto load_step = [&](uint2 (&xx)[kBmDnGroup][4]) {
-                const bool live = lc < CH;
+                const bool live = lc < NCK;
 #pragma unroll
                 for (int u = 0; u < kBmDnGroup; ++u) {
                     if (live && lg * kBmDnGroup + u < n_col) {
-                        const uint2* cp = reinterpret_cast<const uint2*>(s_colp[lg * kBmDnGroup + u] + lc * 4096) + tid;
+                        const uint2* cp = reinterpret_cast<const uint2*>(s_colp[lg * kBmDnGroup + u] + lc * kChunk) + tid;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(cp + g * 256);
+                        for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(cp + g * T);
                     } else {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u);
@@ -535,10 +539,10 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                         s_hi[2 * g + 1] += xx[u][g].y >> 16;
                     }
                 if (++cg == ngroups) {    // the chunk's last group: merge
-                    uint32_t* arow = acc + cc * 4096 + 4 * tid;
+                    uint32_t* arow = acc + cc * kChunk + 4 * tid;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        uint4 a = *reinterpret_cast<const uint4*>(arow + g * 1024);
+                        uint4 a = *reinterpret_cast<const uint4*>(arow + g * kGrp);
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const uint32_t hi = s_hi[2 * g + h];
@@ -548,7 +552,7 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                         }
                         if (last) {
                             if (allow != nullptr) {
-                                const int64_t row = r0 + cc * 4096 + g * 1024 + 4 * tid;  // 4 rows inside one bitmap byte
+                                const int64_t row = r0 + cc * kChunk + g * kGrp + 4 * tid;  // 4 rows inside one bitmap byte
                                 const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
                                 if (!(bits & 1u)) a.x = 0u;
                                 if (!(bits & 2u)) a.y = 0u;
@@ -559,7 +563,7 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                             const uint32_t mg = m01 > m23 ? m01 : m23;
                             m = mg > m ? mg : m;
                         }
-                        *reinterpret_cast<uint4*>(arow + g * 1024) = a;
+                        *reinterpret_cast<uint4*>(arow + g * kGrp) = a;
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
@@ -580,33 +584,33 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
                 do {                                                                                    \
                     _Pragma("unroll") for (int u = 0; u < kBmDnGroup; ++u) {                            \
                         if ((G) * kBmDnGroup + u < n_col) {                                             \
-                            const uint2* q_ = cp[(G) * kBmDnGroup + u] + (c) * 1024;                    \
-                            _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(q_ + g * 256); \
+                            const uint2* q_ = cp[(G) * kBmDnGroup + u] + (c) * (kChunk / 4);                 \
+                            _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(q_ + g * T);   \
                         } else {                                                                        \
                             _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u); \
                         }                                                                               \
                     }                                                                                   \
                 } while (0)
 #pragma unroll 1
-                for (int c = 0; c < CH; ++c) {
+                for (int c = 0; c < NCK; ++c) {
                     // xa holds (c, 0)
                     if (ngroups == 1) {
-                        if (c + 1 < CH) BM25_LOAD_STEP(xb, 0, c + 1);
+                        if (c + 1 < NCK) BM25_LOAD_STEP(xb, 0, c + 1);
                         add_step(xa);
                     } else {
                         BM25_LOAD_STEP(xb, 1, c);
                         add_step(xa);
                         if (ngroups == 2) {
-                            if (c + 1 < CH) BM25_LOAD_STEP(xa, 0, c + 1);
+                            if (c + 1 < NCK) BM25_LOAD_STEP(xa, 0, c + 1);
                             add_step(xb);
                             continue;
                         }
                         BM25_LOAD_STEP(xa, 2, c);
                         add_step(xb);
-                        if (c + 1 < CH) BM25_LOAD_STEP(xb, 0, c + 1);
+                        if (c + 1 < NCK) BM25_LOAD_STEP(xb, 0, c + 1);
                         add_step(xa);
                     }
-                    if (c + 1 < CH) {
+                    if (c + 1 < NCK) {
 #pragma unroll
                         for (int u = 0; u < kBmDnGroup; ++u)
 #pragma unroll
@@ -616,10 +620,10 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
 #undef BM25_LOAD_STEP
             } else {
                 if (++lg == ngroups) { lg = 0; ++lc; }   // step 0 was requested before the run tokens
-                while (cc < CH) {
+                while (cc < NCK) {
                     load_step(xb);
                     add_step(xa);
-                    if (cc >= CH) break;
+                    if (cc >= NCK) break;
                     load_step(xa);
                     add_step(xb);
                 }
@@ -646,8 +650,8 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
             // which of the thread's 4-row groups hold a row >= theta (a handful of rows per warp) ...
             uint32_t gmask = 0u;
 #pragma unroll
-            for (int j = 0; j < CH * 4; ++j) {
-                const uint4 a = *reinterpret_cast<const uint4*>(&acc[j * 1024 + 4 * tid]);
+            for (int j = 0; j < NCK * 4; ++j) {
+                const uint4 a = *reinterpret_cast<const uint4*>(&acc[j * kGrp + 4 * tid]);
                 const uint32_t m01 = a.x > a.y ? a.x : a.y, m23 = a.z > a.w ? a.z : a.w;
                 gmask |= ((m01 > m23 ? m01 : m23) >= theta ? 1u : 0u) << j;
             }
@@ -655,7 +659,7 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
             while (gmask) {
                 const int j = __ffs(gmask) - 1;
                 gmask &= gmask - 1u;
-                const uint32_t loc0 = (uint32_t)j * 1024u;
+                const uint32_t loc0 = (uint32_t)j * (uint32_t)kGrp;
                 const uint4 a = *reinterpret_cast<const uint4*>(&acc[loc0 + 4 * tid]);
                 const uint32_t vv[4] = {a.x, a.y, a.z, a.w};
                 int slot = atomicAdd(&s_nlist, (int)(a.x >= theta) + (int)(a.y >= theta) + (int)(a.z >= theta) + (int)(a.w >= theta));
@@ -674,10 +678,10 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
         for (int h = 0; h <= H; ++h) {
             uint32_t best = 0u, bloc = 0xFFFFFFFFu;
 #pragma unroll 1
-            for (int c = 0; c < CH; ++c)
+            for (int c = 0; c < NCK; ++c)
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const uint32_t base = (uint32_t)(c * 4096 + g * 1024);
+                    const uint32_t base = (uint32_t)(c * kChunk + g * kGrp);
                     const uint4 a = *reinterpret_cast<const uint4*>(&acc[base + 4 * tid]);
                     if (a.x > best) { best = a.x; bloc = base + 0u; }     // ascending rows, strict >: lowest row wins
                     if (a.y > best) { best = a.y; bloc = base + 1u; }
@@ -1044,13 +1048,15 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     cudaError_t e = cudaSuccess;
     if (pl.ch == 4) {
         // (a function attribute belongs to the current device: set on every launch, a sharded index runs on several)
-        e = cudaFuncSetAttribute(bm25_filter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4);
+        // (512-thread CTAs, 2 per SM, were tried for the 32 resident warps: 64 registers spill and the 16-warp
+        // barriers cost more than the occupancy returns: 3.45 vs 2.61 us/query)
+        e = cudaFuncSetAttribute(bm25_filter_kernel<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4);
         if (e != cudaSuccess) return e;
-        bm25_filter_kernel<4><<<grid_a, kBmThreads, 4 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
+        bm25_filter_kernel<4, 256><<<grid_a, 256, 4 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
     } else if (pl.ch == 2) {
-        bm25_filter_kernel<2><<<grid_a, kBmThreads, 2 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
+        bm25_filter_kernel<2, 256><<<grid_a, 256, 2 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
     } else {
-        bm25_filter_kernel<1><<<grid_a, kBmThreads, 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
+        bm25_filter_kernel<1, 256><<<grid_a, 256, 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
