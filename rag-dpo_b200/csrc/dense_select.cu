@@ -219,14 +219,104 @@ select_refine_kernel(const uint64_t* __restrict__ cand, const int32_t* __restric
         const uint64_t* src = cand + (size_t)b * n_lists * list_len;
         const int capacity = n_lists * list_len;
         WarpTopK t;
-        if (flat_counts) {          // ONE contiguous list with a count: 32-key blocks dealt round-robin to the warps
-            t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
+        if (flat_counts) {          // ONE contiguous list with a count (the tensor-core filter's survivors)
             const int raw = counts[b];
             const int total = raw < capacity ? raw : capacity;
             if (overflow && threadIdx.x == 0) overflow[b] = raw > capacity ? 1 : 0;
+            // ---- histogram select (the usual case: ~E = 1024 survivors, kp of them wanted).  The keys stay in
+            // registers (<= 8 per thread); a 256-bin histogram over [min, max] of their ordered scores finds the bin
+            // that holds the kp-th best; the keys at or above that bin — kp and a few, the tail of the score
+            // distribution is sparse — are compacted and ordered by rank counting.  No sort of the other ~900 keys.
+            constexpr int kPerThread = 8;
+            if (total <= kPerThread * (int)blockDim.x && kp >= 32) {        // block-uniform
+                uint64_t key[kPerThread];
+                uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+#pragma unroll
+                for (int u = 0; u < kPerThread; ++u) {
+                    const int i = (int)threadIdx.x + u * (int)blockDim.x;
+                    key[u] = i < total ? src[i] : 0ull;
+                    if (key[u] != 0ull) {
+                        const uint32_t o = (uint32_t)(key[u] >> 32);
+                        lo = o < lo ? o : lo;
+                        hi = o > hi ? o : hi;
+                    }
+                }
+                uint32_t* s_mm = reinterpret_cast<uint32_t*>(sm_keys + (size_t)8 * kp);      // [16]: per-warp min / max
+                uint32_t* hist = s_mm + 16;                                                 // [256]
+                uint64_t* sel = sm_keys + (size_t)2 * kp;                                   // [2 * kp] selected keys
+                lo = __reduce_min_sync(0xffffffffu, lo);
+                hi = __reduce_max_sync(0xffffffffu, hi);
+                if (lane == 0) { s_mm[warp] = lo; s_mm[8 + warp] = hi; }
+                for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+                if (threadIdx.x == 0) { s_n = 0; s_thr = 0ull; }
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < kMergeWarps; ++w) {
+                    lo = s_mm[w] < lo ? s_mm[w] : lo;
+                    hi = s_mm[8 + w] > hi ? s_mm[8 + w] : hi;
+                }
+                int bstar = 0;                       // keys in bins >= bstar are selected (0: all of them)
+                int shift = 0;
+                if (total > kp && hi > lo) {         // block-uniform
+                    const uint32_t range = hi - lo;
+                    shift = 32 - __clz(range) - 8;   // (range >> shift) < 256
+                    if (shift < 0) shift = 0;
+#pragma unroll
+                    for (int u = 0; u < kPerThread; ++u)
+                        if (key[u] != 0ull) atomicAdd(&hist[((uint32_t)(key[u] >> 32) - lo) >> shift], 1u);
+                    __syncthreads();
+                    if (warp == 0) {                 // suffix counts: lane l owns bins 8l .. 8l+7
+                        uint32_t c[8], mine = 0u;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; mine += c[j]; }
+                        uint32_t suf = mine;         // inclusive suffix sum over lanes >= l
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const uint32_t v = __shfl_down_sync(0xffffffffu, suf, off);
+                            if (lane + off < 32) suf += v;
+                        }
+                        const uint32_t above = suf - mine;           // keys in the bins of higher lanes
+                        if (above < (uint32_t)kp && suf >= (uint32_t)kp) {   // exactly one lane
+                            uint32_t run = above;
+                            int j = 7;
+                            for (; j > 0; --j) {
+                                run += c[j];
+                                if (run >= (uint32_t)kp) break;
+                            }
+                            if (j == 0) run += c[0];
+                            // (the loop leaves j at the bin where the count reaches kp; run = keys at or above it)
+                            s_thr = ((uint64_t)(uint32_t)(8 * lane + j) << 32) | run;
+                        }
+                    }
+                    __syncthreads();
+                    bstar = (int)(s_thr >> 32);
+                }
+                const int n_sel = (total > kp && hi > lo) ? (int)(uint32_t)s_thr : total;
+                if (n_sel <= 2 * kp) {               // block-uniform; else (mass ties in the boundary bin) the sort below
+#pragma unroll
+                    for (int u = 0; u < kPerThread; ++u) {
+                        if (key[u] != 0ull && (int)(((uint32_t)(key[u] >> 32) - lo) >> shift) >= bstar)
+                            sel[atomicAdd(&s_n, 1)] = key[u];
+                    }
+                    __syncthreads();
+                    const int ns = s_n;              // == n_sel, or the number of non-empty keys when all are taken
+                    for (int e = threadIdx.x; e < ns; e += blockDim.x) {
+                        const uint64_t me = sel[e];
+                        int rank = 0;
+                        for (int j = 0; j < ns; ++j) rank += sel[j] > me;          // keys are distinct
+                        if (rank < kp) sm_keys[rank] = me;
+                    }
+                    for (int i = ns + threadIdx.x; i < kp; i += blockDim.x) sm_keys[i] = 0ull;
+                    merged = true;
+                }
+                __syncthreads();
+            }
+            if (!merged) {          // 32-key blocks dealt round-robin to the warps, per-warp top-kp, pairwise merge
+            t.init(sm_keys + (size_t)warp * 2 * kp, kp, lane);
             for (int i0 = warp * 32; i0 < total; i0 += kMergeWarps * 32) {
                 const int i = i0 + lane;
                 t.offer(i < total ? src[i] : 0ull, lane);
+            }
             }
         } else {                    // n_lists lists of list_len keys (0 = empty): warp w takes lists w, w+8, ...
             const int32_t* cnt = counts ? counts + (size_t)b * n_lists : nullptr;
