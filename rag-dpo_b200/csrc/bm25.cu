@@ -4,16 +4,16 @@
 // src/rag/bm25_index.py:153,265) and the Python select loop of
 // ChunkBM25Index.search (src/rag/bm25_index.py:267-279).
 //
-// Bit-parity rules: fp64 throughout, numpy's evaluation order,
-// no FMA contraction (explicit __dmul_rn/__ddiv_rn/__dadd_rn), and the score of
-// a row is accumulated token by token in query order.  Within a token every
-// posting hits a distinct row, so no atomics are needed for the accumulation.
-// rag_bm25_search uses the fused bm25_range_kernel (scores of a 4096-row range in
-// shared memory); rag_bm25_scores (full get_scores vector) uses one
-// bm25_accumulate_kernel launch per token over a global accumulator.
+// Bit-parity rules: the scores that are RETURNED are fp64 throughout, numpy's evaluation order, no
+// FMA contraction (explicit __dmul_rn/__ddiv_rn/__dadd_rn), accumulated token by token in query order.
+//   rag_bm25_search  fast path: an integer FILTER over the packed postings / dense columns (fixed-point upper bounds of
+//                    idf*impact; bm25_resolve_kernel + bm25_filter_kernel) finds k + a handful of survivors per
+//                    query, whose exact fp64 scores are recomputed from the postings (bm25_finish_kernel);
+//                    robust path: fp64 accumulators of a 4096-row range in shared memory (bm25_range_kernel);
+//   rag_bm25_scores  (full get_scores vector) one bm25_accumulate_kernel launch per token over a global accumulator.
 //
-// Algorithmic bytes per query: sum over query tokens of df(t) * (4 + 8)
-// (row id + fp64 impact) + 16 * touched rows (accumulator read-modify-write).
+// Algorithmic bytes per query of the fast path: sum over the query's tokens of the term's list in the format that
+// serves it — 4 x df (packed stream) or 2 x n_docs (dense column); exact path: df x 12 (row id + fp64 impact).
 #include <math.h>
 
 #include <algorithm>
