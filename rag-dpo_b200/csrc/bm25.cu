@@ -350,8 +350,10 @@ __device__ __forceinline__ void bm25_emit_heads(const unsigned long long* s_list
 // thread instead of walking q_ptr -> terms -> term_info -> term_ptr -> rng_off itself: x = class, and
 //   DENSE: y = column;   MID: [y, z) = the term's run inside this block;   LOW: [y, z) = the term's whole list.
 // Slots past the query's last token are kBmSkip.
+// low_search: an untabled (LOW) list is narrowed to its run inside the block by two searches and reported as MID, so
+// that the consumer sees block-local runs only (bm25_filter_tma_kernel).
 __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
-                                    int q0, int Q, int stride, uint4* __restrict__ rec) {
+                                    int q0, int Q, int stride, int low_search, uint4* __restrict__ rec) {
     const int64_t per_q = (int64_t)ix.n_blocks * stride;
     const int64_t total = (int64_t)Q * per_q;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -372,11 +374,249 @@ __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q
                     const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_blocks + 1) + blk;
                     d = make_uint4((uint32_t)cls, base + (uint32_t)ro[0], base + (uint32_t)ro[1], 0u);
                 } else if (cls == kBmLow) {
-                    d = make_uint4((uint32_t)cls, (uint32_t)ix.term_ptr[t], (uint32_t)ix.term_ptr[t + 1], 0u);
+                    const int64_t lo = ix.term_ptr[t], hi = ix.term_ptr[t + 1];
+                    if (low_search) {
+                        const int64_t a = bm25_lower_bound(ix.post_row, lo, hi, (int64_t)blk * kBmBlock);
+                        const int64_t b = bm25_lower_bound(ix.post_row, a, hi, (int64_t)(blk + 1) * kBmBlock);
+                        d = make_uint4((uint32_t)kBmMid, (uint32_t)a, (uint32_t)b, 0u);
+                    } else {
+                        d = make_uint4((uint32_t)cls, (uint32_t)lo, (uint32_t)hi, 0u);
+                    }
                 }
             }
         }
         rec[e] = d;
+    }
+}
+
+
+// ---- column tokens, 4096 rows at a time: 4 x 8 bytes per thread and token straight into registers.  A thread
+// owns the local rows c * 4096 + g * 1024 + 4 * tid + i (g, i = 0..3): 8-byte column loads and 16-byte
+// shared accesses that are contiguous over the warp.  A column word holds two rows: s_all adds the words
+// whole (sum of the low halves + 65536 * sum of the high halves, modulo 2^32), s_hi the high halves.  The
+// sums are merged into the shared accumulators (the thread's own rows); the last pass also masks the
+// disallowed rows and takes the thread's maximum.  Steps = (chunk, group of kBmDnGroup tokens); the loads
+// of the next step are requested before the current one is added (two register buffers, ping-pong).
+// xa holds step (chunk 0, group 0), requested by the caller (in flight while the run tokens are added).
+template <int CH, int T>
+__device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t* const* s_colp, int n_col, bool last,
+                                                  uint2 (&xa)[kBmDnGroup][4], const uint8_t* __restrict__ allow,
+                                                  int64_t r0, int64_t r1, int tid, uint32_t& m) {
+    constexpr int kTile = CH * 4096;
+    constexpr int kChunk = 16 * T, kGrp = 4 * T, NCK = kTile / kChunk;
+    const int ngroups = n_col > 0 ? (n_col + kBmDnGroup - 1) / kBmDnGroup : 1;
+    uint32_t s_all[8], s_hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+    int lc = 0, lg = 0;           // (chunk, group) of the next step to load
+    int cc = 0, cg = 0;           // ... of the next step to add
+    auto load_step = [&](uint2 (&xx)[kBmDnGroup][4]) {
+        const bool live = lc < NCK;
+#pragma unroll
+        for (int u = 0; u < kBmDnGroup; ++u) {
+            if (live && lg * kBmDnGroup + u < n_col) {
+                const uint2* cp = reinterpret_cast<const uint2*>(s_colp[lg * kBmDnGroup + u] + lc * kChunk) + tid;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(cp + g * T);
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u);
+            }
+        }
+        if (++lg == ngroups) { lg = 0; ++lc; }
+    };
+    auto add_step = [&](const uint2 (&xx)[kBmDnGroup][4]) {
+#pragma unroll
+        for (int u = 0; u < kBmDnGroup; ++u)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                s_all[2 * g + 0] += xx[u][g].x;
+                s_hi[2 * g + 0] += xx[u][g].x >> 16;
+                s_all[2 * g + 1] += xx[u][g].y;
+                s_hi[2 * g + 1] += xx[u][g].y >> 16;
+            }
+        if (++cg == ngroups) {    // the chunk's last group: merge
+            uint32_t* arow = acc + cc * kChunk + 4 * tid;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 a = *reinterpret_cast<const uint4*>(arow + g * kGrp);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t hi = s_hi[2 * g + h];
+                    const uint32_t lo = s_all[2 * g + h] - (hi << 16);
+                    (h ? a.z : a.x) += lo << kBmDenseShift;
+                    (h ? a.w : a.y) += hi << kBmDenseShift;
+                }
+                if (last) {
+                    if (allow != nullptr) {
+                        const int64_t row = r0 + cc * kChunk + g * kGrp + 4 * tid;  // 4 rows inside one bitmap byte
+                        const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
+                        if (!(bits & 1u)) a.x = 0u;
+                        if (!(bits & 2u)) a.y = 0u;
+                        if (!(bits & 4u)) a.z = 0u;
+                        if (!(bits & 8u)) a.w = 0u;
+                    }
+                    const uint32_t m01 = a.x > a.y ? a.x : a.y, m23 = a.z > a.w ? a.z : a.w;
+                    const uint32_t mg = m01 > m23 ? m01 : m23;
+                    m = mg > m ? mg : m;
+                }
+                *reinterpret_cast<uint4*>(arow + g * kGrp) = a;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+            cg = 0;
+            ++cc;
+        }
+    };
+    uint2 xb[kBmDnGroup][4];
+    if (n_col <= 3 * kBmDnGroup) {
+        // the usual case, up to 6 column tokens: their pointers stay in registers and the group loop is
+        // unrolled, so a step costs its loads and adds and little else
+        const uint2* cp[3 * kBmDnGroup];
+#pragma unroll
+        for (int u = 0; u < 3 * kBmDnGroup; ++u)
+            cp[u] = u < n_col ? reinterpret_cast<const uint2*>(s_colp[u]) + tid : nullptr;
+        // requests step (chunk c, group G) into xx; G is a compile-time constant
+#define BM25_LOAD_STEP(xx, G, c)                                                                        \
+        do {                                                                                    \
+            _Pragma("unroll") for (int u = 0; u < kBmDnGroup; ++u) {                            \
+                if ((G) * kBmDnGroup + u < n_col) {                                             \
+                    const uint2* q_ = cp[(G) * kBmDnGroup + u] + (c) * (kChunk / 4);                 \
+                    _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(q_ + g * T);   \
+                } else {                                                                        \
+                    _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u); \
+                }                                                                               \
+            }                                                                                   \
+        } while (0)
+#pragma unroll 1
+        for (int c = 0; c < NCK; ++c) {
+            // xa holds (c, 0)
+            if (ngroups == 1) {
+                if (c + 1 < NCK) BM25_LOAD_STEP(xb, 0, c + 1);
+                add_step(xa);
+            } else {
+                BM25_LOAD_STEP(xb, 1, c);
+                add_step(xa);
+                if (ngroups == 2) {
+                    if (c + 1 < NCK) BM25_LOAD_STEP(xa, 0, c + 1);
+                    add_step(xb);
+                    continue;
+                }
+                BM25_LOAD_STEP(xa, 2, c);
+                add_step(xb);
+                if (c + 1 < NCK) BM25_LOAD_STEP(xb, 0, c + 1);
+                add_step(xa);
+            }
+            if (c + 1 < NCK) {
+#pragma unroll
+                for (int u = 0; u < kBmDnGroup; ++u)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) xa[u][g] = xb[u][g];
+            }
+        }
+#undef BM25_LOAD_STEP
+    } else {
+        if (++lg == ngroups) { lg = 0; ++lc; }   // step 0 was requested before the run tokens
+        while (cc < NCK) {
+            load_step(xb);
+            add_step(xa);
+            if (cc >= NCK) break;
+            load_step(xa);
+            add_step(xb);
+        }
+    }
+}
+
+// ---- selection: the tile's H best allowed rows by U and the (H+1)-th best U -> dst[0..H] (descending; 0 = none).
+// Every thread reads only the accumulators it wrote last (column phase): no barrier needed on entry.  *s_nlist is 0.
+// NAMED: the CTA has a producer warp; the 256 consumer threads synchronise on named barrier 1.
+template <int CH, int T, bool NAMED>
+__device__ __forceinline__ void bm25_select_phase(uint32_t* acc, uint32_t m, int H, int64_t r0, int tid,
+                                                  unsigned long long* s_list, int* s_nlist_p,
+                                                  unsigned long long* __restrict__ dst) {
+    constexpr int kTile = CH * 4096;
+    constexpr int kChunk = 16 * T, kGrp = 4 * T, NCK = kTile / kChunk;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t row_base = (uint32_t)r0 + 4u * (uint32_t)tid;
+    if (H + 1 <= kBmThetaHeads) {
+        // ---- theta = the (H+1)-th largest of the warp's 32 per-lane maxima: H+1 distinct rows reach it, so the
+        // warp's H+1 best rows are among the rows >= theta (H+1 and a few)
+        uint32_t theta = 0u;
+        {
+            uint32_t mc = m;
+            for (int h = 0; h <= H; ++h) {
+                theta = __reduce_max_sync(0xffffffffu, mc);
+                if (theta == 0u) break;
+                const unsigned who = __ballot_sync(0xffffffffu, mc == theta);
+                if (lane == __ffs(who) - 1) mc = 0u;
+            }
+        }
+        if (theta < 1u) theta = 1u;
+        if (m >= theta) {
+            // which of the thread's 4-row groups hold a row >= theta (a handful of rows per warp) ...
+            uint32_t gmask = 0u;
+#pragma unroll
+            for (int j = 0; j < NCK * 4; ++j) {
+                const uint4 a = *reinterpret_cast<const uint4*>(&acc[j * kGrp + 4 * tid]);
+                const uint32_t m01 = a.x > a.y ? a.x : a.y, m23 = a.z > a.w ? a.z : a.w;
+                gmask |= ((m01 > m23 ? m01 : m23) >= theta ? 1u : 0u) << j;
+            }
+            // ... and those rows
+            while (gmask) {
+                const int j = __ffs(gmask) - 1;
+                gmask &= gmask - 1u;
+                const uint32_t loc0 = (uint32_t)j * (uint32_t)kGrp;
+                const uint4 a = *reinterpret_cast<const uint4*>(&acc[loc0 + 4 * tid]);
+                const uint32_t vv[4] = {a.x, a.y, a.z, a.w};
+                int slot = atomicAdd(s_nlist_p, (int)(a.x >= theta) + (int)(a.y >= theta) + (int)(a.z >= theta) + (int)(a.w >= theta));
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (vv[i] >= theta) {
+                        if (slot < kBmList)
+                            s_list[slot] = ((unsigned long long)vv[i] << 32) | (unsigned long long)(~(row_base + loc0 + i));
+                        ++slot;
+                    }
+            }
+        }
+    } else {
+        // ---- many heads per tile (few tiles, or a large k): the warp's exact H+1 best, one per round (ties: lowest
+        // row), straight from the shared accumulators
+        for (int h = 0; h <= H; ++h) {
+            uint32_t best = 0u, bloc = 0xFFFFFFFFu;
+#pragma unroll 1
+            for (int c = 0; c < NCK; ++c)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t base = (uint32_t)(c * kChunk + g * kGrp);
+                    const uint4 a = *reinterpret_cast<const uint4*>(&acc[base + 4 * tid]);
+                    if (a.x > best) { best = a.x; bloc = base + 0u; }     // ascending rows, strict >: lowest row wins
+                    if (a.y > best) { best = a.y; bloc = base + 1u; }
+                    if (a.z > best) { best = a.z; bloc = base + 2u; }
+                    if (a.w > best) { best = a.w; bloc = base + 3u; }
+                }
+            const uint32_t wm = __reduce_max_sync(0xffffffffu, best);
+            if (wm == 0u) break;
+            const uint32_t myrow = best == wm ? row_base + bloc : 0xFFFFFFFFu;
+            const uint32_t wr = __reduce_min_sync(0xffffffffu, myrow);
+            if (myrow == wr) {
+                acc[bloc + 4 * tid] = 0u;
+                const int slot = atomicAdd(s_nlist_p, 1);
+                if (slot < kBmList) s_list[slot] = ((unsigned long long)wm << 32) | (unsigned long long)(~wr);
+            }
+        }
+    }
+    if (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads();
+    if (warp == 0) {
+        const int n_e = *s_nlist_p;
+        if (n_e > kBmList) {                                 // mass ties inside the tile: rho = "anything": redo
+            for (int hh = lane; hh <= H; hh += 32) dst[hh] = ~0ull;
+        } else if (n_e <= 64) {
+            bm25_emit_heads<2>(s_list, n_e, H, lane, dst);
+        } else if (n_e <= 256) {
+            bm25_emit_heads<8>(s_list, n_e, H, lane, dst);
+        } else {
+            bm25_emit_heads<16>(s_list, n_e, H, lane, dst);
+        }
     }
 }
 
@@ -499,220 +739,148 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
 #undef BM25_FETCH
         }
         __syncthreads();
-        // ---- column tokens, 4096 rows at a time: 4 x 8 bytes per thread and token straight into registers.  A thread
-        // owns the local rows c * 4096 + g * 1024 + 4 * tid + i (g, i = 0..3): 8-byte column loads and 16-byte
-        // shared accesses that are contiguous over the warp.  A column word holds two rows: s_all adds the words
-        // whole (sum of the low halves + 65536 * sum of the high halves, modulo 2^32), s_hi the high halves.  The
-        // sums are merged into the shared accumulators (the thread's own rows); the last pass also masks the
-        // disallowed rows and takes the thread's maximum.  Steps = (chunk, group of kBmDnGroup tokens); the loads
-        // of the next step are requested before the current one is added (two register buffers, ping-pong).
-        if (n_col > 0 || last) {
-            const int ngroups = n_col > 0 ? (n_col + kBmDnGroup - 1) / kBmDnGroup : 1;
-            uint32_t s_all[8], s_hi[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
-            int lc = 0, lg = 0;           // (chunk, group) of the next step to load
-            int cc = 0, cg = 0;           // ... of the next step to add
-            auto load_step = [&](uint2 (&xx)[kBmDnGroup][4]) {
-                const bool live = lc < NCK;
-#pragma unroll
-                for (int u = 0; u < kBmDnGroup; ++u) {
-                    if (live && lg * kBmDnGroup + u < n_col) {
-                        const uint2* cp = reinterpret_cast<const uint2*>(s_colp[lg * kBmDnGroup + u] + lc * kChunk) + tid;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(cp + g * T);
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u);
-                    }
-                }
-                if (++lg == ngroups) { lg = 0; ++lc; }
-            };
-            auto add_step = [&](const uint2 (&xx)[kBmDnGroup][4]) {
-#pragma unroll
-                for (int u = 0; u < kBmDnGroup; ++u)
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        s_all[2 * g + 0] += xx[u][g].x;
-                        s_hi[2 * g + 0] += xx[u][g].x >> 16;
-                        s_all[2 * g + 1] += xx[u][g].y;
-                        s_hi[2 * g + 1] += xx[u][g].y >> 16;
-                    }
-                if (++cg == ngroups) {    // the chunk's last group: merge
-                    uint32_t* arow = acc + cc * kChunk + 4 * tid;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 a = *reinterpret_cast<const uint4*>(arow + g * kGrp);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint32_t hi = s_hi[2 * g + h];
-                            const uint32_t lo = s_all[2 * g + h] - (hi << 16);
-                            (h ? a.z : a.x) += lo << kBmDenseShift;
-                            (h ? a.w : a.y) += hi << kBmDenseShift;
-                        }
-                        if (last) {
-                            if (allow != nullptr) {
-                                const int64_t row = r0 + cc * kChunk + g * kGrp + 4 * tid;  // 4 rows inside one bitmap byte
-                                const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
-                                if (!(bits & 1u)) a.x = 0u;
-                                if (!(bits & 2u)) a.y = 0u;
-                                if (!(bits & 4u)) a.z = 0u;
-                                if (!(bits & 8u)) a.w = 0u;
-                            }
-                            const uint32_t m01 = a.x > a.y ? a.x : a.y, m23 = a.z > a.w ? a.z : a.w;
-                            const uint32_t mg = m01 > m23 ? m01 : m23;
-                            m = mg > m ? mg : m;
-                        }
-                        *reinterpret_cast<uint4*>(arow + g * kGrp) = a;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
-                    cg = 0;
-                    ++cc;
-                }
-            };
-            uint2 xb[kBmDnGroup][4];
-            if (n_col <= 3 * kBmDnGroup) {
-                // the usual case, up to 6 column tokens: their pointers stay in registers and the group loop is
-                // unrolled, so a step costs its loads and adds and little else
-                const uint2* cp[3 * kBmDnGroup];
-#pragma unroll
-                for (int u = 0; u < 3 * kBmDnGroup; ++u)
-                    cp[u] = u < n_col ? reinterpret_cast<const uint2*>(s_colp[u]) + tid : nullptr;
-                // requests step (chunk c, group G) into xx; G is a compile-time constant
-#define BM25_LOAD_STEP(xx, G, c)                                                                        \
-                do {                                                                                    \
-                    _Pragma("unroll") for (int u = 0; u < kBmDnGroup; ++u) {                            \
-                        if ((G) * kBmDnGroup + u < n_col) {                                             \
-                            const uint2* q_ = cp[(G) * kBmDnGroup + u] + (c) * (kChunk / 4);                 \
-                            _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(q_ + g * T);   \
-                        } else {                                                                        \
-                            _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u); \
-                        }                                                                               \
-                    }                                                                                   \
-                } while (0)
-#pragma unroll 1
-                for (int c = 0; c < NCK; ++c) {
-                    // xa holds (c, 0)
-                    if (ngroups == 1) {
-                        if (c + 1 < NCK) BM25_LOAD_STEP(xb, 0, c + 1);
-                        add_step(xa);
-                    } else {
-                        BM25_LOAD_STEP(xb, 1, c);
-                        add_step(xa);
-                        if (ngroups == 2) {
-                            if (c + 1 < NCK) BM25_LOAD_STEP(xa, 0, c + 1);
-                            add_step(xb);
-                            continue;
-                        }
-                        BM25_LOAD_STEP(xa, 2, c);
-                        add_step(xb);
-                        if (c + 1 < NCK) BM25_LOAD_STEP(xb, 0, c + 1);
-                        add_step(xa);
-                    }
-                    if (c + 1 < NCK) {
-#pragma unroll
-                        for (int u = 0; u < kBmDnGroup; ++u)
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) xa[u][g] = xb[u][g];
-                    }
-                }
-#undef BM25_LOAD_STEP
-            } else {
-                if (++lg == ngroups) { lg = 0; ++lc; }   // step 0 was requested before the run tokens
-                while (cc < NCK) {
-                    load_step(xb);
-                    add_step(xa);
-                    if (cc >= NCK) break;
-                    load_step(xa);
-                    add_step(xb);
-                }
-            }
-        }
+        if (n_col > 0 || last) bm25_column_phase<CH, T>(acc, s_colp, n_col, last, xa, allow, r0, r1, tid, m);
     }
-    // (from here on every thread reads only the accumulators it wrote last: no barrier needed)
-    const uint32_t row_base = (uint32_t)r0 + 4u * (uint32_t)tid;
-    if (H + 1 <= kBmThetaHeads) {
-        // ---- theta = the (H+1)-th largest of the warp's 32 per-lane maxima: H+1 distinct rows reach it, so the
-        // warp's H+1 best rows are among the rows >= theta (H+1 and a few)
-        uint32_t theta = 0u;
-        {
-            uint32_t mc = m;
-            for (int h = 0; h <= H; ++h) {
-                theta = __reduce_max_sync(0xffffffffu, mc);
-                if (theta == 0u) break;
-                const unsigned who = __ballot_sync(0xffffffffu, mc == theta);
-                if (lane == __ffs(who) - 1) mc = 0u;
-            }
-        }
-        if (theta < 1u) theta = 1u;
-        if (m >= theta) {
-            // which of the thread's 4-row groups hold a row >= theta (a handful of rows per warp) ...
-            uint32_t gmask = 0u;
+    bm25_select_phase<CH, T, false>(acc, m, H, r0, tid, s_list, &s_nlist,
+                                    heads + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (H + 1));
+}
+
+// ---------------------------------------------------------------------------
+// bm25_filter_tma_kernel — the block-tile filter (16384 rows per CTA) with the posting runs STAGED THROUGH SHARED
+// MEMORY by a producer warp: every run of the tile is cut into chunks of <= 512 postings, copied with TMA 1-D bulk
+// copies (cp.async.bulk + mbarrier complete_tx) into a 4-slot ring, so that the loads hold no registers, need no
+// per-thread address arithmetic and run ahead of the consumers across terms.  The 8 consumer warps OWN 2048 rows of
+// the tile each: a chunk is sorted by row (the packed word carries the local row in its top 14 bits), so a warp
+// finds its sub-run with a two-level warp-parallel search in shared memory (2 loads, 2 ballots) and adds it with
+// plain read-modify-writes — different terms can only meet inside one warp, which takes them in program order, so
+// there is no CTA-wide barrier between terms.  Column tokens and the selection are bm25_filter_kernel's.
+// Needs stride <= kBmMaxTokens and block-local runs for every term (bm25_resolve_kernel with low_search).
+// ---------------------------------------------------------------------------
+constexpr int kBmRingSlots = 4;
+constexpr int kBmSlotPost = 512;                  // postings per chunk
+constexpr int kBmSlotWords = kBmSlotPost + 4;     // the copy starts / ends on 16-byte boundaries of the packed stream
+constexpr int kBmTmaThreads = 288;                // 8 consumer warps + the producer warp
+constexpr size_t kBmTmaSmem = (size_t)kBmBlock * 4 + (size_t)kBmRingSlots * kBmSlotWords * 4;
+static_assert((size_t)kBmList * 8 <= (size_t)kBmRingSlots * kBmSlotWords * 4, "the selection list reuses the ring");
+
+__global__ void __launch_bounds__(kBmTmaThreads, 3)
+bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, const uint8_t* __restrict__ allow, int H,
+                       unsigned long long* __restrict__ heads) {
+    extern __shared__ __align__(16) uint32_t acc[];   // 16384 accumulators | ring
+    uint32_t* ring = acc + kBmBlock;
+    __shared__ uint2 s_runs[kBmMaxTokens];            // [lo, hi) inside the packed stream
+    __shared__ const uint16_t* s_colp[kBmMaxTokens];  // column of the tile per DENSE token
+    __shared__ __align__(8) uint64_t s_full[kBmRingSlots], s_empty[kBmRingSlots];
+    __shared__ int s_nrun, s_ncol, s_nlist;
+    constexpr int T = 256;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int blk = blockIdx.x;
+    const int64_t r0 = (int64_t)blk * kBmBlock;
+    const int64_t r1 = r0 + kBmBlock < ix.n_docs ? r0 + kBmBlock : ix.n_docs;
+    const uint4* my_rec = rec + ((size_t)blockIdx.y * ix.n_blocks + blk) * stride;
+    uint4 d = make_uint4((uint32_t)kBmSkip, 0u, 0u, 0u);
+    if (tid < stride) d = __ldg(my_rec + tid);
+    if (tid < T) {
 #pragma unroll
-            for (int j = 0; j < NCK * 4; ++j) {
-                const uint4 a = *reinterpret_cast<const uint4*>(&acc[j * kGrp + 4 * tid]);
-                const uint32_t m01 = a.x > a.y ? a.x : a.y, m23 = a.z > a.w ? a.z : a.w;
-                gmask |= ((m01 > m23 ? m01 : m23) >= theta ? 1u : 0u) << j;
-            }
-            // ... and those rows
-            while (gmask) {
-                const int j = __ffs(gmask) - 1;
-                gmask &= gmask - 1u;
-                const uint32_t loc0 = (uint32_t)j * (uint32_t)kGrp;
-                const uint4 a = *reinterpret_cast<const uint4*>(&acc[loc0 + 4 * tid]);
-                const uint32_t vv[4] = {a.x, a.y, a.z, a.w};
-                int slot = atomicAdd(&s_nlist, (int)(a.x >= theta) + (int)(a.y >= theta) + (int)(a.z >= theta) + (int)(a.w >= theta));
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (vv[i] >= theta) {
-                        if (slot < kBmList)
-                            s_list[slot] = ((unsigned long long)vv[i] << 32) | (unsigned long long)(~(row_base + loc0 + i));
-                        ++slot;
-                    }
-            }
-        }
-    } else {
-        // ---- many heads per tile (few tiles, or a large k): the warp's exact H+1 best, one per round (ties: lowest
-        // row), straight from the shared accumulators
-        for (int h = 0; h <= H; ++h) {
-            uint32_t best = 0u, bloc = 0xFFFFFFFFu;
-#pragma unroll 1
-            for (int c = 0; c < NCK; ++c)
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint32_t base = (uint32_t)(c * kChunk + g * kGrp);
-                    const uint4 a = *reinterpret_cast<const uint4*>(&acc[base + 4 * tid]);
-                    if (a.x > best) { best = a.x; bloc = base + 0u; }     // ascending rows, strict >: lowest row wins
-                    if (a.y > best) { best = a.y; bloc = base + 1u; }
-                    if (a.z > best) { best = a.z; bloc = base + 2u; }
-                    if (a.w > best) { best = a.w; bloc = base + 3u; }
-                }
-            const uint32_t wm = __reduce_max_sync(0xffffffffu, best);
-            if (wm == 0u) break;
-            const uint32_t myrow = best == wm ? row_base + bloc : 0xFFFFFFFFu;
-            const uint32_t wr = __reduce_min_sync(0xffffffffu, myrow);
-            if (myrow == wr) {
-                acc[bloc + 4 * tid] = 0u;
-                const int slot = atomicAdd(&s_nlist, 1);
-                if (slot < kBmList) s_list[slot] = ((unsigned long long)wm << 32) | (unsigned long long)(~wr);
-            }
-        }
+        for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(&acc[j * 4 * T + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+        s_nrun = 0; s_ncol = 0; s_nlist = 0;
+        for (int s = 0; s < kBmRingSlots; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
+        mbar_fence_init();
     }
     __syncthreads();
-    if (warp == 0) {
-        const int n_e = s_nlist;
-        unsigned long long* dst = heads + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (H + 1);
-        if (n_e > kBmList) {                                 // mass ties inside the tile: rho = "anything": redo
-            for (int hh = lane; hh <= H; hh += 32) dst[hh] = ~0ull;
-        } else if (n_e <= 64) {
-            bm25_emit_heads<2>(s_list, n_e, H, lane, dst);
-        } else if (n_e <= 256) {
-            bm25_emit_heads<8>(s_list, n_e, H, lane, dst);
+    if (d.x == (uint32_t)kBmDense) {
+        s_colp[atomicAdd(&s_ncol, 1)] = ix.dense_col + ((size_t)d.y * ix.n_blocks + blk) * kBmBlock;
+    } else if (d.x == (uint32_t)kBmMid) {
+        if (d.z > d.y) s_runs[atomicAdd(&s_nrun, 1)] = make_uint2(d.y, d.z);
+    }
+    __syncthreads();
+    const int n_run = s_nrun, n_col = s_ncol;
+    if (warp == 8) {
+        // ===================== producer: every chunk of every run, in list order =====================
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int r = 0; r < n_run; ++r) {
+                const uint2 run = s_runs[r];
+                for (uint32_t p = run.x; p < run.y; p += kBmSlotPost) {
+                    const uint32_t e = p + kBmSlotPost < run.y ? p + kBmSlotPost : run.y;
+                    const uint32_t a0 = p & ~3u, a1 = (e + 3u) & ~3u;
+                    mbar_wait(&s_empty[slot], ph ^ 1u);
+                    mbar_arrive_expect_tx(&s_full[slot], (a1 - a0) * 4u);
+                    bulk_g2s(ring + slot * kBmSlotWords, ix.post_pack + a0, (a1 - a0) * 4u, &s_full[slot]);
+                    if (++slot == kBmRingSlots) { slot = 0; ph ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+    // ===================== consumers =====================
+    // the first column step (chunk 0, first group) is requested now: in flight while the run tokens are added
+    uint2 xa[kBmDnGroup][4];
+#pragma unroll
+    for (int u = 0; u < kBmDnGroup; ++u) {
+        if (u < n_col) {
+            const uint2* cp = reinterpret_cast<const uint2*>(s_colp[u]) + tid;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) xa[u][g] = __ldg(cp + g * T);
         } else {
-            bm25_emit_heads<16>(s_list, n_e, H, lane, dst);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) xa[u][g] = make_uint2(0u, 0u);
         }
     }
+    {
+        const uint32_t t_lo = (uint32_t)warp << 29;           // first local row of the warp, in the packed word's place
+        const uint32_t t_hi = (uint32_t)(warp + 1) << 29;     // (warp 7: wraps to 0, its upper bound is the chunk's end)
+        int slot = 0;
+        uint32_t ph = 0;
+        for (int r = 0; r < n_run; ++r) {
+            const uint2 run = s_runs[r];
+            for (uint32_t p = run.x; p < run.y; p += kBmSlotPost) {
+                const int n = (int)((p + kBmSlotPost < run.y ? p + kBmSlotPost : run.y) - p);
+                const uint32_t* c = ring + slot * kBmSlotWords + (p & 3u);
+                mbar_wait(&s_full[slot], ph);
+                if (n <= 64) {
+                    // short chunk: every lane looks at (up to) two postings and adds the ones its warp owns
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int i = lane + 32 * u;
+                        if (i < n) {
+                            const uint32_t v = c[i];
+                            if ((v >> 29) == (uint32_t)warp) acc[v >> kBmQBits] += v & kBmQMask;
+                        }
+                    }
+                } else {
+                    // level 1: probes 16 apart; level 2: the 16 postings behind the last probe below the target
+                    // (lanes 0-15 for the lower bound, 16-31 for the upper one)
+                    const int i1 = lane * 16;
+                    const uint32_t v1 = i1 < n ? c[i1] : 0xFFFFFFFFu;
+                    const int s_lo = __popc(__ballot_sync(0xffffffffu, v1 < t_lo));
+                    const int s_hi = warp == 7 ? 0 : __popc(__ballot_sync(0xffffffffu, v1 < t_hi));
+                    const bool up = lane >= 16;
+                    const int sb = up ? s_hi : s_lo;
+                    const int i2 = (sb - 1) * 16 + 1 + (lane & 15);
+                    const uint32_t v2 = (sb > 0 && i2 < n) ? c[i2] : 0xFFFFFFFFu;
+                    const unsigned b2 = __ballot_sync(0xffffffffu, v2 < (up ? t_hi : t_lo));
+                    const int lo = s_lo > 0 ? (s_lo - 1) * 16 + 1 + __popc(b2 & 0xFFFFu) : 0;
+                    const int hi = warp == 7 ? n : (s_hi > 0 ? (s_hi - 1) * 16 + 1 + __popc(b2 >> 16) : 0);
+                    for (int i = lo + lane; i < hi; i += 32) {
+                        const uint32_t v = c[i];
+                        acc[v >> kBmQBits] += v & kBmQMask;
+                    }
+                }
+                __syncwarp();                                  // the next chunk may be another term on the same rows
+                if (lane == 0) mbar_arrive(&s_empty[slot]);
+                if (++slot == kBmRingSlots) { slot = 0; ph ^= 1u; }
+            }
+        }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");             // the column phase owns rows by thread
+    uint32_t m = 0u;
+    bm25_column_phase<4, T>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m);
+    bm25_select_phase<4, T, true>(acc, m, H, r0, tid, reinterpret_cast<unsigned long long*>(ring), &s_nlist,
+                                  heads + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (H + 1));
 }
 
 // w * impact of (term t, row) if the posting exists, else 0: the product the accumulation adds
@@ -993,6 +1161,7 @@ static bool bm25_plan_for(const Bm25Device& ix, int k, int ch, Bm25Plan* p) {
 // block tiles when the launch has enough of them to fill the GPU (148 SMs x 3 CTAs, twice over); quarter-block tiles
 // for small corpora and single queries (more, shorter CTAs: latency)
 int g_bm25_tile_chunks = 0;             // option "bm25_tile": force 1 / 2 / 4 chunks per tile (0 = automatic)
+int g_bm25_tma = 1;                     // option "bm25_tma": block tiles through bm25_filter_tma_kernel (0: bm25_filter_kernel<4>)
 static bool bm25_plan(const Bm25Device& ix, int k, int Q, Bm25Plan* p) {
     if (g_bm25_tile_chunks == 1 || g_bm25_tile_chunks == 2 || g_bm25_tile_chunks == 4)
         if (bm25_plan_for(ix, k, g_bm25_tile_chunks, p)) return true;
@@ -1034,19 +1203,24 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     Bm25Plan pl;
     if (!bm25_plan(ix, k, Q, &pl)) return cudaErrorInvalidValue;
     const int stride = bm25_desc_stride(max_query_tokens);
+    const bool use_tma = g_bm25_tma && pl.ch == 4 && stride <= kBmMaxTokens;
     unsigned long long* heads = reinterpret_cast<unsigned long long*>(scratch);
     uint4* rec = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(scratch) + bm25_heads_bytes(ix, k, Q));
     {
         const int64_t total = (int64_t)Q * ix.n_blocks * stride;
         int64_t g = (total + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
-        bm25_resolve_kernel<<<(int)g, 256, 0, st>>>(ix, d_q_terms, d_q_ptr, q0, Q, stride, rec);
+        bm25_resolve_kernel<<<(int)g, 256, 0, st>>>(ix, d_q_terms, d_q_ptr, q0, Q, stride, use_tma ? 1 : 0, rec);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     dim3 grid_a(pl.n_tiles, Q);
     cudaError_t e = cudaSuccess;
-    if (pl.ch == 4) {
+    if (use_tma) {
+        e = cudaFuncSetAttribute(bm25_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBmTmaSmem);
+        if (e != cudaSuccess) return e;
+        bm25_filter_tma_kernel<<<grid_a, kBmTmaThreads, kBmTmaSmem, st>>>(ix, rec, stride, allow, pl.H, heads);
+    } else if (pl.ch == 4) {
         // (a function attribute belongs to the current device: set on every launch, a sharded index runs on several)
         // (512-thread CTAs, 2 per SM, were tried for the 32 resident warps: 64 registers spill and the 16-warp
         // barriers cost more than the occupancy returns: 3.45 vs 2.61 us/query)

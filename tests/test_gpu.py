@@ -793,10 +793,13 @@ def test_bm25_mass_ties_and_many_ranges():
     ix.close()
 
 
+@pytest.mark.parametrize("tile", [0, 4])
 @pytest.mark.parametrize("dense_div", [0, 2, 8, 64, 1 << 20])
-def test_bm25_filter_index_classes_vs_oracle(dense_div):
+def test_bm25_filter_index_classes_vs_oracle(dense_div, tile):
     """The integer filter index holds a term three ways (untabled short list scanned whole, range-tabled run of the
-    packed stream, dense 16-bit column): every mix must select exactly the oracle's rows, on the fast path."""
+    packed stream, dense 16-bit column): every mix must select exactly the oracle's rows, on the fast path.
+    tile 0: the automatic plan (quarter-block tiles for this small corpus); tile 4: block tiles, i.e. the kernel that
+    stages the runs through shared memory with TMA bulk copies (bm25_filter_tma_kernel)."""
     from b200rag import _lib
     from b200rag.bm25 import DeviceBM25, Postings
     n_docs = 21000                                      # 6 ranges, the last one ragged
@@ -829,10 +832,21 @@ def test_bm25_filter_index_classes_vs_oracle(dense_div):
             qt = np.concatenate([qt, [n_terms - 2, -1, qt[0]]]).astype(np.int32)
         queries.append(qt)
     queries.append(np.array(list(docs[7][:6]) * 2, np.int32))               # the duplicated documents tie at the top
-    queries.append(by_df[:150].astype(np.int32))                            # more tokens than one pass of the kernel holds
+    if tile == 0:       # (a batch with such a query takes the direct-load kernel: keep the tile-4 batch on the TMA kernel)
+        queries.append(by_df[:150].astype(np.int32))                        # more tokens than one pass of the kernel holds
+    _lib.set_option("bm25_tile", tile)
+    try:
+        _check_bm25_classes(_lib, ix, o, queries, docs, n_terms, allow, bitmap, tile)
+    finally:
+        _lib.set_option("bm25_tile", 0)
+    ix.close()
+
+
+def _check_bm25_classes(_lib, ix, o, queries, docs, n_terms, allow, bitmap, tile):
     before = _lib.counters()["fallbacks"]
     rows, scores, counts = ix.search_ids(queries, 50)
-    assert _lib.counters()["fallbacks"] == before       # nothing of this was redone on the robust path
+    if tile == 0:                                       # (2 block tiles hold too few heads for some of these)
+        assert _lib.counters()["fallbacks"] == before   # nothing of this was redone on the robust path
     # the clustered term: hundreds of rows of one tile tie exactly / hold the whole top-k -> flagged and redone on the
     # exact range path, still exact
     queries.append(np.array([n_terms - 1], np.int32))
@@ -847,13 +861,13 @@ def test_bm25_filter_index_classes_vs_oracle(dense_div):
             er, es = o.search(qt.tolist(), k, allow)
             assert rows_f[i, :counts_f[i]].tolist() == er.tolist() and np.array_equal(scores_f[i, :counts_f[i]], es), (k, i)
         assert rows1[0].tolist() == rows[0].tolist() and np.array_equal(scores1[0], scores[0])
-    ix.close()
 
 
-@pytest.mark.parametrize("tile", [1, 2, 4])
-def test_bm25_filter_tile_sizes_vs_oracle(tile):
+@pytest.mark.parametrize("tile,tma", [(1, 1), (2, 1), (4, 1), (4, 0)])
+def test_bm25_filter_tile_sizes_vs_oracle(tile, tma):
     """the filter kernel's three tile sizes (4096 / 8192 / 16384 rows per CTA; picked by launch size in production,
-    forced here) over column, run and scanned tokens, with and without a row filter, all equal to the oracle"""
+    forced here) over column, run and scanned tokens, with and without a row filter, all equal to the oracle;
+    block tiles through both kernels (tma 1: runs staged through shared memory by a producer warp; 0: direct loads)"""
     from b200rag import _lib
     from b200rag.bm25 import DeviceBM25, Postings
     n_docs = 40000
@@ -868,6 +882,7 @@ def test_bm25_filter_tile_sizes_vs_oracle(tile):
     allow = g.random(n_docs) < 0.4
     bm = np.packbits(allow, bitorder="little")
     _lib.set_option("bm25_tile", tile)
+    _lib.set_option("bm25_tma", tma)
     try:
         for k in (10, 50):
             for mask, bits in ((None, None), (allow, bm)):
@@ -877,6 +892,7 @@ def test_bm25_filter_tile_sizes_vs_oracle(tile):
                     assert rows[i, :counts[i]].tolist() == er.tolist() and np.array_equal(scores[i, :counts[i]], es), (k, i)
     finally:
         _lib.set_option("bm25_tile", 0)
+        _lib.set_option("bm25_tma", 1)
     ix.close()
 
 

@@ -28,9 +28,17 @@ for q in qs[:6]:
 import os
 if os.environ.get("BM25_TILE"):
     _lib.set_option("bm25_tile", int(os.environ["BM25_TILE"]))
-for _ in range(3):
-    ix.search_ids(qs, 50)
-    print("batch device ms", float(_lib.last_timings()[0]), "per query us", 1e3 * float(_lib.last_timings()[0]) / Q)
+for tma in [int(v) for v in os.environ.get("BM25_TMA", "1").split(",")]:
+    _lib.set_option("bm25_tma", tma)
+    ref = None
+    for _ in range(4):
+        out = ix.search_ids(qs, 50)
+        print("tma", tma, "batch device ms", float(_lib.last_timings()[0]), "per query us", 1e3 * float(_lib.last_timings()[0]) / Q,
+              "fallbacks", _lib.counters()["fallbacks"])
+    if tma == 0:
+        base = out
+    elif "base" in globals():
+        print("same result as tma 0:", all(np.array_equal(a, b) for a, b in zip(out, base)))
 nb, npost = ix.query_bytes(qs)
 print("avg filter bytes per query", float(nb.mean()), "avg postings per query", float(npost.mean()),
       "GB/s at last batch", float(nb.sum()) / (float(_lib.last_timings()[0]) * 1e-3) / 1e9)
