@@ -476,7 +476,6 @@ int rag_set_option(const char* key, int64_t value) {
     else if (!strcmp(key, "balance_tail")) gemm_set_balance_tail((int)value);
     else if (!strcmp(key, "pair_mode")) gemm_set_pair_mode((int)value);
     else if (!strcmp(key, "sample_resident")) gemm_set_sample_resident((int)value);
-    else if (!strcmp(key, "sample_rotate")) gemm_set_sample_rotate((int)value);
     else if (!strcmp(key, "exchange_timeout_ms")) g_exchange_timeout_ms = (int)std::max<int64_t>(1, std::min<int64_t>(value, 600000));
     else if (bm25_set_option(key, value) == RAG_OK) return RAG_OK;
     else return fail(RAG_EINVAL, "unknown option %s", key);

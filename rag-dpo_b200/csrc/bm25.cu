@@ -765,7 +765,7 @@ static_assert((size_t)kBmList * 8 <= (size_t)kBmRingSlots * kBmSlotWords * 4, "t
 
 __global__ void __launch_bounds__(kBmTmaThreads, 3)
 bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, const uint8_t* __restrict__ allow, int H,
-                       unsigned long long* __restrict__ heads) {
+                       int by_block, unsigned long long* __restrict__ heads) {
     extern __shared__ __align__(16) uint32_t acc[];   // 16384 accumulators | ring
     uint32_t* ring = acc + kBmBlock;
     __shared__ uint2 s_runs[kBmMaxTokens];            // [lo, hi) inside the packed stream
@@ -774,10 +774,13 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     __shared__ int s_nrun, s_ncol, s_nlist;
     constexpr int T = 256;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int blk = blockIdx.x;
+    // grid (queries, blocks) or (blocks, queries): CTAs are dealt x-fastest, so `by_block` runs all queries of one
+    // block back to back — the block's columns and runs are then shared in L2 by the CTAs that are resident together
+    const int blk = by_block ? blockIdx.y : blockIdx.x;
+    const int qy = by_block ? blockIdx.x : blockIdx.y;
     const int64_t r0 = (int64_t)blk * kBmBlock;
     const int64_t r1 = r0 + kBmBlock < ix.n_docs ? r0 + kBmBlock : ix.n_docs;
-    const uint4* my_rec = rec + ((size_t)blockIdx.y * ix.n_blocks + blk) * stride;
+    const uint4* my_rec = rec + ((size_t)qy * ix.n_blocks + blk) * stride;
     uint4 d = make_uint4((uint32_t)kBmSkip, 0u, 0u, 0u);
     if (tid < stride) d = __ldg(my_rec + tid);
     if (tid < T) {
@@ -797,9 +800,13 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     }
     __syncthreads();
     const int n_run = s_nrun, n_col = s_ncol;
+    const uint32_t full0 = smem_u32(&s_full[0]), empty0 = smem_u32(&s_empty[0]), ring0 = smem_u32(ring);
     if (warp == 8) {
         // ===================== producer: every chunk of every run, in list order =====================
         if (lane == 0) {
+            // the tile's columns are asked into L2 first: the consumers' register loads then find them there
+            for (int u = 0; u < n_col; ++u)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s_colp[u]), "r"(kBmBlock * 2) : "memory");
             int slot = 0;
             uint32_t ph = 0;
             for (int r = 0; r < n_run; ++r) {
@@ -807,9 +814,9 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
                 for (uint32_t p = run.x; p < run.y; p += kBmSlotPost) {
                     const uint32_t e = p + kBmSlotPost < run.y ? p + kBmSlotPost : run.y;
                     const uint32_t a0 = p & ~3u, a1 = (e + 3u) & ~3u;
-                    mbar_wait(&s_empty[slot], ph ^ 1u);
-                    mbar_arrive_expect_tx(&s_full[slot], (a1 - a0) * 4u);
-                    bulk_g2s(ring + slot * kBmSlotWords, ix.post_pack + a0, (a1 - a0) * 4u, &s_full[slot]);
+                    mbar_wait_a(empty0 + 8u * slot, ph ^ 1u);
+                    mbar_arrive_expect_tx_a(full0 + 8u * slot, (a1 - a0) * 4u);
+                    bulk_g2s_a(ring0 + slot * (kBmSlotWords * 4), ix.post_pack + a0, (a1 - a0) * 4u, full0 + 8u * slot);
                     if (++slot == kBmRingSlots) { slot = 0; ph ^= 1u; }
                 }
             }
@@ -840,7 +847,7 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
             for (uint32_t p = run.x; p < run.y; p += kBmSlotPost) {
                 const int n = (int)((p + kBmSlotPost < run.y ? p + kBmSlotPost : run.y) - p);
                 const uint32_t* c = ring + slot * kBmSlotWords + (p & 3u);
-                mbar_wait(&s_full[slot], ph);
+                mbar_wait_a(full0 + 8u * slot, ph);
                 if (n <= 64) {
                     // short chunk: every lane looks at (up to) two postings and adds the ones its warp owns
 #pragma unroll
@@ -871,7 +878,7 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
                     }
                 }
                 __syncwarp();                                  // the next chunk may be another term on the same rows
-                if (lane == 0) mbar_arrive(&s_empty[slot]);
+                if (lane == 0) mbar_arrive_a(empty0 + 8u * slot);
                 if (++slot == kBmRingSlots) { slot = 0; ph ^= 1u; }
             }
         }
@@ -880,7 +887,7 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     uint32_t m = 0u;
     bm25_column_phase<4, T>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m);
     bm25_select_phase<4, T, true>(acc, m, H, r0, tid, reinterpret_cast<unsigned long long*>(ring), &s_nlist,
-                                  heads + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (H + 1));
+                                  heads + ((size_t)qy * ix.n_blocks + blk) * (H + 1));
 }
 
 // w * impact of (term t, row) if the posting exists, else 0: the product the accumulation adds
@@ -931,15 +938,14 @@ __device__ __forceinline__ void bm25_exact_topk(const Bm25Device& ix, const int3
         // the usual case (k + a handful of survivors): order by rank counting, no sort
         Bm25Key me{0ull, 0u, 0u};
         if ((int)threadIdx.x < n) me = keys[threadIdx.x];
-        int rank = 0, valid = 0;
-        for (int j = 0; j < n; ++j) {
-            const Bm25Key o = keys[j];
-            rank += me < o;
-            valid += o.s != 0ull;
-        }
-        if (me.s != 0ull && rank < k) {
-            out_rows[rank] = (int32_t)(~me.nrow);
-            out_scores[rank] = __longlong_as_double((long long)me.s);
+        const int valid = __syncthreads_count(me.s != 0ull);
+        if (me.s != 0ull) {                                   // (the warps past the n-th survivor have nothing to rank)
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += me < keys[j];
+            if (rank < k) {
+                out_rows[rank] = (int32_t)(~me.nrow);
+                out_scores[rank] = __longlong_as_double((long long)me.s);
+            }
         }
         const int nout = valid < k ? valid : k;
         for (int i = nout + threadIdx.x; i < k; i += blockDim.x) { out_rows[i] = -1; out_scores[i] = 0.0; }
@@ -972,11 +978,11 @@ bm25_finish_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int
                    int32_t* out_rows, double* out_scores, int32_t* out_counts) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     // [ 32 KB: tau sort buffer, later the staged products | survivors' keys | survivors' rows ]
-    unsigned long long* sbuf = reinterpret_cast<unsigned long long*>(sm_raw);
     double* contrib = reinterpret_cast<double*>(sm_raw);
     Bm25Key* keys = reinterpret_cast<Bm25Key*>(sm_raw + (size_t)kBmContrib * sizeof(double));
     uint32_t* surv = reinterpret_cast<uint32_t*>(keys + kBmSurvivors);
     __shared__ int s_n, s_flag, s_extra;
+    __shared__ uint32_t s_hist[256], s_sel[2];
     const int q = blockIdx.x;
     const int n_ranges = n_tiles;
     const unsigned long long* hq = heads + (size_t)q * n_ranges * (H + 1);
@@ -985,10 +991,49 @@ bm25_finish_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int
     if (threadIdx.x == 0) { s_n = 0; s_flag = 0; s_extra = 0; }
     // tau: the k-th largest of the first h_tau heads of every range (distinct rows), minus the slack
     const int n_tau = n_ranges * h_tau;
-    for (int e = threadIdx.x; e < nsort_tau; e += blockDim.x)
-        sbuf[e] = e < n_tau ? hq[(size_t)(e / h_tau) * (H + 1) + (e % h_tau)] : 0ull;
-    block_bitonic_desc(sbuf, nsort_tau);
-    const uint32_t tau_u = k <= n_tau ? (uint32_t)(sbuf[k - 1] >> 32) : 0u;
+    // (radix select, one byte per pass from the top: 12 barriers instead of the ~55 of a block sort of 1024 heads)
+    uint32_t* su = reinterpret_cast<uint32_t*>(sm_raw);       // the n_tau upper bounds (<= 4096)
+    for (int e = threadIdx.x; e < n_tau; e += blockDim.x)
+        su[e] = (uint32_t)(hq[(size_t)(e / h_tau) * (H + 1) + (e % h_tau)] >> 32);
+    uint32_t tau_u = 0u;
+    if (k <= n_tau) {
+        uint32_t prefix = 0u, kr = (uint32_t)k;               // the kr-th largest of the entries that match the prefix
+        for (int sh = 24; sh >= 0; sh -= 8) {
+            if (threadIdx.x < 256) s_hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const uint32_t himask = sh == 24 ? 0u : (0xFFFFFFFFu << (sh + 8));
+            for (int e = threadIdx.x; e < n_tau; e += blockDim.x) {
+                const uint32_t u = su[e];
+                if ((u & himask) == prefix) atomicAdd(&s_hist[(u >> sh) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {                           // lane l owns the bins [8l, 8l + 8)
+                const int lane = threadIdx.x;
+                uint32_t c[8], sum = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = s_hist[8 * lane + j]; sum += c[j]; }
+                uint32_t incl = sum;                          // entries in this lane's bins and above
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+                    if (lane + o < 32) incl += t;
+                }
+                uint32_t a = incl - sum;                      // entries above this lane's bins
+                if (a < kr && kr <= a + sum) {
+#pragma unroll
+                    for (int j = 7; j >= 0; --j) {
+                        if (a + c[j] >= kr) { s_sel[0] = prefix | ((uint32_t)(8 * lane + j) << sh); s_sel[1] = kr - a; break; }
+                        a += c[j];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = s_sel[0];
+            kr = s_sel[1];
+        }
+        tau_u = prefix;
+    }
+    __syncthreads();
     // U - slack <= score / unit <= U: a packed posting is at most 2 units above its product, a column entry at
     // most 2 + 15 (tokens beyond kBmMaxQueryTokens: the query is redone on the robust path anyway)
     for (int i = threadIdx.x; i < nt && i < kBmMaxQueryTokens; i += blockDim.x) {
@@ -1161,6 +1206,7 @@ static bool bm25_plan_for(const Bm25Device& ix, int k, int ch, Bm25Plan* p) {
 // block tiles when the launch has enough of them to fill the GPU (148 SMs x 3 CTAs, twice over); quarter-block tiles
 // for small corpora and single queries (more, shorter CTAs: latency)
 int g_bm25_tile_chunks = 0;             // option "bm25_tile": force 1 / 2 / 4 chunks per tile (0 = automatic)
+int g_bm25_by_block = 1;                // option "bm25_by_block": the TMA kernel's CTAs in (block, query) order
 int g_bm25_tma = 1;                     // option "bm25_tma": block tiles through bm25_filter_tma_kernel (0: bm25_filter_kernel<4>)
 static bool bm25_plan(const Bm25Device& ix, int k, int Q, Bm25Plan* p) {
     if (g_bm25_tile_chunks == 1 || g_bm25_tile_chunks == 2 || g_bm25_tile_chunks == 4)
@@ -1219,7 +1265,9 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     if (use_tma) {
         e = cudaFuncSetAttribute(bm25_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBmTmaSmem);
         if (e != cudaSuccess) return e;
-        bm25_filter_tma_kernel<<<grid_a, kBmTmaThreads, kBmTmaSmem, st>>>(ix, rec, stride, allow, pl.H, heads);
+        const bool by_block = g_bm25_by_block && pl.n_tiles <= 65535;
+        bm25_filter_tma_kernel<<<by_block ? dim3(Q, pl.n_tiles) : grid_a, kBmTmaThreads, kBmTmaSmem, st>>>(
+            ix, rec, stride, allow, pl.H, by_block ? 1 : 0, heads);
     } else if (pl.ch == 4) {
         // (a function attribute belongs to the current device: set on every launch, a sharded index runs on several)
         // (512-thread CTAs, 2 per SM, were tried for the 32 resident warps: 64 registers spill and the 16-warp

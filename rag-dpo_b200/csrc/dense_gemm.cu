@@ -182,7 +182,7 @@ struct WorkIter {
     int64_t n_tiles, i, i_first;
     int step, max_tiles, n_qitems;
     int worker, n_workers;
-    int taken, qb, qrot;
+    int taken, qb;
     bool started;
     // MODE 1 tail: the n_tiles % n_workers leftover tiles are split by (tile, query item) ITEMS over all
     // workers, so that they finish within a few items of each other instead of a whole tile apart
@@ -202,9 +202,6 @@ struct WorkIter {
             const int64_t span = n_tiles / n_workers - (int64_t)(max_tiles - 1) * step;   // tiles every CTA has
             if (span > 1) i_first = (int64_t)((worker * 2654435761u) % (uint32_t)span);
         }
-        // sample pass: all CTAs stream the SAME query tiles from L2; CTA c starts at query block c mod n (and at K
-        // block (c / n) mod dim/64, see the kernel) so that they do not all ask the same L2 slices at the same time
-        qrot = MODE == 0 && p.sample_rotate ? worker % n_qitems : 0;
         i = i_first; taken = 0; qb = 0; started = false;
         in_tail = false;
         full_rounds = n_tiles / n_workers;
@@ -229,7 +226,7 @@ struct WorkIter {
             }
             if (qb < n_qitems && tile_ok()) {
                 t = worker + i * n_workers;
-                qitem = qb + qrot < n_qitems ? qb + qrot : qb + qrot - n_qitems;
+                qitem = qb;
                 return true;
             }
             if (MODE == 0) return false;
@@ -271,9 +268,6 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.dim / GT_K;
     const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair
-    // resident sample pass: K blocks are taken in a rotated order per CTA (any order gives a valid filter score)
-    const int kb_rot = (MODE == 0 && p.sample_resident && p.sample_rotate)
-                           ? (int)((blockIdx.x / (unsigned)((p.n_qblocks + NCTA - 1) / NCTA)) % (unsigned)num_kb) : 0;
     WorkIter<MODE, NCTA> work;
     work.init(p);
 
@@ -322,9 +316,8 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (resident) {
                         uint8_t* sa = a_ring + (size_t)stage * GT_A_BYTES;
-                        const int kbr = kb + kb_rot < num_kb ? kb + kb_rot : kb + kb_rot - num_kb;
                         mbar_arrive_expect_tx(&full_bar[stage], GT_A_BYTES);
-                        tma_load_2d(sa, &map_q, kbr * GT_K, qi * GT_M, &full_bar[stage]);
+                        tma_load_2d(sa, &map_q, kb * GT_K, qi * GT_M, &full_bar[stage]);
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
@@ -365,8 +358,7 @@ dense_gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     tc_fence_after();
                     const uint8_t* sa = resident ? a_ring + (size_t)stage * GT_A_BYTES : stages + (size_t)stage * STAGE_BYTES;
                     const uint64_t a_desc = umma_desc_sw128(sa);
-                    const int kbr = kb + kb_rot < num_kb ? kb + kb_rot : kb + kb_rot - num_kb;   // (kb_rot = 0 unless resident)
-                    const uint64_t b_desc = umma_desc_sw128(resident ? stages + (size_t)kbr * RES_B_BYTES : sa + GT_A_BYTES);
+                    const uint64_t b_desc = umma_desc_sw128(resident ? stages + (size_t)kb * RES_B_BYTES : sa + GT_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < GT_K / 16; ++k) {             // +32 B per K=16 step inside the swizzle atom
                         if (NCTA == 2) tc_mma_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
@@ -664,8 +656,6 @@ int g_pair_mode = 1;      // main pass as CTA pairs (tcgen05 cta_group::2) when 
 void gemm_set_pair_mode(int v) { g_pair_mode = v != 0; }
 int g_sample_resident = 1;   // small samples keep their rows resident in shared memory (option "sample_resident")
 void gemm_set_sample_resident(int v) { g_sample_resident = v != 0; }
-int g_sample_rotate = 1;     // sample pass: per-CTA rotation of the query block / K block order (option "sample_rotate")
-void gemm_set_sample_rotate(int v) { g_sample_rotate = v != 0; }
 int g_sample_div = 1;     // multiplies the survivor target of the sample pass (option "sample_div", experiments)
 void gemm_set_sample_div(int v) { g_sample_div = v < 1 ? 1 : (v > 8 ? 8 : v); }
 int gemm_sample_m() { return kSampleM; }
@@ -686,7 +676,6 @@ size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out) {
     *grid_out = grid;
     p.n_lists = grid;
     p.balance_tail = g_balance_tail;
-    p.sample_rotate = g_sample_rotate;
     // pair mode (main pass): 32 KB stages, one CTA pair per row tile; only when the query blocks pair up
     // (an odd block count would leave one CTA of the last pair multiplying padding) and every pair has work
     {

@@ -63,7 +63,6 @@ struct GemmParams {
     int ring_bytes;              // bytes of the operand ring in front of the barriers (set per launch)
     // resident sample (small samples): decided by gemm_plan
     int sample_resident, n_stages_sample, ring_bytes_sample;
-    int sample_rotate;           // sample pass: every CTA starts at its own (query block, K block), see WorkIter
     size_t smem_sample;
 };
 int gemm_sample_m();
@@ -71,7 +70,6 @@ void gemm_set_sample_div(int v);
 void gemm_set_balance_tail(int v);
 void gemm_set_pair_mode(int v);
 void gemm_set_sample_resident(int v);
-void gemm_set_sample_rotate(int v);
 int gemm_max_batch();
 int gemm_padded_queries(int n_queries);
 size_t gemm_plan(GemmParams& p, int sm_count, int smem_limit, int* grid_out);
