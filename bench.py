@@ -491,6 +491,28 @@ class DenseJob:
         self.env.torch.cuda.empty_cache()
 
 
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def profile_traffic(csv_name, kernel_substr):
+    """`traffic` of a roofline object: dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, read
+    from the committed `ncu --set full` raw page under profiles/ (the capture of the same workload shape; ncu cannot
+    run inside the timed bench).  None when the file or the kernel is missing: never a pasted literal."""
+    import csv
+    path = os.path.join(ROOT, "profiles", csv_name)
+    try:
+        rows = list(csv.reader(open(path)))
+        h, u = rows[0], rows[1]
+        kn, ir, iw = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+        vals = [float(r[ir]) * _UNIT[u[ir]] + float(r[iw]) * _UNIT[u[iw]] for r in rows[2:] if kernel_substr in r[kn]]
+        if not vals:
+            return None
+        return {"bytes_per_launch": float(np.mean(vals)), "launches_in_capture": len(vals),
+                "source": f"profiles/{csv_name} ({kernel_substr})"}
+    except (OSError, ValueError, KeyError, IndexError):
+        return None
+
+
 def tensor_roofline(env, B, n_local, main_ms, sustained=False):
     flops = 2.0 * B * n_local * DIM
     ach = flops / (main_ms / 1e3) / 1e12
@@ -584,6 +606,10 @@ def run_c2(env, args):
     tc_min = int(os.environ.get("B200RAG_TC_MIN_BATCH", "2"))
     if B >= tc_min:
         roof = tensor_roofline(env, B, n_local, main_ms)
+        if (n_local, B, k, args.dtype) == (1_000_000, 1024, 10, "f32"):     # the shape the committed capture was taken on
+            tr = profile_traffic("r2_dense_step_ncu_full_raw.csv", "dense_gemm_topk_kernel<1, 2>")
+            if tr:
+                roof["traffic"], roof["traffic_source"] = tr["bytes_per_launch"], tr["source"]
         roof["filter_stage_ms"] = stage_ms          # query prep, sample pass, threshold kernel, main pass
         roof["select_refine_ms"] = refine_ms
         roof["whole_step_frac"] = 2.0 * B * n_local * d / (ms_step / 1e3) / 1e12 / env.peaks["bf16_tflops"]
@@ -1011,9 +1037,15 @@ def run_c4(env, args):
     c.fill_synthetic(seed=1004, nrows=n_docs)
     qv = synth.unit_queries(Q * 4, DIM, 2004)
     c.topk(qv[:8], 50)
-    t0 = time.perf_counter()
-    rows_d, scores_d, counts_d = c.topk(qv, 50)
-    t_dense = time.perf_counter() - t0
+    c.topk(qv, 50)                                  # warm-up (first call of this shape allocates scratch)
+    dense_wall, dense_dev = [], []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        rows_d, scores_d, counts_d = c.topk(qv, 50)
+        dense_wall.append(time.perf_counter() - t0)
+        tm = _lib.last_timings()
+        dense_dev.append(float(tm[0]) + float(tm[2]))
+    t_dense = float(np.median(dense_wall))
     lat_d4 = []
     for i in range(16):
         t0 = time.perf_counter()
@@ -1036,6 +1068,8 @@ def run_c4(env, args):
             raise SystemExit(f"C4 parity check failed: RRF of question {qi} differs from the oracle")
     ach = bytes_per_query * len(queries) / (dev_batch_ms / 1e3) / 1e9
     ach1 = bytes_per_query / (float(np.percentile(dev_ms, 50)) / 1e3) / 1e9
+    # DRAM bytes of one 256-query filter launch from the committed capture of this shape (tools/prof_bm25.py)
+    tr = profile_traffic("r2_bm25_filter_ncu_full_raw.csv", "bm25_filter") if (n_docs, len(queries)) == (1_000_000, 256) else None
     out = {"workload": f"C4 hybrid: {n_docs} chunks, vocab {n_terms}, doc length U[40,250], Zipf 1.07 ({len(post.post_row)} "
                        f"postings); {Q} questions x 4 query variants, BM25 top-50 + dense top-50 (bf16) each, RRF k=60",
            "bm25": {"batch_queries_per_s": len(queries) / t_batch, "batch_device_ms": dev_batch_ms,
@@ -1044,15 +1078,19 @@ def run_c4(env, args):
                     "single_query_call_ms_p99": float(np.percentile(lat, 99)),
                     "single_query_device_ms_p50": float(np.percentile(dev_ms, 50)),
                     "avg_postings_per_query": postings_per_query, "bytes_per_posting": bytes_per_posting,
-                    "roofline": {"bound": "hbm", "kernel": "bm25_filter_kernel: integer filter pass over packed postings + dense columns (batched call)",
+                    "roofline": {"bound": "hbm", "kernel": "bm25_filter_tma_kernel: integer filter pass over packed postings (TMA-staged runs) + dense columns (batched call: resolve + filter + finish)",
                                  "achieved": ach, "peak": env.peaks["hbm_gbs"], "unit": "GB/s",
-                                 "frac": ach / env.peaks["hbm_gbs"], "traffic": None,
+                                 "frac": ach / env.peaks["hbm_gbs"],
+                                 "traffic": tr["bytes_per_launch"] if tr else None,
+                                 "traffic_source": tr["source"] if tr else None,
+                                 "algorithmic_bytes_per_launch": bytes_per_query * len(queries),
                                  "algorithmic_bytes_per_query": bytes_per_query,
                                  "bytes_if_all_packed_4B_postings": postings_per_query * 4.0},
                     "roofline_single_query": {"bound": "hbm", "achieved": ach1, "peak": env.peaks["hbm_gbs"],
                                               "unit": "GB/s", "frac": ach1 / env.peaks["hbm_gbs"]},
                     "cpu_oracle_ms_per_query": float(np.median(cpu_ms)) if cpu_ms else None},
-           "dense_top50": {"queries_per_s": len(qv) / t_dense, "four_variant_call_ms_p50": float(np.percentile(lat_d4, 50))},
+           "dense_top50": {"queries_per_s": len(qv) / t_dense, "batch_call_ms": 1e3 * t_dense,
+                           "batch_device_ms_filter_plus_refine": float(np.median(dense_dev)), "four_variant_call_ms_p50": float(np.percentile(lat_d4, 50))},
            "rrf": {"questions_per_s": Q / t_rrf, "batch_ms": 1e3 * t_rrf},
            "hybrid_questions_per_s": Q / (t_batch + t_dense + t_rrf),
            "host_corpus_gen_s": t_gen, "host_csr_build_s": t_host_build, "device_build_s": t_dev_build,

@@ -29,8 +29,7 @@ import os
 if os.environ.get("BM25_TILE"):
     _lib.set_option("bm25_tile", int(os.environ["BM25_TILE"]))
 for tma in [int(v) for v in os.environ.get("BM25_TMA", "1").split(",")]:
-    _lib.set_option("bm25_tma", tma & 1)
-    _lib.set_option("bm25_by_block", 0 if tma & 2 else 1)        # 3: the TMA kernel in (query, block) order
+    _lib.set_option("bm25_tma", tma)
     ref = None
     for _ in range(4):
         out = ix.search_ids(qs, 50)
