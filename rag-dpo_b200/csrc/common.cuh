@@ -89,22 +89,25 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// (try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~1 ms passes, so a
+// waiting warp — a producer in front of a full ring — does not burn issue slots polling)
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(1000000u)
         : "memory");
     return ok != 0;
 }
+// Bounded: a protocol bug traps (-> CUDA error) after a few seconds instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait_a(bar, parity)) return;
-    long long t0 = clock64();
+    int spins = 0;
     while (!mbar_try_wait_a(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (++spins > (1 << 22)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s_a(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
