@@ -408,6 +408,45 @@ class DenseJob:
             self._steps[nq] = self.index.make_device_step(self.q_dev.data_ptr(), nq, self.k)
         return self._steps[nq]
 
+    def local_step(self, nq=None):
+        """this rank's local top-k only (no exchange, no merge): what the sharded step adds is read off the difference"""
+        nq = self.B if nq is None else nq
+        torch, k = self.env.torch, self.k
+        key = ("local", nq)
+        if key not in self._steps:
+            o = (torch.empty((nq, k), dtype=torch.int32, device=self.env.dev),
+                 torch.empty((nq, k), dtype=torch.float64, device=self.env.dev),
+                 torch.empty((nq,), dtype=torch.int32, device=self.env.dev))
+            qp = self.q_dev.data_ptr()
+
+            def step():
+                self.corpus.topk_dev(qp, nq, k, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr())
+            self._steps[key] = (step, o)
+        return self._steps[key][0]
+
+    def exchange_cost(self, ms_step, steps=5):
+        """sharded runs: per-rank time of the local top-k alone (min / max over ranks) and what exchange + merge (and
+        waiting for the slowest rank) add to the step"""
+        env = self.env
+        if env.world == 1:
+            return None
+        fn = self.local_step()
+        fn()
+        torch = env.torch
+        env.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(env.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(env.stream)
+        env.barrier()
+        mine = e0.elapsed_time(e1) / steps
+        t = torch.tensor([mine, -mine], device=env.dev, dtype=torch.float64)
+        env.dist.all_reduce(t, op=env.dist.ReduceOp.MAX)
+        hi, lo = float(t[0].item()), -float(t[1].item())
+        return {"local_topk_ms_max_over_ranks": hi, "local_topk_ms_min_over_ranks": lo,
+                "exchange_merge_ms": ms_step - hi}
+
     def host_step(self, nq=None):
         nq = self.B if nq is None else nq
         if self.env.world > 1:
@@ -634,6 +673,7 @@ def run_c2(env, args):
         "gpu_launches": int(launches),
         "parity": parity,
         "exchange": job.exchange_kind(),
+        "exchange_cost": job.exchange_cost(ms_step, min(args.steps, 10)),
         "sustained": {"seconds": ms_sus / 1e3, "steps": n_sus, "ms_per_step": ms_sus / n_sus,
                       "queries_per_s": B / (ms_sus / n_sus / 1e3), "main_pass_ms": sus_main,
                       "roofline_frac_of_sustained_peak": 2.0 * B * n_local * d / (sus_main / 1e3) / 1e12 /
@@ -680,13 +720,15 @@ def run_c3(env, args):
         ms_e2e, _ = env.timed(job.host_step, 3)
     parity = job.parity(64, full=False)
     ms_step = ms / 5
+    xc = job.exchange_cost(ms_step)
     out = {"workload": f"C3: {total} x {DIM} bf16 over {env.world} GPU(s) ({n_local} rows per GPU), batch {B}, top-{k}",
            "scaling": "strong", "ms": ms_step, "queries_per_s": B / (ms_step / 1e3),
            "e2e": {"queries_per_s": B / (ms_e2e / 3 / 1e3), "ms": ms_e2e / 3, "h2d_bytes_per_step": B * DIM * 4,
                    "d2h_bytes_per_step": B * k * 16 + B * 4},
            "roofline": dict(tensor_roofline(env, B, n_local, main_ms, sustained=True), filter_stage_ms=stage_ms,
                             select_refine_ms=refine_ms),
-           "gpu_launches": int(launches), "parity": parity, "exchange": job.exchange_kind(), "clocks": clocks.summary()}
+           "gpu_launches": int(launches), "parity": parity, "exchange": job.exchange_kind(), "exchange_cost": xc,
+           "clocks": clocks.summary()}
     job.close()
     return out
 

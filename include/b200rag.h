@@ -169,6 +169,8 @@ int rag_merge_topk_dev(const double* scores_dev, const int64_t* ids_dev, int G, 
  *                         any means (e.g. torch.distributed.all_gather_object);
  *   rag_exchange_connect  handles = world x RAG_IPC_HANDLE_BYTES bytes, rank-major (this rank's own entry is
  *                         ignored).
+ * Every rank's list must be what rag_dense_topk(_dev) returns: sorted by (score desc, id asc), padding (-1) at the end,
+ * ids of different ranks disjoint — the merge RANKS the entries by binary search in the other lists instead of sorting.
  * rag_exchange_merge_*_dev are STREAM-ORDERED (two launches, no host synchronisation); all ranks must call one
  * of them once per step with the same B and k, always on the same stream.  A rank that never arrives does not
  * hang the others: after "exchange_timeout_ms" their queries of that step carry out_counts = -2 and

@@ -40,7 +40,32 @@ exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const
     uint64_t* d64 = reinterpret_cast<uint64_t*>(dst);
     const uint64_t* s0 = reinterpret_cast<const uint64_t*>(my_scores);
     const uint64_t* s1 = reinterpret_cast<const uint64_t*>(my_ids);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_elems; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if ((n_elems & 1) == 0 && my_rows != nullptr) {
+        // pairs: 16-byte loads of the scores / 8-byte loads of two local rows, 16-byte stores into the peer's buffer
+        const int64_t half = n_elems >> 1;
+        ulonglong2* d128 = reinterpret_cast<ulonglong2*>(dst);
+        const ulonglong2* sc2 = reinterpret_cast<const ulonglong2*>(my_scores);
+        const int2* rw2 = reinterpret_cast<const int2*>(my_rows);
+#pragma unroll 4
+        for (int64_t i = tid0; i < n_elems; i += nthr) {
+            ulonglong2 v;
+            if (i < half) {
+                v = sc2[i];
+            } else {
+                const int64_t pr = i - half, e = 2 * pr;
+                const int2 r = rw2[pr];
+                v.x = (unsigned long long)(r.x < 0 ? (int64_t)-1 : (int64_t)r.x + row_lo);
+                v.y = (unsigned long long)(r.y < 0 ? (int64_t)-1 : (int64_t)r.y + row_lo);
+                if (my_counts != nullptr) {      // (see below: an unfinished query is announced with id -2 in its first slot)
+                    if (e % k == 0 && my_counts[e / k] < 0) v.x = (unsigned long long)(int64_t)-2;
+                    if ((e + 1) % k == 0 && my_counts[(e + 1) / k] < 0) v.y = (unsigned long long)(int64_t)-2;
+                }
+            }
+            d128[i] = v;
+        }
+    } else
+    for (int64_t i = tid0; i < 2 * n_elems; i += nthr) {
         uint64_t v;
         if (i < n_elems) {
             v = s0[i];
@@ -122,28 +147,50 @@ exchange_merge_kernel(ExchangeDev ex, int B, int k, uint64_t epoch, int nsort, d
     }
     const uint8_t* base = ex.my_base + (size_t)parity * ex.world * ex.slot_bytes;
     const int64_t n_elems = (int64_t)B * k;
+    const int n_e = ex.world * k;
     int local = 0;
-    for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
+    for (int i = threadIdx.x; i < n_e; i += blockDim.x) {
         XKey e;
         e.s = -INFINITY; e.id = INT64_MAX;
-        if (i < ex.world * k) {
-            const int g = i / k, j = i % k;
-            const double* sc = reinterpret_cast<const double*>(base + (size_t)g * ex.slot_bytes);
-            const int64_t* ids = reinterpret_cast<const int64_t*>(sc + n_elems);
-            const int64_t id = ids[(size_t)b * k + j];
-            if (id >= 0) { e.s = sc[(size_t)b * k + j]; e.id = id; ++local; }
-            else if (id == -2) local += 1 << 20;          // some rank could not finish this query exactly
-        }
+        const int g = i / k, j = i % k;
+        const double* sc = reinterpret_cast<const double*>(base + (size_t)g * ex.slot_bytes);
+        const int64_t* ids = reinterpret_cast<const int64_t*>(sc + n_elems);
+        const int64_t id = ids[(size_t)b * k + j];
+        if (id >= 0) { e.s = sc[(size_t)b * k + j]; e.id = id; ++local; }
+        else if (id == -2) local += 1 << 20;          // some rank could not finish this query exactly
         ek[i] = e;
     }
     atomicAdd(&s_count, local);
-    block_bitonic_desc(ek, nsort);
+    __syncthreads();
     const bool unresolved = s_count >= (1 << 20);
     const int n_valid = s_count & ((1 << 20) - 1);
     const int nout = n_valid < k ? n_valid : k;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        out_ids[(size_t)b * k + i] = i < nout ? ek[i].id : -1;
-        out_scores[(size_t)b * k + i] = i < nout ? ek[i].s : 0.0;
+    // Every list arrives sorted (score desc, id asc) and the ids of different ranks are disjoint: the global rank of
+    // entry j of list g is j + the number of entries of every other list that precede it — one binary search per
+    // other list, no sort, no further barrier.
+    for (int i = threadIdx.x; i < n_e; i += blockDim.x) {
+        const XKey e = ek[i];
+        if (e.id == INT64_MAX) continue;
+        const int g = i / k;
+        int rank = i - g * k;
+        for (int o = 0; o < ex.world && rank < k; ++o) {
+            if (o == g) continue;
+            const XKey* L = ek + o * k;
+            int lo = 0, hi = k;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (e < L[mid]) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            out_ids[(size_t)b * k + rank] = e.id;
+            out_scores[(size_t)b * k + rank] = e.s;
+        }
+    }
+    for (int i = nout + threadIdx.x; i < k; i += blockDim.x) {
+        out_ids[(size_t)b * k + i] = -1;
+        out_scores[(size_t)b * k + i] = 0.0;
     }
     if (threadIdx.x == 0) out_counts[b] = unresolved ? -1 : nout;
 }
@@ -154,7 +201,7 @@ cudaError_t exchange_push_launch(const ExchangeDev& ex, const double* my_scores,
     const int64_t n_elems = (int64_t)B * k;
     int bx = (int)((2 * n_elems + 256 * 8 - 1) / (256 * 8));
     if (bx < 1) bx = 1;
-    if (bx > 32) bx = 32;
+    if (bx > 64) bx = 64;
     dim3 grid(bx, ex.world);
     exchange_push_kernel<<<grid, 256, 0, st>>>(ex, my_scores, my_ids, my_rows, row_lo, my_counts, k, n_elems, epoch);
     return cudaGetLastError();
@@ -162,8 +209,7 @@ cudaError_t exchange_push_launch(const ExchangeDev& ex, const double* my_scores,
 
 cudaError_t exchange_merge_launch(const ExchangeDev& ex, int B, int k, uint64_t epoch, double* out_scores,
                                   int64_t* out_ids, int32_t* out_counts, cudaStream_t st) {
-    int nsort = 32;
-    while (nsort < ex.world * k) nsort <<= 1;
+    const int nsort = ex.world * k;                  // (entries held in shared memory; they are ranked, not sorted)
     const size_t smem = (size_t)nsort * sizeof(XKey);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -2,6 +2,7 @@
 C ABI (libb200rag.so) and is compared bit-for-bit with the oracle / the golden
 vectors produced by the reference's own code."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -523,6 +524,27 @@ def test_peer_exchange_single_rank_roundtrip():
                                              o_i.data_ptr(), o_c.data_ptr()) != 0
     finally:
         _lib.check(L.rag_exchange_destroy(h))
+
+
+def test_two_rank_peer_exchange_vs_oracle():
+    """one process per GPU (torch.distributed.run, 2 ranks): row shards in DeviceCorpus, the stream-ordered device
+    step with the NVLink peer-memory exchange (different B / k per case, a delayed rank, several epochs) and the
+    host-buffer call, merged result compared with the oracle over the whole corpus on every rank
+    (tests/dist_gpu_worker.py).  Needs 2 GPUs: skipped on a 1-GPU box."""
+    import socket
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "dist_gpu_worker.py")]
+    res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, (res.stdout[-3000:], res.stderr[-3000:])
 
 
 # --------------------------------------------------- BASELINE-size cases ----
