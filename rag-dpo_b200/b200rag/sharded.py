@@ -200,7 +200,8 @@ class ShardedDenseIndex:
                 my_ids[:, :kl] = torch.where(gid >= 0, gid + self.row_lo, gid)
         ex = self.exchange(B, kk) if shared else None
         unresolved_local = None
-        if not exact_local and kl > 0:
+        if not exact_local and kl > 0 and not (ex is not None and kl == kk):
+            # (the peer exchange carries the flag in-band: no extra kernels on the step's critical path)
             unresolved_local = (buf["o_counts"] < 0).any().to(torch.int32).reshape(1)
         if ex is not None:
             # stores into the peers' buffers + epoch flags + merge: two launches, no collective call
@@ -229,7 +230,7 @@ class ShardedDenseIndex:
         h[1].copy_(buf["m_scores"], non_blocking=True)
         h[2].copy_(buf["m_counts"], non_blocking=True)
         redo_all = False
-        if unresolved_local is not None and not (ex is not None and kl == kk):
+        if unresolved_local is not None:
             # paths without the in-band flag (NCCL all-gather, padded lists): agree with one tiny all-reduce
             if self.world > 1:
                 dist.all_reduce(unresolved_local, op=dist.ReduceOp.MAX, group=self.group)

@@ -398,10 +398,13 @@ __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q
 // disallowed rows and takes the thread's maximum.  Steps = (chunk, group of kBmDnGroup tokens); the loads
 // of the next step are requested before the current one is added (two register buffers, ping-pong).
 // xa holds step (chunk 0, group 0), requested by the caller (in flight while the run tokens are added).
-template <int CH, int T>
+// A16: the accumulators are 16 bits wide, two rows per 32-bit word (even row in the low half — the layout of a column
+// word), in units coarser by 2^cshift than a packed posting's q: a column sum (entries = ceil(q / 4)) is divided by
+// 2^(cshift - 2), rounding up, before it is added (still an upper bound; the caller widens the slack).
+template <int CH, int T, bool A16 = false>
 __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t* const* s_colp, int n_col, bool last,
                                                   uint2 (&xa)[kBmDnGroup][4], const uint8_t* __restrict__ allow,
-                                                  int64_t r0, int64_t r1, int tid, uint32_t& m) {
+                                                  int64_t r0, int64_t r1, int tid, uint32_t& m, int cshift = 0) {
     constexpr int kTile = CH * 4096;
     constexpr int kChunk = 16 * T, kGrp = 4 * T, NCK = kTile / kChunk;
     const int ngroups = n_col > 0 ? (n_col + kBmDnGroup - 1) / kBmDnGroup : 1;
@@ -435,7 +438,40 @@ __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t*
                 s_all[2 * g + 1] += xx[u][g].y;
                 s_hi[2 * g + 1] += xx[u][g].y >> 16;
             }
-        if (++cg == ngroups) {    // the chunk's last group: merge
+        if (A16 && ++cg == ngroups) {    // the chunk's last group: merge (16-bit accumulators)
+            uint32_t* arow = acc + ((cc * kChunk + 4 * tid) >> 1);
+            const int cs = cshift - kBmDenseShift;
+            const uint32_t rnd = (1u << cs) - 1u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint2 a = *reinterpret_cast<const uint2*>(arow + g * (kGrp / 2));
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t hi = s_hi[2 * g + h];
+                    const uint32_t lo = s_all[2 * g + h] - (hi << 16);
+                    (h ? a.y : a.x) += ((lo + rnd) >> cs) | (((hi + rnd) >> cs) << 16);
+                }
+                if (last) {
+                    if (allow != nullptr) {
+                        const int64_t row = r0 + cc * kChunk + g * kGrp + 4 * tid;  // 4 rows inside one bitmap byte
+                        const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
+                        if (!(bits & 1u)) a.x &= 0xFFFF0000u;
+                        if (!(bits & 2u)) a.x &= 0x0000FFFFu;
+                        if (!(bits & 4u)) a.y &= 0xFFFF0000u;
+                        if (!(bits & 8u)) a.y &= 0x0000FFFFu;
+                    }
+                    const uint32_t x0 = a.x & 0xFFFFu, x1 = a.x >> 16, y0 = a.y & 0xFFFFu, y1 = a.y >> 16;
+                    const uint32_t m01 = x0 > x1 ? x0 : x1, m23 = y0 > y1 ? y0 : y1;
+                    const uint32_t mg = m01 > m23 ? m01 : m23;
+                    m = mg > m ? mg : m;
+                }
+                *reinterpret_cast<uint2*>(arow + g * (kGrp / 2)) = a;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+            cg = 0;
+            ++cc;
+        } else if (!A16 && ++cg == ngroups) {    // the chunk's last group: merge
             uint32_t* arow = acc + cc * kChunk + 4 * tid;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -530,10 +566,23 @@ __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t*
 // ---- selection: the tile's H best allowed rows by U and the (H+1)-th best U -> dst[0..H] (descending; 0 = none).
 // Every thread reads only the accumulators it wrote last (column phase): no barrier needed on entry.  *s_nlist is 0.
 // NAMED: the CTA has a producer warp; the 256 consumer threads synchronise on named barrier 1.
-template <int CH, int T, bool NAMED, int LIST = kBmList>
+// the 4 accumulators at local rows [row, row + 4) (row a multiple of 4)
+template <bool A16>
+__device__ __forceinline__ void bm25_load4(const uint32_t* acc, uint32_t row, uint32_t (&v)[4]) {
+    if constexpr (A16) {
+        const uint2 a = *reinterpret_cast<const uint2*>(acc + (row >> 1));
+        v[0] = a.x & 0xFFFFu; v[1] = a.x >> 16; v[2] = a.y & 0xFFFFu; v[3] = a.y >> 16;
+    } else {
+        const uint4 a = *reinterpret_cast<const uint4*>(acc + row);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+}
+
+// A16: 16-bit accumulators in units of 2^ushift (see bm25_column_phase); the heads are written in the fine unit.
+template <int CH, int T, bool NAMED, int LIST = kBmList, bool A16 = false>
 __device__ __forceinline__ void bm25_select_phase(uint32_t* acc, uint32_t m, int H, int64_t r0, int tid,
                                                   unsigned long long* s_list, int* s_nlist_p,
-                                                  unsigned long long* __restrict__ dst) {
+                                                  unsigned long long* __restrict__ dst, int ushift = 0) {
     constexpr int kTile = CH * 4096;
     constexpr int kChunk = 16 * T, kGrp = 4 * T, NCK = kTile / kChunk;
     const int warp = tid >> 5, lane = tid & 31;
@@ -557,8 +606,9 @@ __device__ __forceinline__ void bm25_select_phase(uint32_t* acc, uint32_t m, int
             uint32_t gmask = 0u;
 #pragma unroll
             for (int j = 0; j < NCK * 4; ++j) {
-                const uint4 a = *reinterpret_cast<const uint4*>(&acc[j * kGrp + 4 * tid]);
-                const uint32_t m01 = a.x > a.y ? a.x : a.y, m23 = a.z > a.w ? a.z : a.w;
+                uint32_t a[4];
+                bm25_load4<A16>(acc, (uint32_t)(j * kGrp + 4 * tid), a);
+                const uint32_t m01 = a[0] > a[1] ? a[0] : a[1], m23 = a[2] > a[3] ? a[2] : a[3];
                 gmask |= ((m01 > m23 ? m01 : m23) >= theta ? 1u : 0u) << j;
             }
             // ... and those rows
@@ -566,14 +616,14 @@ __device__ __forceinline__ void bm25_select_phase(uint32_t* acc, uint32_t m, int
                 const int j = __ffs(gmask) - 1;
                 gmask &= gmask - 1u;
                 const uint32_t loc0 = (uint32_t)j * (uint32_t)kGrp;
-                const uint4 a = *reinterpret_cast<const uint4*>(&acc[loc0 + 4 * tid]);
-                const uint32_t vv[4] = {a.x, a.y, a.z, a.w};
-                int slot = atomicAdd(s_nlist_p, (int)(a.x >= theta) + (int)(a.y >= theta) + (int)(a.z >= theta) + (int)(a.w >= theta));
+                uint32_t vv[4];
+                bm25_load4<A16>(acc, loc0 + 4u * (uint32_t)tid, vv);
+                int slot = atomicAdd(s_nlist_p, (int)(vv[0] >= theta) + (int)(vv[1] >= theta) + (int)(vv[2] >= theta) + (int)(vv[3] >= theta));
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (vv[i] >= theta) {
                         if (slot < LIST)
-                            s_list[slot] = ((unsigned long long)vv[i] << 32) | (unsigned long long)(~(row_base + loc0 + i));
+                            s_list[slot] = ((unsigned long long)(vv[i] << ushift) << 32) | (unsigned long long)(~(row_base + loc0 + i));
                         ++slot;
                     }
             }
@@ -588,20 +638,21 @@ __device__ __forceinline__ void bm25_select_phase(uint32_t* acc, uint32_t m, int
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const uint32_t base = (uint32_t)(c * kChunk + g * kGrp);
-                    const uint4 a = *reinterpret_cast<const uint4*>(&acc[base + 4 * tid]);
-                    if (a.x > best) { best = a.x; bloc = base + 0u; }     // ascending rows, strict >: lowest row wins
-                    if (a.y > best) { best = a.y; bloc = base + 1u; }
-                    if (a.z > best) { best = a.z; bloc = base + 2u; }
-                    if (a.w > best) { best = a.w; bloc = base + 3u; }
+                    uint32_t a[4];
+                    bm25_load4<A16>(acc, base + 4u * (uint32_t)tid, a);
+#pragma unroll
+                    for (uint32_t i = 0; i < 4; ++i)
+                        if (a[i] > best) { best = a[i]; bloc = base + i; }     // ascending rows, strict >: lowest row wins
                 }
             const uint32_t wm = __reduce_max_sync(0xffffffffu, best);
             if (wm == 0u) break;
             const uint32_t myrow = best == wm ? row_base + bloc : 0xFFFFFFFFu;
             const uint32_t wr = __reduce_min_sync(0xffffffffu, myrow);
             if (myrow == wr) {
-                acc[bloc + 4 * tid] = 0u;
+                if constexpr (A16) reinterpret_cast<uint16_t*>(acc)[bloc + 4 * tid] = (uint16_t)0;
+                else acc[bloc + 4 * tid] = 0u;
                 const int slot = atomicAdd(s_nlist_p, 1);
-                if (slot < LIST) s_list[slot] = ((unsigned long long)wm << 32) | (unsigned long long)(~wr);
+                if (slot < LIST) s_list[slot] = ((unsigned long long)(wm << ushift) << 32) | (unsigned long long)(~wr);
             }
         }
     }
@@ -764,14 +815,21 @@ constexpr int kBmRingSlots = 4;
 constexpr int kBmSlotPost = 512;                  // postings per chunk
 constexpr int kBmSlotWords = kBmSlotPost + 4;     // the copy starts / ends on 16-byte boundaries of the packed stream
 constexpr int kBmTmaThreads = 288;                // 8 consumer warps + the producer warp
-constexpr size_t kBmTmaSmem = (size_t)kBmBlock * 4 + (size_t)kBmRingSlots * kBmSlotWords * 4;
+constexpr size_t bm25_tma_smem(bool a16) {
+    return (size_t)kBmBlock * (a16 ? 2 : 4) + (size_t)kBmRingSlots * kBmSlotWords * 4;
+}
 static_assert((size_t)kBmList * 8 <= (size_t)kBmRingSlots * kBmSlotWords * 4, "the selection list reuses the ring");
 
-__global__ void __launch_bounds__(kBmTmaThreads, 3)
+// A16: 16-bit accumulators (two rows per word) in units of 2^cshift: 32 KB instead of 64 KB per tile, so FOUR CTAs are
+// resident per SM instead of three (the kernel is bound by resident warps, not by bytes).  A posting adds
+// ceil(q / 2^cshift); the caller picks cshift so that the sum of a query's tokens cannot reach 2^16 and widens the
+// finish kernel's slack by 2^cshift per token.
+template <bool A16>
+__global__ void __launch_bounds__(kBmTmaThreads, A16 ? 4 : 3)
 bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, const uint8_t* __restrict__ allow, int H,
-                       int by_block, unsigned long long* __restrict__ heads) {
+                       int by_block, int cshift, unsigned long long* __restrict__ heads) {
     extern __shared__ __align__(16) uint32_t acc[];   // 16384 accumulators | ring
-    uint32_t* ring = acc + kBmBlock;
+    uint32_t* ring = acc + (A16 ? kBmBlock / 2 : kBmBlock);
     __shared__ uint2 s_runs[kBmMaxTokens];            // [lo, hi) inside the packed stream
     __shared__ const uint16_t* s_colp[kBmMaxTokens];  // column of the tile per DENSE token
     __shared__ __align__(8) uint64_t s_full[kBmRingSlots], s_empty[kBmRingSlots];
@@ -789,7 +847,8 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     if (tid < stride) d = __ldg(my_rec + tid);
     if (tid < T) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(&acc[j * 4 * T + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < (A16 ? 8 : 16); ++j)
+            *reinterpret_cast<uint4*>(&acc[j * 4 * T + 4 * tid]) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
         s_nrun = 0; s_ncol = 0; s_nlist = 0;
@@ -844,6 +903,17 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     {
         const uint32_t t_lo = (uint32_t)warp << 29;           // first local row of the warp, in the packed word's place
         const uint32_t t_hi = (uint32_t)(warp + 1) << 29;     // (warp 7: wraps to 0, its upper bound is the chunk's end)
+        uint16_t* acc16 = reinterpret_cast<uint16_t*>(acc);
+        const uint32_t rnd = (1u << cshift) - 1u;
+        // adds one posting to its row's accumulator
+        auto add = [&](uint32_t v) {
+            if constexpr (A16) {
+                const uint32_t loc = v >> kBmQBits;
+                acc16[loc] = (uint16_t)(acc16[loc] + (((v & kBmQMask) + rnd) >> cshift));
+            } else {
+                acc[v >> kBmQBits] += v & kBmQMask;
+            }
+        };
         int slot = 0;
         uint32_t ph = 0;
         for (int r = 0; r < n_run; ++r) {
@@ -859,7 +929,7 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
                         const int i = lane + 32 * u;
                         if (i < n) {
                             const uint32_t v = c[i];
-                            if ((v >> 29) == (uint32_t)warp) acc[v >> kBmQBits] += v & kBmQMask;
+                            if ((v >> 29) == (uint32_t)warp) add(v);
                         }
                     }
                 } else {
@@ -876,10 +946,7 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
                     const unsigned b2 = __ballot_sync(0xffffffffu, v2 < (up ? t_hi : t_lo));
                     const int lo = s_lo > 0 ? (s_lo - 1) * 16 + 1 + __popc(b2 & 0xFFFFu) : 0;
                     const int hi = warp == 7 ? n : (s_hi > 0 ? (s_hi - 1) * 16 + 1 + __popc(b2 >> 16) : 0);
-                    for (int i = lo + lane; i < hi; i += 32) {
-                        const uint32_t v = c[i];
-                        acc[v >> kBmQBits] += v & kBmQMask;
-                    }
+                    for (int i = lo + lane; i < hi; i += 32) add(c[i]);
                 }
                 __syncwarp();                                  // the next chunk may be another term on the same rows
                 if (lane == 0) mbar_arrive_a(empty0 + 8u * slot);
@@ -889,9 +956,9 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");             // the column phase owns rows by thread
     uint32_t m = 0u;
-    bm25_column_phase<4, T>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m);
-    bm25_select_phase<4, T, true>(acc, m, H, r0, tid, reinterpret_cast<unsigned long long*>(ring), &s_nlist,
-                                  heads + ((size_t)qy * ix.n_blocks + blk) * (H + 1));
+    bm25_column_phase<4, T, A16>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m, cshift);
+    bm25_select_phase<4, T, true, kBmList, A16>(acc, m, H, r0, tid, reinterpret_cast<unsigned long long*>(ring), &s_nlist,
+                                                heads + ((size_t)qy * ix.n_blocks + blk) * (H + 1), A16 ? cshift : 0);
 }
 
 // w * impact of (term t, row) if the posting exists, else 0: the product the accumulation adds
@@ -978,7 +1045,7 @@ __device__ __forceinline__ void bm25_exact_topk(const Bm25Device& ix, const int3
 constexpr int kBmFinishThreads = 1024;   // (survivor, token) look-ups are chains of dependent loads: all of them at once
 __global__ void __launch_bounds__(kBmFinishThreads)
 bm25_finish_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr, int q0,
-                   const unsigned long long* __restrict__ heads, int n_tiles, int H, int h_tau, int nsort_tau, int k,
+                   const unsigned long long* __restrict__ heads, int n_tiles, int H, int h_tau, int coarse_shift, int k,
                    int32_t* out_rows, double* out_scores, int32_t* out_counts) {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     // [ 32 KB: tau sort buffer, later the staged products | survivors' keys | survivors' rows ]
@@ -1045,7 +1112,9 @@ bm25_finish_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int
         if (t >= 0 && t < ix.n_terms && (int)((unsigned)ix.term_info[t].x >> 30) == kBmDense) atomicAdd(&s_extra, 1);
     }
     __syncthreads();
-    const uint32_t slack = 2u * (uint32_t)nt + (uint32_t)((1 << kBmDenseShift) - 1) * (uint32_t)s_extra + 2u;
+    // (16-bit accumulators: every token was rounded up to the coarse unit once more)
+    const uint32_t slack = 2u * (uint32_t)nt + (uint32_t)((1 << kBmDenseShift) - 1) * (uint32_t)s_extra + 2u +
+                           (coarse_shift > 0 ? ((uint32_t)nt << coarse_shift) : 0u);
     uint32_t thr = tau_u > slack ? tau_u - slack : 0u;
     if (thr < 1u) thr = 1u;                                  // no bound: every row with a positive upper bound
     __syncthreads();
@@ -1210,6 +1279,7 @@ static bool bm25_plan_for(const Bm25Device& ix, int k, int ch, Bm25Plan* p) {
 // block tiles when the launch has enough of them to fill the GPU (148 SMs x 3 CTAs, twice over); quarter-block tiles
 // for small corpora and single queries (more, shorter CTAs: latency)
 int g_bm25_tile_chunks = 0;             // option "bm25_tile": force 1 / 2 / 4 chunks per tile (0 = automatic)
+int g_bm25_acc16 = 1;                   // option "bm25_acc16": 16-bit accumulators (4 CTAs per SM) in the TMA kernel
 int g_bm25_by_block = 1;                // option "bm25_by_block": the TMA kernel's CTAs in (block, query) order
 int g_bm25_tma = 1;                     // option "bm25_tma": block tiles through bm25_filter_tma_kernel (0: bm25_filter_kernel<4>)
 static bool bm25_plan(const Bm25Device& ix, int k, int Q, Bm25Plan* p) {
@@ -1266,12 +1336,29 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     }
     dim3 grid_a(pl.n_tiles, Q);
     cudaError_t e = cudaSuccess;
+    // 16-bit accumulators: the coarsest unit 2^cshift for which a query's tokens cannot sum to 2^16
+    int cshift = 0;
+    if (use_tma && g_bm25_acc16) {
+        cshift = kBmDenseShift;
+        while (cshift <= 8 && (int64_t)stride * ((1 << (kBmQBits - cshift)) + 1) > 65535) ++cshift;
+        if (cshift > 8) cshift = 0;             // too many tokens: the unit would be too coarse to select with
+    }
     if (use_tma) {
-        e = cudaFuncSetAttribute(bm25_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBmTmaSmem);
-        if (e != cudaSuccess) return e;
         const bool by_block = g_bm25_by_block && pl.n_tiles <= 65535;
-        bm25_filter_tma_kernel<<<by_block ? dim3(Q, pl.n_tiles) : grid_a, kBmTmaThreads, kBmTmaSmem, st>>>(
-            ix, rec, stride, allow, pl.H, by_block ? 1 : 0, heads);
+        const dim3 grid_t = by_block ? dim3(Q, pl.n_tiles) : grid_a;
+        if (cshift > 0) {
+            e = cudaFuncSetAttribute(bm25_filter_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)bm25_tma_smem(true));
+            if (e != cudaSuccess) return e;
+            bm25_filter_tma_kernel<true><<<grid_t, kBmTmaThreads, bm25_tma_smem(true), st>>>(
+                ix, rec, stride, allow, pl.H, by_block ? 1 : 0, cshift, heads);
+        } else {
+            e = cudaFuncSetAttribute(bm25_filter_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)bm25_tma_smem(false));
+            if (e != cudaSuccess) return e;
+            bm25_filter_tma_kernel<false><<<grid_t, kBmTmaThreads, bm25_tma_smem(false), st>>>(
+                ix, rec, stride, allow, pl.H, by_block ? 1 : 0, 0, heads);
+        }
     } else if (pl.ch == 4) {
         // (a function attribute belongs to the current device: set on every launch, a sharded index runs on several)
         // (512-thread CTAs, 2 per SM, were tried for the 32 resident warps: 64 registers spill and the 16-warp
@@ -1286,12 +1373,10 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    int nsort = 32;
-    while (nsort < pl.n_tiles * pl.h_tau) nsort <<= 1;
     const size_t smem = (size_t)kBmContrib * sizeof(double) + (size_t)kBmSurvivors * (sizeof(Bm25Key) + 4);
     e = cudaFuncSetAttribute(bm25_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bm25_finish_kernel<<<Q, kBmFinishThreads, smem, st>>>(ix, d_q_terms, d_q_ptr, q0, heads, pl.n_tiles, pl.H, pl.h_tau, nsort, k,
+    bm25_finish_kernel<<<Q, kBmFinishThreads, smem, st>>>(ix, d_q_terms, d_q_ptr, q0, heads, pl.n_tiles, pl.H, pl.h_tau, cshift, k,
                                              out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_counts + q0);
     return cudaGetLastError();
 }

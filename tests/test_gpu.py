@@ -885,11 +885,12 @@ def _check_bm25_classes(_lib, ix, o, queries, docs, n_terms, allow, bitmap, tile
         assert rows1[0].tolist() == rows[0].tolist() and np.array_equal(scores1[0], scores[0])
 
 
-@pytest.mark.parametrize("tile,tma", [(1, 1), (2, 1), (4, 1), (4, 0)])
-def test_bm25_filter_tile_sizes_vs_oracle(tile, tma):
+@pytest.mark.parametrize("tile,tma,acc16", [(1, 1, 1), (2, 1, 1), (4, 1, 1), (4, 1, 0), (4, 0, 0)])
+def test_bm25_filter_tile_sizes_vs_oracle(tile, tma, acc16):
     """the filter kernel's three tile sizes (4096 / 8192 / 16384 rows per CTA; picked by launch size in production,
     forced here) over column, run and scanned tokens, with and without a row filter, all equal to the oracle;
-    block tiles through both kernels (tma 1: runs staged through shared memory by a producer warp; 0: direct loads)"""
+    block tiles through both kernels (tma 1: runs staged through shared memory by a producer warp, with 16-bit
+    accumulators in a coarser unit — 4 CTAs per SM — or 32-bit ones; 0: direct loads)"""
     from b200rag import _lib
     from b200rag.bm25 import DeviceBM25, Postings
     n_docs = 40000
@@ -905,6 +906,7 @@ def test_bm25_filter_tile_sizes_vs_oracle(tile, tma):
     bm = np.packbits(allow, bitorder="little")
     _lib.set_option("bm25_tile", tile)
     _lib.set_option("bm25_tma", tma)
+    _lib.set_option("bm25_acc16", acc16)
     try:
         for k in (10, 50):
             for mask, bits in ((None, None), (allow, bm)):
@@ -915,6 +917,7 @@ def test_bm25_filter_tile_sizes_vs_oracle(tile, tma):
     finally:
         _lib.set_option("bm25_tile", 0)
         _lib.set_option("bm25_tma", 1)
+        _lib.set_option("bm25_acc16", 1)
     ix.close()
 
 
