@@ -401,24 +401,24 @@ __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q
 // A16: the accumulators are 16 bits wide, two rows per 32-bit word (even row in the low half — the layout of a column
 // word), in units coarser by 2^cshift than a packed posting's q: a column sum (entries = ceil(q / 4)) is divided by
 // 2^(cshift - 2), rounding up, before it is added (still an upper bound; the caller widens the slack).
-template <int CH, int T, bool A16 = false>
+template <int CH, int T, bool A16 = false, int DG = kBmDnGroup>
 __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t* const* s_colp, int n_col, bool last,
-                                                  uint2 (&xa)[kBmDnGroup][4], const uint8_t* __restrict__ allow,
+                                                  uint2 (&xa)[DG][4], const uint8_t* __restrict__ allow,
                                                   int64_t r0, int64_t r1, int tid, uint32_t& m, int cshift = 0) {
     constexpr int kTile = CH * 4096;
     constexpr int kChunk = 16 * T, kGrp = 4 * T, NCK = kTile / kChunk;
-    const int ngroups = n_col > 0 ? (n_col + kBmDnGroup - 1) / kBmDnGroup : 1;
+    const int ngroups = n_col > 0 ? (n_col + DG - 1) / DG : 1;
     uint32_t s_all[8], s_hi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
     int lc = 0, lg = 0;           // (chunk, group) of the next step to load
     int cc = 0, cg = 0;           // ... of the next step to add
-    auto load_step = [&](uint2 (&xx)[kBmDnGroup][4]) {
+    auto load_step = [&](uint2 (&xx)[DG][4]) {
         const bool live = lc < NCK;
 #pragma unroll
-        for (int u = 0; u < kBmDnGroup; ++u) {
-            if (live && lg * kBmDnGroup + u < n_col) {
-                const uint2* cp = reinterpret_cast<const uint2*>(s_colp[lg * kBmDnGroup + u] + lc * kChunk) + tid;
+        for (int u = 0; u < DG; ++u) {
+            if (live && lg * DG + u < n_col) {
+                const uint2* cp = reinterpret_cast<const uint2*>(s_colp[lg * DG + u] + lc * kChunk) + tid;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(cp + g * T);
             } else {
@@ -428,9 +428,9 @@ __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t*
         }
         if (++lg == ngroups) { lg = 0; ++lc; }
     };
-    auto add_step = [&](const uint2 (&xx)[kBmDnGroup][4]) {
+    auto add_step = [&](const uint2 (&xx)[DG][4]) {
 #pragma unroll
-        for (int u = 0; u < kBmDnGroup; ++u)
+        for (int u = 0; u < DG; ++u)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 s_all[2 * g + 0] += xx[u][g].x;
@@ -504,20 +504,20 @@ __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t*
             ++cc;
         }
     };
-    uint2 xb[kBmDnGroup][4];
-    if (n_col <= 3 * kBmDnGroup) {
+    uint2 xb[DG][4];
+    if (n_col <= 3 * DG) {
         // the usual case, up to 6 column tokens: their pointers stay in registers and the group loop is
         // unrolled, so a step costs its loads and adds and little else
-        const uint2* cp[3 * kBmDnGroup];
+        const uint2* cp[3 * DG];
 #pragma unroll
-        for (int u = 0; u < 3 * kBmDnGroup; ++u)
+        for (int u = 0; u < 3 * DG; ++u)
             cp[u] = u < n_col ? reinterpret_cast<const uint2*>(s_colp[u]) + tid : nullptr;
         // requests step (chunk c, group G) into xx; G is a compile-time constant
 #define BM25_LOAD_STEP(xx, G, c)                                                                        \
         do {                                                                                    \
-            _Pragma("unroll") for (int u = 0; u < kBmDnGroup; ++u) {                            \
-                if ((G) * kBmDnGroup + u < n_col) {                                             \
-                    const uint2* q_ = cp[(G) * kBmDnGroup + u] + (c) * (kChunk / 4);                 \
+            _Pragma("unroll") for (int u = 0; u < DG; ++u) {                            \
+                if ((G) * DG + u < n_col) {                                             \
+                    const uint2* q_ = cp[(G) * DG + u] + (c) * (kChunk / 4);                 \
                     _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = __ldg(q_ + g * T);   \
                 } else {                                                                        \
                     _Pragma("unroll") for (int g = 0; g < 4; ++g) xx[u][g] = make_uint2(0u, 0u); \
@@ -545,7 +545,7 @@ __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t*
             }
             if (c + 1 < NCK) {
 #pragma unroll
-                for (int u = 0; u < kBmDnGroup; ++u)
+                for (int u = 0; u < DG; ++u)
 #pragma unroll
                     for (int g = 0; g < 4; ++g) xa[u][g] = xb[u][g];
             }
@@ -825,7 +825,7 @@ static_assert((size_t)kBmList * 8 <= (size_t)kBmRingSlots * kBmSlotWords * 4, "t
 // ceil(q / 2^cshift); the caller picks cshift so that the sum of a query's tokens cannot reach 2^16 and widens the
 // finish kernel's slack by 2^cshift per token.
 template <bool A16>
-__global__ void __launch_bounds__(kBmTmaThreads, A16 ? 4 : 3)
+__global__ void __launch_bounds__(kBmTmaThreads, A16 ? 5 : 3)
 bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, const uint8_t* __restrict__ allow, int H,
                        int by_block, int cshift, unsigned long long* __restrict__ heads) {
     extern __shared__ __align__(16) uint32_t acc[];   // 16384 accumulators | ring
@@ -835,6 +835,7 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     __shared__ __align__(8) uint64_t s_full[kBmRingSlots], s_empty[kBmRingSlots];
     __shared__ int s_nrun, s_ncol, s_nlist;
     constexpr int T = 256;
+    constexpr int DG = A16 ? 1 : kBmDnGroup;          // column tokens in flight together (A16: 40 registers, 5 CTAs/SM)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // grid (queries, blocks) or (blocks, queries): CTAs are dealt x-fastest, so `by_block` runs all queries of one
     // block back to back — the block's columns and runs are then shared in L2 by the CTAs that are resident together
@@ -888,9 +889,9 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     }
     // ===================== consumers =====================
     // the first column step (chunk 0, first group) is requested now: in flight while the run tokens are added
-    uint2 xa[kBmDnGroup][4];
+    uint2 xa[DG][4];
 #pragma unroll
-    for (int u = 0; u < kBmDnGroup; ++u) {
+    for (int u = 0; u < DG; ++u) {
         if (u < n_col) {
             const uint2* cp = reinterpret_cast<const uint2*>(s_colp[u]) + tid;
 #pragma unroll
@@ -956,7 +957,7 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");             // the column phase owns rows by thread
     uint32_t m = 0u;
-    bm25_column_phase<4, T, A16>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m, cshift);
+    bm25_column_phase<4, T, A16, DG>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m, cshift);
     bm25_select_phase<4, T, true, kBmList, A16>(acc, m, H, r0, tid, reinterpret_cast<unsigned long long*>(ring), &s_nlist,
                                                 heads + ((size_t)qy * ix.n_blocks + blk) * (H + 1), A16 ? cshift : 0);
 }
