@@ -1120,7 +1120,7 @@ def run_c4(env, args):
                     "single_query_call_ms_p99": float(np.percentile(lat, 99)),
                     "single_query_device_ms_p50": float(np.percentile(dev_ms, 50)),
                     "avg_postings_per_query": postings_per_query, "bytes_per_posting": bytes_per_posting,
-                    "roofline": {"bound": "hbm", "kernel": "bm25_filter_tma_kernel: integer filter pass over packed postings (TMA-staged runs) + dense columns (batched call: resolve + filter + finish)",
+                    "roofline": {"bound": "hbm", "kernel": "bm25_filter_tma_kernel<16-bit accumulators>: integer filter pass over packed postings (TMA-staged runs) + dense columns (whole batched call: resolve + filter + finish)",
                                  "achieved": ach, "peak": env.peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": ach / env.peaks["hbm_gbs"],
                                  "traffic": tr["bytes_per_launch"] if tr else None,
