@@ -206,6 +206,7 @@ int shard_build(Bm25Shard** out, int slot, int64_t n_docs, int64_t n_terms, int6
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return bail("filter index");
         s->n_dense = (int)dense.size();
+        d.n_dense = (int)dense.size();
         s->n_tabled = (int)tabled.size();
         s->h_cls.resize((size_t)n_terms);
         for (int64_t t = 0; t < n_terms; ++t) s->h_cls[(size_t)t] = (uint8_t)((unsigned)info[(size_t)t].x >> 30);

@@ -566,6 +566,90 @@ __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t*
 // ---- selection: the tile's H best allowed rows by U and the (H+1)-th best U -> dst[0..H] (descending; 0 = none).
 // Every thread reads only the accumulators it wrote last (column phase): no barrier needed on entry.  *s_nlist is 0.
 // NAMED: the CTA has a producer warp; the 256 consumer threads synchronise on named barrier 1.
+// Column tokens of the 16-bit kernel (T = 256, one block): the same sums as bm25_column_phase<.., A16>, written for few
+// instructions and few registers — a column is addressed by a 32-bit offset (in 8-byte words) from the column base, so
+// a step costs one shared load, one wide multiply-add, four 8-byte loads and their adds; the steps (chunk, token) are
+// double buffered (xa holds step (0, 0), requested by the caller).
+__device__ __forceinline__ void bm25_column_phase16(uint32_t* acc, const uint32_t* s_colo, const uint2* __restrict__ colbase,
+                                                    int n_col, uint2 (&xa)[4], const uint8_t* __restrict__ allow,
+                                                    int64_t r0, int64_t r1, int tid, int cshift, uint32_t& m) {
+    constexpr int T = 256, kChunk = 16 * T, kGrp = 4 * T, NCK = kBmBlock / kChunk;
+    const int cs = cshift - kBmDenseShift;
+    const uint32_t rnd = (1u << cs) - 1u;
+    const uint2* tb = colbase + tid;
+    uint32_t s_all[8], s_hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
+    auto add = [&](const uint2 (&xx)[4]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            s_all[2 * g + 0] += xx[g].x;
+            s_hi[2 * g + 0] += xx[g].x >> 16;
+            s_all[2 * g + 1] += xx[g].y;
+            s_hi[2 * g + 1] += xx[g].y >> 16;
+        }
+    };
+    auto load = [&](uint2 (&xx)[4], int u, int c) {
+        const uint2* q_ = tb + (size_t)s_colo[u] + c * (kChunk / 4);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xx[g] = __ldg(q_ + g * T);
+    };
+    auto merge = [&](int c) {
+        uint32_t* arow = acc + ((c * kChunk + 4 * tid) >> 1);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint2 a = *reinterpret_cast<const uint2*>(arow + g * (kGrp / 2));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t hi = s_hi[2 * g + h];
+                const uint32_t lo = s_all[2 * g + h] - (hi << 16);
+                (h ? a.y : a.x) += ((lo + rnd) >> cs) | (((hi + rnd) >> cs) << 16);
+                s_all[2 * g + h] = 0u;
+                s_hi[2 * g + h] = 0u;
+            }
+            if (allow != nullptr) {
+                const int64_t row = r0 + c * kChunk + g * kGrp + 4 * tid;      // 4 rows inside one bitmap byte
+                const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
+                if (!(bits & 1u)) a.x &= 0xFFFF0000u;
+                if (!(bits & 2u)) a.x &= 0x0000FFFFu;
+                if (!(bits & 4u)) a.y &= 0xFFFF0000u;
+                if (!(bits & 8u)) a.y &= 0x0000FFFFu;
+            }
+            const uint32_t x0 = a.x & 0xFFFFu, x1 = a.x >> 16, y0 = a.y & 0xFFFFu, y1 = a.y >> 16;
+            const uint32_t m01 = x0 > x1 ? x0 : x1, m23 = y0 > y1 ? y0 : y1;
+            const uint32_t mg = m01 > m23 ? m01 : m23;
+            m = mg > m ? mg : m;
+            *reinterpret_cast<uint2*>(arow + g * (kGrp / 2)) = a;
+        }
+    };
+    if (n_col == 0) {
+#pragma unroll 1
+        for (int c = 0; c < NCK; ++c) merge(c);
+        return;
+    }
+    uint2 xb[4];
+    int u = 0, c = 0;                      // the step xa holds
+#pragma unroll 1
+    while (true) {
+        // ---- xa is current, the next step goes to xb
+        int nu = u + 1, nc = c;
+        if (nu == n_col) { nu = 0; ++nc; }
+        if (nc < NCK) load(xb, nu, nc);
+        add(xa);
+        if (nu == 0) merge(c);
+        if (nc >= NCK) break;
+        u = nu; c = nc;
+        // ---- xb is current, the next step goes to xa
+        nu = u + 1; nc = c;
+        if (nu == n_col) { nu = 0; ++nc; }
+        if (nc < NCK) load(xa, nu, nc);
+        add(xb);
+        if (nu == 0) merge(c);
+        if (nc >= NCK) break;
+        u = nu; c = nc;
+    }
+}
+
 // the 4 accumulators at local rows [row, row + 4) (row a multiple of 4)
 template <bool A16>
 __device__ __forceinline__ void bm25_load4(const uint32_t* acc, uint32_t row, uint32_t (&v)[4]) {
@@ -832,6 +916,7 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     uint32_t* ring = acc + (A16 ? kBmBlock / 2 : kBmBlock);
     __shared__ uint2 s_runs[kBmMaxTokens];            // [lo, hi) inside the packed stream
     __shared__ const uint16_t* s_colp[kBmMaxTokens];  // column of the tile per DENSE token
+    __shared__ uint32_t s_colo[kBmMaxTokens];         // A16: the same as an offset from the column base, in 8-byte words
     __shared__ __align__(8) uint64_t s_full[kBmRingSlots], s_empty[kBmRingSlots];
     __shared__ int s_nrun, s_ncol, s_nlist;
     constexpr int T = 256;
@@ -858,7 +943,9 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     }
     __syncthreads();
     if (d.x == (uint32_t)kBmDense) {
-        s_colp[atomicAdd(&s_ncol, 1)] = ix.dense_col + ((size_t)d.y * ix.n_blocks + blk) * kBmBlock;
+        const int slot_c = atomicAdd(&s_ncol, 1);
+        s_colp[slot_c] = ix.dense_col + ((size_t)d.y * ix.n_blocks + blk) * kBmBlock;
+        s_colo[slot_c] = (uint32_t)(((size_t)d.y * ix.n_blocks + blk) * (kBmBlock / 4));
     } else if (d.x == (uint32_t)kBmMid) {
         if (d.z > d.y) s_runs[atomicAdd(&s_nrun, 1)] = make_uint2(d.y, d.z);
     }
@@ -957,7 +1044,11 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");             // the column phase owns rows by thread
     uint32_t m = 0u;
-    bm25_column_phase<4, T, A16, DG>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m, cshift);
+    if constexpr (A16)
+        bm25_column_phase16(acc, s_colo, reinterpret_cast<const uint2*>(ix.dense_col), n_col, xa[0], allow, r0, r1, tid,
+                            cshift, m);
+    else
+        bm25_column_phase<4, T, A16, DG>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m, cshift);
     bm25_select_phase<4, T, true, kBmList, A16>(acc, m, H, r0, tid, reinterpret_cast<unsigned long long*>(ring), &s_nlist,
                                                 heads + ((size_t)qy * ix.n_blocks + blk) * (H + 1), A16 ? cshift : 0);
 }
@@ -1339,7 +1430,7 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     cudaError_t e = cudaSuccess;
     // 16-bit accumulators: the coarsest unit 2^cshift for which a query's tokens cannot sum to 2^16
     int cshift = 0;
-    if (use_tma && g_bm25_acc16) {
+    if (use_tma && g_bm25_acc16 && (size_t)ix.n_dense * ix.n_blocks * (kBmBlock / 4) < ((size_t)1 << 32)) {
         cshift = kBmDenseShift;
         while (cshift <= 8 && (int64_t)stride * ((1 << (kBmQBits - cshift)) + 1) > 65535) ++cshift;
         if (cshift > 8) cshift = 0;             // too many tokens: the unit would be too coarse to select with

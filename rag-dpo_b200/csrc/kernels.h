@@ -201,6 +201,7 @@ struct Bm25Device {
     int32_t* rng_off;       // n_tabled x (n_blocks + 1): first posting with row >= b * 16384, relative to term_ptr[t]
     uint16_t* dense_col;    // n_dense x (n_blocks * 16384): ceil(q / 4) of the term's posting on that row, 0 = no posting
     int n_blocks;
+    int n_dense;            // dense columns
     int fast_ok;            // 1: all idf >= 0 and the packed stream exists -> the integer filter bound is valid
 };
 // term classes (term_info.x >> 30)

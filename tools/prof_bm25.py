@@ -28,7 +28,7 @@ for q in qs[:6]:
 import os
 if os.environ.get("BM25_TILE"):
     _lib.set_option("bm25_tile", int(os.environ["BM25_TILE"]))
-for tma in [int(v) for v in os.environ.get("BM25_TMA", "1").split(",")]:
+for tma in [int(v) for v in os.environ.get("BM25_TMA", "3").split(",")]:
     _lib.set_option("bm25_tma", tma & 1)
     _lib.set_option("bm25_acc16", 1 if tma & 2 else 0)           # 3: 16-bit accumulators, 4 CTAs per SM
     ref = None
