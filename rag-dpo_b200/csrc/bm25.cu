@@ -398,13 +398,10 @@ __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q
 // disallowed rows and takes the thread's maximum.  Steps = (chunk, group of kBmDnGroup tokens); the loads
 // of the next step are requested before the current one is added (two register buffers, ping-pong).
 // xa holds step (chunk 0, group 0), requested by the caller (in flight while the run tokens are added).
-// A16: the accumulators are 16 bits wide, two rows per 32-bit word (even row in the low half — the layout of a column
-// word), in units coarser by 2^cshift than a packed posting's q: a column sum (entries = ceil(q / 4)) is divided by
-// 2^(cshift - 2), rounding up, before it is added (still an upper bound; the caller widens the slack).
-template <int CH, int T, bool A16 = false, int DG = kBmDnGroup>
+template <int CH, int T, int DG = kBmDnGroup>
 __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t* const* s_colp, int n_col, bool last,
                                                   uint2 (&xa)[DG][4], const uint8_t* __restrict__ allow,
-                                                  int64_t r0, int64_t r1, int tid, uint32_t& m, int cshift = 0) {
+                                                  int64_t r0, int64_t r1, int tid, uint32_t& m) {
     constexpr int kTile = CH * 4096;
     constexpr int kChunk = 16 * T, kGrp = 4 * T, NCK = kTile / kChunk;
     const int ngroups = n_col > 0 ? (n_col + DG - 1) / DG : 1;
@@ -438,40 +435,7 @@ __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t*
                 s_all[2 * g + 1] += xx[u][g].y;
                 s_hi[2 * g + 1] += xx[u][g].y >> 16;
             }
-        if (A16 && ++cg == ngroups) {    // the chunk's last group: merge (16-bit accumulators)
-            uint32_t* arow = acc + ((cc * kChunk + 4 * tid) >> 1);
-            const int cs = cshift - kBmDenseShift;
-            const uint32_t rnd = (1u << cs) - 1u;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                uint2 a = *reinterpret_cast<const uint2*>(arow + g * (kGrp / 2));
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t hi = s_hi[2 * g + h];
-                    const uint32_t lo = s_all[2 * g + h] - (hi << 16);
-                    (h ? a.y : a.x) += ((lo + rnd) >> cs) | (((hi + rnd) >> cs) << 16);
-                }
-                if (last) {
-                    if (allow != nullptr) {
-                        const int64_t row = r0 + cc * kChunk + g * kGrp + 4 * tid;  // 4 rows inside one bitmap byte
-                        const uint32_t bits = row < r1 ? ((uint32_t)allow[row >> 3] >> (row & 7)) : 0u;
-                        if (!(bits & 1u)) a.x &= 0xFFFF0000u;
-                        if (!(bits & 2u)) a.x &= 0x0000FFFFu;
-                        if (!(bits & 4u)) a.y &= 0xFFFF0000u;
-                        if (!(bits & 8u)) a.y &= 0x0000FFFFu;
-                    }
-                    const uint32_t x0 = a.x & 0xFFFFu, x1 = a.x >> 16, y0 = a.y & 0xFFFFu, y1 = a.y >> 16;
-                    const uint32_t m01 = x0 > x1 ? x0 : x1, m23 = y0 > y1 ? y0 : y1;
-                    const uint32_t mg = m01 > m23 ? m01 : m23;
-                    m = mg > m ? mg : m;
-                }
-                *reinterpret_cast<uint2*>(arow + g * (kGrp / 2)) = a;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { s_all[j] = 0u; s_hi[j] = 0u; }
-            cg = 0;
-            ++cc;
-        } else if (!A16 && ++cg == ngroups) {    // the chunk's last group: merge
+        if (++cg == ngroups) {    // the chunk's last group: merge
             uint32_t* arow = acc + cc * kChunk + 4 * tid;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -566,8 +530,10 @@ __device__ __forceinline__ void bm25_column_phase(uint32_t* acc, const uint16_t*
 // ---- selection: the tile's H best allowed rows by U and the (H+1)-th best U -> dst[0..H] (descending; 0 = none).
 // Every thread reads only the accumulators it wrote last (column phase): no barrier needed on entry.  *s_nlist is 0.
 // NAMED: the CTA has a producer warp; the 256 consumer threads synchronise on named barrier 1.
-// Column tokens of the 16-bit kernel (T = 256, one block): the same sums as bm25_column_phase<.., A16>, written for few
-// instructions and few registers — a column is addressed by a 32-bit offset (in 8-byte words) from the column base, so
+// Column tokens of the 16-bit kernel (T = 256, one block).  The accumulators are 16 bits wide, two rows per 32-bit word
+// (even row in the low half — the layout of a column word), in units coarser by 2^cshift than a packed posting's q: a
+// column sum (entries = ceil(q / 4)) is divided by 2^(cshift - 2), rounding up, before it is added (still an upper
+// bound; the caller widens the slack).  The same sums as bm25_column_phase, written for few instructions and registers — a column is addressed by a 32-bit offset (in 8-byte words) from the column base, so
 // a step costs one shared load, one wide multiply-add, four 8-byte loads and their adds; the steps (chunk, token) are
 // double buffered (xa holds step (0, 0), requested by the caller).
 __device__ __forceinline__ void bm25_column_phase16(uint32_t* acc, const uint32_t* s_colo, const uint2* __restrict__ colbase,
@@ -1048,7 +1014,7 @@ bm25_filter_tma_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride,
         bm25_column_phase16(acc, s_colo, reinterpret_cast<const uint2*>(ix.dense_col), n_col, xa[0], allow, r0, r1, tid,
                             cshift, m);
     else
-        bm25_column_phase<4, T, A16, DG>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m, cshift);
+        bm25_column_phase<4, T, DG>(acc, s_colp, n_col, true, xa, allow, r0, r1, tid, m);
     bm25_select_phase<4, T, true, kBmList, A16>(acc, m, H, r0, tid, reinterpret_cast<unsigned long long*>(ring), &s_nlist,
                                                 heads + ((size_t)qy * ix.n_blocks + blk) * (H + 1), A16 ? cshift : 0);
 }
