@@ -921,6 +921,39 @@ def test_bm25_filter_tile_sizes_vs_oracle(tile, tma, acc16):
     ix.close()
 
 
+def test_bm25_16bit_accumulators_at_their_limit():
+    """the batched block-tile kernel keeps 16-bit accumulators in a unit chosen from the launch's longest query, so that
+    a query's tokens cannot sum to 2^16: repeat the term with the LARGEST idf*impact product 15 / 16 / 31 / 32 / 63 /
+    64 / 100 times (duplicates count again, bm25_index.py:265 -> rank_bm25 get_scores) next to frequent (column) terms —
+    every unit the kernel can pick and the hand-over to the 32-bit kernel, all bit-equal to the oracle"""
+    from b200rag import _lib
+    from b200rag.bm25 import DeviceBM25, Postings
+    n_docs = 40000
+    docs, n_terms = helpers.zipf_docs(n_docs, 2000, seed=13, lo=10, hi=40)
+    # a rare term in short documents: large idf and large impact -> the largest products of the index
+    rare = n_terms
+    for r in (5, 16383, 16384, 20001, 39999):
+        docs[r] = np.concatenate([docs[r][:3], [rare, rare, rare]])
+    n_terms += 1
+    p = Postings.from_term_ids(docs, n_terms=n_terms)
+    o = no.CsrBM25(docs)
+    ix = DeviceBM25(p)
+    by_df = np.argsort(-np.diff(p.term_ptr))
+    _lib.set_option("bm25_tile", 4)
+    try:
+        for reps in (15, 16, 31, 32, 63, 64, 100):
+            qs = [np.array([rare] * reps, np.int32),
+                  np.concatenate([by_df[:3], [rare] * (reps - 3)]).astype(np.int32),
+                  np.concatenate([[rare] * (reps - 4), by_df[1:3], by_df[40:42]]).astype(np.int32)]
+            rows, scores, counts = ix.search_ids(qs, 10)
+            for i, qt in enumerate(qs):
+                er, es = o.search(qt.tolist(), 10)
+                assert rows[i, :counts[i]].tolist() == er.tolist() and np.array_equal(scores[i, :counts[i]], es), (reps, i)
+    finally:
+        _lib.set_option("bm25_tile", 0)
+    ix.close()
+
+
 def test_clustered_corpus_through_the_tensor_core_path():
     """Rows sorted by cluster (adjacent rows are near-duplicates, as chunks of one document are): every query's
     neighbours sit in one or two row tiles, and the sample may miss the query's cluster entirely."""
