@@ -74,7 +74,8 @@ int rag_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_by
  * an index is built, default 8; 0 = none), "bm25_tile" (force 1 / 2 / 4 chunks of 4096 rows per filter CTA,
  * default 0 = by launch size), "bm25_tma" (1 = block tiles through the kernel that stages the posting runs through
  * shared memory with TMA bulk copies, default 1), "bm25_acc16" (1 = that kernel keeps 16-bit accumulators in a
- * coarser unit: 5 CTAs per SM, default 1), "bm25_by_block" (1 = its CTAs in (block, query) order, default 1) */
+ * coarser unit: 5 CTAs per SM, default 1), "bm25_by_block" (1 = its CTAs in (block, query) order, default 1), "bm25_inline_resolve" (1 = launches of <= 4
+ * queries resolve their token records inside the filter kernel instead of a separate launch, default 1) */
 int rag_set_option(const char* key, int64_t value);
 /* page-locked host memory: buffers allocated here are DMA'd directly by the host-pointer entry points
  * (no staging copy); any other host pointer is staged through an internal pinned block. */

@@ -8,7 +8,7 @@
 #include "api_common.h"
 
 using namespace b200rag;
-namespace b200rag { extern int g_bm25_tile_chunks; extern int g_bm25_tma; extern int g_bm25_by_block; extern int g_bm25_acc16; }      // bm25.cu: options "bm25_tile", "bm25_tma"
+namespace b200rag { extern int g_bm25_tile_chunks; extern int g_bm25_tma; extern int g_bm25_by_block; extern int g_bm25_acc16; extern int g_bm25_inline_resolve; }      // bm25.cu: options "bm25_tile", "bm25_tma"
 
 namespace {
 
@@ -426,6 +426,7 @@ int bm25_set_option(const char* key, int64_t value) {
     else if (!strcmp(key, "bm25_tma")) b200rag::g_bm25_tma = (int)value;
     else if (!strcmp(key, "bm25_by_block")) b200rag::g_bm25_by_block = (int)value;
     else if (!strcmp(key, "bm25_acc16")) b200rag::g_bm25_acc16 = (int)value;
+    else if (!strcmp(key, "bm25_inline_resolve")) b200rag::g_bm25_inline_resolve = (int)value;
     else if (!strcmp(key, "bm25_dense_div")) g_bm25_dense_div = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     else if (!strcmp(key, "bm25_rows_max")) g_bm25_rows_max = (int)std::max<int64_t>(0, std::min<int64_t>(value, kBm25MaxListedRows));
     else return RAG_EINVAL;

@@ -352,6 +352,37 @@ __device__ __forceinline__ void bm25_emit_heads(const unsigned long long* s_list
 // Slots past the query's last token are kBmSkip.
 // low_search: an untabled (LOW) list is narrowed to its run inside the block by two searches and reported as MID, so
 // that the consumer sees block-local runs only (bm25_filter_tma_kernel).
+// the record of token slot i of (query q0 + q, block blk)
+__device__ __forceinline__ uint4 bm25_resolve_one(const Bm25Device& ix, const int32_t* __restrict__ q_terms,
+                                                  const int32_t* __restrict__ q_ptr, int q, int blk, int i, int low_search) {
+    const int lo = q_ptr[q], nt = q_ptr[q + 1] - lo;
+    uint4 d = make_uint4((uint32_t)kBmSkip, 0u, 0u, 0u);
+    if (i < nt) {
+        const int32_t t = q_terms[lo + i];
+        if (t >= 0 && t < ix.n_terms) {
+            const int2 info = ix.term_info[t];
+            const int cls = (int)((unsigned)info.x >> 30);
+            if (cls == kBmDense) {
+                d = make_uint4((uint32_t)cls, (uint32_t)info.y, 0u, 0u);
+            } else if (cls == kBmMid) {
+                const uint32_t base = (uint32_t)ix.term_ptr[t];
+                const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_blocks + 1) + blk;
+                d = make_uint4((uint32_t)cls, base + (uint32_t)ro[0], base + (uint32_t)ro[1], 0u);
+            } else if (cls == kBmLow) {
+                const int64_t lo_p = ix.term_ptr[t], hi_p = ix.term_ptr[t + 1];
+                if (low_search) {
+                    const int64_t a = bm25_lower_bound(ix.post_row, lo_p, hi_p, (int64_t)blk * kBmBlock);
+                    const int64_t b = bm25_lower_bound(ix.post_row, a, hi_p, (int64_t)(blk + 1) * kBmBlock);
+                    d = make_uint4((uint32_t)kBmMid, (uint32_t)a, (uint32_t)b, 0u);
+                } else {
+                    d = make_uint4((uint32_t)cls, (uint32_t)lo_p, (uint32_t)hi_p, 0u);
+                }
+            }
+        }
+    }
+    return d;
+}
+
 __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_ptr,
                                     int q0, int Q, int stride, int low_search, uint4* __restrict__ rec) {
     const int64_t per_q = (int64_t)ix.n_blocks * stride;
@@ -360,35 +391,9 @@ __global__ void bm25_resolve_kernel(Bm25Device ix, const int32_t* __restrict__ q
         const int q = (int)(e / per_q);
         const int rem = (int)(e - (int64_t)q * per_q);
         const int blk = rem / stride, i = rem - blk * stride;
-        const int lo = q_ptr[q0 + q], nt = q_ptr[q0 + q + 1] - lo;
-        uint4 d = make_uint4((uint32_t)kBmSkip, 0u, 0u, 0u);
-        if (i < nt) {
-            const int32_t t = q_terms[lo + i];
-            if (t >= 0 && t < ix.n_terms) {
-                const int2 info = ix.term_info[t];
-                const int cls = (int)((unsigned)info.x >> 30);
-                if (cls == kBmDense) {
-                    d = make_uint4((uint32_t)cls, (uint32_t)info.y, 0u, 0u);
-                } else if (cls == kBmMid) {
-                    const uint32_t base = (uint32_t)ix.term_ptr[t];
-                    const int32_t* ro = ix.rng_off + (size_t)(info.x & 0x3FFFFFFF) * (ix.n_blocks + 1) + blk;
-                    d = make_uint4((uint32_t)cls, base + (uint32_t)ro[0], base + (uint32_t)ro[1], 0u);
-                } else if (cls == kBmLow) {
-                    const int64_t lo = ix.term_ptr[t], hi = ix.term_ptr[t + 1];
-                    if (low_search) {
-                        const int64_t a = bm25_lower_bound(ix.post_row, lo, hi, (int64_t)blk * kBmBlock);
-                        const int64_t b = bm25_lower_bound(ix.post_row, a, hi, (int64_t)(blk + 1) * kBmBlock);
-                        d = make_uint4((uint32_t)kBmMid, (uint32_t)a, (uint32_t)b, 0u);
-                    } else {
-                        d = make_uint4((uint32_t)cls, (uint32_t)lo, (uint32_t)hi, 0u);
-                    }
-                }
-            }
-        }
-        rec[e] = d;
+        rec[e] = bm25_resolve_one(ix, q_terms, q_ptr, q0 + q, blk, i, low_search);
     }
 }
-
 
 // ---- column tokens, 4096 rows at a time: 4 x 8 bytes per thread and token straight into registers.  A thread
 // owns the local rows c * 4096 + g * 1024 + 4 * tid + i (g, i = 0..3): 8-byte column loads and 16-byte
@@ -726,7 +731,8 @@ __device__ __forceinline__ void bm25_select_phase(uint32_t* acc, uint32_t m, int
 template <int CH, int T>
 __global__ void __launch_bounds__(T, T >= 512 ? 2 : 3)
 bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, const uint8_t* __restrict__ allow, int H,
-                   unsigned long long* __restrict__ heads) {
+                   unsigned long long* __restrict__ heads, const int32_t* __restrict__ q_terms,
+                   const int32_t* __restrict__ q_ptr, int q0) {
     extern __shared__ __align__(16) uint32_t acc[];   // CH x 4096 accumulators
     __shared__ uint2 s_runs[kBmMaxTokens];            // [lo, hi) inside the packed stream: tabled runs from the front,
     __shared__ const uint16_t* s_colp[kBmMaxTokens];  // scanned lists from the back; column of the tile per DENSE token
@@ -751,7 +757,9 @@ bm25_filter_kernel(Bm25Device ix, const uint4* __restrict__ rec, int stride, con
         const int tn = stride - t0 < kBmMaxTokens ? stride - t0 : kBmMaxTokens;
         const bool last = t0 + kBmMaxTokens >= stride;
         uint4 d = make_uint4((uint32_t)kBmSkip, 0u, 0u, 0u);
-        if (tid < tn) d = __ldg(my_rec + t0 + tid);
+        // (rec == nullptr: small launches — a single query — resolve their records here and save the resolve launch)
+        if (tid < tn) d = rec != nullptr ? __ldg(my_rec + t0 + tid)
+                                         : bm25_resolve_one(ix, q_terms, q_ptr, q0 + (int)blockIdx.y, blk, t0 + tid, 0);
         __syncthreads();                  // accumulators zeroed / previous pass done with the token table
         if (tid == 0) { s_ntab = 0; s_nscan = 0; s_ncol = 0; }
         __syncthreads();
@@ -1337,6 +1345,7 @@ static bool bm25_plan_for(const Bm25Device& ix, int k, int ch, Bm25Plan* p) {
 // block tiles when the launch has enough of them to fill the GPU (148 SMs x 3 CTAs, twice over); quarter-block tiles
 // for small corpora and single queries (more, shorter CTAs: latency)
 int g_bm25_tile_chunks = 0;             // option "bm25_tile": force 1 / 2 / 4 chunks per tile (0 = automatic)
+int g_bm25_inline_resolve = 1;          // option "bm25_inline_resolve": launches of <= 4 queries resolve their records in the filter kernel
 int g_bm25_acc16 = 1;                   // option "bm25_acc16": 16-bit accumulators (4 CTAs per SM) in the TMA kernel
 int g_bm25_by_block = 1;                // option "bm25_by_block": the TMA kernel's CTAs in (block, query) order
 int g_bm25_tma = 1;                     // option "bm25_tma": block tiles through bm25_filter_tma_kernel (0: bm25_filter_kernel<4>)
@@ -1384,7 +1393,12 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     const bool use_tma = g_bm25_tma && pl.ch == 4 && stride <= kBmMaxTokens;
     unsigned long long* heads = reinterpret_cast<unsigned long long*>(scratch);
     uint4* rec = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(scratch) + bm25_heads_bytes(ix, k, Q));
-    {
+    // small launches of the small-tile kernels (a single query: the latency path) resolve their records inside the
+    // filter kernel: one launch less
+    const bool inline_resolve = g_bm25_inline_resolve && !use_tma && pl.ch != 4 && Q <= 4;
+    if (inline_resolve) {
+        rec = nullptr;
+    } else {
         const int64_t total = (int64_t)Q * ix.n_blocks * stride;
         int64_t g = (total + 255) / 256;
         if (g > 148 * 16) g = 148 * 16;
@@ -1423,11 +1437,11 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
         // barriers cost more than the occupancy returns: 3.45 vs 2.61 us/query)
         e = cudaFuncSetAttribute(bm25_filter_kernel<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4);
         if (e != cudaSuccess) return e;
-        bm25_filter_kernel<4, 256><<<grid_a, 256, 4 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
+        bm25_filter_kernel<4, 256><<<grid_a, 256, 4 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads, d_q_terms, d_q_ptr, q0);
     } else if (pl.ch == 2) {
-        bm25_filter_kernel<2, 256><<<grid_a, 256, 2 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
+        bm25_filter_kernel<2, 256><<<grid_a, 256, 2 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads, d_q_terms, d_q_ptr, q0);
     } else {
-        bm25_filter_kernel<1, 256><<<grid_a, 256, 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads);
+        bm25_filter_kernel<1, 256><<<grid_a, 256, 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads, d_q_terms, d_q_ptr, q0);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -25,6 +25,14 @@ qs = [np.concatenate([g.choice(n_terms, size=g.integers(8, 13), p=p), g.integers
 for q in qs[:6]:
     ix.search_ids([q], 50)
     print("single device ms", float(_lib.last_timings()[0]))
+for inl in (0, 1, 0, 1):
+    _lib.set_option("bm25_inline_resolve", inl)
+    ms = []
+    for q in qs[:40]:
+        ix.search_ids([q], 50)
+        ms.append(float(_lib.last_timings()[0]))
+    print("single query, inline resolve", inl, "device ms p50", float(np.median(ms)), "min", min(ms))
+_lib.set_option("bm25_inline_resolve", 1)
 import os
 if os.environ.get("BM25_TILE"):
     _lib.set_option("bm25_tile", int(os.environ["BM25_TILE"]))
