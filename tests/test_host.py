@@ -207,3 +207,18 @@ def test_chroma_store_reader_roundtrip(tmp_path):
         assert np.array_equal(st["embeddings"][40:], emb[40:])
     with pytest.raises(KeyError):
         cs.read_chroma_store(str(d), "no_such_collection")
+
+
+def test_bench_reads_roofline_traffic_from_the_committed_profiles():
+    """bench.py's `roofline.traffic` is the DRAM byte count of the named kernel in the committed ncu raw pages (never a
+    literal): the reader finds both kernels and returns bytes in a plausible range, and None for what is not there"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    dense = bench.profile_traffic("r2_dense_step_ncu_full_raw.csv", "dense_gemm_topk_kernel<1, 2>")
+    assert dense is not None and 2.0e9 < dense["bytes_per_launch"] < 2.3e9       # one pass over 1M x 1024 bf16 + lists
+    bm25 = bench.profile_traffic("r2_bm25_filter_ncu_full_raw.csv", "bm25_filter")
+    assert bm25 is not None and 1.0e8 < bm25["bytes_per_launch"] < 2.9e9          # <= the algorithmic 2.78 GB
+    assert bench.profile_traffic("r2_bm25_filter_ncu_full_raw.csv", "no_such_kernel") is None
+    assert bench.profile_traffic("no_such_file.csv", "bm25_filter") is None
