@@ -7,7 +7,7 @@
 // Bit-parity rules: the scores that are RETURNED are fp64 throughout, numpy's evaluation order, no
 // FMA contraction (explicit __dmul_rn/__ddiv_rn/__dadd_rn), accumulated token by token in query order.
 //   rag_bm25_search  fast path: an integer FILTER over the packed postings / dense columns (fixed-point upper bounds of
-//                    idf*impact; bm25_resolve_kernel + bm25_filter_kernel) finds k + a handful of survivors per
+//                    idf*impact; bm25_resolve_kernel + bm25_filter_tma_kernel / bm25_filter_kernel) finds k + a handful of survivors per
 //                    query, whose exact fp64 scores are recomputed from the postings (bm25_finish_kernel);
 //                    robust path: fp64 accumulators of a 4096-row range in shared memory (bm25_range_kernel);
 //   rag_bm25_scores  (full get_scores vector) one bm25_accumulate_kernel launch per token over a global accumulator.
@@ -287,7 +287,9 @@ bm25_range_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restric
 // + 5 per column token.
 //   R  bm25_resolve_kernel  one record per (query, block, token): class and the term's run inside the block (range
 //        table: no search) — a flat, fully parallel kernel pays the dependent look-ups once instead of every CTA.
-//   A  bm25_filter_kernel<CH>  grid (tiles, queries), a tile = CH x 4096 rows (CH = 4: one block, used when the
+//   A  bm25_filter_tma_kernel (block tiles of batched launches: posting runs staged through shared memory by a TMA
+//        producer warp, rows owned by warps, 16-bit accumulators, 5 CTAs per SM — described at the kernel) or
+//      bm25_filter_kernel<CH>  grid (tiles, queries), a tile = CH x 4096 rows (CH = 4: one block, used when the
 //        launch has enough tiles to fill the GPU; CH = 1: a quarter block, for small corpora / single queries).
 //        Run tokens: integer accumulators of the tile in shared memory; the CTA adds one token at a time, thread i
 //        the i-th posting of the run (plain read-modify-write: the postings of one term are distinct rows), 8 loads
