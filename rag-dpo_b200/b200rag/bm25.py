@@ -29,6 +29,18 @@ class BM25Result:
     metadata: Dict
 
 
+def _pack_queries(queries_term_ids):
+    """list of term-id sequences -> (flat int32 terms, q_ptr int32[Q + 1]); one concatenate over the list (the
+    per-query conversions it replaces were half of the host time of a 256-query call)"""
+    Q = len(queries_term_ids)
+    q_ptr = np.zeros(Q + 1, dtype=np.int32)
+    np.cumsum(np.fromiter(map(len, queries_term_ids), dtype=np.int64, count=Q), out=q_ptr[1:])
+    if not q_ptr[-1]:
+        return np.zeros(1, np.int32), q_ptr
+    flat = np.concatenate(queries_term_ids) if Q > 1 else np.asarray(queries_term_ids[0])
+    return np.ascontiguousarray(flat, dtype=np.int32), q_ptr
+
+
 class Postings:
     """CSR postings + BM25Okapi statistics built on the host."""
 
@@ -168,11 +180,7 @@ class DeviceBM25:
         Q = len(queries_term_ids)
         if k > _lib.RAG_MAX_K:
             return self._search_multipass(queries_term_ids, int(k), allow_bitmap)
-        q_ptr = np.zeros(Q + 1, dtype=np.int32)
-        np.cumsum([len(t) for t in queries_term_ids], out=q_ptr[1:])
-        flat = (np.concatenate([np.asarray(t, dtype=np.int32) for t in queries_term_ids])
-                if q_ptr[-1] else np.zeros(1, np.int32))
-        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        flat, q_ptr = _pack_queries(queries_term_ids)
         rows = np.empty((Q, k), dtype=np.int32)
         scores = np.empty((Q, k), dtype=np.float64)
         counts = np.empty(Q, dtype=np.int32)
@@ -184,11 +192,7 @@ class DeviceBM25:
     def query_bytes(self, queries_term_ids):
         """measurement helper: (bytes the filter pass streams, postings) per query, int64 arrays"""
         Q = len(queries_term_ids)
-        q_ptr = np.zeros(Q + 1, dtype=np.int32)
-        np.cumsum([len(t) for t in queries_term_ids], out=q_ptr[1:])
-        flat = (np.concatenate([np.asarray(t, dtype=np.int32) for t in queries_term_ids])
-                if q_ptr[-1] else np.zeros(1, np.int32))
-        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        flat, q_ptr = _pack_queries(queries_term_ids)
         nbytes = np.zeros(Q, dtype=np.int64)
         npost = np.zeros(Q, dtype=np.int64)
         _lib.check(self._L.rag_bm25_query_bytes(self._h, _lib.ptr(flat), _lib.ptr(q_ptr), Q, _lib.ptr(nbytes), _lib.ptr(npost)))
