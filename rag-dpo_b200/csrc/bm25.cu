@@ -1421,23 +1421,20 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
         const bool by_block = g_bm25_by_block && pl.n_tiles <= 65535;
         const dim3 grid_t = by_block ? dim3(Q, pl.n_tiles) : grid_a;
         if (cshift > 0) {
-            e = cudaFuncSetAttribute(bm25_filter_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)bm25_tma_smem(true));
+            e = ensure_dynamic_smem_of(bm25_filter_tma_kernel<true>, (size_t)(bm25_tma_smem(true)));
             if (e != cudaSuccess) return e;
             bm25_filter_tma_kernel<true><<<grid_t, kBmTmaThreads, bm25_tma_smem(true), st>>>(
                 ix, rec, stride, allow, pl.H, by_block ? 1 : 0, cshift, heads);
         } else {
-            e = cudaFuncSetAttribute(bm25_filter_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)bm25_tma_smem(false));
+            e = ensure_dynamic_smem_of(bm25_filter_tma_kernel<false>, (size_t)(bm25_tma_smem(false)));
             if (e != cudaSuccess) return e;
             bm25_filter_tma_kernel<false><<<grid_t, kBmTmaThreads, bm25_tma_smem(false), st>>>(
                 ix, rec, stride, allow, pl.H, by_block ? 1 : 0, 0, heads);
         }
     } else if (pl.ch == 4) {
-        // (a function attribute belongs to the current device: set on every launch, a sharded index runs on several)
         // (512-thread CTAs, 2 per SM, were tried for the 32 resident warps: 64 registers spill and the 16-warp
         // barriers cost more than the occupancy returns: 3.45 vs 2.61 us/query)
-        e = cudaFuncSetAttribute(bm25_filter_kernel<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4);
+        e = ensure_dynamic_smem_of(bm25_filter_kernel<4, 256>, (size_t)(4 * 4096 * 4));
         if (e != cudaSuccess) return e;
         bm25_filter_kernel<4, 256><<<grid_a, 256, 4 * 4096 * 4, st>>>(ix, rec, stride, allow, pl.H, heads, d_q_terms, d_q_ptr, q0);
     } else if (pl.ch == 2) {
@@ -1448,7 +1445,7 @@ cudaError_t bm25_fast_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t smem = (size_t)kBmContrib * sizeof(double) + (size_t)kBmSurvivors * (sizeof(Bm25Key) + 4);
-    e = cudaFuncSetAttribute(bm25_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem_of(bm25_finish_kernel, (size_t)(smem));
     if (e != cudaSuccess) return e;
     bm25_finish_kernel<<<Q, kBmFinishThreads, smem, st>>>(ix, d_q_terms, d_q_ptr, q0, heads, pl.n_tiles, pl.H, pl.h_tau, cshift, k,
                                              out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_counts + q0);
@@ -1461,7 +1458,7 @@ cudaError_t bm25_rows_launch(const Bm25Device& ix, const int32_t* d_q_terms, con
     int cap = 32;
     while (cap < n_rows) cap <<= 1;
     const size_t smem = (size_t)kBmContrib * sizeof(double) + (size_t)cap * sizeof(Bm25Key);
-    cudaError_t e = cudaFuncSetAttribute(bm25_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem_of(bm25_rows_kernel, (size_t)(smem));
     if (e != cudaSuccess) return e;
     bm25_rows_kernel<<<Q, 256, smem, st>>>(ix, d_q_terms, d_q_ptr, d_rows, n_rows, k, out_rows, out_scores, out_counts);
     return cudaGetLastError();
@@ -1562,7 +1559,7 @@ cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, co
                               int32_t* out_rows, double* out_scores, int32_t* out_counts, cudaStream_t st) {
     const int n_ranges = bm25_range_lists(ix.n_docs);
     size_t smem = (size_t)kBmRange * sizeof(double) + (size_t)8 * 2 * kp * sizeof(Bm25Key);
-    cudaError_t e = cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem_of(bm25_range_kernel, (size_t)(smem));
     if (e != cudaSuccess) return e;
     for (int q0 = 0; q0 < Q; q0 += 32768) {            // gridDim.y limit
         const int nq = Q - q0 < 32768 ? Q - q0 : 32768;
@@ -1577,7 +1574,7 @@ cudaError_t bm25_range_launch(const Bm25Device& ix, const int32_t* d_q_terms, co
     const size_t entries = (size_t)std::max(kBmMaxHeads, 16 * kp);
     const size_t smem2 = entries * sizeof(Bm25Key);
     if (smem2 > 48 * 1024) {
-        e = cudaFuncSetAttribute(bm25_select_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        e = ensure_dynamic_smem_of(bm25_select_batch_kernel, (size_t)(smem2));
         if (e != cudaSuccess) return e;
     }
     bm25_select_batch_kernel<<<Q, 256, smem2, st>>>(reinterpret_cast<const Bm25Key*>(cand), n_ranges, kp, k, out_rows,

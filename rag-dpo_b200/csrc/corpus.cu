@@ -7,6 +7,9 @@
 // src/processing/ingest_enterprise.py:241-246; collection.delete at
 // src/processing/ingest_enterprise.py:272,304.
 #include "common.cuh"
+#include <map>
+#include <mutex>
+
 #include "kernels.h"
 
 namespace b200rag {
@@ -152,6 +155,27 @@ cudaError_t gather_rows_launch(const void* src, void* dst, const int64_t* keep, 
     gather_rows_kernel<<<g, 128, 0, st>>>(reinterpret_cast<const uint8_t*>(src), reinterpret_cast<uint8_t*>(dst), keep,
                                           nkeep, row_bytes);
     return cudaGetLastError();
+}
+
+
+// ---- per-(device, kernel) cache of the dynamic shared-memory opt-in ----------------------------------------------
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    struct Key {
+        const void* fn;
+        int dev;
+        bool operator<(const Key& o) const { return fn < o.fn || (fn == o.fn && dev < o.dev); }
+    };
+    static std::mutex mu;
+    static std::map<Key, size_t> seen;            // the largest size already set
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = seen.find(Key{kernel, dev});
+    if (it != seen.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) seen[Key{kernel, dev}] = bytes;
+    return e;
 }
 
 }  // namespace b200rag

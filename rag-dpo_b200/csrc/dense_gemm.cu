@@ -741,7 +741,7 @@ static cudaError_t gemm_launch_pair(const GemmParams& p, const void* q16, const 
         return cudaErrorNotSupported;
     if (!make_map(&map_x, x16, p.n_rows, p.dim, GT_N / 2, p.fp16_operands)) return cudaErrorNotSupported;
     auto kern = dense_gemm_topk_kernel<1, 2>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_pair);
+    cudaError_t e = ensure_dynamic_smem_of(kern, (size_t)(p.smem_pair));
     if (e != cudaSuccess) return e;
     GemmParams pp = p;
     pp.n_stages = p.n_stages_pair;
@@ -790,7 +790,7 @@ cudaError_t gemm_launch(const GemmParams& p, int mode, const void* q16, const vo
         return cudaErrorNotSupported;
     if (!make_map(&map_x, x16, p.n_rows, p.dim, resident ? 64 : GT_N, p.fp16_operands)) return cudaErrorNotSupported;
     auto kern = mode == 0 ? dense_gemm_topk_kernel<0, 1> : dense_gemm_topk_kernel<1, 1>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem_of(kern, (size_t)(smem));
     if (e != cudaSuccess) return e;
     kern<<<grid, GT_THREADS, smem, st>>>(map_q, map_x, pp);
     return cudaGetLastError();

@@ -218,7 +218,7 @@ template <int DT, int NCH, int NQ, int MODE>
 static cudaError_t launch_inst(const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
     constexpr int CW = NQ <= 2 ? 16 : 8;
     auto kern = dense_scan_kernel<DT, NCH, NQ, CW, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem_of(kern, (size_t)(smem));
     if (e != cudaSuccess) return e;
     kern<<<grid, 32 + CW * 32, smem, st>>>(p);
     return cudaGetLastError();

@@ -566,7 +566,7 @@ static cudaError_t select_refine_dt(const uint64_t* cand, const int32_t* counts,
     constexpr int kBig = DT == RAG_F32 ? 5 : 6;
     auto kern = p.B >= 512 ? select_refine_kernel<DT, kBig> : select_refine_kernel<DT, 2>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dynamic_smem_of(kern, (size_t)(smem));
         if (e != cudaSuccess) return e;
     }
     kern<<<p.B, 256, smem, st>>>(cand, counts, flat_counts, n_lists, list_len, sorted_lists, overflow, p);
@@ -700,7 +700,7 @@ cudaError_t merge_exact_launch(const double* scores, const int64_t* ids, int G, 
     while (nsort < G * k) nsort <<= 1;
     size_t smem = (size_t)nsort * sizeof(ExactKey64);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(merge_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dynamic_smem_of(merge_exact_kernel, (size_t)(smem));
         if (e != cudaSuccess) return e;
     }
     merge_exact_kernel<<<B, 256, smem, st>>>(scores, ids, G, B, k, rank_stride, nsort, out_scores, out_ids, out_counts);

@@ -212,7 +212,7 @@ cudaError_t exchange_merge_launch(const ExchangeDev& ex, int B, int k, uint64_t 
     const int nsort = ex.world * k;                  // (entries held in shared memory; they are ranked, not sorted)
     const size_t smem = (size_t)nsort * sizeof(XKey);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dynamic_smem_of(exchange_merge_kernel, (size_t)(smem));
         if (e != cudaSuccess) return e;
     }
     exchange_merge_kernel<<<B, 256, smem, st>>>(ex, B, k, epoch, nsort, out_scores, out_ids, out_counts);

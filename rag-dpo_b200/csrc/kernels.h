@@ -8,6 +8,15 @@
 
 namespace b200rag {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size) instead of before every launch: the
+// attribute belongs to the current device's copy of the function, and the call is not free on a latency path
+// (a single-query search is three or four launches).  Thread-safe; defined in corpus.cu.
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
+template <typename K>
+inline cudaError_t ensure_dynamic_smem_of(K kernel, size_t bytes) {
+    return ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 // ---- dense_scan.cu ---------------------------------------------------------
 struct ScanParams {
     const void* rows;        // n_rows x dim, storage dtype, row-major

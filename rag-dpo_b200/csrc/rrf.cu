@@ -150,7 +150,7 @@ cudaError_t rrf_launch(const int32_t* ids, const double* weights, int Q, int R, 
     const int np = (R * L + 7) & ~7;
     const size_t smem = (size_t)np * (8 + 4 + 2 + 1);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(rrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dynamic_smem_of(rrf_kernel, (size_t)(smem));
         if (e != cudaSuccess) return e;
     }
     rrf_kernel<<<Q, 256, smem, st>>>(ids, weights, R, L, rrf_k, top, out_ids, out_scores, out_counts);
