@@ -32,7 +32,7 @@ __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p) {
 __global__ void __launch_bounds__(256)
 exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const int64_t* __restrict__ my_ids,
                      const int32_t* __restrict__ my_rows, int64_t row_lo, const int32_t* __restrict__ my_counts, int k,
-                     int64_t n_elems /* B*k */, uint64_t epoch) {
+                     int64_t n_elems /* B*k */, uint64_t epoch, int vec_ok) {
     const int peer = blockIdx.y;
     const int parity = (int)(epoch & 1);
     uint8_t* dst = ex.peer_base[peer] + ((size_t)parity * ex.world + ex.rank) * ex.slot_bytes;
@@ -41,7 +41,7 @@ exchange_push_kernel(ExchangeDev ex, const double* __restrict__ my_scores, const
     const uint64_t* s0 = reinterpret_cast<const uint64_t*>(my_scores);
     const uint64_t* s1 = reinterpret_cast<const uint64_t*>(my_ids);
     const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-    if ((n_elems & 1) == 0 && my_rows != nullptr) {
+    if (vec_ok) {           // even element count, 16-byte aligned scores, 8-byte aligned rows (checked by the launcher)
         // pairs: 16-byte loads of the scores / 8-byte loads of two local rows, 16-byte stores into the peer's buffer
         const int64_t half = n_elems >> 1;
         ulonglong2* d128 = reinterpret_cast<ulonglong2*>(dst);
@@ -203,7 +203,9 @@ cudaError_t exchange_push_launch(const ExchangeDev& ex, const double* my_scores,
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
     dim3 grid(bx, ex.world);
-    exchange_push_kernel<<<grid, 256, 0, st>>>(ex, my_scores, my_ids, my_rows, row_lo, my_counts, k, n_elems, epoch);
+    const int vec_ok = my_rows != nullptr && (n_elems & 1) == 0 && (reinterpret_cast<uintptr_t>(my_scores) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(my_rows) & 7) == 0;
+    exchange_push_kernel<<<grid, 256, 0, st>>>(ex, my_scores, my_ids, my_rows, row_lo, my_counts, k, n_elems, epoch, vec_ok);
     return cudaGetLastError();
 }
 
